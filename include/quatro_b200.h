@@ -1,0 +1,208 @@
+/*
+ * quatro_b200.h -- C-ABI of the B200-native global-registration hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one stage
+ * boundary of the reference (url-kaist/Quatro, paths relative to the reference root):
+ *
+ *   qb200_voxelize              <- voxelize<T>()                    include/quatro.hpp:49-57
+ *   qb200_compute_fpfh          <- FPFHEstimation::computeFPFHFeatures  src/teaser_utils/fpfh.cc:44-75
+ *   qb200_match                 <- Matcher::calculateCorrespondences    include/teaser_utils/feature_matcher.h:42-74
+ *                                  + Matcher::advancedMatching          src/teaser_utils/feature_matcher.cc:77-265
+ *   qb200_build_graph           <- Quatro::computeTIMs + solveForScale + inlier_graph_.addEdge loop
+ *                                  include/quatro.hpp:307-386, 784-789
+ *   qb200_max_clique            <- teaser::MaxCliqueSolver::findMaxClique   src/graph.cc:12-130
+ *   qb200_solve_pose            <- chain TIMs + GNC-TLS yaw + COTE      include/quatro.hpp:817-936
+ *   qb200_solve_correspondences <- Quatro::computeTransformation(Eigen::Matrix4d&)  include/quatro.hpp:769-936
+ *   qb200_match_and_pack        <- FPFHManager::setFeaturePair          include/fpfh_manager.hpp:98-153
+ *   qb200_register_pair/_batch  <- examples/run_global_registration.cpp:206-246 (voxelize .. computeTransformation)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.  All pointers are HOST pointers
+ *     unless a function takes a qb200_mem_kind (then QB200_MEM_DEVICE pointers are accepted).
+ *   - Points are 16-byte records {x, y, z, w} (pcl::PointXYZ layout, include/utility.h:109;
+ *     KITTI .bin records, examples/run_global_registration.cpp:384-399).
+ *   - Every function returns a qb200_status (0 = ok, <0 = bad argument / CUDA failure,
+ *     >0 = per-pair degenerate result).  Nothing throws across this boundary.
+ *   - There is NO CPU fallback: if no CUDA device is usable qb200_create() fails with
+ *     QB200_ERR_NO_DEVICE and no other entry point can be called.
+ *   - One handle = one device + one stream; a handle is not thread-safe, several handles are.
+ */
+#ifndef QUATRO_B200_H_
+#define QUATRO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_VERSION 100
+
+typedef enum qb200_status {
+  QB200_OK = 0,
+  /* >0: the call worked, the pair is degenerate (mirrors solution_.valid=false, quatro.hpp:809-813) */
+  QB200_DEGENERATE_CLIQUE = 1,   /* max clique size <= 1 */
+  QB200_DEGENERATE_INPUT = 2,    /* fewer than 2 correspondences / empty cloud */
+  QB200_CAPACITY_EXCEEDED = 3,   /* a per-pair buffer (voxels / correspondences) overflowed; result invalid */
+  /* <0: errors */
+  QB200_ERR_BAD_ARG = -1,
+  QB200_ERR_NO_DEVICE = -2,
+  QB200_ERR_CUDA = -3,
+  QB200_ERR_UNSUPPORTED = -4,    /* e.g. PMC_EXACT is not implemented on the device */
+  QB200_ERR_VOXEL_OVERFLOW = -5  /* dx*dy*dz > INT_MAX: PCL warns and returns the input unfiltered */
+} qb200_status;
+
+/* Quatro::INLIER_SELECTION_MODE, include/quatro.hpp:184-189 */
+enum { QB200_PMC_EXACT = 0, QB200_PMC_HEU = 1, QB200_KCORE_HEU = 2, QB200_INLIER_NONE = 3 };
+/* Params::cote_mode, include/quatro.hpp:209 */
+enum { QB200_COTE_MEDIAN = 0, QB200_COTE_WEIGHTED_MEAN = 1 };
+typedef enum qb200_mem_kind { QB200_MEM_HOST = 0, QB200_MEM_DEVICE = 1 } qb200_mem_kind;
+
+/* One POD for every knob on the path.  Defaults (qb200_default_params) = config/params.yaml:22-44
+ * + the hard-coded matcher flags of include/fpfh_manager.hpp:126-127. */
+typedef struct qb200_params {
+  /* front end */
+  float voxel_size;              /* 0.3   voxelize leaf                      params.yaml:22 */
+  float normal_radius;           /* 0.5                                      params.yaml:24 */
+  float fpfh_radius;             /* 0.75                                     params.yaml:25 */
+  float grid_cell;               /* 0 -> voxel_size. Cell of the neighbour-search lattice; only fixes
+                                    the (cell,index) order in which neighbours are accumulated. */
+  float tuple_scale;             /* 0.95                                     fpfh_manager.hpp:127 */
+  int32_t use_crosscheck;        /* 1 */
+  int32_t use_tuple_test;        /* 1 */
+  int32_t tuple_trials_per_corr; /* 100                                      feature_matcher.cc:195 */
+  int32_t skip_flagged;          /* 1: voxelize drops points with w < 0 (stand-in for the reference's
+                                    ground/sub-cluster removal, which is out of scope; PCL itself only
+                                    drops non-finite points) */
+  int32_t reserved0;
+  uint64_t seed;                 /* tuple-test RNG seed (replaces srand(time(NULL)), feature_matcher.cc:189) */
+  /* solver, include/quatro.hpp:202-268 */
+  double noise_bound;            /* 0.3   */
+  double cbar2;                  /* 1.0   */
+  double rot_noise_bound;        /* 0 -> 2*noise_bound (the value the reference's function-local static
+                                    latches on its first call, quatro.hpp:469-470 after :851) */
+  double cote_noise_bound;       /* 0.3   Quatro::noise_bound_ ctor constant, quatro.hpp:115,601 */
+  double rotation_gnc_factor;    /* 1.4   */
+  double rotation_cost_threshold;/* 1.1e-4 */
+  double kcore_heuristic_threshold; /* 0.5 */
+  int32_t rotation_max_iterations;  /* 50 */
+  int32_t inlier_selection_mode;    /* QB200_PMC_HEU */
+  int32_t cote_mode;                /* QB200_COTE_MEDIAN */
+  int32_t using_rot_inliers_when_estimating_cote; /* 0 */
+  int32_t use_pre_estimated_RyRx;   /* 0 */
+  int32_t reserved1;
+  double RyRx[9];                   /* row-major 3x3, setPreEstaimatedRyRx, quatro.hpp:276-279 */
+} qb200_params;
+
+/* Handle configuration: device and per-pair capacities (device workspaces are sized once). */
+typedef struct qb200_config {
+  int32_t device;            /* CUDA ordinal */
+  int32_t max_batch_slots;   /* pairs resident in one wave of the batch pipeline (default 64) */
+  int32_t max_raw_points;    /* per cloud (default 131072) */
+  int32_t max_voxel_points;  /* per cloud (default 8192)  */
+  int32_t max_corr;          /* per pair  (default 4096)  */
+  int32_t reserved[3];
+} qb200_config;
+
+/* Fixed-size per-pair record (also the unit gathered across GPUs). */
+typedef struct qb200_result {
+  int32_t valid;             /* solution_.valid */
+  int32_t status;            /* qb200_status for this pair */
+  int32_t n_src_vox, n_tgt_vox;
+  int32_t n_mutual;          /* mutual nearest neighbours before the tuple test */
+  int32_t n_corr;            /* L: correspondences after tuple test + dedupe */
+  int32_t max_core;          /* pmc max core number (graph.cc:60) */
+  int32_t clique_size;
+  int32_t gnc_iters;
+  int32_t n_rot_inliers;     /* getNumRotaionInliers */
+  int32_t n_final_inliers;
+  int32_t reserved;
+  int64_t n_edges;
+  double cost;               /* Quatro::cost_ */
+  double T[16];              /* column-major 4x4 (Eigen::Matrix4d memory order); identity when !valid */
+} qb200_result;
+
+typedef struct qb200_pair {
+  const float* src; /* n_src x 4 floats */
+  const float* tgt;
+  int32_t n_src, n_tgt;
+} qb200_pair;
+
+typedef struct qb200_handle qb200_handle;
+
+void qb200_default_params(qb200_params* p);
+void qb200_default_config(qb200_config* c);
+int qb200_version(void);
+
+int qb200_create(const qb200_config* cfg, qb200_handle** out);
+void qb200_destroy(qb200_handle* h);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the handle's own stream. */
+int qb200_set_stream(qb200_handle* h, void* cuda_stream);
+const char* qb200_last_error(const qb200_handle* h);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t qb200_launch_count(const qb200_handle* h);
+
+/* --- stage boundaries (host pointers) ------------------------------------------------------ */
+
+/* pcl::VoxelGrid semantics: centroid per occupied leaf cube, output ordered by ascending
+ * (k,j,i) cell; non-finite points (and w<0 points when skip_flagged) are dropped. */
+int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, int32_t skip_flagged,
+                   float* out4, int32_t cap, int32_t* n_out);
+
+/* normals4: n x {nx,ny,nz,curvature}; desc33: n x 33 floats (pcl::FPFHSignature33). Either may be NULL. */
+int qb200_compute_fpfh(qb200_handle* h, const float* pts4, int32_t n, float normal_radius,
+                       float fpfh_radius, float grid_cell, float* normals4, float* desc33);
+
+/* corr: n_corr x {src_idx, tgt_idx}, sorted lexicographically, unique. */
+int qb200_match(qb200_handle* h, const float* src4, int32_t n_src, const float* src_desc33,
+                const float* tgt4, int32_t n_tgt, const float* tgt_desc33, const qb200_params* p,
+                int32_t* corr, int32_t cap, int32_t* n_corr, int32_t* n_mutual);
+
+/* adj: L rows x words_per_row uint32, bit j of row i set iff edge (i,j); full symmetric matrix.
+ * words_per_row >= ceil(L/32).  degree (L) and n_edges may be NULL. */
+int qb200_build_graph(qb200_handle* h, const float* a4, const float* b4, int32_t L,
+                      double noise_bound, double cbar2, uint32_t* adj, int32_t words_per_row,
+                      int32_t* degree, int64_t* n_edges);
+
+/* clique: ascending vertex ids.  kcore (L, pmc's core number + 1) and kcore_order (L) may be NULL. */
+int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row,
+                     int32_t mode, double kcore_heuristic_threshold, int32_t* clique, int32_t* n_clique,
+                     int32_t* kcore, int32_t* kcore_order, int32_t* max_core);
+
+/* rotation + translation given the (sorted) clique. inlier_mask (n_clique bytes) may be NULL. */
+int qb200_solve_pose(qb200_handle* h, const float* a4, const float* b4, int32_t L,
+                     const int32_t* clique, int32_t n_clique, const qb200_params* p,
+                     qb200_result* res, uint8_t* rot_inlier_mask, uint8_t* trans_inlier_mask);
+
+/* = Quatro::computeTransformation on matched point pairs. */
+int qb200_solve_correspondences(qb200_handle* h, const float* a4, const float* b4, int32_t L,
+                                const qb200_params* p, qb200_result* res);
+
+/* voxelized clouds in -> correspondences + matched point copies (FPFHManager::setFeaturePair). */
+int qb200_match_and_pack(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4,
+                         int32_t n_tgt, const qb200_params* p, int32_t* corr, float* src_matched4,
+                         float* tgt_matched4, int32_t cap, int32_t* n_corr);
+
+/* raw scans in -> pose out. */
+int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4,
+                        int32_t n_tgt, const qb200_params* p, qb200_result* res);
+
+/* Batch of independent pairs.  kind says where pairs[i].src/tgt live; results is a host array. */
+int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs,
+                         const qb200_params* p, qb200_mem_kind kind, qb200_result* results);
+
+/* Introspection of the most recent single-pair solve on this handle (getMaxCliques,
+ * getFinalInliersIndices, getCorrespondences; quatro.hpp:949-972, fpfh_manager.hpp:234-236). */
+int qb200_get_last_clique(qb200_handle* h, int32_t* idx, int32_t cap, int32_t* n);
+int qb200_get_last_final_inliers(qb200_handle* h, int32_t* idx, int32_t cap, int32_t* n);
+int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_matched4,
+                                   float* tgt_matched4, int32_t cap, int32_t* n);
+
+/* Per-stage device time of the last qb200_register_batch call in milliseconds (CUDA events):
+ * [0]=h2d [1]=voxel [2]=fpfh [3]=match [4]=graph [5]=clique [6]=pose [7]=d2h; n<=8. */
+int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUATRO_B200_H_ */

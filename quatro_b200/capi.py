@@ -1,0 +1,340 @@
+"""ctypes binding of include/quatro_b200.h (one Python method per C entry point).
+
+Used by tests/ and bench.py; mirrors the C-ABI 1:1 so the parity tests read like calls a C/C++
+caller (the reference's run_global_registration.cpp) would make.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _build
+
+PMC_EXACT, PMC_HEU, KCORE_HEU, INLIER_NONE = 0, 1, 2, 3
+COTE_MEDIAN, COTE_WEIGHTED_MEAN = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+STATUS_NAMES = {0: "OK", 1: "DEGENERATE_CLIQUE", 2: "DEGENERATE_INPUT", 3: "CAPACITY_EXCEEDED", -1: "ERR_BAD_ARG",
+                -2: "ERR_NO_DEVICE", -3: "ERR_CUDA", -4: "ERR_UNSUPPORTED", -5: "ERR_VOXEL_OVERFLOW"}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("voxel_size", C.c_float), ("normal_radius", C.c_float), ("fpfh_radius", C.c_float), ("grid_cell", C.c_float),
+        ("tuple_scale", C.c_float), ("use_crosscheck", C.c_int32), ("use_tuple_test", C.c_int32),
+        ("tuple_trials_per_corr", C.c_int32), ("skip_flagged", C.c_int32), ("reserved0", C.c_int32),
+        ("seed", C.c_uint64),
+        ("noise_bound", C.c_double), ("cbar2", C.c_double), ("rot_noise_bound", C.c_double),
+        ("cote_noise_bound", C.c_double), ("rotation_gnc_factor", C.c_double),
+        ("rotation_cost_threshold", C.c_double), ("kcore_heuristic_threshold", C.c_double),
+        ("rotation_max_iterations", C.c_int32), ("inlier_selection_mode", C.c_int32), ("cote_mode", C.c_int32),
+        ("using_rot_inliers_when_estimating_cote", C.c_int32), ("use_pre_estimated_RyRx", C.c_int32),
+        ("reserved1", C.c_int32), ("RyRx", C.c_double * 9),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_batch_slots", C.c_int32), ("max_raw_points", C.c_int32),
+                ("max_voxel_points", C.c_int32), ("max_corr", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("valid", C.c_int32), ("status", C.c_int32), ("n_src_vox", C.c_int32), ("n_tgt_vox", C.c_int32),
+        ("n_mutual", C.c_int32), ("n_corr", C.c_int32), ("max_core", C.c_int32), ("clique_size", C.c_int32),
+        ("gnc_iters", C.c_int32), ("n_rot_inliers", C.c_int32), ("n_final_inliers", C.c_int32),
+        ("reserved", C.c_int32), ("n_edges", C.c_int64), ("cost", C.c_double), ("T", C.c_double * 16),
+    ]
+
+    def matrix(self) -> np.ndarray:
+        """4x4 pose (row/col indexing as usual); T is stored column-major."""
+        return np.array(self.T[:], dtype=np.float64).reshape(4, 4).T.copy()
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("T", "reserved")}
+        d["T"] = self.matrix()
+        return d
+
+
+class Pair(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("tgt", C.c_void_p), ("n_src", C.c_int32), ("n_tgt", C.c_int32)]
+
+
+RESULT_DTYPE = np.dtype([
+    ("valid", "<i4"), ("status", "<i4"), ("n_src_vox", "<i4"), ("n_tgt_vox", "<i4"), ("n_mutual", "<i4"),
+    ("n_corr", "<i4"), ("max_core", "<i4"), ("clique_size", "<i4"), ("gnc_iters", "<i4"), ("n_rot_inliers", "<i4"),
+    ("n_final_inliers", "<i4"), ("reserved", "<i4"), ("n_edges", "<i8"), ("cost", "<f8"), ("T", "<f8", (16,)),
+])
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
+class QuatroB200Error(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{where}: {STATUS_NAMES.get(code, code)} {detail}")
+
+
+_LIB: Optional[C.CDLL] = None
+
+
+def _f32(a, cols=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None:
+        assert a.ndim == 2 and a.shape[1] == cols, (a.shape, cols)
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def load_library(build: bool = True) -> C.CDLL:
+    """Load libquatro_b200.so (building it with nvcc if stale).  Raises if it cannot be built/loaded."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.build_cuda() if build else _build.CUDA_LIB
+    lib = C.CDLL(str(path))
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+    P = C.POINTER
+    sig = {
+        "qb200_default_params": (None, [P(Params)]),
+        "qb200_default_config": (None, [P(Config)]),
+        "qb200_version": (i32, []),
+        "qb200_create": (i32, [P(Config), P(vp)]),
+        "qb200_destroy": (None, [vp]),
+        "qb200_set_stream": (i32, [vp, vp]),
+        "qb200_last_error": (C.c_char_p, [vp]),
+        "qb200_launch_count": (i64, [vp]),
+        "qb200_voxelize": (i32, [vp, vp, i32, f32, i32, vp, i32, P(i32)]),
+        "qb200_compute_fpfh": (i32, [vp, vp, i32, f32, f32, f32, vp, vp]),
+        "qb200_match": (i32, [vp, vp, i32, vp, vp, i32, vp, P(Params), vp, i32, P(i32), P(i32)]),
+        "qb200_build_graph": (i32, [vp, vp, vp, i32, f64, f64, vp, i32, vp, P(i64)]),
+        "qb200_max_clique": (i32, [vp, vp, i32, i32, i32, f64, vp, P(i32), vp, vp, P(i32)]),
+        "qb200_solve_pose": (i32, [vp, vp, vp, i32, vp, i32, P(Params), P(Result), vp, vp]),
+        "qb200_solve_correspondences": (i32, [vp, vp, vp, i32, P(Params), P(Result)]),
+        "qb200_match_and_pack": (i32, [vp, vp, i32, vp, i32, P(Params), vp, vp, vp, i32, P(i32)]),
+        "qb200_register_pair": (i32, [vp, vp, i32, vp, i32, P(Params), P(Result)]),
+        "qb200_register_batch": (i32, [vp, P(Pair), i32, P(Params), i32, vp]),
+        "qb200_get_last_clique": (i32, [vp, vp, i32, P(i32)]),
+        "qb200_get_last_final_inliers": (i32, [vp, vp, i32, P(i32)]),
+        "qb200_get_last_correspondences": (i32, [vp, vp, vp, vp, i32, P(i32)]),
+        "qb200_get_stage_ms": (i32, [vp, vp, i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "qb200_default_params", "qb200_default_config", "qb200_version", "qb200_create", "qb200_destroy",
+    "qb200_set_stream", "qb200_last_error", "qb200_launch_count", "qb200_voxelize", "qb200_compute_fpfh",
+    "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_solve_pose", "qb200_solve_correspondences",
+    "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
+    "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms",
+]
+
+
+def default_params() -> Params:
+    """config/params.yaml defaults.  Pure-Python mirror of qb200_default_params (so CPU-only tests can
+    build a Params without loading the CUDA library); test_capi checks the two agree."""
+    p = Params()
+    p.voxel_size, p.normal_radius, p.fpfh_radius, p.grid_cell = 0.3, 0.5, 0.75, 0.0
+    p.tuple_scale, p.use_crosscheck, p.use_tuple_test, p.tuple_trials_per_corr = 0.95, 1, 1, 100
+    p.skip_flagged, p.seed = 1, 0x5EED
+    p.noise_bound, p.cbar2, p.rot_noise_bound, p.cote_noise_bound = 0.3, 1.0, 0.0, 0.3
+    p.rotation_gnc_factor, p.rotation_cost_threshold, p.kcore_heuristic_threshold = 1.4, 0.00011, 0.5
+    p.rotation_max_iterations, p.inlier_selection_mode, p.cote_mode = 50, PMC_HEU, COTE_MEDIAN
+    p.using_rot_inliers_when_estimating_cote, p.use_pre_estimated_RyRx = 0, 0
+    for i in range(9):
+        p.RyRx[i] = 1.0 if i in (0, 4, 8) else 0.0
+    return p
+
+
+def default_config() -> Config:
+    c = Config()
+    c.device, c.max_batch_slots, c.max_raw_points, c.max_voxel_points, c.max_corr = 0, 64, 131072, 8192, 4096
+    return c
+
+
+class Handle:
+    """RAII wrapper of qb200_handle.  Raises QuatroB200Error(ERR_NO_DEVICE) when no GPU is usable."""
+
+    def __init__(self, config: Optional[Config] = None, **kw):
+        self.lib = load_library()
+        cfg = config or default_config()
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        st = self.lib.qb200_create(C.byref(cfg), C.byref(h))
+        if st != 0:
+            raise QuatroB200Error(st, "qb200_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int, where: str):
+        if st < 0:
+            msg = self.lib.qb200_last_error(self.h)
+            raise QuatroB200Error(st, where, (msg or b"").decode())
+        return st
+
+    def set_stream(self, stream_ptr: int):
+        self._check(self.lib.qb200_set_stream(self.h, C.c_void_p(stream_ptr)), "qb200_set_stream")
+
+    def launch_count(self) -> int:
+        return int(self.lib.qb200_launch_count(self.h))
+
+    # ---- stages -------------------------------------------------------------------------------
+    def voxelize(self, pts4, leaf: float, skip_flagged: int = 1, cap: Optional[int] = None):
+        pts4 = _f32(pts4, 4)
+        cap = cap or max(1, len(pts4))
+        out = np.zeros((cap, 4), np.float32)
+        n = C.c_int32(0)
+        st = self._check(self.lib.qb200_voxelize(self.h, _ptr(pts4), len(pts4), leaf, skip_flagged, _ptr(out), cap, C.byref(n)),
+                         "qb200_voxelize")
+        return out[: min(n.value, cap)].copy(), st
+
+    def compute_fpfh(self, pts4, normal_radius: float, fpfh_radius: float, grid_cell: float):
+        pts4 = _f32(pts4, 4)
+        n = len(pts4)
+        normals = np.zeros((n, 4), np.float32)
+        desc = np.zeros((n, 33), np.float32)
+        self._check(self.lib.qb200_compute_fpfh(self.h, _ptr(pts4), n, normal_radius, fpfh_radius, grid_cell, _ptr(normals), _ptr(desc)),
+                    "qb200_compute_fpfh")
+        return normals, desc
+
+    def match(self, src4, sdesc, tgt4, tdesc, params: Params, cap: Optional[int] = None):
+        src4, tgt4, sdesc, tdesc = _f32(src4, 4), _f32(tgt4, 4), _f32(sdesc, 33), _f32(tdesc, 33)
+        cap = cap or max(1, min(len(src4), len(tgt4)))
+        corr = np.zeros((cap, 2), np.int32)
+        n, nm = C.c_int32(0), C.c_int32(0)
+        st = self._check(self.lib.qb200_match(self.h, _ptr(src4), len(src4), _ptr(sdesc), _ptr(tgt4), len(tgt4), _ptr(tdesc),
+                                              C.byref(params), _ptr(corr), cap, C.byref(n), C.byref(nm)), "qb200_match")
+        return corr[: min(n.value, cap)].copy(), nm.value, st
+
+    def build_graph(self, a4, b4, noise_bound: float, cbar2: float, words_per_row: Optional[int] = None):
+        a4, b4 = _f32(a4, 4), _f32(b4, 4)
+        L = len(a4)
+        wpr = words_per_row or (L + 31) // 32
+        adj = np.zeros((L, wpr), np.uint32)
+        deg = np.zeros(L, np.int32)
+        ne = C.c_int64(0)
+        self._check(self.lib.qb200_build_graph(self.h, _ptr(a4), _ptr(b4), L, noise_bound, cbar2, _ptr(adj), wpr, _ptr(deg), C.byref(ne)),
+                    "qb200_build_graph")
+        return adj, deg, ne.value
+
+    def max_clique(self, adj, mode: int = PMC_HEU, kcore_thr: float = 0.5):
+        adj = np.ascontiguousarray(adj, np.uint32)
+        L, wpr = adj.shape
+        clique = np.zeros(max(L, 1), np.int32)
+        kcore = np.zeros(max(L, 1), np.int32)
+        order = np.zeros(max(L, 1), np.int32)
+        n, mc = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.qb200_max_clique(self.h, _ptr(adj), L, wpr, mode, kcore_thr, _ptr(clique), C.byref(n), _ptr(kcore),
+                                              _ptr(order), C.byref(mc)), "qb200_max_clique")
+        return clique[: n.value].copy(), kcore[:L].copy(), order[:L].copy(), mc.value
+
+    def solve_pose(self, a4, b4, clique, params: Params):
+        a4, b4 = _f32(a4, 4), _f32(b4, 4)
+        clique = np.ascontiguousarray(clique, np.int32)
+        res = Result()
+        rm = np.zeros(max(len(clique), 1), np.uint8)
+        tm = np.zeros(max(len(clique), 1), np.uint8)
+        st = self._check(self.lib.qb200_solve_pose(self.h, _ptr(a4), _ptr(b4), len(a4), _ptr(clique), len(clique), C.byref(params),
+                                                   C.byref(res), _ptr(rm), _ptr(tm)), "qb200_solve_pose")
+        return res, rm[: len(clique)], tm[: len(clique)], st
+
+    def solve_correspondences(self, a4, b4, params: Params):
+        a4, b4 = _f32(a4, 4), _f32(b4, 4)
+        res = Result()
+        st = self._check(self.lib.qb200_solve_correspondences(self.h, _ptr(a4), _ptr(b4), len(a4), C.byref(params), C.byref(res)),
+                         "qb200_solve_correspondences")
+        return res, st
+
+    def match_and_pack(self, src4, tgt4, params: Params, cap: Optional[int] = None):
+        src4, tgt4 = _f32(src4, 4), _f32(tgt4, 4)
+        cap = cap or max(1, min(len(src4), len(tgt4)))
+        corr = np.zeros((cap, 2), np.int32)
+        sm = np.zeros((cap, 4), np.float32)
+        tm = np.zeros((cap, 4), np.float32)
+        n = C.c_int32(0)
+        st = self._check(self.lib.qb200_match_and_pack(self.h, _ptr(src4), len(src4), _ptr(tgt4), len(tgt4), C.byref(params), _ptr(corr),
+                                                       _ptr(sm), _ptr(tm), cap, C.byref(n)), "qb200_match_and_pack")
+        m = min(n.value, cap)
+        return corr[:m].copy(), sm[:m].copy(), tm[:m].copy(), st
+
+    def register_pair(self, src4, tgt4, params: Params):
+        src4, tgt4 = _f32(src4, 4), _f32(tgt4, 4)
+        res = Result()
+        st = self._check(self.lib.qb200_register_pair(self.h, _ptr(src4), len(src4), _ptr(tgt4), len(tgt4), C.byref(params), C.byref(res)),
+                         "qb200_register_pair")
+        return res, st
+
+    def register_batch(self, pairs: Sequence, params: Params, kind: int = MEM_HOST) -> np.ndarray:
+        """pairs: sequence of (src, tgt).  MEM_HOST: numpy (n,4) float32 arrays; MEM_DEVICE:
+        (src_ptr, n_src, tgt_ptr, n_tgt) tuples of raw device addresses.  Returns a RESULT_DTYPE array."""
+        n = len(pairs)
+        arr = (Pair * n)()
+        keep = []
+        for i, pr in enumerate(pairs):
+            if kind == MEM_HOST:
+                s, t = _f32(pr[0], 4), _f32(pr[1], 4)
+                keep.append((s, t))
+                arr[i].src, arr[i].n_src, arr[i].tgt, arr[i].n_tgt = s.ctypes.data, len(s), t.ctypes.data, len(t)
+            else:
+                arr[i].src, arr[i].n_src, arr[i].tgt, arr[i].n_tgt = pr[0], pr[1], pr[2], pr[3]
+        out = np.zeros(n, RESULT_DTYPE)
+        self._check(self.lib.qb200_register_batch(self.h, arr, n, C.byref(params), kind, _ptr(out)), "qb200_register_batch")
+        return out
+
+    def register_batch_raw(self, pair_array, n: int, params: Params, kind: int, out: np.ndarray):
+        """Zero-overhead variant for bench.py: pre-built (Pair * n) array and RESULT_DTYPE output."""
+        return self._check(self.lib.qb200_register_batch(self.h, pair_array, n, C.byref(params), kind, _ptr(out)), "qb200_register_batch")
+
+    def last_clique(self, cap: int = 1 << 16):
+        idx = np.zeros(cap, np.int32)
+        n = C.c_int32(0)
+        self._check(self.lib.qb200_get_last_clique(self.h, _ptr(idx), cap, C.byref(n)), "qb200_get_last_clique")
+        return idx[: n.value].copy()
+
+    def last_final_inliers(self, cap: int = 1 << 16):
+        idx = np.zeros(cap, np.int32)
+        n = C.c_int32(0)
+        self._check(self.lib.qb200_get_last_final_inliers(self.h, _ptr(idx), cap, C.byref(n)), "qb200_get_last_final_inliers")
+        return idx[: n.value].copy()
+
+    def last_correspondences(self, cap: int = 1 << 16):
+        corr = np.zeros((cap, 2), np.int32)
+        sm = np.zeros((cap, 4), np.float32)
+        tm = np.zeros((cap, 4), np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.qb200_get_last_correspondences(self.h, _ptr(corr), _ptr(sm), _ptr(tm), cap, C.byref(n)),
+                    "qb200_get_last_correspondences")
+        return corr[: n.value].copy(), sm[: n.value].copy(), tm[: n.value].copy()
+
+    def stage_ms(self) -> np.ndarray:
+        ms = np.zeros(8, np.float32)
+        self.lib.qb200_get_stage_ms(self.h, _ptr(ms), 8)
+        return ms

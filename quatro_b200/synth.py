@@ -1,0 +1,67 @@
+"""Synthetic scan pairs (host side, deterministic per seed) -- input generator for tests and bench.
+
+outdoor_pair() wraps quatro_b200/synth/synth.cpp (64-ring HDL-64E geometry).
+matched_pairs() makes correspondence sets (inliers under a known yaw/translation + outliers) for
+the back-end stages.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _build
+
+_LIB = None
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = C.CDLL(str(_build.build_synth()))
+        lib.qb200_synth_outdoor_pair.restype = C.c_int
+        lib.qb200_synth_outdoor_pair.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
+                                                 C.POINTER(C.c_int), C.c_int, C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def outdoor_pair(seed: int, rings: int = 64, azimuths: int = 1800):
+    """Returns (src (n,4) float32, tgt (m,4) float32, T_gt 4x4 float64) with p_tgt = T_gt @ p_src.
+    w = -1 marks ground returns."""
+    cap = rings * azimuths
+    src = np.zeros((cap, 4), np.float32)
+    tgt = np.zeros((cap, 4), np.float32)
+    ns, nt = C.c_int(0), C.c_int(0)
+    T = np.zeros(16, np.float64)
+    _lib().qb200_synth_outdoor_pair(seed, rings, azimuths, src.ctypes.data, C.byref(ns), tgt.ctypes.data, C.byref(nt), cap, T.ctypes.data)
+    return src[: ns.value].copy(), tgt[: nt.value].copy(), T.reshape(4, 4).T.copy()
+
+
+def matched_pairs(seed: int, L: int, inlier_ratio: float = 0.3, noise: float = 0.05, extent: float = 50.0,
+                  yaw_deg: float | None = None, trans=None):
+    """L matched point pairs (a_i, b_i): inliers b = Rz(yaw) a + t + noise, outliers random.
+    Returns a4 (L,4) f32, b4 (L,4) f32, T_gt 4x4, inlier mask."""
+    rng = np.random.default_rng(seed)
+    yaw = np.deg2rad(rng.uniform(-180, 180) if yaw_deg is None else yaw_deg)
+    t = rng.uniform(-5, 5, 3) * np.array([1, 1, 0.05]) if trans is None else np.asarray(trans, float)
+    R = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+    a = rng.uniform(-extent, extent, (L, 3)) * np.array([1, 1, 0.1])
+    inl = rng.uniform(size=L) < inlier_ratio
+    b = a @ R.T + t + rng.normal(0, noise, (L, 3))
+    b[~inl] = rng.uniform(-extent, extent, ((~inl).sum(), 3)) * np.array([1, 1, 0.1])
+    a4 = np.ones((L, 4), np.float32)
+    b4 = np.ones((L, 4), np.float32)
+    a4[:, :3] = a
+    b4[:, :3] = b
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = t
+    return a4, b4, T, inl
+
+
+def pose_error(T_est: np.ndarray, T_ref: np.ndarray):
+    """(rotation error in degrees, translation error in metres)."""
+    dR = T_est[:3, :3] @ T_ref[:3, :3].T
+    c = np.clip((np.trace(dR) - 1) / 2, -1, 1)
+    return float(np.degrees(np.arccos(c))), float(np.linalg.norm(T_est[:3, 3] - T_ref[:3, 3]))
