@@ -145,7 +145,8 @@ int voxelize(const P4* pts, int n, float leaf, int skip_flagged, std::vector<P4>
 // ---------------------------------------------------------------------------------------------
 constexpr int kOffIJ = 1 << 17, kOffK = 1 << 15;
 inline bool cell_ok(int i, int j, int k) {
-  return i >= -kOffIJ && i < kOffIJ && j >= -kOffIJ && j < kOffIJ && k >= -kOffK && k < kOffK;
+  // the all-ones cell value is reserved (device sort keys use it as the "dropped point" marker)
+  return i >= -kOffIJ && i < kOffIJ - 1 && j >= -kOffIJ && j < kOffIJ - 1 && k >= -kOffK && k < kOffK - 1;
 }
 inline uint64_t cell_key(int i, int j, int k) {
   return ((uint64_t)(k + kOffK) << 36) | ((uint64_t)(j + kOffIJ) << 18) | (uint64_t)(i + kOffIJ);
@@ -198,8 +199,8 @@ struct Lattice {
       for (int dj = -m; dj <= m; ++dj) {
         const int k = ck[q] + dk, j = cj[q] + dj;
         int ilo = ci[q] - m, ihi = ci[q] + m;
-        if (k < -kOffK || k >= kOffK || j < -kOffIJ || j >= kOffIJ) continue;
-        ilo = std::max(ilo, -kOffIJ); ihi = std::min(ihi, kOffIJ - 1);
+        if (k < -kOffK || k >= kOffK - 1 || j < -kOffIJ || j >= kOffIJ - 1) continue;
+        ilo = std::max(ilo, -kOffIJ); ihi = std::min(ihi, kOffIJ - 2);
         const uint64_t lo = cell_key(ilo, j, k), hi = cell_key(ihi, j, k);
         size_t c = std::lower_bound(ckeys.begin(), ckeys.end(), lo) - ckeys.begin();
         for (; c < ckeys.size() && ckeys[c] <= hi; ++c) {
@@ -292,6 +293,33 @@ inline void eigen33_smallest(const float cov[9], float* eigenvalue, float evec[3
   evec[0] = v[0] / sl; evec[1] = v[1] / sl; evec[2] = v[2] / sl;
 }
 
+// covariance sums -> normal + curvature (computeMeanAndCovarianceMatrix tail, solvePlaneParameters, flip)
+inline P4 normal_from_accu(float accu[9], int cnt, const P4& pq) {
+  P4 nn{NAN, NAN, NAN, NAN};
+  if (cnt >= 3) {
+    const float fc = (float)cnt;
+    for (int i = 0; i < 9; ++i) accu[i] /= fc;
+    float cov[9];
+    cov[0] = accu[0] - accu[6] * accu[6];
+    cov[1] = accu[1] - accu[6] * accu[7];
+    cov[2] = accu[2] - accu[6] * accu[8];
+    cov[4] = accu[3] - accu[7] * accu[7];
+    cov[5] = accu[4] - accu[7] * accu[8];
+    cov[8] = accu[5] - accu[8] * accu[8];
+    cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+    float ev, e[3];
+    eigen33_smallest(cov, &ev, e);
+    const float eig_sum = cov[0] + cov[4] + cov[8];
+    const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+    // flipNormalTowardsViewpoint, vp = 0
+    const float vx = 0.0f - pq.x, vy = 0.0f - pq.y, vz = 0.0f - pq.z;
+    const float cos_theta = (vx * e[0] + vy * e[1]) + vz * e[2];
+    if (cos_theta < 0.0f) { e[0] *= -1.0f; e[1] *= -1.0f; e[2] *= -1.0f; }
+    nn = P4{e[0], e[1], e[2], curv};
+  }
+  return nn;
+}
+
 void compute_normals(const P4* pts, int n, const Lattice& lat, float radius, P4* normals) {
 #pragma omp parallel for schedule(dynamic, 64)
   for (int q = 0; q < n; ++q) {
@@ -304,29 +332,7 @@ void compute_normals(const P4* pts, int n, const Lattice& lat, float radius, P4*
       accu[6] += x; accu[7] += y; accu[8] += z;
       ++cnt;
     });
-    P4 nn{NAN, NAN, NAN, NAN};
-    if (cnt >= 3) {
-      const float fc = (float)cnt;
-      for (int i = 0; i < 9; ++i) accu[i] /= fc;
-      float cov[9];
-      cov[0] = accu[0] - accu[6] * accu[6];
-      cov[1] = accu[1] - accu[6] * accu[7];
-      cov[2] = accu[2] - accu[6] * accu[8];
-      cov[4] = accu[3] - accu[7] * accu[7];
-      cov[5] = accu[4] - accu[7] * accu[8];
-      cov[8] = accu[5] - accu[8] * accu[8];
-      cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
-      float ev, e[3];
-      eigen33_smallest(cov, &ev, e);
-      const float eig_sum = cov[0] + cov[4] + cov[8];
-      const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
-      // flipNormalTowardsViewpoint, vp = 0
-      const float vx = 0.0f - pts[q].x, vy = 0.0f - pts[q].y, vz = 0.0f - pts[q].z;
-      const float cos_theta = (vx * e[0] + vy * e[1]) + vz * e[2];
-      if (cos_theta < 0.0f) { e[0] *= -1.0f; e[1] *= -1.0f; e[2] *= -1.0f; }
-      nn = P4{e[0], e[1], e[2], curv};
-    }
-    normals[q] = nn;
+    normals[q] = normal_from_accu(accu, cnt, pts[q]);
   }
 }
 
@@ -1189,6 +1195,18 @@ void qo_test_sincosf(float x, float* s, float* c) { qo_sincosf(x, s, c); }
 void qo_test_philox(uint64_t seed, uint64_t ctr, uint32_t* out4) { philox4x32_10(seed, ctr, out4); }
 void qo_test_svd2x2(const double* H, double* U, double* S, double* V) { svd2x2(H, U, S, V); }
 void qo_test_svd_rot2d(const double* X, const double* Y, const double* W, int c, double* R) { svd_rot2d(X, Y, W, c, R); }
+void qo_test_normal_from_accu(const float* accu9, int cnt, const float* p3, float* out4) {
+  float a[9];
+  for (int i = 0; i < 9; ++i) a[i] = accu9[i];
+  const P4 n = normal_from_accu(a, cnt, P4{p3[0], p3[1], p3[2], 1.0f});
+  out4[0] = n.x; out4[1] = n.y; out4[2] = n.z; out4[3] = n.w;
+}
+void qo_test_feature_bins(float f1, float f2, float f3, int* b) {
+  const float d_pi = 1.0f / (2.0f * (float)M_PI);
+  b[0] = bin_of(11 * (((double)f1 + M_PI) * (double)d_pi));
+  b[1] = bin_of(11 * (((double)f2 + 1.0) * 0.5));
+  b[2] = bin_of(11 * (((double)f3 + 1.0) * 0.5));
+}
 int qo_test_pair_features(const float* p1, const float* n1, const float* p2, const float* n2, float* f) {
   return pair_features(*reinterpret_cast<const P4*>(p1), *reinterpret_cast<const P4*>(n1), *reinterpret_cast<const P4*>(p2),
                        *reinterpret_cast<const P4*>(n2), f[0], f[1], f[2]) ? 1 : 0;

@@ -72,15 +72,3 @@ def build_synth(force: bool = False) -> Path:
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
     return SYNTH_LIB
-
-
-def build_oracle(force: bool = False) -> Path:
-    """Builds the TEST oracle (oracle/Makefile). Building the checker is not using it."""
-    odir = ROOT / "oracle"
-    out = odir / "build" / "libquatro_oracle.so"
-    deps = [odir / "quatro_oracle.cpp", odir / "qo_math.h", ROOT / "include" / "quatro_b200.h"]
-    if force or _newer(out, deps):
-        r = subprocess.run(["make", "-C", str(odir)], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
-    return out

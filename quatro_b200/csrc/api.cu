@@ -1,0 +1,621 @@
+// api.cu -- the C-ABI of include/quatro_b200.h: handle lifetime, stage entry points, batch pipeline.
+//
+// Every entry point enqueues the SAME kernels the batch pipeline uses (a stage call is a wave of
+// one), so the per-stage parity tests exercise the production kernels.  There is no CPU
+// implementation of any stage in this library.
+#include <math.h>
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "handle.cuh"
+
+using namespace qb;
+
+namespace qb {
+int launch_degree(qb200_handle* h, int n_pairs);
+}
+
+namespace {
+
+__global__ void wave_init_kernel(int* ctr_block, int n_ints, int* bbox, int n_clouds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_ints) ctr_block[i] = 0;
+  if (i < n_clouds * 6) bbox[i] = (i % 6) < 3 ? INT_MAX : INT_MIN;
+}
+
+template <class T>
+cudaError_t dalloc(T** p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+}
+
+#define QB_ALLOC(h, ptr, count)                                                    \
+  do {                                                                             \
+    cudaError_t _e = dalloc(&(ptr), (size_t)(count));                              \
+    if (_e != cudaSuccess) {                                                       \
+      (h)->fail(__FILE__, __LINE__, cudaGetErrorString(_e));                       \
+      return QB200_ERR_CUDA;                                                       \
+    }                                                                              \
+  } while (0)
+
+int alloc_all(qb200_handle* h) {
+  const size_t S = h->S, R = h->R, V = h->V, Lc = h->Lc, W = h->W, C = 2 * S;
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->d_cloud_ptr, C * sizeof(float4*)));
+  QB_ALLOC(h, h->d_cloud_n, C);
+  QB_ALLOC(h, h->d_raw_off, C + 1);
+  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_cloud_ptr, C * sizeof(float4*)));
+  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_cloud_n, C * sizeof(int)));
+  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_raw_off, (C + 1) * sizeof(int)));
+  QB_ALLOC(h, h->raw_stage, C * R);
+  QB_ALLOC(h, h->key_a, C * R);
+  QB_ALLOC(h, h->key_b, C * R);
+  QB_ALLOC(h, h->val_a, C * R);
+  QB_ALLOC(h, h->val_b, C * R);
+  h->cub_bytes = sort_temp_bytes((int)(C * R));
+  QB_CUDA_TRY(h, cudaMalloc(&h->cub_temp, h->cub_bytes));
+  QB_ALLOC(h, h->vox_start, C * (V + 1));
+  QB_ALLOC(h, h->vox_pts, C * V);
+  QB_ALLOC(h, h->cell_key, C * V);
+  QB_ALLOC(h, h->cell_start, C * (V + 1));
+  QB_ALLOC(h, h->normals, C * V);
+  QB_ALLOC(h, h->spfh, C * V * kDescDim);
+  QB_ALLOC(h, h->desc_t, C * kDescPad * V);
+  QB_CUDA_TRY(h, cudaMemset(h->desc_t, 0, C * kDescPad * V * sizeof(float)));
+  QB_ALLOC(h, h->rowbest, S * V);
+  QB_ALLOC(h, h->colpart, S * h->NS * V);
+  QB_ALLOC(h, h->colbest, S * V);
+  QB_ALLOC(h, h->mut_i, S * V);
+  QB_ALLOC(h, h->mut_j, S * V);
+  QB_ALLOC(h, h->mark, S * V);
+  QB_ALLOC(h, h->partner, S * V);
+  QB_ALLOC(h, h->mean, C * 4);
+  QB_ALLOC(h, h->corr_src, S * Lc);
+  QB_ALLOC(h, h->corr_tgt, S * Lc);
+  QB_ALLOC(h, h->ma, S * Lc);
+  QB_ALLOC(h, h->mb, S * Lc);
+  QB_ALLOC(h, h->adj, S * Lc * W);
+  QB_ALLOC(h, h->adjp, S * Lc * W);
+  QB_ALLOC(h, h->deg, S * Lc);
+  QB_ALLOC(h, h->kcore, S * (Lc + 2));
+  QB_ALLOC(h, h->korder, S * (Lc + 2));
+  QB_ALLOC(h, h->rank_of, S * (Lc + 2));
+  QB_ALLOC(h, h->by_rank, S * (Lc + 2));
+  QB_ALLOC(h, h->kbin, S * (Lc + 2));
+  QB_ALLOC(h, h->clique, S * Lc);
+  QB_ALLOC(h, h->final_inl, S * Lc);
+  QB_ALLOC(h, h->rot_mask, S * Lc);
+  QB_ALLOC(h, h->trans_mask, S * Lc);
+  QB_ALLOC(h, h->d_results, S);
+  QB_CUDA_TRY(h, cudaMemset(h->d_results, 0, S * sizeof(qb200_result)));
+  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_results, S * sizeof(qb200_result)));
+  // counters: one int block so a wave reset is a single launch.  n_edges (long long) lives at an 8-byte offset.
+  const size_t n_ints = C * 5 + C * 6 + S * 6 + 2 * S + 2;
+  QB_ALLOC(h, h->ctr_block, n_ints);
+  h->ctr_ints = n_ints;
+  int* p = h->ctr_block;
+  h->ctr.n_edges = reinterpret_cast<long long*>(p); p += 2 * S;
+  h->ctr.n_valid = p; p += C;
+  h->ctr.n_vox = p; p += C;
+  h->ctr.n_lat = p; p += C;
+  h->ctr.n_cells = p; p += C;
+  h->ctr.cloud_status = p; p += C;
+  h->ctr.bbox = p; p += C * 6;
+  h->ctr.n_mutual = p; p += S;
+  h->ctr.n_corr = p; p += S;
+  h->ctr.swapped = p; p += S;
+  h->ctr.n_clique = p; p += S;
+  h->ctr.max_core = p; p += S;
+  h->ctr.n_final = p; p += S;
+  for (int i = 0; i < 9; ++i) QB_CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+  return QB200_OK;
+}
+
+int wave_reset(qb200_handle* h, int n_clouds) {
+  const int n = (int)h->ctr_ints;
+  wave_init_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->ctr_block, n, h->ctr.bbox, n_clouds);
+  h->launches++;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
+int set_counter(qb200_handle* h, int* dptr, int value) {
+  QB_CUDA_TRY(h, cudaMemcpyAsync(dptr, &value, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // 'value' is a stack variable
+  return QB200_OK;
+}
+
+int get_counter(qb200_handle* h, const int* dptr, int* value) {
+  QB_CUDA_TRY(h, cudaMemcpyAsync(value, dptr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return QB200_OK;
+}
+
+bool params_ok(const qb200_params* p) {
+  if (!p) return false;
+  if (!(p->voxel_size > 0) || !(p->normal_radius > 0) || !(p->fpfh_radius > 0)) return false;
+  if (p->normal_radius > p->fpfh_radius) return false;  // FPFHManager::setFeaturePair throws here, fpfh_manager.hpp:99-102
+  if (!(p->noise_bound > 0) || !(p->cbar2 > 0) || !(p->cote_noise_bound > 0)) return false;
+  if (p->cote_mode != QB200_COTE_MEDIAN && p->cote_mode != QB200_COTE_WEIGHTED_MEAN) return false;  // quatro.hpp:911
+  if (p->inlier_selection_mode < 0 || p->inlier_selection_mode > 3) return false;
+  if (p->rotation_max_iterations < 0 || p->tuple_trials_per_corr < 0) return false;
+  return true;
+}
+
+float lattice_cell(const qb200_params& p) { return p.grid_cell > 0 ? p.grid_cell : p.voxel_size; }
+
+// graph -> clique -> pose for pairs [0, n) whose matched points / n_corr are already on the device
+int run_solver(qb200_handle* h, int n_pairs, const qb200_params& p, int have_frontend) {
+  int rc;
+  if (p.inlier_selection_mode == QB200_INLIER_NONE) {
+    // the reference leaves max_clique_ empty in this mode (quatro.hpp:782); TEASER++ semantics: all measurements
+    if ((rc = launch_iota_clique(h, n_pairs))) return rc;
+  } else {
+    if ((rc = launch_graph(h, n_pairs, p.noise_bound, p.cbar2))) return rc;
+    if (h->ev[5]) cudaEventRecord(h->ev[5], h->stream);
+    if ((rc = launch_clique(h, n_pairs, p.inlier_selection_mode, p.kcore_heuristic_threshold))) return rc;
+  }
+  if (h->ev[6]) cudaEventRecord(h->ev[6], h->stream);
+  if ((rc = launch_fill_counters(h, n_pairs, have_frontend))) return rc;
+  if ((rc = launch_pose(h, n_pairs, p))) return rc;
+  if ((rc = launch_finalize_status(h, n_pairs))) return rc;
+  return QB200_OK;
+}
+
+int upload_matched(qb200_handle* h, const float* a4, const float* b4, int L) {
+  if (L > h->Lc) {
+    h->fail(__FILE__, __LINE__, "L exceeds max_corr");
+    return QB200_ERR_BAD_ARG;
+  }
+  int rc = wave_reset(h, 2);
+  if (rc) return rc;
+  if (L > 0) {
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->ma, a4, (size_t)L * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->mb, b4, (size_t)L * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  }
+  return set_counter(h, h->ctr.n_corr, L);
+}
+
+int upload_cloud_as_voxels(qb200_handle* h, int cloud, const float* pts4, int n) {
+  if (n > h->V) {
+    h->fail(__FILE__, __LINE__, "cloud exceeds max_voxel_points");
+    return QB200_ERR_BAD_ARG;
+  }
+  if (n > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(h->vox_pts + (size_t)cloud * h->V, pts4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  return set_counter(h, h->ctr.n_vox + cloud, n);
+}
+
+int fetch_result(qb200_handle* h, qb200_result* res) {
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results, sizeof(qb200_result), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  *res = h->h_results[0];
+  h->last_n_corr = res->n_corr;
+  h->last_n_clique = res->clique_size;
+  h->last_n_final = res->n_final_inliers;
+  return res->status;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qb200_version(void) { return QB200_VERSION; }
+
+void qb200_default_params(qb200_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->voxel_size = 0.3f; p->normal_radius = 0.5f; p->fpfh_radius = 0.75f; p->grid_cell = 0.0f;  // config/params.yaml:22-25
+  p->tuple_scale = 0.95f; p->use_crosscheck = 1; p->use_tuple_test = 1; p->tuple_trials_per_corr = 100;  // fpfh_manager.hpp:126-127
+  p->skip_flagged = 1; p->seed = 0x5EED;
+  p->noise_bound = 0.3; p->cbar2 = 1.0; p->rot_noise_bound = 0.0; p->cote_noise_bound = 0.3;  // params.yaml:31,34; quatro.hpp:115
+  p->rotation_gnc_factor = 1.4; p->rotation_cost_threshold = 0.00011; p->kcore_heuristic_threshold = 0.5;  // params.yaml:41,44
+  p->rotation_max_iterations = 50; p->inlier_selection_mode = QB200_PMC_HEU; p->cote_mode = QB200_COTE_MEDIAN;  // params.yaml:38
+  p->using_rot_inliers_when_estimating_cote = 0; p->use_pre_estimated_RyRx = 0;
+  p->RyRx[0] = p->RyRx[4] = p->RyRx[8] = 1.0;
+}
+
+void qb200_default_config(qb200_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->device = 0; c->max_batch_slots = 64; c->max_raw_points = 131072; c->max_voxel_points = 8192; c->max_corr = 4096;
+}
+
+int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {
+  if (!out) return QB200_ERR_BAD_ARG;
+  *out = nullptr;
+  qb200_config cfg;
+  if (cfg_in) cfg = *cfg_in; else qb200_default_config(&cfg);
+  if (cfg.max_batch_slots < 1 || cfg.max_batch_slots > 2048 || cfg.max_raw_points < 1 || cfg.max_voxel_points < kMatchTile ||
+      cfg.max_voxel_points % kMatchTile != 0 || cfg.max_voxel_points > 65536 || cfg.max_corr < 32 || cfg.max_corr % 32 != 0 ||
+      cfg.max_corr > 4096 || (long long)cfg.max_batch_slots * 2 * cfg.max_raw_points > 2000000000LL)
+    return QB200_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg.device < 0 || cfg.device >= ndev) return QB200_ERR_NO_DEVICE;
+  if (cudaSetDevice(cfg.device) != cudaSuccess) return QB200_ERR_NO_DEVICE;
+  qb200_handle* h = new (std::nothrow) qb200_handle();
+  if (!h) return QB200_ERR_CUDA;
+  memset(h, 0, sizeof(*h));
+  h->cfg = cfg; h->device = cfg.device;
+  h->S = cfg.max_batch_slots; h->R = cfg.max_raw_points; h->V = cfg.max_voxel_points; h->Lc = cfg.max_corr;
+  h->W = h->Lc / 32; h->NS = h->V / kMatchTile;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return QB200_ERR_CUDA; }
+  h->stream = h->own_stream;
+  const int rc = alloc_all(h);
+  if (rc != QB200_OK) {
+    fprintf(stderr, "qb200_create: %s\n", h->err);
+    qb200_destroy(h);
+    return rc;
+  }
+  cudaStreamSynchronize(h->stream);
+  *out = h;
+  return QB200_OK;
+}
+
+void qb200_destroy(qb200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
+                      h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->desc_t, h->rowbest, h->colpart, h->colbest,
+                      h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
+                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
+                      h->ctr_block};
+  for (void* p : dev_ptrs)
+    if (p) cudaFree(p);
+  if (h->h_cloud_ptr) cudaFreeHost((void*)h->h_cloud_ptr);
+  if (h->h_cloud_n) cudaFreeHost(h->h_cloud_n);
+  if (h->h_raw_off) cudaFreeHost(h->h_raw_off);
+  if (h->h_results) cudaFreeHost(h->h_results);
+  for (int i = 0; i < 9; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int qb200_set_stream(qb200_handle* h, void* cuda_stream) {
+  if (!h) return QB200_ERR_BAD_ARG;
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return QB200_OK;
+}
+
+const char* qb200_last_error(const qb200_handle* h) { return h ? h->err : "null handle"; }
+int64_t qb200_launch_count(const qb200_handle* h) { return h ? h->launches : 0; }
+
+// ---- stage: voxelize ----------------------------------------------------------------------------
+int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, int32_t skip_flagged, float* out4, int32_t cap,
+                   int32_t* n_out) {
+  if (!h || !n_out || n < 0 || (n > 0 && !pts4) || !(leaf > 0) || cap < 0 || (cap > 0 && !out4)) return QB200_ERR_BAD_ARG;
+  *n_out = 0;
+  if (n > h->R) { h->fail(__FILE__, __LINE__, "n exceeds max_raw_points"); return QB200_ERR_BAD_ARG; }
+  cudaSetDevice(h->device);
+  if (n == 0) return QB200_OK;
+  int rc = wave_reset(h, 1);
+  if (rc) return rc;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->raw_stage, pts4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  h->h_cloud_ptr[0] = h->raw_stage; h->h_cloud_n[0] = n; h->h_raw_off[0] = 0; h->h_raw_off[1] = n;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_ptr, h->h_cloud_ptr, sizeof(float4*), cudaMemcpyHostToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_n, h->h_cloud_n, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_raw_off, h->h_raw_off, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_voxel(h, 1, n, leaf, skip_flagged))) return rc;
+  int nv = 0, st = 0;
+  if ((rc = get_counter(h, h->ctr.n_vox, &nv))) return rc;
+  if ((rc = get_counter(h, h->ctr.cloud_status, &st))) return rc;
+  if (st == QB200_ERR_VOXEL_OVERFLOW) {
+    // [EXT] pcl::VoxelGrid: "leaf size is too small ... integer indices would overflow" -> output = input
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+      const float* p = pts4 + 4 * (size_t)i;
+      if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2])) || (skip_flagged && p[3] < 0.0f)) continue;
+      if (m < cap) memcpy(out4 + 4 * (size_t)m, p, 4 * sizeof(float));
+      ++m;
+    }
+    *n_out = m;
+    return m > cap ? QB200_CAPACITY_EXCEEDED : QB200_ERR_VOXEL_OVERFLOW;
+  }
+  *n_out = nv;
+  const int m = nv < cap ? nv : cap;
+  if (m > 0) {
+    QB_CUDA_TRY(h, cudaMemcpyAsync(out4, h->vox_pts, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  if (st == QB200_CAPACITY_EXCEEDED || nv > cap) return QB200_CAPACITY_EXCEEDED;
+  return QB200_OK;
+}
+
+// ---- stage: normals + FPFH ------------------------------------------------------------------------
+int qb200_compute_fpfh(qb200_handle* h, const float* pts4, int32_t n, float normal_radius, float fpfh_radius, float grid_cell,
+                       float* normals4, float* desc33) {
+  if (!h || n < 0 || (n > 0 && !pts4) || !(normal_radius > 0) || !(fpfh_radius > 0) || !(grid_cell > 0)) return QB200_ERR_BAD_ARG;
+  if (normal_radius > fpfh_radius) return QB200_ERR_BAD_ARG;  // fpfh_manager.hpp:99-102
+  cudaSetDevice(h->device);
+  if (n == 0) return QB200_OK;
+  int rc = wave_reset(h, 1);
+  if (rc) return rc;
+  if ((rc = upload_cloud_as_voxels(h, 0, pts4, n))) return rc;
+  if ((rc = launch_fpfh(h, 1, normal_radius, fpfh_radius, grid_cell))) return rc;
+  if (normals4) QB_CUDA_TRY(h, cudaMemcpyAsync(normals4, h->normals, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  if (desc33) {
+    float* scratch = reinterpret_cast<float*>(h->key_a);  // sort input is dead after the lattice sort
+    if ((rc = launch_desc_to_aos(h, 0, n, scratch))) return rc;
+    QB_CUDA_TRY(h, cudaMemcpyAsync(desc33, scratch, (size_t)n * kDescDim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return QB200_OK;
+}
+
+// ---- stage: matching ------------------------------------------------------------------------------
+static int download_corr(qb200_handle* h, int32_t* corr, float* sm4, float* tm4, int cap, int32_t* n_corr, int32_t* n_mutual) {
+  int nc = 0, nm = 0, st = 0, rc;
+  if ((rc = get_counter(h, h->ctr.n_corr, &nc))) return rc;
+  if ((rc = get_counter(h, h->ctr.n_mutual, &nm))) return rc;
+  if ((rc = get_counter(h, h->ctr.cloud_status, &st))) return rc;
+  *n_corr = nc;
+  if (n_mutual) *n_mutual = nm;
+  h->last_n_corr = nc;
+  const int m = nc < cap ? nc : cap;
+  if (m > 0) {
+    std::vector<int> s(m), t(m);
+    QB_CUDA_TRY(h, cudaMemcpyAsync(s.data(), h->corr_src, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(t.data(), h->corr_tgt, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (sm4) QB_CUDA_TRY(h, cudaMemcpyAsync(sm4, h->ma, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (tm4) QB_CUDA_TRY(h, cudaMemcpyAsync(tm4, h->mb, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (corr)
+      for (int i = 0; i < m; ++i) { corr[2 * i] = s[i]; corr[2 * i + 1] = t[i]; }
+  }
+  if (st == QB200_CAPACITY_EXCEEDED || nc > cap) return QB200_CAPACITY_EXCEEDED;
+  return QB200_OK;
+}
+
+int qb200_match(qb200_handle* h, const float* src4, int32_t n_src, const float* src_desc33, const float* tgt4, int32_t n_tgt,
+                const float* tgt_desc33, const qb200_params* p, int32_t* corr, int32_t cap, int32_t* n_corr, int32_t* n_mutual) {
+  if (!h || !p || !n_corr || n_src < 0 || n_tgt < 0 || cap < 0) return QB200_ERR_BAD_ARG;
+  if ((n_src > 0 && (!src4 || !src_desc33)) || (n_tgt > 0 && (!tgt4 || !tgt_desc33))) return QB200_ERR_BAD_ARG;
+  if (!p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
+  *n_corr = 0;
+  if (n_mutual) *n_mutual = 0;
+  if (n_src > h->V || n_tgt > h->V) { h->fail(__FILE__, __LINE__, "cloud exceeds max_voxel_points"); return QB200_ERR_BAD_ARG; }
+  cudaSetDevice(h->device);
+  if (n_src == 0 || n_tgt == 0) return QB200_OK;
+  int rc = wave_reset(h, 2);
+  if (rc) return rc;
+  if ((rc = upload_cloud_as_voxels(h, 0, src4, n_src))) return rc;
+  if ((rc = upload_cloud_as_voxels(h, 1, tgt4, n_tgt))) return rc;
+  float* scratch = reinterpret_cast<float*>(h->key_a);
+  QB_CUDA_TRY(h, cudaMemcpyAsync(scratch, src_desc33, (size_t)n_src * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_desc_from_aos(h, 0, n_src, scratch))) return rc;
+  float* scratch2 = scratch + (size_t)h->V * kDescDim;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(scratch2, tgt_desc33, (size_t)n_tgt * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_desc_from_aos(h, 1, n_tgt, scratch2))) return rc;
+  if ((rc = launch_match(h, 1, *p))) return rc;
+  return download_corr(h, corr, nullptr, nullptr, cap, n_corr, n_mutual);
+}
+
+int qb200_match_and_pack(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4, int32_t n_tgt, const qb200_params* p,
+                         int32_t* corr, float* src_matched4, float* tgt_matched4, int32_t cap, int32_t* n_corr) {
+  if (!h || !n_corr || !params_ok(p) || n_src < 0 || n_tgt < 0 || cap < 0) return QB200_ERR_BAD_ARG;
+  if (!p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
+  *n_corr = 0;
+  if (n_src > h->V || n_tgt > h->V) { h->fail(__FILE__, __LINE__, "cloud exceeds max_voxel_points"); return QB200_ERR_BAD_ARG; }
+  cudaSetDevice(h->device);
+  if (n_src == 0 || n_tgt == 0) return QB200_OK;
+  int rc = wave_reset(h, 2);
+  if (rc) return rc;
+  if ((rc = upload_cloud_as_voxels(h, 0, src4, n_src))) return rc;
+  if ((rc = upload_cloud_as_voxels(h, 1, tgt4, n_tgt))) return rc;
+  if ((rc = launch_fpfh(h, 2, p->normal_radius, p->fpfh_radius, lattice_cell(*p)))) return rc;
+  if ((rc = launch_match(h, 1, *p))) return rc;
+  return download_corr(h, corr, src_matched4, tgt_matched4, cap, n_corr, nullptr);
+}
+
+// ---- stage: graph ---------------------------------------------------------------------------------
+int qb200_build_graph(qb200_handle* h, const float* a4, const float* b4, int32_t L, double noise_bound, double cbar2, uint32_t* adj,
+                      int32_t words_per_row, int32_t* degree, int64_t* n_edges) {
+  if (!h || L < 0 || (L > 0 && (!a4 || !b4 || !adj)) || words_per_row < (L + 31) / 32 || !(noise_bound > 0) || !(cbar2 > 0))
+    return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (n_edges) *n_edges = 0;
+  if (L == 0) return QB200_OK;
+  int rc = upload_matched(h, a4, b4, L);
+  if (rc) return rc;
+  if ((rc = launch_graph(h, 1, noise_bound, cbar2))) return rc;
+  const int nb = (L + 31) / 32;
+  memset(adj, 0, (size_t)L * words_per_row * sizeof(uint32_t));
+  QB_CUDA_TRY(h, cudaMemcpy2DAsync(adj, (size_t)words_per_row * 4, h->adj, (size_t)h->W * 4, (size_t)nb * 4, L, cudaMemcpyDeviceToHost, h->stream));
+  if (degree) QB_CUDA_TRY(h, cudaMemcpyAsync(degree, h->deg, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  long long e2 = 0;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(&e2, h->ctr.n_edges, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (n_edges) *n_edges = e2 / 2;
+  return QB200_OK;
+}
+
+// ---- stage: max clique ------------------------------------------------------------------------------
+int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row, int32_t mode, double kcore_thr,
+                     int32_t* clique, int32_t* n_clique, int32_t* kcore, int32_t* kcore_order, int32_t* max_core) {
+  if (!h || !n_clique || L < 0 || (L > 0 && (!adj || !clique)) || words_per_row < (L + 31) / 32) return QB200_ERR_BAD_ARG;
+  if (mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
+  if (mode != QB200_PMC_HEU && mode != QB200_KCORE_HEU) return QB200_ERR_BAD_ARG;
+  *n_clique = 0;
+  if (max_core) *max_core = 0;
+  if (L > h->Lc) { h->fail(__FILE__, __LINE__, "L exceeds max_corr"); return QB200_ERR_BAD_ARG; }
+  cudaSetDevice(h->device);
+  if (L == 0) return QB200_OK;
+  int rc = wave_reset(h, 2);
+  if (rc) return rc;
+  const int nb = (L + 31) / 32;
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->adj, 0, (size_t)L * h->W * 4, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpy2DAsync(h->adj, (size_t)h->W * 4, adj, (size_t)words_per_row * 4, (size_t)nb * 4, L, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = set_counter(h, h->ctr.n_corr, L))) return rc;
+  if ((rc = launch_degree(h, 1))) return rc;
+  if ((rc = launch_clique(h, 1, mode, kcore_thr))) return rc;
+  int nc = 0, mc = 0;
+  if ((rc = get_counter(h, h->ctr.n_clique, &nc))) return rc;
+  if ((rc = get_counter(h, h->ctr.max_core, &mc))) return rc;
+  *n_clique = nc;
+  if (max_core) *max_core = mc;
+  if (nc > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(clique, h->clique, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (kcore) QB_CUDA_TRY(h, cudaMemcpyAsync(kcore, h->kcore, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (kcore_order) QB_CUDA_TRY(h, cudaMemcpyAsync(kcore_order, h->korder, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->last_n_clique = nc;
+  return QB200_OK;
+}
+
+// ---- stage: pose given the clique -------------------------------------------------------------------
+int qb200_solve_pose(qb200_handle* h, const float* a4, const float* b4, int32_t L, const int32_t* clique, int32_t n_clique,
+                     const qb200_params* p, qb200_result* res, uint8_t* rot_inlier_mask, uint8_t* trans_inlier_mask) {
+  if (!h || !res || !params_ok(p) || L < 0 || n_clique < 0 || n_clique > L || (n_clique > 0 && !clique)) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  int rc = upload_matched(h, a4, b4, L);
+  if (rc) return rc;
+  if (n_clique > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(h->clique, clique, (size_t)n_clique * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = set_counter(h, h->ctr.n_clique, n_clique))) return rc;
+  if ((rc = launch_fill_counters(h, 1, 0))) return rc;
+  if ((rc = launch_pose(h, 1, *p))) return rc;
+  rc = fetch_result(h, res);
+  if (rc < 0) return rc;
+  if (res->valid) {
+    const int nc = res->clique_size;
+    if (rot_inlier_mask) QB_CUDA_TRY(h, cudaMemcpyAsync(rot_inlier_mask, h->rot_mask, (size_t)nc, cudaMemcpyDeviceToHost, h->stream));
+    if (trans_inlier_mask) QB_CUDA_TRY(h, cudaMemcpyAsync(trans_inlier_mask, h->trans_mask, (size_t)nc, cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return rc;
+}
+
+// ---- Quatro::computeTransformation ------------------------------------------------------------------
+int qb200_solve_correspondences(qb200_handle* h, const float* a4, const float* b4, int32_t L, const qb200_params* p, qb200_result* res) {
+  if (!h || !res || !params_ok(p) || L < 0 || (L > 0 && (!a4 || !b4))) return QB200_ERR_BAD_ARG;
+  if (p->inlier_selection_mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
+  cudaSetDevice(h->device);
+  int rc = upload_matched(h, a4, b4, L);
+  if (rc) return rc;
+  if ((rc = run_solver(h, 1, *p, 0))) return rc;
+  return fetch_result(h, res);
+}
+
+// ---- raw scans -> pose ------------------------------------------------------------------------------
+int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_mem_kind kind,
+                         qb200_result* results) {
+  if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
+  if (p->inlier_selection_mode == QB200_PMC_EXACT || !p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (pairs[i].n_src < 0 || pairs[i].n_tgt < 0 || pairs[i].n_src > h->R || pairs[i].n_tgt > h->R ||
+        (pairs[i].n_src > 0 && !pairs[i].src) || (pairs[i].n_tgt > 0 && !pairs[i].tgt)) {
+      h->fail(__FILE__, __LINE__, "pair has a null cloud or exceeds max_raw_points");
+      return QB200_ERR_BAD_ARG;
+    }
+  }
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
+  const float cell = lattice_cell(*p);
+  for (int w0 = 0; w0 < n_pairs; w0 += h->S) {
+    const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
+    const int ncl = 2 * np;
+    int rc;
+    cudaEventRecord(h->ev[0], h->stream);
+    int total = 0;
+    for (int s = 0; s < np; ++s) {
+      const qb200_pair& pr = pairs[w0 + s];
+      const float* ptr[2] = {pr.src, pr.tgt};
+      const int cnt[2] = {pr.n_src, pr.n_tgt};
+      for (int k = 0; k < 2; ++k) {
+        const int cloud = 2 * s + k;
+        h->h_raw_off[cloud] = total;
+        h->h_cloud_n[cloud] = cnt[k];
+        if (kind == QB200_MEM_HOST) {
+          float4* dst = h->raw_stage + (size_t)total;
+          if (cnt[k] > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(dst, ptr[k], (size_t)cnt[k] * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+          h->h_cloud_ptr[cloud] = dst;
+        } else {
+          h->h_cloud_ptr[cloud] = reinterpret_cast<const float4*>(ptr[k]);
+        }
+        total += cnt[k];
+      }
+    }
+    h->h_raw_off[ncl] = total;
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_ptr, h->h_cloud_ptr, (size_t)ncl * sizeof(float4*), cudaMemcpyHostToDevice, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_n, h->h_cloud_n, (size_t)ncl * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_raw_off, h->h_raw_off, (size_t)(ncl + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = wave_reset(h, ncl))) return rc;
+    cudaEventRecord(h->ev[1], h->stream);
+    if ((rc = launch_voxel(h, ncl, total, p->voxel_size, p->skip_flagged))) return rc;
+    cudaEventRecord(h->ev[2], h->stream);
+    if ((rc = launch_fpfh(h, ncl, p->normal_radius, p->fpfh_radius, cell))) return rc;
+    cudaEventRecord(h->ev[3], h->stream);
+    if ((rc = launch_match(h, np, *p))) return rc;
+    cudaEventRecord(h->ev[4], h->stream);
+    cudaEventRecord(h->ev[5], h->stream);  // re-recorded inside run_solver when the graph stage runs
+    if ((rc = run_solver(h, np, *p, 1))) return rc;
+    cudaEventRecord(h->ev[7], h->stream);
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results, (size_t)np * sizeof(qb200_result), cudaMemcpyDeviceToHost, h->stream));
+    cudaEventRecord(h->ev[8], h->stream);
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(results + w0, h->h_results, (size_t)np * sizeof(qb200_result));
+    for (int i = 0; i < 8; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
+    }
+    // the wave's own reads of h_cloud_* / h_raw_off are complete after the synchronize above
+  }
+  if (n_pairs == 1) {
+    h->last_n_corr = results[0].n_corr;
+    h->last_n_clique = results[0].clique_size;
+    h->last_n_final = results[0].n_final_inliers;
+  }
+  return QB200_OK;
+}
+
+int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4, int32_t n_tgt, const qb200_params* p,
+                        qb200_result* res) {
+  if (!res) return QB200_ERR_BAD_ARG;
+  qb200_pair pr;
+  pr.src = src4; pr.tgt = tgt4; pr.n_src = n_src; pr.n_tgt = n_tgt;
+  const int rc = qb200_register_batch(h, &pr, 1, p, QB200_MEM_HOST, res);
+  if (rc != QB200_OK) return rc;
+  return res->status;
+}
+
+// ---- introspection ----------------------------------------------------------------------------------
+static int copy_ints(qb200_handle* h, const int* dsrc, int n_have, int32_t* dst, int32_t cap, int32_t* n) {
+  if (!h || !n || cap < 0) return QB200_ERR_BAD_ARG;
+  *n = n_have;
+  const int m = n_have < cap ? n_have : cap;
+  cudaSetDevice(h->device);
+  if (m > 0 && dst) {
+    QB_CUDA_TRY(h, cudaMemcpyAsync(dst, dsrc, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return n_have > cap ? QB200_CAPACITY_EXCEEDED : QB200_OK;
+}
+int qb200_get_last_clique(qb200_handle* h, int32_t* idx, int32_t cap, int32_t* n) {
+  return h ? copy_ints(h, h->clique, h->last_n_clique, idx, cap, n) : QB200_ERR_BAD_ARG;
+}
+int qb200_get_last_final_inliers(qb200_handle* h, int32_t* idx, int32_t cap, int32_t* n) {
+  return h ? copy_ints(h, h->final_inl, h->last_n_final, idx, cap, n) : QB200_ERR_BAD_ARG;
+}
+int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_matched4, float* tgt_matched4, int32_t cap, int32_t* n) {
+  if (!h || !n || cap < 0) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  const int nc = h->last_n_corr;
+  *n = nc;
+  const int m = nc < cap ? nc : cap;
+  if (m > 0) {
+    std::vector<int> s(m), t(m);
+    QB_CUDA_TRY(h, cudaMemcpyAsync(s.data(), h->corr_src, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(t.data(), h->corr_tgt, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (src_matched4) QB_CUDA_TRY(h, cudaMemcpyAsync(src_matched4, h->ma, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (tgt_matched4) QB_CUDA_TRY(h, cudaMemcpyAsync(tgt_matched4, h->mb, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (corr)
+      for (int i = 0; i < m; ++i) { corr[2 * i] = s[i]; corr[2 * i + 1] = t[i]; }
+  }
+  return nc > cap ? QB200_CAPACITY_EXCEEDED : QB200_OK;
+}
+
+int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n) {
+  if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
+  for (int i = 0; i < n && i < 8; ++i) ms[i] = h->stage_ms[i];
+  return QB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// common.cuh -- shared device/host declarations of libquatro_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "quatro_b200.h"
+
+namespace qb {
+
+// ------------------------------------------------------------------------------------------------
+// Lattice / voxel sort keys.  A cell (i,j,k) = floorf(p * inv_cell) is packed so that unsigned
+// comparison orders cells by (k, j, i) -- the order of PCL's linear voxel index
+// i + j*dx + k*dx*dy ([EXT] pcl::VoxelGrid, called from include/quatro.hpp:49-57) -- and the cloud
+// id sits above it so that ONE radix sort orders every cloud of a batch wave at once.
+//   [63:52] cloud   [51:36] k + 2^15   [35:18] j + 2^17   [17:0] i + 2^17
+// The all-ones cell value marks a dropped point (non-finite, flagged, outside the lattice).
+// ------------------------------------------------------------------------------------------------
+constexpr int kOffIJ = 1 << 17;
+constexpr int kOffK = 1 << 15;
+constexpr uint64_t kCellMask = (1ull << 52) - 1;
+constexpr uint64_t kCellInvalid = kCellMask;
+constexpr int kCloudShift = 52;
+
+__host__ __device__ __forceinline__ bool cell_ok(int i, int j, int k) {
+  return i >= -kOffIJ && i < kOffIJ - 1 && j >= -kOffIJ && j < kOffIJ - 1 && k >= -kOffK && k < kOffK - 1;
+}
+__host__ __device__ __forceinline__ uint64_t cell_key(int i, int j, int k) {
+  return ((uint64_t)(k + kOffK) << 36) | ((uint64_t)(j + kOffIJ) << 18) | (uint64_t)(i + kOffIJ);
+}
+
+constexpr int kDescDim = 33;   // pcl::FPFHSignature33
+constexpr int kDescPad = 36;   // rows of the dim-major descriptor matrix (16-byte multiple)
+constexpr int kMatchTile = 128;
+
+// Per-cloud / per-pair counters that live on the device for a whole wave (no host round trips
+// between stages).  Arrays are indexed by cloud (2 per pair: 2*s = source, 2*s+1 = target) or slot.
+struct WaveCounters {
+  int* n_valid;      // [clouds] points kept by the voxel key pass
+  int* n_vox;        // [clouds]
+  int* n_lat;        // [clouds] points inside the neighbour lattice
+  int* n_cells;      // [clouds]
+  int* cloud_status; // [clouds] qb200_status (0 ok)
+  int* bbox;         // [clouds*6] ordered-int encoded min xyz / max xyz of kept raw points
+  int* n_mutual;     // [slots]
+  int* n_corr;       // [slots]
+  int* swapped;      // [slots]  target cloud larger than source (feature_matcher.cc:84-89)
+  int* n_clique;     // [slots]
+  int* max_core;     // [slots]
+  int* n_final;      // [slots]
+  long long* n_edges;// [slots]
+};
+
+#define QB_CUDA_TRY(h, expr)                                                                    \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      (h)->fail(__FILE__, __LINE__, cudaGetErrorString(_e));                                    \
+      return QB200_ERR_CUDA;                                                                    \
+    }                                                                                           \
+  } while (0)
+
+__device__ __forceinline__ int float_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__host__ __device__ __forceinline__ float ordered_float(int i) {
+  const int j = i >= 0 ? i : i ^ 0x7FFFFFFF;
+#ifdef __CUDA_ARCH__
+  return __int_as_float(j);
+#else
+  float f;
+  memcpy(&f, &j, 4);
+  return f;
+#endif
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+
+// exclusive prefix sum of one int per lane (32-wide), returns the exclusive value; total via *total
+__device__ __forceinline__ int warp_excl_scan(int v, int* total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((int)lane_id() >= o) inc += n;
+  }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// block-wide exclusive scan (blockDim.x multiple of 32, <= 1024). smem: 33 ints. All threads call.
+__device__ __forceinline__ int block_excl_scan(int v, int* smem, int* block_total) {
+  const int lane = lane_id(), warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int wt;
+  const int ex = warp_excl_scan(v, &wt);
+  __syncthreads();  // protect smem reuse across calls
+  if (lane == 31) smem[warp] = wt;
+  __syncthreads();
+  if (warp == 0) {
+    int t = lane < nw ? smem[lane] : 0, tot;
+    const int e = warp_excl_scan(t, &tot);
+    smem[lane] = e;
+    if (lane == 0) smem[32] = tot;
+  }
+  __syncthreads();
+  *block_total = smem[32];
+  return ex + smem[warp];
+}
+
+}  // namespace qb

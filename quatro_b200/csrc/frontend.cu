@@ -1,0 +1,439 @@
+// frontend.cu -- K1..K5: voxel down-sampling, neighbour lattice, normals, SPFH, FPFH  (sm_100a)
+//
+// Replaces: voxelize<T>() (include/quatro.hpp:49-57 -> [EXT] pcl::VoxelGrid) and
+// FPFHEstimation::computeFPFHFeatures (src/teaser_utils/fpfh.cc:44-75 -> [EXT] pcl::NormalEstimation,
+// pcl::FPFHEstimationOMP, pcl::search::KdTree).
+//
+// Design: every cloud of a batch wave is processed by the same launches (grid.y = cloud); sizes
+// stay on the device.  Voxelisation is one 64-bit radix sort of (cloud | cell) keys followed by a
+// segmented, in-order centroid sum (bit-identical to the sequential CPU sum).  The kd-tree is
+// replaced by a sorted-cell lattice: a point's neighbours are found by (2m+1)^2 binary searches for
+// x-runs of cells, visited in ascending (cell, index) order -- the accumulation order the CPU oracle
+// uses, so the single-pass float covariance matches bit for bit.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "fpfh_math.cuh"
+#include "handle.cuh"
+
+namespace qb {
+
+// ------------------------------------------------------------------------------------------------
+// sort plumbing
+// ------------------------------------------------------------------------------------------------
+size_t sort_temp_bytes(int max_items) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, max_items, 0, 64, (cudaStream_t)0);
+  return bytes;
+}
+
+int sort_pairs(qb200_handle* h, int n_items, int end_bit) {
+  if (n_items <= 0) return QB200_OK;
+  size_t bytes = h->cub_bytes;
+  QB_CUDA_TRY(h, cub::DeviceRadixSort::SortPairs(h->cub_temp, bytes, h->key_a, h->key_b, h->val_a, h->val_b, n_items, 0, end_bit,
+                                                 h->stream));
+  h->launches += 1 + (end_bit + 7) / 8;  // onesweep: histogram + one pass per 8 key bits
+  return QB200_OK;
+}
+
+static int clog2(int n) {
+  int b = 0;
+  while ((1 << b) < n) ++b;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a: raw point -> (cloud | voxel cell) key.  128-bit loads, one pass over the raw scan.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
+                                                         const int* __restrict__ raw_off, float inv_leaf, int skip_flagged,
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ bbox,
+                                                         int* __restrict__ n_valid, int* __restrict__ cloud_status) {
+  const int cloud = blockIdx.y;
+  const int n = cloud_n[cloud], off = raw_off[cloud];
+  const float4* __restrict__ pts = cloud_ptr[cloud];
+  int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN, cnt = 0, bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(pts + i);
+    bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(skip_flagged && p.w < 0.0f);
+    uint64_t cell = kCellInvalid;
+    if (ok) {
+      const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
+      if (cell_ok(ci, cj, ck)) {
+        cell = cell_key(ci, cj, ck);
+        const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
+        mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+        mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+        ++cnt;
+      } else {
+        bad = 1;  // outside the representable lattice: PCL's index would overflow as well
+      }
+    }
+    keys[off + i] = ((uint64_t)cloud << kCloudShift) | cell;
+    vals[off + i] = (uint32_t)i;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+    mn2 = min(mn2, __shfl_xor_sync(0xffffffffu, mn2, o)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o); bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (lane_id() == 0) {
+    if (cnt) {
+      int* b = bbox + cloud * 6;
+      atomicMin(b + 0, mn0); atomicMin(b + 1, mn1); atomicMin(b + 2, mn2);
+      atomicMax(b + 3, mx0); atomicMax(b + 4, mx1); atomicMax(b + 5, mx2);
+      atomicAdd(n_valid + cloud, cnt);
+    }
+    if (bad) cloud_status[cloud] = QB200_ERR_VOXEL_OVERFLOW;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b / K2b: run heads of the sorted keys of one cloud -> start position of every voxel / cell.
+// One CTA per cloud walks its segment with a carried block scan (sizes never leave the device).
+//   mode 0 (voxels): segment = [raw_off, raw_off + n_raw), writes starts[], n_out = #voxels
+//   mode 1 (cells):  segment = [cloud*V, cloud*V + V),     writes starts[] and cell keys
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_t* __restrict__ keys, const int* __restrict__ seg_off,
+                                                         const int* __restrict__ seg_n, int V, float inv_leaf, const int* __restrict__ bbox,
+                                                         const int* __restrict__ n_valid_in, int* __restrict__ starts,
+                                                         uint64_t* __restrict__ cell_keys, int* __restrict__ n_out, int* __restrict__ n_valid_out,
+                                                         int* __restrict__ cloud_status) {
+  __shared__ int sm[33];
+  __shared__ int s_overflow;
+  const int cloud = blockIdx.x;
+  const int off = mode == 0 ? seg_off[cloud] : cloud * V;
+  const int n = mode == 0 ? seg_n[cloud] : V;
+  if (threadIdx.x == 0) {
+    int ov = 0;
+    if (mode == 0 && n_valid_in[cloud] > 0) {
+      // [EXT] pcl::VoxelGrid: dx*dy*dz > INT_MAX -> "leaf size too small", input returned unfiltered
+      const int* b = bbox + cloud * 6;
+      const long long dx = (long long)((ordered_float(b[3]) - ordered_float(b[0])) * inv_leaf) + 1;
+      const long long dy = (long long)((ordered_float(b[4]) - ordered_float(b[1])) * inv_leaf) + 1;
+      const long long dz = (long long)((ordered_float(b[5]) - ordered_float(b[2])) * inv_leaf) + 1;
+      if (dx * dy * dz > (long long)INT_MAX) ov = 1;
+    }
+    if (mode == 0 && cloud_status[cloud] == QB200_ERR_VOXEL_OVERFLOW) ov = 1;
+    s_overflow = ov;
+  }
+  __syncthreads();
+  if (s_overflow) {
+    if (threadIdx.x == 0) {
+      n_out[cloud] = 0;
+      cloud_status[cloud] = QB200_ERR_VOXEL_OVERFLOW;
+      starts[(size_t)cloud * (V + 1)] = 0;
+    }
+    return;
+  }
+  int carry = 0, valid_total = 0;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int p = base + threadIdx.x;
+    uint64_t k = 0, kprev = 0;
+    bool valid = false;
+    if (p < n) {
+      k = keys[off + p];
+      valid = (k & kCellMask) != kCellInvalid;
+      if (p > 0) kprev = keys[off + p - 1];
+    }
+    const int head = (valid && (p == 0 || k != kprev)) ? 1 : 0;
+    int tot, vtot;
+    const int ex = block_excl_scan(head, sm, &tot);
+    (void)block_excl_scan(valid ? 1 : 0, sm, &vtot);
+    const int rank = carry + ex;
+    if (head && rank <= V) {
+      starts[(size_t)cloud * (V + 1) + rank] = p;
+      if (mode == 1 && rank < V) cell_keys[(size_t)cloud * V + rank] = k & kCellMask;
+    }
+    carry += tot;
+    valid_total += vtot;
+  }
+  if (threadIdx.x == 0) {
+    int nv = carry;
+    if (nv > V) {
+      nv = V;
+      cloud_status[cloud] = QB200_CAPACITY_EXCEEDED;
+    } else {
+      starts[(size_t)cloud * (V + 1) + nv] = valid_total;  // end sentinel: valid points sort to the front
+    }
+    n_out[cloud] = nv;
+    if (n_valid_out) n_valid_out[cloud] = valid_total;
+  }
+}
+
+// K1c: centroid of each voxel, summed in original point order (stable sort) -> identical to the
+// sequential CPU sum.  One thread per voxel; points are gathered through the sorted index.
+__global__ void __launch_bounds__(128) voxel_centroid_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ raw_off,
+                                                             const uint32_t* __restrict__ sorted_idx, const int* __restrict__ starts,
+                                                             const int* __restrict__ n_vox, int V, float4* __restrict__ vox_pts) {
+  const int cloud = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_vox[cloud]) return;
+  const float4* __restrict__ pts = cloud_ptr[cloud];
+  const int off = raw_off[cloud];
+  const int a = starts[(size_t)cloud * (V + 1) + r], b = starts[(size_t)cloud * (V + 1) + r + 1];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int t = a; t < b; ++t) {
+    const float4 p = __ldg(pts + sorted_idx[off + t]);
+    sx += p.x; sy += p.y; sz += p.z;
+  }
+  const float cnt = (float)(b - a);
+  vox_pts[(size_t)cloud * V + r] = make_float4(sx / cnt, sy / cnt, sz / cnt, 1.0f);
+}
+
+// K2a: lattice keys of the (voxelised) clouds
+__global__ void __launch_bounds__(256) lattice_keys_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V, float inv_cell,
+                                                           uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int cloud = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= V) return;
+  uint64_t cell = kCellInvalid;
+  if (r < n_pts[cloud]) {
+    const float4 p = pts[(size_t)cloud * V + r];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const int ci = (int)floorf(p.x * inv_cell), cj = (int)floorf(p.y * inv_cell), ck = (int)floorf(p.z * inv_cell);
+      if (cell_ok(ci, cj, ck)) cell = cell_key(ci, cj, ck);
+    }
+  }
+  keys[(size_t)cloud * V + r] = ((uint64_t)cloud << kCloudShift) | cell;
+  vals[(size_t)cloud * V + r] = (uint32_t)r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbour walk (device): ascending (cell, index) order; set = {d2 < r2}, self included.
+// ------------------------------------------------------------------------------------------------
+struct LatticeView {
+  const float4* pts;       // cloud's points
+  const uint64_t* ckeys;   // occupied cells, ascending
+  const int* cstart;       // n_cells + 1
+  const uint32_t* order;   // point indices sorted by (cell, index)
+  int n_cells;
+  float inv;
+};
+
+template <class F>
+__device__ __forceinline__ void for_each_neighbor(const LatticeView& L, const float4 pq, int m, float r2, F&& f) {
+  if (!(isfinite(pq.x) && isfinite(pq.y) && isfinite(pq.z))) return;
+  const int ci = (int)floorf(pq.x * L.inv), cj = (int)floorf(pq.y * L.inv), ck = (int)floorf(pq.z * L.inv);
+  if (!cell_ok(ci, cj, ck)) return;
+  for (int dk = -m; dk <= m; ++dk) {
+    const int k = ck + dk;
+    if (k < -kOffK || k >= kOffK - 1) continue;
+    for (int dj = -m; dj <= m; ++dj) {
+      const int j = cj + dj;
+      if (j < -kOffIJ || j >= kOffIJ - 1) continue;
+      const int ilo = max(ci - m, -kOffIJ), ihi = min(ci + m, kOffIJ - 2);
+      const uint64_t lo = cell_key(ilo, j, k), hi = cell_key(ihi, j, k);
+      int a = 0, b = L.n_cells;
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (L.ckeys[mid] < lo) a = mid + 1; else b = mid;
+      }
+      for (int c = a; c < L.n_cells && L.ckeys[c] <= hi; ++c) {
+        const int t1 = L.cstart[c + 1];
+        for (int t = L.cstart[c]; t < t1; ++t) {
+          const int p = (int)L.order[t];
+          const float4 pp = L.pts[p];
+          const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
+          const float d2 = (dx * dx + dy * dy) + dz * dz;
+          if (d2 < r2) f(p, d2, pp);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ LatticeView make_view(int cloud, int V, const float4* pts, const uint64_t* cell_key, const int* cell_start,
+                                                 const uint32_t* order, const int* n_cells, float inv) {
+  LatticeView L;
+  L.pts = pts + (size_t)cloud * V;
+  L.ckeys = cell_key + (size_t)cloud * V;
+  L.cstart = cell_start + (size_t)cloud * (V + 1);
+  L.order = order + (size_t)cloud * V;
+  L.n_cells = n_cells[cloud];
+  L.inv = inv;
+  return L;
+}
+
+// K3: normals.  One thread per point, sequential float accumulation in lattice order.
+__global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                      const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
+                                                      const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv, int m,
+                                                      float r2, float4* __restrict__ normals) {
+  const int cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_pts[cloud]) return;
+  const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
+  const float4 pq = L.pts[q];
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+  for_each_neighbor(L, pq, m, r2, [&](int, float, const float4 pp) {
+    accu[0] += pp.x * pp.x; accu[1] += pp.x * pp.y; accu[2] += pp.x * pp.z;
+    accu[3] += pp.y * pp.y; accu[4] += pp.y * pp.z; accu[5] += pp.z * pp.z;
+    accu[6] += pp.x; accu[7] += pp.y; accu[8] += pp.z;
+    ++cnt;
+  });
+  float out[4];
+  qb_normal_from_accu(accu, cnt, pq.x, pq.y, pq.z, out);
+  normals[(size_t)cloud * V + q] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// K4: SPFH.  Bin COUNTS are order-free; the float histogram value is rebuilt by repeated addition
+// of the same increment, which is what the sequential reference loop produces.
+constexpr int kSpfhThreads = 128;
+__global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __restrict__ pts, const float4* __restrict__ normals,
+                                                            const int* __restrict__ n_pts, int V, const uint64_t* __restrict__ cell_key,
+                                                            const int* __restrict__ cell_start, const uint32_t* __restrict__ order,
+                                                            const int* __restrict__ n_cells, float inv, int m, float r2,
+                                                            float* __restrict__ spfh) {
+  __shared__ unsigned short cnts[kDescDim][kSpfhThreads];
+  const int cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_pts[cloud]) return;
+  const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
+  const float4* __restrict__ nrm = normals + (size_t)cloud * V;
+  const float4 pq = L.pts[q];
+  const float4 nq = nrm[q];
+#pragma unroll
+  for (int b = 0; b < kDescDim; ++b) cnts[b][threadIdx.x] = 0;
+  int k = 0;
+  for_each_neighbor(L, pq, m, r2, [&](int p, float, const float4 pp) {
+    ++k;
+    if (p == q) return;
+    const float4 np = nrm[p];
+    float f1, f2, f3;
+    if (!qb_pair_features(pq.x, pq.y, pq.z, nq.x, nq.y, nq.z, pp.x, pp.y, pp.z, np.x, np.y, np.z, &f1, &f2, &f3)) return;
+    int b1, b2, b3;
+    qb_feature_bins(f1, f2, f3, &b1, &b2, &b3);
+    cnts[b1][threadIdx.x]++;
+    cnts[11 + b2][threadIdx.x]++;
+    cnts[22 + b3][threadIdx.x]++;
+  });
+  float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescDim;
+  const float incr = k >= 2 ? 100.0f / (float)(k - 1) : 0.0f;
+  for (int b = 0; b < kDescDim; ++b) {
+    const int c = cnts[b][threadIdx.x];
+    float v = 0.0f;
+    for (int t = 0; t < c; ++t) v += incr;
+    out[b] = v;
+  }
+}
+
+// K5: FPFH = per-third renormalised sum of neighbour SPFHs weighted by 1/d^2, neighbours in lattice
+// order.  Output is written dimension-major (desc_t[d][q]) for the matching kernel's tile loads.
+__global__ void __launch_bounds__(128) fpfh_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                   const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
+                                                   const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv, int m,
+                                                   float r2, const float* __restrict__ spfh, float* __restrict__ desc_t) {
+  const int cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_pts[cloud]) return;
+  const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
+  const float* __restrict__ sp = spfh + (size_t)cloud * V * kDescDim;
+  const float4 pq = L.pts[q];
+  float o[kDescDim];
+#pragma unroll
+  for (int b = 0; b < kDescDim; ++b) o[b] = 0.0f;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for_each_neighbor(L, pq, m, r2, [&](int p, float d2, const float4) {
+    if (d2 == 0.0f) return;
+    const float weight = 1.0f / d2;
+    const float* __restrict__ s = sp + (size_t)p * kDescDim;
+#pragma unroll
+    for (int b = 0; b < 11; ++b) { const float v = s[b] * weight; s0 += v; o[b] += v; }
+#pragma unroll
+    for (int b = 11; b < 22; ++b) { const float v = s[b] * weight; s1 += v; o[b] += v; }
+#pragma unroll
+    for (int b = 22; b < 33; ++b) { const float v = s[b] * weight; s2 += v; o[b] += v; }
+  });
+  if (s0 != 0.0) s0 = 100.0 / s0;
+  if (s1 != 0.0) s1 = 100.0 / s1;
+  if (s2 != 0.0) s2 = 100.0 / s2;
+  const float g0 = (float)s0, g1 = (float)s1, g2 = (float)s2;
+  float* __restrict__ out = desc_t + (size_t)cloud * kDescPad * V + q;
+#pragma unroll
+  for (int b = 0; b < 11; ++b) out[(size_t)b * V] = o[b] * g0;
+#pragma unroll
+  for (int b = 11; b < 22; ++b) out[(size_t)b * V] = o[b] * g1;
+#pragma unroll
+  for (int b = 22; b < 33; ++b) out[(size_t)b * V] = o[b] * g2;
+}
+
+// descriptor layout converters for the stage API (pcl::FPFHSignature33 rows <-> dimension-major)
+__global__ void desc_to_aos_kernel(const float* __restrict__ desc_t, int V, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kDescDim) return;
+  const int q = i / kDescDim, d = i % kDescDim;
+  out[i] = desc_t[(size_t)d * V + q];
+}
+__global__ void desc_from_aos_kernel(const float* __restrict__ in, int V, int n, float* __restrict__ desc_t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kDescDim) return;
+  const int q = i / kDescDim, d = i % kDescDim;
+  desc_t[(size_t)d * V + q] = in[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int skip_flagged) {
+  if (n_clouds <= 0) return QB200_OK;
+  const float inv = 1.0f / leaf;
+  const dim3 gk(64, n_clouds);
+  voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->key_a, h->val_a, h->ctr.bbox,
+                                               h->ctr.n_valid, h->ctr.cloud_status);
+  h->launches++;
+  const int rc = sort_pairs(h, total_raw, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
+  if (rc) return rc;
+  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(0, h->key_b, h->d_raw_off, h->d_cloud_n, h->V, inv, h->ctr.bbox, h->ctr.n_valid,
+                                                     h->vox_start, nullptr, h->ctr.n_vox, nullptr, h->ctr.cloud_status);
+  const dim3 gc((h->V + 127) / 128, n_clouds);
+  voxel_centroid_kernel<<<gc, 128, 0, h->stream>>>(h->d_cloud_ptr, h->d_raw_off, h->val_b, h->vox_start, h->ctr.n_vox, h->V, h->vox_pts);
+  h->launches += 2;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
+int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_radius, float cell) {
+  if (n_clouds <= 0) return QB200_OK;
+  const int V = h->V;
+  const float inv = 1.0f / cell;
+  const int mn = (int)ceilf(normal_radius * inv + 1e-3f), mf = (int)ceilf(fpfh_radius * inv + 1e-3f);
+  const float rn2 = (float)((double)normal_radius * (double)normal_radius), rf2 = (float)((double)fpfh_radius * (double)fpfh_radius);
+  const dim3 gl((V + 255) / 256, n_clouds);
+  lattice_keys_kernel<<<gl, 256, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, inv, h->key_a, h->val_a);
+  h->launches++;
+  const int rc = sort_pairs(h, n_clouds * V, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
+  if (rc) return rc;
+  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, V, inv, nullptr, nullptr, h->cell_start, h->cell_key,
+                                                     h->ctr.n_cells, h->ctr.n_lat, h->ctr.cloud_status);
+  const dim3 gp((V + 127) / 128, n_clouds);
+  normals_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mn, rn2,
+                                            h->normals);
+  spfh_kernel<<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
+                                                  h->ctr.n_cells, inv, mf, rf2, h->spfh);
+  fpfh_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf, rf2,
+                                         h->spfh, h->desc_t);
+  h->launches += 4;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
+int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33) {
+  if (n <= 0) return QB200_OK;
+  desc_to_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(h->desc_t + (size_t)cloud * kDescPad * h->V, h->V, n, d_out33);
+  h->launches++;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33) {
+  if (n <= 0) return QB200_OK;
+  desc_from_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(d_in33, h->V, n, h->desc_t + (size_t)cloud * kDescPad * h->V);
+  h->launches++;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
+}  // namespace qb

@@ -1,0 +1,92 @@
+// handle.cuh -- the opaque qb200_handle: one device, one stream, device workspaces for one wave of
+// max_batch_slots pairs.  Replaces the reference's process-global state (function-local statics at
+// include/quatro.hpp:53,64,469-470,660 and include/fpfh_manager.hpp:110) with per-handle state.
+#pragma once
+#include <string.h>
+
+#include "common.cuh"
+
+struct qb200_handle {
+  qb200_config cfg;
+  int S, R, V, Lc, W;        // slots, raw cap / cloud, voxel cap / cloud, corr cap / pair, words per adjacency row
+  int NS;                    // match stripes per pair = V / kMatchTile
+  int device;
+  cudaStream_t own_stream, stream;
+  char err[512];
+  int64_t launches;
+
+  // ---- wave description (host-known inputs) ----
+  const float4** d_cloud_ptr; // [2S]
+  int* d_cloud_n;             // [2S]
+  int* d_raw_off;             // [2S+1] offsets into the concatenated sort arrays
+  const float4** h_cloud_ptr; int* h_cloud_n; int* h_raw_off;  // pinned mirrors
+  float4* raw_stage;          // [2S*R] staging for host inputs
+  float4* h_stage;            // pinned host staging [2S*R] (allocated on first host-batch call)
+  size_t h_stage_elems;
+
+  // ---- sort workspace (voxel sort, then lattice sort) ----
+  uint64_t *key_a, *key_b;    // [2S*R]
+  uint32_t *val_a, *val_b;    // [2S*R]
+  void* cub_temp; size_t cub_bytes;
+
+  // ---- front end ----
+  int* vox_start;             // [2S*(V+1)] position (in the sorted raw array) of each voxel's first point
+  float4* vox_pts;            // [2S*V] centroids, ascending (k,j,i)
+  uint64_t* cell_key;         // [2S*V] occupied lattice cells, ascending
+  int* cell_start;            // [2S*(V+1)]
+  float4* normals;            // [2S*V]
+  float* spfh;                // [2S*V*33]
+  float* desc_t;              // [2S*36*V] FPFH, dimension-major per cloud (row d = bin d over all points)
+  // ---- matching ----
+  unsigned long long* rowbest;// [S*V] packed (dist bits << 32 | tgt idx) per source point
+  unsigned long long* colpart;// [S*NS*V] per-stripe partial column minima
+  unsigned long long* colbest;// [S*V]
+  int *mut_i, *mut_j;         // [S*V] mutual NN list (larger-cloud idx, smaller-cloud idx)
+  unsigned char* mark;        // [S*V] tuple-test survivors
+  int* partner;               // [S*V] tgt partner per source index (-1)
+  float* mean;                // [2S*4]
+  int *corr_src, *corr_tgt;   // [S*Lc]
+  float4 *ma, *mb;            // [S*Lc] matched points (src, tgt)
+  // ---- graph / clique ----
+  uint32_t *adj, *adjp;       // [S*Lc*W] adjacency bits, and the same in (core, id)-rank space
+  int* deg;                   // [S*Lc]
+  int *kcore, *korder, *rank_of, *by_rank, *kbin;  // [S*(Lc+2)]
+  int* clique;                // [S*Lc] ascending ids
+  int* final_inl;             // [S*Lc]
+  unsigned char *rot_mask, *trans_mask;  // [S*Lc]
+  // ---- results ----
+  qb200_result* d_results;    // [S]
+  qb200_result* h_results;    // pinned [S]
+  qb::WaveCounters ctr;
+  int* ctr_block; size_t ctr_ints;
+
+  // ---- state mirrored from the reference's statics ----
+  double rot_noise_bound_latched;  // quatro.hpp:469-470 (0 = not latched yet)
+  int last_n_corr, last_n_clique, last_n_final;  // slot 0 of the most recent single-pair call
+
+  cudaEvent_t ev[9];
+  float stage_ms[8];
+
+  void fail(const char* file, int line, const char* msg) {
+    snprintf(err, sizeof(err), "%s:%d: %s", file, line, msg);
+  }
+};
+
+namespace qb {
+
+// Stage launchers (each enqueues kernels on h->stream for clouds/pairs [0, n) of the current wave).
+int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int skip_flagged);
+int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_radius, float cell);
+int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p);
+int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2);
+int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr);
+int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p);
+int launch_fill_counters(qb200_handle* h, int n_pairs, int have_frontend);
+int launch_finalize_status(qb200_handle* h, int n_pairs);
+int launch_iota_clique(qb200_handle* h, int n_pairs);
+int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33);
+int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33);
+size_t sort_temp_bytes(int max_items);
+int sort_pairs(qb200_handle* h, int n_items, int end_bit);
+
+}  // namespace qb

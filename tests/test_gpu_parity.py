@@ -1,0 +1,332 @@
+"""GPU parity: every stage of the CUDA path, called through the C-ABI, against the CPU oracle on the
+same seeded inputs.  Integer outputs (voxel membership, correspondences, adjacency bits, core numbers,
+clique membership) must be bit-exact; fp64 poses within 1e-9; end-to-end within 2 deg / 0.3 m."""
+import numpy as np
+import pytest
+
+from conftest import adj_to_dense, dense_to_adj
+from quatro_b200 import synth
+from quatro_b200.capi import default_params, PMC_HEU, KCORE_HEU, INLIER_NONE, COTE_WEIGHTED_MEAN, RESULT_DTYPE
+
+pytestmark = pytest.mark.gpu
+
+
+def P4(xyz, w=1.0):
+    xyz = np.asarray(xyz, np.float32).reshape(-1, 3)
+    out = np.full((len(xyz), 4), w, np.float32)
+    out[:, :3] = xyz
+    return out
+
+
+@pytest.fixture(scope="module")
+def scan_pair():
+    return synth.outdoor_pair(1)
+
+
+@pytest.fixture(scope="module")
+def small_pair():
+    return synth.outdoor_pair(3, rings=32, azimuths=900)
+
+
+# ---- K1 voxel ----------------------------------------------------------------------------------
+def test_voxelize_bit_exact(handle, oracle, scan_pair, small_pair):
+    for cloud in (scan_pair[0], scan_pair[1], small_pair[0]):
+        for skip in (1, 0):
+            ref, st_r = oracle.voxelize(cloud, 0.3, skip)
+            got, st_g = handle.voxelize(cloud, 0.3, skip)
+            if len(ref) > handle.cfg.max_voxel_points:
+                assert st_g == 3  # QB200_CAPACITY_EXCEEDED is reported, not silently truncated
+                continue
+            assert st_g == st_r == 0
+            assert got.shape == ref.shape
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))  # centroids bit for bit, same order
+
+
+def test_voxelize_edge_cases(handle, oracle):
+    pts = P4([[0.1, 0.1, 0.1], [np.nan, 0, 0], [0.2, 0.1, 0.1], [5, 5, 5], [-0.1, 0, 0], [np.inf, 1, 1]])
+    pts[3, 3] = -1.0
+    for skip in (0, 1):
+        ref, _ = oracle.voxelize(pts, 0.3, skip)
+        got, st = handle.voxelize(pts, 0.3, skip)
+        assert st == 0 and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    got, st = handle.voxelize(P4(np.zeros((0, 3))), 0.3, 1)
+    assert len(got) == 0 and st == 0
+    got, st = handle.voxelize(P4([[np.nan, 0, 0]]), 0.3, 1)
+    assert len(got) == 0
+    # leaf so small that dx*dy*dz overflows int32: PCL returns the input unfiltered
+    big = P4([[0, 0, 0], [3000, 3000, 300]])
+    ref, st_r = oracle.voxelize(big, 0.001, 0)
+    got, st_g = handle.voxelize(big, 0.001, 0)
+    assert st_r == st_g == -5 and np.array_equal(got, ref)
+
+
+# ---- K2-K5 normals + FPFH ------------------------------------------------------------------------------
+def test_fpfh_bit_exact(handle, oracle, scan_pair, small_pair):
+    for raw in (scan_pair[0], small_pair[1]):
+        vox, _ = oracle.voxelize(raw, 0.3, 1)
+        n_ref, d_ref = oracle.compute_fpfh(vox, 0.5, 0.75, 0.3)
+        n_got, d_got = handle.compute_fpfh(vox, 0.5, 0.75, 0.3)
+        same_n = (n_got.view(np.uint32) == n_ref.view(np.uint32)) | (np.isnan(n_got) & np.isnan(n_ref))
+        assert same_n.all(), f"{(~same_n).any(1).sum()} of {len(vox)} normals differ"
+        same_d = d_got.view(np.uint32) == d_ref.view(np.uint32)
+        assert same_d.all(), f"{(~same_d).any(1).sum()} of {len(vox)} descriptors differ, max abs {np.abs(d_got - d_ref).max()}"
+
+
+def test_fpfh_other_lattice_and_unsorted_input(handle, oracle):
+    rng = np.random.default_rng(5)
+    g = np.arange(-4, 4.01, 0.25)
+    xx, yy = np.meshgrid(g, g)
+    pts = np.concatenate([np.stack([xx.ravel(), yy.ravel(), np.full(xx.size, -1.7)], 1),
+                          np.stack([np.full(xx.size, 5.0), xx.ravel(), yy.ravel()], 1),
+                          rng.uniform(-4, 4, (500, 3))])
+    pts = pts[rng.permutation(len(pts))] + rng.normal(0, 0.01, (len(pts), 3))
+    for cell in (0.3, 0.5, 0.2):
+        n_ref, d_ref = oracle.compute_fpfh(P4(pts), 0.5, 0.75, cell)
+        n_got, d_got = handle.compute_fpfh(P4(pts), 0.5, 0.75, cell)
+        assert np.array_equal(d_got.view(np.uint32), d_ref.view(np.uint32))
+        assert ((n_got.view(np.uint32) == n_ref.view(np.uint32)) | (np.isnan(n_got) & np.isnan(n_ref))).all()
+    # isolated / too-few-neighbour points: NaN normals, finite descriptors
+    iso = P4([[0, 0, 0], [0.1, 0, 0], [10, 10, 10]])
+    n_got, d_got = handle.compute_fpfh(iso, 0.5, 0.75, 0.3)
+    n_ref, d_ref = oracle.compute_fpfh(iso, 0.5, 0.75, 0.3)
+    assert np.isnan(n_got[:, :3]).all() and np.array_equal(d_got, d_ref)
+
+
+# ---- K6/K7 matching ------------------------------------------------------------------------------------
+def test_match_bit_exact(handle, oracle, scan_pair):
+    src, tgt, _ = scan_pair
+    sv, _ = oracle.voxelize(src, 0.3, 1)
+    tv, _ = oracle.voxelize(tgt, 0.3, 1)
+    _, sd = oracle.compute_fpfh(sv, 0.5, 0.75, 0.3)
+    _, td = oracle.compute_fpfh(tv, 0.5, 0.75, 0.3)
+    p = default_params()
+    for a, ad, b, bd in ((sv, sd, tv, td), (tv, td, sv, sd)):   # second case: source larger than target (no swap)
+        c_ref, nm_ref, _ = oracle.match(a, ad, b, bd, p)
+        c_got, nm_got, st = handle.match(a, ad, b, bd, p)
+        assert st == 0 and nm_got == nm_ref
+        assert np.array_equal(c_got, c_ref)
+    p2 = default_params(); p2.use_tuple_test = 0
+    c_ref, nm_ref, _ = oracle.match(sv, sd, tv, td, p2)
+    c_got, nm_got, _ = handle.match(sv, sd, tv, td, p2)
+    assert np.array_equal(c_got, c_ref) and len(c_got) == nm_got
+    p3 = default_params(); p3.seed = 12345
+    assert np.array_equal(handle.match(sv, sd, tv, td, p3)[0], oracle.match(sv, sd, tv, td, p3)[0])
+
+
+def test_match_ties_and_small_inputs(handle, oracle):
+    pts = P4([[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    d = np.zeros((3, 33), np.float32)
+    p = default_params(); p.use_tuple_test = 0
+    assert handle.match(pts, d, pts, d, p)[0].tolist() == [[0, 0]]       # lowest-index tie-break both ways
+    rng = np.random.default_rng(2)
+    for na, nb in ((1, 1), (5, 130), (129, 127), (300, 257)):
+        a, b = P4(rng.uniform(-5, 5, (na, 3))), P4(rng.uniform(-5, 5, (nb, 3)))
+        ad, bd = rng.uniform(0, 100, (na, 33)).astype(np.float32), rng.uniform(0, 100, (nb, 33)).astype(np.float32)
+        bd[: min(na, nb) // 2] = ad[: min(na, nb) // 2]                # exact duplicates -> zero distances
+        for prm in (p, default_params()):
+            ref = oracle.match(a, ad, b, bd, prm)
+            got = handle.match(a, ad, b, bd, prm)
+            assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+
+
+def test_match_and_pack(handle, oracle, small_pair):
+    sv, _ = oracle.voxelize(small_pair[0], 0.3, 1)
+    tv, _ = oracle.voxelize(small_pair[1], 0.3, 1)
+    p = default_params()
+    c_ref, sm_ref, tm_ref, _ = oracle.match_and_pack(sv, tv, p)
+    c_got, sm_got, tm_got, st = handle.match_and_pack(sv, tv, p)
+    assert st == 0 and np.array_equal(c_got, c_ref) and np.array_equal(sm_got, sm_ref) and np.array_equal(tm_got, tm_ref)
+    cc, sm2, tm2 = handle.last_correspondences()
+    assert np.array_equal(cc, c_ref) and np.array_equal(sm2, sm_ref)
+    bad = default_params(); bad.normal_radius = 1.0   # normal_radius > fpfh_radius: the reference throws invalid_argument
+    from quatro_b200.capi import QuatroB200Error
+    with pytest.raises(QuatroB200Error):
+        handle.match_and_pack(sv, tv, bad)
+
+
+# ---- K8 graph ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,ratio", [(2, 1.0), (33, 0.5), (200, 0.4), (1000, 0.3), (3000, 0.3), (4096, 0.1)])
+def test_graph_bit_exact(handle, oracle, L, ratio):
+    a4, b4, T, inl = synth.matched_pairs(100 + L, L, inlier_ratio=ratio, noise=0.05)
+    adj_r, deg_r, ne_r = oracle.build_graph(a4, b4, 0.3, 1.0)
+    adj_g, deg_g, ne_g = handle.build_graph(a4, b4, 0.3, 1.0)
+    assert np.array_equal(adj_g, adj_r)
+    assert np.array_equal(deg_g, deg_r) and ne_g == ne_r
+
+
+def test_graph_boundary_and_duplicates(handle, oracle):
+    # pairs sitting exactly on / next to the |db - da| = 0.6 boundary, duplicate points, large coordinates
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-80, 80, (600, 3))
+    b = a.copy()
+    d = rng.normal(size=(600, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b[::2] += d[::2] * 0.6
+    b[1::4] += d[1::4] * np.float32(0.6000001)
+    a[10] = a[11]; b[20] = b[21]; a[30] = a[31]; b[30] = b[31]
+    a4, b4 = P4(a), P4(b)
+    for nb in (0.3, 0.25):
+        assert np.array_equal(handle.build_graph(a4, b4, nb, 1.0)[0], oracle.build_graph(a4, b4, nb, 1.0)[0])
+
+
+# ---- K9 k-core + clique ------------------------------------------------------------------------------
+def _random_graph(rng, n, p, planted=0):
+    R = rng.uniform(size=(n, n)) < p
+    R = np.triu(R, 1); R = R | R.T
+    if planted:
+        m = np.sort(rng.choice(n, planted, replace=False))
+        R[np.ix_(m, m)] = True
+    np.fill_diagonal(R, False)
+    return R
+
+
+@pytest.mark.parametrize("n,p,planted", [(1, 0, 0), (2, 1.0, 0), (40, 0.3, 0), (150, 0.03, 25), (500, 0.1, 60), (1000, 0.02, 0),
+                                         (3000, 0.02, 300), (4096, 0.01, 100), (700, 0.5, 0)])
+def test_kcore_and_clique_bit_exact(handle, oracle, n, p, planted):
+    R = _random_graph(np.random.default_rng(n + planted), n, p, planted)
+    adj = dense_to_adj(R)
+    c_ref, k_ref, o_ref, mc_ref = oracle.max_clique(adj, PMC_HEU)
+    c_got, k_got, o_got, mc_got = handle.max_clique(adj, PMC_HEU)
+    assert mc_got == mc_ref
+    assert np.array_equal(k_got, k_ref), "core numbers differ"
+    assert np.array_equal(o_got, o_ref), "peel (degeneracy) order differs"
+    assert np.array_equal(c_got, c_ref), "clique membership differs"
+
+
+def test_clique_on_registration_graphs(handle, oracle):
+    for L, ratio in ((300, 0.3), (1500, 0.2), (3000, 0.35)):
+        a4, b4, _, inl = synth.matched_pairs(7 * L, L, inlier_ratio=ratio, noise=0.05)
+        adj, _, _ = oracle.build_graph(a4, b4, 0.3, 1.0)
+        ref = oracle.max_clique(adj, PMC_HEU)
+        got = handle.max_clique(adj, PMC_HEU)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2]) and got[3] == ref[3]
+        ref = oracle.max_clique(adj, KCORE_HEU, 0.1)
+        got = handle.max_clique(adj, KCORE_HEU, 0.1)
+        assert np.array_equal(got[0], ref[0])
+
+
+# ---- K10/K11 pose --------------------------------------------------------------------------------------
+def test_solve_pose_matches_oracle(handle, oracle):
+    for seed, L, ratio in ((1, 300, 0.3), (2, 2000, 0.25), (3, 64, 0.9)):
+        a4, b4, T, inl = synth.matched_pairs(seed, L, inlier_ratio=ratio, noise=0.04)
+        adj, _, _ = oracle.build_graph(a4, b4, 0.3, 1.0)
+        clique = oracle.max_clique(adj, PMC_HEU)[0]
+        for mode in (0, COTE_WEIGHTED_MEAN):
+            p = default_params(); p.cote_mode = mode
+            r_ref, rm_ref, tm_ref, st_r = oracle.solve_pose(a4, b4, clique, p)
+            r_got, rm_got, tm_got, st_g = handle.solve_pose(a4, b4, clique, p)
+            assert st_g == st_r == 0 and r_got.valid == 1
+            assert np.allclose(r_got.matrix(), r_ref.matrix(), atol=1e-9, rtol=0)
+            assert r_got.gnc_iters == r_ref.gnc_iters
+            assert np.array_equal(rm_got, rm_ref) and np.array_equal(tm_got, tm_ref)
+            assert (r_got.n_rot_inliers, r_got.n_final_inliers) == (r_ref.n_rot_inliers, r_ref.n_final_inliers)
+            assert abs(r_got.cost - r_ref.cost) < 1e-9 * max(1.0, abs(r_ref.cost))
+    p = default_params(); p.using_rot_inliers_when_estimating_cote = 1
+    r_ref, _, tm_ref, _ = oracle.solve_pose(a4, b4, clique, p)
+    r_got, _, tm_got, _ = handle.solve_pose(a4, b4, clique, p)
+    assert np.allclose(r_got.matrix(), r_ref.matrix(), atol=1e-9) and r_got.n_final_inliers == r_ref.n_final_inliers
+
+
+def test_solve_pose_with_ryrx_prior(handle, oracle):
+    a4, b4, T, inl = synth.matched_pairs(5, 400, inlier_ratio=0.4, noise=0.03)
+    adj, _, _ = oracle.build_graph(a4, b4, 0.3, 1.0)
+    clique = oracle.max_clique(adj, PMC_HEU)[0]
+    p = default_params(); p.use_pre_estimated_RyRx = 1
+    ang = np.deg2rad(0.5)
+    Ry = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    for i, v in enumerate(Ry.ravel()):
+        p.RyRx[i] = v
+    r_ref, *_ = oracle.solve_pose(a4, b4, clique, p)
+    r_got, *_ = handle.solve_pose(a4, b4, clique, p)
+    assert np.allclose(r_got.matrix(), r_ref.matrix(), atol=1e-9)
+
+
+def test_solve_correspondences_and_degenerate(handle, oracle):
+    for seed, L in ((21, 500), (22, 3000)):
+        a4, b4, T, inl = synth.matched_pairs(seed, L, inlier_ratio=0.3, noise=0.04)
+        p = default_params()
+        r_ref, st_r, c_ref, f_ref = oracle.solve_correspondences(a4, b4, p, want_sets=True)
+        r_got, st_g = handle.solve_correspondences(a4, b4, p)
+        assert st_g == st_r == 0
+        assert np.array_equal(handle.last_clique(), c_ref)                       # max-clique membership bit-exact
+        assert np.array_equal(handle.last_final_inliers(), f_ref)
+        assert (r_got.n_edges, r_got.max_core, r_got.clique_size) == (r_ref.n_edges, r_ref.max_core, r_ref.clique_size)
+        assert np.allclose(r_got.matrix(), r_ref.matrix(), atol=1e-9)
+        rot, tr = synth.pose_error(r_got.matrix(), T)
+        assert rot < 0.5 and tr < 0.1
+    a = P4([[0, 0, 0], [10, 0, 0], [0, 10, 0]]); b = P4([[0, 0, 0], [50, 0, 0], [0, 90, 0]])
+    r, st = handle.solve_correspondences(a, b, default_params())
+    assert st == 1 and r.valid == 0 and np.array_equal(r.matrix(), np.eye(4))
+    r, st = handle.solve_correspondences(a[:1], b[:1], default_params())
+    assert st == 2 and r.valid == 0
+    pn = default_params(); pn.inlier_selection_mode = INLIER_NONE
+    a4, b4, T, _ = synth.matched_pairs(30, 200, inlier_ratio=0.9, noise=0.02)
+    r_got, _ = handle.solve_correspondences(a4, b4, pn)
+    r_ref, _ = oracle.solve_correspondences(a4, b4, pn)
+    assert np.allclose(r_got.matrix(), r_ref.matrix(), atol=1e-9)
+
+
+# ---- end to end ----------------------------------------------------------------------------------------
+def _same_record(g, r):
+    for k in ("valid", "status", "n_src_vox", "n_tgt_vox", "n_mutual", "n_corr", "n_edges", "max_core", "clique_size", "gnc_iters",
+              "n_rot_inliers", "n_final_inliers"):
+        assert g[k] == getattr(r, k), (k, g[k], getattr(r, k))
+    assert np.allclose(np.asarray(g["T"]).reshape(4, 4).T, r.matrix(), atol=1e-9)
+
+
+def test_register_pair_end_to_end(handle, oracle, scan_pair):
+    src, tgt, T = scan_pair
+    p = default_params()
+    r_ref, st_r = oracle.register_pair(src, tgt, p)
+    r_got, st_g = handle.register_pair(src, tgt, p)
+    assert st_g == st_r == 0
+    _same_record({k: getattr(r_got, k) for k, _ in r_got._fields_ if k != "T"} | {"T": np.array(r_got.T[:])}, r_ref)
+    rot, tr = synth.pose_error(r_got.matrix(), T)
+    assert rot < 2.0 and tr < 0.5        # vs ground truth (the z offset of a yaw-only model stays in the budget)
+    rot, tr = synth.pose_error(r_got.matrix(), r_ref.matrix())
+    assert rot < 1e-6 and tr < 1e-6      # vs the CPU reference path: north_star asks for 2 deg / 0.3 m
+
+
+def test_register_batch_matches_single_and_oracle(handle, oracle):
+    p = default_params()
+    pairs = [synth.outdoor_pair(s, rings=32, azimuths=900)[:2] for s in range(10, 21)]   # 11 pairs > 8 slots: two waves
+    out = handle.register_batch(pairs, p)
+    assert out.dtype == RESULT_DTYPE and len(out) == len(pairs)
+    for (src, tgt), g in zip(pairs, out):
+        r_ref, _ = oracle.register_pair(src, tgt, p)
+        _same_record(g, r_ref)
+    # order / batch composition must not change any pair's result
+    out2 = handle.register_batch(pairs[::-1], p)
+    assert out2[::-1].tobytes() == out.tobytes()
+
+
+def test_register_batch_device_resident_inputs(handle, oracle):
+    import torch
+    p = default_params()
+    host = [synth.outdoor_pair(s, rings=32, azimuths=900)[:2] for s in (31, 32, 33)]
+    dev = [(torch.from_numpy(s).cuda(), torch.from_numpy(t).cuda()) for s, t in host]
+    ptrs = [(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0]) for a, b in dev]
+    torch.cuda.synchronize()
+    out_d = handle.register_batch(ptrs, p, kind=1)
+    out_h = handle.register_batch(host, p)
+    assert out_d.tobytes() == out_h.tobytes()
+
+
+def test_empty_and_degenerate_clouds_in_batch(handle):
+    p = default_params()
+    good = synth.outdoor_pair(40, rings=32, azimuths=900)[:2]
+    empty = np.zeros((0, 4), np.float32)
+    ground_only = good[0][good[0][:, 3] < 0]
+    out = handle.register_batch([good, (empty, good[1]), (ground_only, good[1]), good], p)
+    assert out["valid"].tolist() == [1, 0, 0, 1]
+    assert out["status"][1] == 2 and out["status"][2] == 2
+    assert np.array_equal(out["T"][1], np.eye(4).ravel())
+    assert out[0].tobytes() == out[3].tobytes()
+
+
+def test_launch_counter_and_stage_times(handle):
+    p = default_params()
+    before = handle.launch_count()
+    handle.register_batch([synth.outdoor_pair(50, rings=16, azimuths=450)[:2]], p)
+    assert handle.launch_count() - before >= 25
+    ms = handle.stage_ms()
+    assert (ms >= 0).all() and ms[1:7].sum() > 0

@@ -87,3 +87,61 @@ int main(){
     subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-o", str(exe), str(src)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout + r.stderr
+
+
+def test_cuda_fpfh_math_matches_oracle_bitwise(tmp_path):
+    """quatro_b200/csrc/fpfh_math.cuh (normal from covariance sums, Darboux features, bins) compiled for
+    the HOST must agree bit-for-bit with the oracle's exported routines on random inputs."""
+    hdr = ROOT / "quatro_b200" / "csrc" / "fpfh_math.cuh"
+    from oracle import Oracle
+    Oracle()  # builds oracle/build/libquatro_oracle.so if stale
+    src = tmp_path / "cmp2.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <random>
+#define QB_HD
+#include "%s"
+extern "C" void qo_test_normal_from_accu(const float*, int, const float*, float*);
+extern "C" int qo_test_pair_features(const float*, const float*, const float*, const float*, float*);
+extern "C" void qo_test_feature_bins(float, float, float, int*);
+static bool same(float a, float b){ uint32_t x,y; memcpy(&x,&a,4); memcpy(&y,&b,4); return x==y || (a!=a && b!=b); }
+int main(){
+  std::mt19937 g(7); std::normal_distribution<float> nd(0.f,1.f); std::uniform_real_distribution<float> ud(-1.f,1.f);
+  long bad=0;
+  for(int it=0; it<200000; ++it){
+    // a small neighbourhood around a far-away centre: accumulate like the kernels do
+    float cx=60.f*ud(g), cy=60.f*ud(g), cz=2.f*ud(g); int cnt=3+(it%%20);
+    float nx=nd(g), ny=nd(g), nz=nd(g);
+    float accu[9]={0,0,0,0,0,0,0,0,0};
+    for(int k=0;k<cnt;++k){ float a=0.5f*ud(g), b=0.5f*ud(g); float x=cx+a, y=cy+b, z=cz+0.02f*ud(g)+(it%%3==0? 0.3f*a*nx:0.f);
+      accu[0]+=x*x; accu[1]+=x*y; accu[2]+=x*z; accu[3]+=y*y; accu[4]+=y*z; accu[5]+=z*z; accu[6]+=x; accu[7]+=y; accu[8]+=z; }
+    (void)ny; (void)nz;
+    float a1[9], o1[4], o2[4], p3[3]={cx,cy,cz}; memcpy(a1,accu,sizeof(a1));
+    qb_normal_from_accu(a1, cnt, cx, cy, cz, o1);
+    qo_test_normal_from_accu(accu, cnt, p3, o2);
+    for(int k=0;k<4;++k) if(!same(o1[k],o2[k])) ++bad;
+    // pair features on random unit-ish normals
+    float p1[4]={ud(g),ud(g),ud(g),0}, p2[4]={ud(g),ud(g),ud(g),0}, n1[4]={nd(g),nd(g),nd(g),0}, n2[4]={nd(g),nd(g),nd(g),0};
+    float l1=std::sqrt(n1[0]*n1[0]+n1[1]*n1[1]+n1[2]*n1[2]), l2=std::sqrt(n2[0]*n2[0]+n2[1]*n2[1]+n2[2]*n2[2]);
+    for(int k=0;k<3;++k){ n1[k]/=l1; n2[k]/=l2; }
+    if(it%%50==0){ n2[0]=n1[0]; n2[1]=n1[1]; n2[2]=n1[2]; }
+    if(it%%77==0){ n1[0]=NAN; }
+    float f[3]={0,0,0}, h1,h2,h3;
+    bool okp = qb_pair_features(p1[0],p1[1],p1[2],n1[0],n1[1],n1[2],p2[0],p2[1],p2[2],n2[0],n2[1],n2[2],&h1,&h2,&h3);
+    int oko = qo_test_pair_features(p1,n1,p2,n2,f);
+    if((int)okp!=oko) ++bad;
+    if(okp && oko){ if(!same(h1,f[0])||!same(h2,f[1])||!same(h3,f[2])) ++bad;
+      int b[3], c1,c2,c3; qo_test_feature_bins(f[0],f[1],f[2],b); qb_feature_bins(h1,h2,h3,&c1,&c2,&c3);
+      if(b[0]!=c1||b[1]!=c2||b[2]!=c3) ++bad; }
+  }
+  printf("%%ld\n", bad); return bad!=0;
+}''' % hdr)
+    exe = tmp_path / "cmp2"
+    libdir = ROOT / "oracle" / "build"
+    subprocess.run(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-o", str(exe), str(src), f"-L{libdir}", "-lquatro_oracle",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "0", r.stdout + r.stderr
