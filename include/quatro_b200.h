@@ -202,6 +202,11 @@ int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_ma
  * [0]=h2d [1]=voxel [2]=fpfh [3]=match [4]=graph [5]=clique [6]=pose [7]=d2h; n<=8. */
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n);
 
+/* Device time (CUDA events on the handle's stream) and launch count of the two roofline kernels
+ * during the last qb200_register_batch call: [0] = match_stripe_kernel (33-D all-pairs NN),
+ * [1] = tim_graph_kernel (TIM consistency graph); n <= 2. */
+int qb200_get_kernel_ms(qb200_handle* h, float* ms, int32_t* launches, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_get_last_final_inliers": (i32, [vp, vp, i32, P(i32)]),
         "qb200_get_last_correspondences": (i32, [vp, vp, vp, vp, i32, P(i32)]),
         "qb200_get_stage_ms": (i32, [vp, vp, i32]),
+        "qb200_get_kernel_ms": (i32, [vp, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
@@ -136,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "qb200_set_stream", "qb200_last_error", "qb200_launch_count", "qb200_voxelize", "qb200_compute_fpfh",
     "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_solve_pose", "qb200_solve_correspondences",
     "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
-    "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms",
+    "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
 ]
 
 
@@ -212,8 +213,9 @@ class Handle:
         cap = cap or max(1, len(pts4))
         out = np.zeros((cap, 4), np.float32)
         n = C.c_int32(0)
-        st = self._check(self.lib.qb200_voxelize(self.h, _ptr(pts4), len(pts4), leaf, skip_flagged, _ptr(out), cap, C.byref(n)),
-                         "qb200_voxelize")
+        st = self.lib.qb200_voxelize(self.h, _ptr(pts4), len(pts4), leaf, skip_flagged, _ptr(out), cap, C.byref(n))
+        if st != -5:  # ERR_VOXEL_OVERFLOW = PCL's "leaf too small" pass-through: output is the unfiltered input
+            self._check(st, "qb200_voxelize")
         return out[: min(n.value, cap)].copy(), st
 
     def compute_fpfh(self, pts4, normal_radius: float, fpfh_radius: float, grid_cell: float):
@@ -333,6 +335,14 @@ class Handle:
         self._check(self.lib.qb200_get_last_correspondences(self.h, _ptr(corr), _ptr(sm), _ptr(tm), cap, C.byref(n)),
                     "qb200_get_last_correspondences")
         return corr[: n.value].copy(), sm[: n.value].copy(), tm[: n.value].copy()
+
+    def kernel_ms(self):
+        """(ms, launches) of the two roofline kernels during the last register_batch:
+        index 0 = match_stripe_kernel (K6), 1 = tim_graph_kernel (K8)."""
+        ms = np.zeros(2, np.float32)
+        calls = np.zeros(2, np.int32)
+        self.lib.qb200_get_kernel_ms(self.h, _ptr(ms), _ptr(calls), 2)
+        return ms, calls
 
     def stage_ms(self) -> np.ndarray:
         ms = np.zeros(8, np.float32)

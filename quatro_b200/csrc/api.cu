@@ -108,6 +108,7 @@ int alloc_all(qb200_handle* h) {
   h->ctr.max_core = p; p += S;
   h->ctr.n_final = p; p += S;
   for (int i = 0; i < 9; ++i) QB_CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
+  for (int i = 0; i < 4; ++i) QB_CUDA_TRY(h, cudaEventCreate(&h->kev[i]));
   return QB200_OK;
 }
 
@@ -266,6 +267,8 @@ void qb200_destroy(qb200_handle* h) {
   if (h->h_results) cudaFreeHost(h->h_results);
   for (int i = 0; i < 9; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 4; ++i)
+    if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -507,6 +510,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   }
   cudaSetDevice(h->device);
   for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
+  for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
   const float cell = lattice_cell(*p);
   for (int w0 = 0; w0 < n_pairs; w0 += h->S) {
     const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
@@ -554,6 +558,14 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
     for (int i = 0; i < 8; ++i) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
+    }
+    for (int k = 0; k < 2; ++k) {
+      float ms = 0.f;
+      if (h->kev_armed[k] && cudaEventElapsedTime(&ms, h->kev[2 * k], h->kev[2 * k + 1]) == cudaSuccess) {
+        h->kernel_ms[k] += ms;
+        h->kernel_calls[k] += 1;
+      }
+      h->kev_armed[k] = 0;
     }
     // the wave's own reads of h_cloud_* / h_raw_off are complete after the synchronize above
   }
@@ -615,6 +627,15 @@ int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_ma
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n) {
   if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->stage_ms[i];
+  return QB200_OK;
+}
+
+int qb200_get_kernel_ms(qb200_handle* h, float* ms, int32_t* launches, int32_t n) {
+  if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
+  for (int i = 0; i < n && i < 2; ++i) {
+    ms[i] = h->kernel_ms[i];
+    if (launches) launches[i] = h->kernel_calls[i];
+  }
   return QB200_OK;
 }
 

@@ -136,7 +136,10 @@ int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2)
   if (n_pairs <= 0) return QB200_OK;
   const double beta = 2 * noise_bound * sqrt(cbar2);  // quatro.hpp:367
   const dim3 g(148, n_pairs);
+  cudaEventRecord(h->kev[2], h->stream);
   tim_graph_kernel<<<g, kGraphWarps * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, h->Lc, h->W, beta, h->adj);
+  cudaEventRecord(h->kev[3], h->stream);
+  h->kev_armed[1] = 1;
   const dim3 gd((h->Lc + 7) / 8, n_pairs);
   degree_kernel<<<gd, 256, 0, h->stream>>>(h->adj, h->ctr.n_corr, h->Lc, h->W, h->deg, h->ctr.n_edges);
   h->launches += 2;

@@ -66,6 +66,10 @@ struct qb200_handle {
 
   cudaEvent_t ev[9];
   float stage_ms[8];
+  cudaEvent_t kev[4];        // [0,1] around match_stripe_kernel, [2,3] around tim_graph_kernel (last wave)
+  float kernel_ms[2];
+  int kernel_calls[2];
+  int kev_armed[2];
 
   void fail(const char* file, int line, const char* msg) {
     snprintf(err, sizeof(err), "%s:%d: %s", file, line, msg);

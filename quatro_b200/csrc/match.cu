@@ -350,7 +350,10 @@ int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p) {
     attr_set = true;
   }
   const dim3 gs(h->NS, n_pairs);
+  cudaEventRecord(h->kev[0], h->stream);
   match_stripe_kernel<<<gs, kMatchThreads, smem, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->NS, h->rowbest, h->colpart);
+  cudaEventRecord(h->kev[1], h->stream);
+  h->kev_armed[0] = 1;
   const dim3 gf((V + 255) / 256, n_pairs);
   match_colfold_kernel<<<gf, 256, 0, h->stream>>>(h->colpart, h->ctr.n_vox, V, h->NS, h->colbest);
   match_mutual_kernel<<<n_pairs, 1024, 0, h->stream>>>(h->rowbest, h->colbest, h->ctr.n_vox, V, h->mut_i, h->mut_j, h->ctr.n_mutual,
