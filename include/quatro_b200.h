@@ -99,7 +99,7 @@ typedef struct qb200_config {
   int32_t device;            /* CUDA ordinal */
   int32_t max_batch_slots;   /* pairs resident in one wave of the batch pipeline (default 64) */
   int32_t max_raw_points;    /* per cloud (default 131072) */
-  int32_t max_voxel_points;  /* per cloud (default 8192)  */
+  int32_t max_voxel_points;  /* per cloud (default 16384; multiple of 128) */
   int32_t max_corr;          /* per pair  (default 4096)  */
   int32_t reserved[3];
 } qb200_config;

@@ -159,7 +159,7 @@ def default_params() -> Params:
 
 def default_config() -> Config:
     c = Config()
-    c.device, c.max_batch_slots, c.max_raw_points, c.max_voxel_points, c.max_corr = 0, 64, 131072, 8192, 4096
+    c.device, c.max_batch_slots, c.max_raw_points, c.max_voxel_points, c.max_corr = 0, 64, 131072, 16384, 4096
     return c
 
 

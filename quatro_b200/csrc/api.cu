@@ -216,7 +216,7 @@ void qb200_default_params(qb200_params* p) {
 
 void qb200_default_config(qb200_config* c) {
   memset(c, 0, sizeof(*c));
-  c->device = 0; c->max_batch_slots = 64; c->max_raw_points = 131072; c->max_voxel_points = 8192; c->max_corr = 4096;
+  c->device = 0; c->max_batch_slots = 64; c->max_raw_points = 131072; c->max_voxel_points = 16384; c->max_corr = 4096;
 }
 
 int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {

@@ -29,6 +29,15 @@ def small_pair():
 
 
 # ---- K1 voxel ----------------------------------------------------------------------------------
+def test_voxel_capacity_is_reported(oracle, scan_pair):
+    from quatro_b200.capi import Handle
+    with Handle(max_batch_slots=2, max_voxel_points=1024) as h:
+        got, st = h.voxelize(scan_pair[0], 0.3, 1)
+        assert st == 3 and len(got) == 1024     # QB200_CAPACITY_EXCEEDED, never silent truncation
+        out = h.register_batch([scan_pair[:2]], default_params())
+        assert out["valid"][0] == 0 and out["status"][0] == 3 and np.array_equal(out["T"][0], np.eye(4).ravel())
+
+
 def test_voxelize_bit_exact(handle, oracle, scan_pair, small_pair):
     for cloud in (scan_pair[0], scan_pair[1], small_pair[0]):
         for skip in (1, 0):
