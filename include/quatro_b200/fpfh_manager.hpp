@@ -26,8 +26,7 @@ class FPFHManager {
     normal_radius_ = normal_radius; fpfh_radius_ = fpfh_radius; interval_ = interval;
   }
   void clearInputs() { is_initial_ = true; corr.clear(); }
-  // lattice cell of the neighbour search (only fixes the accumulation order); defaults to 0.6 * normal_radius,
-  // which is the voxel leaf for config/params.yaml (0.3 / 0.5)
+  // lattice cell of the neighbour search (only fixes the accumulation order); 0 = library default (fpfh_radius)
   void setGridCell(float cell) { grid_cell_ = cell; }
   void setSeed(uint64_t seed) { seed_ = seed; }  // tuple-test RNG (the reference seeds with time(NULL))
 
@@ -41,7 +40,7 @@ class FPFHManager {
     qb200_default_params(&p);
     p.normal_radius = (float)normal_radius_;
     p.fpfh_radius = (float)fpfh_radius_;
-    p.grid_cell = grid_cell_ > 0 ? grid_cell_ : 0.6f * (float)normal_radius_;
+    p.grid_cell = grid_cell_;
     p.seed = seed_;
     const int32_t cap = (int32_t)std::min(src->points.size(), target->points.size());
     std::vector<int32_t> c(2 * (size_t)std::max(cap, 1));

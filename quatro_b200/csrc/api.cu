@@ -59,7 +59,7 @@ int alloc_all(qb200_handle* h) {
   QB_ALLOC(h, h->cell_key, C * V);
   QB_ALLOC(h, h->cell_start, C * (V + 1));
   QB_ALLOC(h, h->normals, C * V);
-  QB_ALLOC(h, h->spfh, C * V * kDescDim);
+  QB_ALLOC(h, h->spfh, C * V * kDescPad);
   QB_ALLOC(h, h->desc_t, C * kDescPad * V);
   QB_CUDA_TRY(h, cudaMemset(h->desc_t, 0, C * kDescPad * V * sizeof(float)));
   QB_ALLOC(h, h->rowbest, S * V);
@@ -143,7 +143,7 @@ bool params_ok(const qb200_params* p) {
   return true;
 }
 
-float lattice_cell(const qb200_params& p) { return p.grid_cell > 0 ? p.grid_cell : p.voxel_size; }
+float lattice_cell(const qb200_params& p) { return p.grid_cell > 0 ? p.grid_cell : p.fpfh_radius; }
 
 // graph -> clique -> pose for pairs [0, n) whose matched points / n_corr are already on the device
 int run_solver(qb200_handle* h, int n_pairs, const qb200_params& p, int have_frontend) {

@@ -82,14 +82,16 @@ __device__ void warp_bucket_sort(const unsigned short* __restrict__ key, int n, 
 
 // One warp per pair.  smem layout: deg, pos, vert, nbl (u16 x Lc each), bin (int x (Lc + 2)).
 __global__ void __launch_bounds__(32) kcore_kernel(const uint32_t* __restrict__ adj, const int* __restrict__ deg_in, const int* __restrict__ n_corr,
-                                                   int Lc, int W, int* __restrict__ kcore, int* __restrict__ korder, int* __restrict__ rank_of,
-                                                   int* __restrict__ by_rank, int* __restrict__ kbin, int* __restrict__ max_core_out) {
+                                                   int Lc, int W, int cache_words, int* __restrict__ kcore, int* __restrict__ korder,
+                                                   int* __restrict__ rank_of, int* __restrict__ by_rank, int* __restrict__ kbin,
+                                                   int* __restrict__ max_core_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned short* deg = reinterpret_cast<unsigned short*>(smem_raw);
   unsigned short* pos = deg + Lc;
   unsigned short* vert = pos + Lc;
   unsigned short* nbl = vert + Lc;
   int* bin = reinterpret_cast<int*>(nbl + Lc);
+  uint32_t* cache = reinterpret_cast<uint32_t*>(bin + Lc + 2);  // [cache_words] adjacency rows when the graph fits
   const int pair = blockIdx.x, lane = lane_id();
   const int L = n_corr[pair];
   int* __restrict__ kc = kcore + (size_t)pair * (Lc + 2);
@@ -102,7 +104,18 @@ __global__ void __launch_bounds__(32) kcore_kernel(const uint32_t* __restrict__ 
     return;
   }
   const uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
-  const int nwl = (((L + 31) >> 5) + 31) >> 5;  // adjacency words per lane (<= kMaxWordsPerLane)
+  const int nbw = (L + 31) >> 5;                 // adjacency words per row
+  const int nwl = (nbw + 31) >> 5;               // adjacency words per lane (<= kMaxWordsPerLane)
+  // The peel is a chain of dependent row loads; a graph that fits is staged in shared memory once.
+  const bool cached = (long long)L * nbw <= (long long)cache_words;
+  if (cached) {
+    for (int idx = lane; idx < L * nbw; idx += 32) cache[idx] = G[(size_t)(idx / nbw) * W + (idx % nbw)];
+    __syncwarp();
+  }
+  auto row_word = [&](int v, int wi) -> uint32_t {
+    if (wi >= nbw) return 0u;
+    return cached ? cache[v * nbw + wi] : G[(size_t)v * W + wi];
+  };
 
   int md = 0;
   for (int v = lane; v < L; v += 32) {
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(32) kcore_kernel(const uint32_t* __restrict__ 
   uint32_t wn[kMaxWordsPerLane];
   int guess = vert[0];
 #pragma unroll
-  for (int k = 0; k < kMaxWordsPerLane; ++k) wn[k] = (k < nwl) ? G[(size_t)guess * W + lane + 32 * k] : 0u;
+  for (int k = 0; k < kMaxWordsPerLane; ++k) wn[k] = (k < nwl) ? row_word(guess, lane + 32 * k) : 0u;
   for (int i = 0; i < L; ++i) {
     const int v = vert[i];
     const int dv = deg[v];
@@ -128,12 +141,12 @@ __global__ void __launch_bounds__(32) kcore_kernel(const uint32_t* __restrict__ 
       for (int k = 0; k < kMaxWordsPerLane; ++k) w[k] = wn[k];
     } else {
 #pragma unroll
-      for (int k = 0; k < kMaxWordsPerLane; ++k) w[k] = (k < nwl) ? G[(size_t)v * W + lane + 32 * k] : 0u;
+      for (int k = 0; k < kMaxWordsPerLane; ++k) w[k] = (k < nwl) ? row_word(v, lane + 32 * k) : 0u;
     }
     // speculative prefetch of the next row (the vertex at position i+1 rarely changes while v is processed)
     guess = (i + 1 < L) ? vert[i + 1] : v;
 #pragma unroll
-    for (int k = 0; k < kMaxWordsPerLane; ++k) wn[k] = (k < nwl) ? G[(size_t)guess * W + lane + 32 * k] : 0u;
+    for (int k = 0; k < kMaxWordsPerLane; ++k) wn[k] = (k < nwl) ? row_word(guess, lane + 32 * k) : 0u;
     if (dv == 0) continue;  // current degree 0: no unprocessed neighbour left, processed ones have degree <= 0
     // expand the row to an ascending neighbour list
     int cnt = 0;
@@ -229,10 +242,12 @@ __global__ void __launch_bounds__(256) permute_adj_kernel(const uint32_t* __rest
 __global__ void __launch_bounds__(32) clique_kernel(const uint32_t* __restrict__ adjp, const int* __restrict__ n_corr, int Lc, int W,
                                                     const int* __restrict__ kcore, const int* __restrict__ korder, const int* __restrict__ rank_of,
                                                     const int* __restrict__ by_rank, const int* __restrict__ kbin, const int* __restrict__ max_core_in,
-                                                    int mode, double kcore_thr, int* __restrict__ clique, int* __restrict__ n_clique) {
+                                                    int mode, double kcore_thr, int cache_words, int* __restrict__ clique,
+                                                    int* __restrict__ n_clique) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned short* chain = reinterpret_cast<unsigned short*>(smem_raw);      // [Lc]
   uint32_t* idbits = reinterpret_cast<uint32_t*>(chain + Lc);               // [W]
+  uint32_t* cache = idbits + W;                                              // [cache_words]
   const int pair = blockIdx.x, lane = lane_id();
   const int L = n_corr[pair];
   int* __restrict__ out = clique + (size_t)pair * Lc;
@@ -247,7 +262,17 @@ __global__ void __launch_bounds__(32) clique_kernel(const uint32_t* __restrict__
   const int* __restrict__ kb = kbin + (size_t)pair * (Lc + 2);
   const uint32_t* __restrict__ G = adjp + (size_t)pair * Lc * W;
   const int max_core = max_core_in[pair];
-  const int nwl = (((L + 31) >> 5) + 31) >> 5;
+  const int nbw = (L + 31) >> 5;
+  const int nwl = (nbw + 31) >> 5;
+  // every descent step is a dependent row load: keep the rank-space adjacency in shared memory when it fits
+  const bool cached = (long long)L * nbw <= (long long)cache_words;
+  if (cached) {
+    for (int idx = lane; idx < L * nbw; idx += 32) cache[idx] = G[(size_t)(idx / nbw) * W + (idx % nbw)];
+  }
+  auto row_word = [&](int r, int wi) -> uint32_t {
+    if (wi >= nbw) return 0u;
+    return cached ? cache[r * nbw + wi] : G[(size_t)r * W + wi];
+  };
   for (int w = lane; w < W; w += 32) idbits[w] = 0;
   __syncwarp();
   int csize = 0;
@@ -273,7 +298,7 @@ __global__ void __launch_bounds__(32) clique_kernel(const uint32_t* __restrict__
         P[k] = 0;
         if (k < nwl) {
           const int wi = lane + 32 * k;
-          uint32_t x = G[(size_t)rv * W + wi];
+          uint32_t x = row_word(rv, wi);
           const int lo = wi * 32;
           if (thr >= lo + 32) x = 0;
           else if (thr > lo) x &= ~0u << (thr - lo);
@@ -296,7 +321,7 @@ __global__ void __launch_bounds__(32) clique_kernel(const uint32_t* __restrict__
         ++sz;
 #pragma unroll
         for (int k = 0; k < kMaxWordsPerLane; ++k)
-          if (k < nwl) P[k] &= G[(size_t)top * W + lane + 32 * k];
+          if (k < nwl) P[k] &= row_word(top, lane + 32 * k);
       }
       if (sz > mc) {
         mc = sz;
@@ -333,19 +358,22 @@ int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
   if (n_pairs <= 0) return QB200_OK;
   if (mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
   const int Lc = h->Lc, W = h->W;
-  const size_t sm_kcore = (size_t)4 * Lc * sizeof(unsigned short) + (size_t)(Lc + 2) * sizeof(int);
-  const size_t sm_clique = (size_t)Lc * sizeof(unsigned short) + (size_t)W * sizeof(uint32_t);
+  // shared-memory adjacency cache: 14336 words (56 KB) hold graphs up to L ~ 660; two CTAs per SM still fit
+  const int cache_words = 14336;
+  const size_t sm_kcore = (size_t)4 * Lc * sizeof(unsigned short) + (size_t)(Lc + 2) * sizeof(int) + (size_t)cache_words * 4;
+  const size_t sm_clique = (size_t)Lc * sizeof(unsigned short) + (size_t)W * sizeof(uint32_t) + (size_t)cache_words * 4;
   static bool attr_set = false;
   if (!attr_set) {
     QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_kcore));
+    QB_CUDA_TRY(h, cudaFuncSetAttribute(clique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_clique));
     attr_set = true;
   }
-  kcore_kernel<<<n_pairs, 32, sm_kcore, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin,
-                                                     h->ctr.max_core);
+  kcore_kernel<<<n_pairs, 32, sm_kcore, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, cache_words, h->kcore, h->korder, h->rank_of,
+                                                     h->by_rank, h->kbin, h->ctr.max_core);
   const dim3 gp((Lc + 7) / 8, n_pairs);
   permute_adj_kernel<<<gp, 256, 8 * W * sizeof(uint32_t), h->stream>>>(h->adj, h->ctr.n_corr, Lc, W, h->rank_of, h->adjp);
   clique_kernel<<<n_pairs, 32, sm_clique, h->stream>>>(h->adjp, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin,
-                                                       h->ctr.max_core, mode, kcore_thr, h->clique, h->ctr.n_clique);
+                                                       h->ctr.max_core, mode, kcore_thr, cache_words, h->clique, h->ctr.n_clique);
   h->launches += 3;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
     cnts[11 + b2][threadIdx.x]++;
     cnts[22 + b3][threadIdx.x]++;
   });
-  float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescDim;
+  float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescPad;  // rows padded to 36 floats: 16-byte gathers in K5
   const float incr = k >= 2 ? 100.0f / (float)(k - 1) : 0.0f;
   for (int b = 0; b < kDescDim; ++b) {
     const int c = cnts[b][threadIdx.x];
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
     for (int t = 0; t < c; ++t) v += incr;
     out[b] = v;
   }
+  out[33] = 0.0f; out[34] = 0.0f; out[35] = 0.0f;
 }
 
 // K5: FPFH = per-third renormalised sum of neighbour SPFHs weighted by 1/d^2, neighbours in lattice
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(128) fpfh_kernel(const float4* __restrict__ pt
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_pts[cloud]) return;
   const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
-  const float* __restrict__ sp = spfh + (size_t)cloud * V * kDescDim;
+  const float4* __restrict__ sp = reinterpret_cast<const float4*>(spfh + (size_t)cloud * V * kDescPad);
   const float4 pq = L.pts[q];
   float o[kDescDim];
 #pragma unroll
@@ -340,7 +341,12 @@ __global__ void __launch_bounds__(128) fpfh_kernel(const float4* __restrict__ pt
   for_each_neighbor(L, pq, m, r2, [&](int p, float d2, const float4) {
     if (d2 == 0.0f) return;
     const float weight = 1.0f / d2;
-    const float* __restrict__ s = sp + (size_t)p * kDescDim;
+    float s[kDescPad];
+#pragma unroll
+    for (int v4 = 0; v4 < kDescPad / 4; ++v4) {
+      const float4 t = __ldg(sp + (size_t)p * (kDescPad / 4) + v4);
+      s[4 * v4] = t.x; s[4 * v4 + 1] = t.y; s[4 * v4 + 2] = t.z; s[4 * v4 + 3] = t.w;
+    }
 #pragma unroll
     for (int b = 0; b < 11; ++b) { const float v = s[b] * weight; s0 += v; o[b] += v; }
 #pragma unroll

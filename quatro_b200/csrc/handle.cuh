@@ -35,7 +35,7 @@ struct qb200_handle {
   uint64_t* cell_key;         // [2S*V] occupied lattice cells, ascending
   int* cell_start;            // [2S*(V+1)]
   float4* normals;            // [2S*V]
-  float* spfh;                // [2S*V*33]
+  float* spfh;                // [2S*V*36] rows padded to 36 floats
   float* desc_t;              // [2S*36*V] FPFH, dimension-major per cloud (row d = bin d over all points)
   // ---- matching ----
   unsigned long long* rowbest;// [S*V] packed (dist bits << 32 | tgt idx) per source point
