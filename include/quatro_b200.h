@@ -203,9 +203,14 @@ int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_ma
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n);
 
 /* Device time (CUDA events on the handle's stream) and launch count of the two roofline kernels
- * during the last qb200_register_batch call: [0] = match_stripe_kernel (33-D all-pairs NN),
+ * during the last qb200_register_batch call: [0] = the tensor-core nearest-neighbour passes (tc_match_kernel x3),
  * [1] = tim_graph_kernel (TIM consistency graph); n <= 2. */
 int qb200_get_kernel_ms(qb200_handle* h, float* ms, int32_t* launches, int32_t n);
+
+/* Diagnostics: the tensor-core (tcgen05, 3xTF32) approximate squared distances that pre-filter the 33-D
+ * nearest-neighbour search, for up to 128 x 128 descriptors (out[128*128], row = a).  The matcher's results
+ * never depend on these values (exact fp32 re-rank); tests use this to measure the filter's error margin. */
+int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, const float* b33, int32_t nb, float* out);
 
 #ifdef __cplusplus
 }

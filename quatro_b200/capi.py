@@ -123,6 +123,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_get_last_correspondences": (i32, [vp, vp, vp, vp, i32, P(i32)]),
         "qb200_get_stage_ms": (i32, [vp, vp, i32]),
         "qb200_get_kernel_ms": (i32, [vp, vp, vp, i32]),
+        "qb200_debug_tc_distances": (i32, [vp, vp, i32, vp, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
@@ -138,6 +139,7 @@ EXPORTED_SYMBOLS = [
     "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_solve_pose", "qb200_solve_correspondences",
     "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
+    "qb200_debug_tc_distances",
 ]
 
 
@@ -335,6 +337,12 @@ class Handle:
         self._check(self.lib.qb200_get_last_correspondences(self.h, _ptr(corr), _ptr(sm), _ptr(tm), cap, C.byref(n)),
                     "qb200_get_last_correspondences")
         return corr[: n.value].copy(), sm[: n.value].copy(), tm[: n.value].copy()
+
+    def debug_tc_distances(self, a33, b33) -> np.ndarray:
+        a33, b33 = _f32(a33, 33), _f32(b33, 33)
+        out = np.zeros((128, 128), np.float32)
+        self._check(self.lib.qb200_debug_tc_distances(self.h, _ptr(a33), len(a33), _ptr(b33), len(b33), _ptr(out)), "qb200_debug_tc_distances")
+        return out[: len(a33), : len(b33)].copy()
 
     def kernel_ms(self):
         """(ms, launches) of the two roofline kernels during the last register_batch:

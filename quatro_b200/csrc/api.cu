@@ -60,8 +60,19 @@ int alloc_all(qb200_handle* h) {
   QB_ALLOC(h, h->cell_start, C * (V + 1));
   QB_ALLOC(h, h->normals, C * V);
   QB_ALLOC(h, h->spfh, C * V * kDescPad);
-  QB_ALLOC(h, h->desc_t, C * kDescPad * V);
-  QB_CUDA_TRY(h, cudaMemset(h->desc_t, 0, C * kDescPad * V * sizeof(float)));
+  QB_ALLOC(h, h->desc_t, C * kDescK * V);
+  QB_CUDA_TRY(h, cudaMemset(h->desc_t, 0, C * kDescK * V * sizeof(float)));
+  QB_ALLOC(h, h->desc_hi, C * kDescK * V);
+  QB_ALLOC(h, h->desc_lo, C * kDescK * V);
+  QB_CUDA_TRY(h, cudaMemset(h->desc_hi, 0, C * kDescK * V * sizeof(float)));
+  QB_CUDA_TRY(h, cudaMemset(h->desc_lo, 0, C * kDescK * V * sizeof(float)));
+  QB_ALLOC(h, h->desc_norm, C * V);
+  QB_ALLOC(h, h->norm_max, C);
+  QB_ALLOC(h, h->approx_min, C * V);
+  h->qcap = 8 * (int)V;
+  QB_ALLOC(h, h->cand_q, S * (size_t)h->qcap);
+  QB_ALLOC(h, h->cand_n, S);
+  QB_ALLOC(h, h->tc_fallback, S);
   QB_ALLOC(h, h->rowbest, S * V);
   QB_ALLOC(h, h->colpart, S * h->NS * V);
   QB_ALLOC(h, h->colbest, S * V);
@@ -237,6 +248,8 @@ int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {
   h->cfg = cfg; h->device = cfg.device;
   h->S = cfg.max_batch_slots; h->R = cfg.max_raw_points; h->V = cfg.max_voxel_points; h->Lc = cfg.max_corr;
   h->W = h->Lc / 32; h->NS = h->V / kMatchTile;
+  const char* fe = getenv("QB200_MATCH_EXACT");
+  h->force_exact_match = (fe && fe[0] == '1') ? 1 : 0;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return QB200_ERR_CUDA; }
   h->stream = h->own_stream;
   const int rc = alloc_all(h);
@@ -256,6 +269,7 @@ void qb200_destroy(qb200_handle* h) {
   cudaDeviceSynchronize();
   void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->desc_t, h->rowbest, h->colpart, h->colbest,
+                      h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max, h->approx_min, h->cand_q, h->cand_n, h->tc_fallback,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
                       h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
                       h->ctr_block};
@@ -627,6 +641,29 @@ int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_ma
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n) {
   if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->stage_ms[i];
+  return QB200_OK;
+}
+
+// Validation hook: tensor-core (3xTF32) approximate squared distances between up to 128 source and 128 target
+// descriptors -> out[128*128] (row = source).  Lets tests measure the filter's error against the exact chain.
+int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, const float* b33, int32_t nb, float* out) {
+  if (!h || !a33 || !b33 || !out || na < 1 || nb < 1 || na > 128 || nb > 128) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  int rc = wave_reset(h, 2);
+  if (rc) return rc;
+  if ((rc = set_counter(h, h->ctr.n_vox + 0, na))) return rc;
+  if ((rc = set_counter(h, h->ctr.n_vox + 1, nb))) return rc;
+  float* scratch = reinterpret_cast<float*>(h->key_a);
+  QB_CUDA_TRY(h, cudaMemcpyAsync(scratch, a33, (size_t)na * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_desc_from_aos(h, 0, na, scratch))) return rc;
+  float* scratch2 = scratch + (size_t)128 * kDescDim;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(scratch2, b33, (size_t)nb * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_desc_from_aos(h, 1, nb, scratch2))) return rc;
+  float* d_out = scratch2 + (size_t)128 * kDescDim;
+  QB_CUDA_TRY(h, cudaMemsetAsync(d_out, 0, 128 * 128 * sizeof(float), h->stream));
+  if ((rc = launch_tc_debug_tile(h, d_out))) return rc;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(out, d_out, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return QB200_OK;
 }
 

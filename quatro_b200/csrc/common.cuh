@@ -30,7 +30,9 @@ __host__ __device__ __forceinline__ uint64_t cell_key(int i, int j, int k) {
 }
 
 constexpr int kDescDim = 33;   // pcl::FPFHSignature33
-constexpr int kDescPad = 36;   // rows of the dim-major descriptor matrix (16-byte multiple)
+constexpr int kDescPad = 36;   // floats per SPFH row (16-byte multiple: float4 gathers)
+constexpr int kDescK = 40;     // rows (K extent) of the dimension-major FPFH matrices: 33 bins + zero padding to a multiple of
+                               // the TF32 tensor-core K step (8)
 constexpr int kMatchTile = 128;
 
 // Per-cloud / per-pair counters that live on the device for a whole wave (no host round trips

@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(128) fpfh_kernel(const float4* __restrict__ pt
   if (s1 != 0.0) s1 = 100.0 / s1;
   if (s2 != 0.0) s2 = 100.0 / s2;
   const float g0 = (float)s0, g1 = (float)s1, g2 = (float)s2;
-  float* __restrict__ out = desc_t + (size_t)cloud * kDescPad * V + q;
+  float* __restrict__ out = desc_t + (size_t)cloud * kDescK * V + q;
 #pragma unroll
   for (int b = 0; b < 11; ++b) out[(size_t)b * V] = o[b] * g0;
 #pragma unroll
@@ -429,14 +429,14 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
 
 int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33) {
   if (n <= 0) return QB200_OK;
-  desc_to_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(h->desc_t + (size_t)cloud * kDescPad * h->V, h->V, n, d_out33);
+  desc_to_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(h->desc_t + (size_t)cloud * kDescK * h->V, h->V, n, d_out33);
   h->launches++;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
 }
 int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33) {
   if (n <= 0) return QB200_OK;
-  desc_from_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(d_in33, h->V, n, h->desc_t + (size_t)cloud * kDescPad * h->V);
+  desc_from_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(d_in33, h->V, n, h->desc_t + (size_t)cloud * kDescK * h->V);
   h->launches++;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;

@@ -36,7 +36,16 @@ struct qb200_handle {
   int* cell_start;            // [2S*(V+1)]
   float4* normals;            // [2S*V]
   float* spfh;                // [2S*V*36] rows padded to 36 floats
-  float* desc_t;              // [2S*36*V] FPFH, dimension-major per cloud (row d = bin d over all points)
+  float* desc_t;              // [2S*40*V] FPFH, dimension-major per cloud (row d = bin d over all points; rows 33..39 zero)
+  float *desc_hi, *desc_lo;   // [2S*40*V] TF32 split of desc_t (hi = top 19 bits, lo = TF32(x - hi)) for the tensor-core filter
+  float* desc_norm;           // [2S*V] squared norms (fp32 fma chain)
+  unsigned* norm_max;         // [2S] per-cloud max squared norm (float bits)
+  float* approx_min;          // [2S*V] tensor-core approximate NN distance per point
+  unsigned* cand_q;           // [S*QCAP] candidate (src << 16 | tgt) pairs for the exact re-rank
+  int* cand_n;                // [S]
+  int* tc_fallback;           // [S] 1 = candidate queue overflowed: pair re-done by the exact fp32 kernel
+  int qcap;
+  int force_exact_match;      // QB200_MATCH_EXACT=1 in the environment: skip the tensor-core filter (A/B and triage)
   // ---- matching ----
   unsigned long long* rowbest;// [S*V] packed (dist bits << 32 | tgt idx) per source point
   unsigned long long* colpart;// [S*NS*V] per-stripe partial column minima
@@ -88,6 +97,9 @@ int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p);
 int launch_fill_counters(qb200_handle* h, int n_pairs, int have_frontend);
 int launch_finalize_status(qb200_handle* h, int n_pairs);
 int launch_iota_clique(qb200_handle* h, int n_pairs);
+int launch_match_nn(qb200_handle* h, int n_pairs);
+int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);
+int launch_tc_debug_tile(qb200_handle* h, float* d_out);
 int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33);
 int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33);
 size_t sort_temp_bytes(int max_items);

@@ -46,8 +46,8 @@ __device__ __forceinline__ void load_tile_async(float (*dst)[kMT], const float* 
 }
 
 __global__ void __launch_bounds__(kMatchThreads, 2)
-match_stripe_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V, int NS, unsigned long long* __restrict__ rowbest,
-                    unsigned long long* __restrict__ colpart) {
+match_stripe_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V, int NS, const int* __restrict__ only,
+                    unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colpart) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float(*As)[kMT] = reinterpret_cast<float(*)[kMT]>(smem_raw);                                    // [33][128]
   float(*Bs0)[kMT] = reinterpret_cast<float(*)[kMT]>(smem_raw + sizeof(float) * kDescDim * kMT);  // [33][128]
@@ -56,11 +56,12 @@ match_stripe_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_
       reinterpret_cast<unsigned long long(*)[kMT]>(smem_raw + 3 * sizeof(float) * kDescDim * kMT);  // [8][128]
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
+  if (only != nullptr && only[pair] == 0) return;  // fallback mode: only the pairs whose tensor-core queue overflowed
   const int nA = n_vox[2 * pair], nB = n_vox[2 * pair + 1];
   const int r0 = stripe * kMT;
   if (r0 >= nA || nB <= 0) return;
-  const float* __restrict__ A = desc_t + (size_t)(2 * pair) * kDescPad * V;
-  const float* __restrict__ B = desc_t + (size_t)(2 * pair + 1) * kDescPad * V;
+  const float* __restrict__ A = desc_t + (size_t)(2 * pair) * kDescK * V;
+  const float* __restrict__ B = desc_t + (size_t)(2 * pair + 1) * kDescK * V;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4, warp = threadIdx.x >> 5;
 
   load_tile_async(As, A, V, r0);
@@ -152,8 +153,9 @@ match_stripe_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_
 
 // fold per-stripe column minima
 __global__ void __launch_bounds__(256) match_colfold_kernel(const unsigned long long* __restrict__ colpart, const int* __restrict__ n_vox, int V,
-                                                            int NS, unsigned long long* __restrict__ colbest) {
+                                                            int NS, const int* __restrict__ only, unsigned long long* __restrict__ colbest) {
   const int pair = blockIdx.y;
+  if (only != nullptr && only[pair] == 0) return;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int nA = n_vox[2 * pair], nB = n_vox[2 * pair + 1];
   if (col >= nB) return;
@@ -340,8 +342,9 @@ __global__ void __launch_bounds__(1024) pack_corr_kernel(const int* __restrict__
 
 size_t match_smem_bytes() { return 3 * sizeof(float) * kDescDim * kMT + 8 * kMT * sizeof(unsigned long long); }
 
-int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p) {
-  if (n_pairs <= 0) return QB200_OK;
+// exact fp32 CUDA-core nearest neighbours (both directions).  only == nullptr: every pair; otherwise just the
+// pairs flagged in only[] (the tensor-core filter's overflow fallback).
+int launch_match_exact(qb200_handle* h, int n_pairs, const int* only) {
   const int V = h->V;
   static bool attr_set = false;
   const size_t smem = match_smem_bytes();
@@ -350,15 +353,27 @@ int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p) {
     attr_set = true;
   }
   const dim3 gs(h->NS, n_pairs);
-  cudaEventRecord(h->kev[0], h->stream);
-  match_stripe_kernel<<<gs, kMatchThreads, smem, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->NS, h->rowbest, h->colpart);
-  cudaEventRecord(h->kev[1], h->stream);
-  h->kev_armed[0] = 1;
+  if (only == nullptr) cudaEventRecord(h->kev[0], h->stream);
+  match_stripe_kernel<<<gs, kMatchThreads, smem, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->NS, only, h->rowbest, h->colpart);
+  if (only == nullptr) {
+    cudaEventRecord(h->kev[1], h->stream);
+    h->kev_armed[0] = 1;
+  }
   const dim3 gf((V + 255) / 256, n_pairs);
-  match_colfold_kernel<<<gf, 256, 0, h->stream>>>(h->colpart, h->ctr.n_vox, V, h->NS, h->colbest);
+  match_colfold_kernel<<<gf, 256, 0, h->stream>>>(h->colpart, h->ctr.n_vox, V, h->NS, only, h->colbest);
+  h->launches += 2;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
+int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p) {
+  if (n_pairs <= 0) return QB200_OK;
+  const int V = h->V;
+  int rc = h->force_exact_match ? launch_match_exact(h, n_pairs, nullptr) : launch_match_nn(h, n_pairs);
+  if (rc) return rc;
   match_mutual_kernel<<<n_pairs, 1024, 0, h->stream>>>(h->rowbest, h->colbest, h->ctr.n_vox, V, h->mut_i, h->mut_j, h->ctr.n_mutual,
                                                        h->ctr.swapped, h->mark, h->partner);
-  h->launches += 3;
+  h->launches += 1;
   const int use_tuple = (p.use_tuple_test && p.tuple_scale != 0.0f) ? 1 : 0;
   if (use_tuple) {
     cloud_mean_kernel<<<2 * n_pairs, 32, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->mean);

@@ -138,6 +138,61 @@ def test_match_ties_and_small_inputs(handle, oracle):
             assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
 
 
+def _fpfh_like(rng, n):
+    d = rng.gamma(0.3, 1.0, (n, 33)).astype(np.float32)
+    for t in range(3):
+        d[:, 11 * t:11 * t + 11] *= 100.0 / np.maximum(d[:, 11 * t:11 * t + 11].sum(1, keepdims=True), 1e-6)
+    return d.astype(np.float32)
+
+
+def test_tc_filter_error_bound(handle):
+    """The tensor-core (tcgen05, 3xTF32) approximate distances must stay well inside the margin the candidate
+    filter assumes: |d~ - d| <= kappa/4 * (|a|^2 + |b|^2) with kappa = 1e-4 (csrc/tc_match.cu)."""
+    rng = np.random.default_rng(11)
+    worst = 0.0
+    for trial in range(4):
+        a, b = _fpfh_like(rng, 128), _fpfh_like(rng, 100 + trial)
+        if trial == 3:
+            b[:50] = a[:50]                                    # exact duplicates: d = 0 rows
+        got = handle.debug_tc_distances(a, b).astype(np.float64)
+        a64, b64 = a.astype(np.float64), b.astype(np.float64)
+        ref = ((a64[:, None, :] - b64[None, :, :]) ** 2).sum(2)
+        scale = (a64 ** 2).sum(1)[:, None] + (b64 ** 2).sum(1)[None, :]
+        assert np.isfinite(got).all()
+        rel = np.abs(got - ref) / scale
+        worst = max(worst, rel.max())
+        assert np.abs(got - ref).max() < 0.05 * np.sqrt(ref.max() + 1), "tensor-core tile is not even approximately the distance matrix"
+    assert worst < 2.5e-5, worst
+
+
+def test_match_exact_fallback_paths(oracle, scan_pair):
+    """(a) QB200_MATCH_EXACT=1 skips the tensor-core filter; (b) thousands of identical descriptors overflow the
+    candidate queue and are redone by the exact kernel.  Both must equal the oracle."""
+    import os
+    from quatro_b200.capi import Handle
+    rng = np.random.default_rng(4)
+    n = 2600
+    a, b = P4(rng.uniform(-30, 30, (n, 3))), P4(rng.uniform(-30, 30, (n - 7, 3)))
+    ad, bd = _fpfh_like(rng, n), _fpfh_like(rng, n - 7)
+    ad[:2200] = ad[0]; bd[:2100] = ad[0]                        # massive exact ties -> lowest-index tie-breaks everywhere
+    p = default_params(); p.use_tuple_test = 0
+    ref = oracle.match(a, ad, b, bd, p)
+    with Handle(max_batch_slots=2) as h:
+        got = h.match(a, ad, b, bd, p)
+        assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+    os.environ["QB200_MATCH_EXACT"] = "1"
+    try:
+        with Handle(max_batch_slots=2) as h:
+            got = h.match(a, ad, b, bd, p)
+            assert np.array_equal(got[0], ref[0])
+            src, tgt, _ = scan_pair
+            r_ref, _ = oracle.register_pair(src, tgt, default_params())
+            r_got, _ = h.register_pair(src, tgt, default_params())
+            assert (r_got.n_mutual, r_got.n_corr, r_got.clique_size) == (r_ref.n_mutual, r_ref.n_corr, r_ref.clique_size)
+    finally:
+        del os.environ["QB200_MATCH_EXACT"]
+
+
 def test_match_and_pack(handle, oracle, small_pair):
     sv, _ = oracle.voxelize(small_pair[0], 0.3, 1)
     tv, _ = oracle.voxelize(small_pair[1], 0.3, 1)
