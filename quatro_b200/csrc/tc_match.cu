@@ -20,8 +20,8 @@
 //
 // Kernel anatomy (one CTA = 128 source rows, 2 CTAs per SM so one CTA's epilogue overlaps the other's
 // loads and MMAs):
-//   operands  : dimension-major fp32 matrices -> shared memory in the canonical MN-major, no-swizzle
-//               UMMA layout (8 K-rows x 16 B core matrices) by 16-byte cp.async; fence.proxy.async
+//   operands  : point-major TF32 hi/lo rows -> shared memory in the canonical K-major, no-swizzle UMMA layout
+//               (8 points x 16 B core matrices) by 16-byte cp.async; fence.proxy.async
 //   MMA       : one thread issues 15 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) into a
 //               128-column TMEM accumulator, tcgen05.commit -> mbarrier
 //   epilogue  : 8 warps, tcgen05.ld.32x32b.x32 (lane = row), fused  nb_j - 2 dot  + min / threshold test
@@ -42,17 +42,20 @@ __device__ __forceinline__ void tc_cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
 }
 
-// canonical MN-major / no-swizzle operand tile: [kb][g][r][4 floats]; core matrix = 8 K-rows x 16 B
-__device__ __forceinline__ void tc_fill_tile(uint32_t dst_base, const float* __restrict__ src, int V, int p0) {
-  for (int t = threadIdx.x; t < kDescK * 32; t += kTcThreads) {
-    const int r = t & 7, g = (t >> 3) & 31, kb = t >> 8;
-    tc_cp_async16(dst_base + kb * 4096 + g * 128 + r * 16, src + (size_t)(kb * 8 + r) * V + p0 + 4 * g);
+// Canonical K-major / no-swizzle operand tile (validated by tools/tc_probe.cu on B200; MN-major TF32 without swizzle
+// yields zeros): core matrix = 8 points x 16 B (4 consecutive K values); [kc = K/4][point group = p/8][p % 8][4 floats],
+// i.e. byte offset kc*2048 + p*16.  The source is point-major (row p = 40 contiguous floats), so every 16-byte chunk
+// is one cp.async and consecutive threads write consecutive shared-memory addresses.
+__device__ __forceinline__ void tc_fill_tile(uint32_t dst_base, const float* __restrict__ src_rows /* [V][kDescK] */, int p0) {
+  for (int t = threadIdx.x; t < 128 * (kDescK / 4); t += kTcThreads) {
+    const int p = t & 127, kc = t >> 7;
+    tc_cp_async16(dst_base + kc * 2048 + p * 16, src_rows + (size_t)(p0 + p) * kDescK + kc * 4);
   }
 }
 
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
-  // start address >> 4 | LBO (K-block stride, 4096 B) | SBO (MN-group stride, 128 B) | version 1 (sm_100) | SWIZZLE_NONE
-  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+  // start address >> 4 | LBO = 2048 B (next 4-wide K chunk) | SBO = 128 B (next 8-point group) | version 1 (sm_100) | SWIZZLE_NONE
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -90,13 +93,21 @@ __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict
   float acc = 0.0f;
   if (q < n) {
     const size_t base = (size_t)cloud * kDescK * V + q;
-    for (int d = 0; d < kDescDim; ++d) {
-      const float x = desc_t[base + (size_t)d * V];
-      const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-      const float l = __uint_as_float(__float_as_uint(x - h) & 0xFFFFE000u);
-      hi[base + (size_t)d * V] = h;
-      lo[base + (size_t)d * V] = l;
-      acc = __fmaf_rn(x, x, acc);
+    float4* __restrict__ ho = reinterpret_cast<float4*>(hi + ((size_t)cloud * V + q) * kDescK);  // point-major rows of 40 floats
+    float4* __restrict__ lw = reinterpret_cast<float4*>(lo + ((size_t)cloud * V + q) * kDescK);
+#pragma unroll
+    for (int c4 = 0; c4 < kDescK / 4; ++c4) {
+      float hv[4], lv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 4 * c4 + e;
+        const float x = d < kDescDim ? desc_t[base + (size_t)d * V] : 0.0f;
+        hv[e] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        lv[e] = __uint_as_float(__float_as_uint(x - hv[e]) & 0xFFFFE000u);
+        if (d < kDescDim) acc = __fmaf_rn(x, x, acc);
+      }
+      ho[c4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      lw[c4] = make_float4(lv[0], lv[1], lv[2], lv[3]);
     }
     norm[(size_t)cloud * V + q] = acc;
   }
@@ -126,10 +137,10 @@ tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sA_hi = smem_u32(smem), sA_lo = sA_hi + kTcTileBytes, sB_hi = sA_lo + kTcTileBytes, sB_lo = sB_hi + kTcTileBytes;
-  const float* __restrict__ Ahi = hi + (size_t)cloudA * kDescK * V;
-  const float* __restrict__ Alo = lo + (size_t)cloudA * kDescK * V;
-  const float* __restrict__ Bhi = hi + (size_t)cloudB * kDescK * V;
-  const float* __restrict__ Blo = lo + (size_t)cloudB * kDescK * V;
+  const float* __restrict__ Ahi = hi + (size_t)cloudA * V * kDescK;  // point-major [V][40]
+  const float* __restrict__ Alo = lo + (size_t)cloudA * V * kDescK;
+  const float* __restrict__ Bhi = hi + (size_t)cloudB * V * kDescK;
+  const float* __restrict__ Blo = lo + (size_t)cloudB * V * kDescK;
   const float* __restrict__ nA_ = norm + (size_t)cloudA * V;
   const float* __restrict__ nB_ = norm + (size_t)cloudB * V;
 
@@ -146,8 +157,8 @@ tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict_
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
 
-  tc_fill_tile(sA_hi, Ahi, V, r0);
-  tc_fill_tile(sA_lo, Alo, V, r0);
+  tc_fill_tile(sA_hi, Ahi, r0);
+  tc_fill_tile(sA_lo, Alo, r0);
 
   // this thread's accumulator row and column half
   const int quad = warp & 3, chalf = warp >> 2;
@@ -160,16 +171,16 @@ tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict_
   if (MODE == 1) Ri = row_ok ? (approx_min[(size_t)cloudA * V + gi] + kTcKappa * (na_i + nmaxB)) - na_i : -INFINITY;
   const float negna = -na_i;
 
-  // instruction descriptor: D=F32, A=B=TF32, both MN-major, N=128, M=128
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+  // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
   uint32_t parity = 0;
   bool dead = false;
   const int n_tiles = (nB + kTcN - 1) / kTcN;
 
   for (int jt = 0; jt < n_tiles; ++jt) {
     const int c0 = jt * kTcN;
-    tc_fill_tile(sB_hi, Bhi, V, c0);
-    tc_fill_tile(sB_lo, Blo, V, c0);
+    tc_fill_tile(sB_hi, Bhi, c0);
+    tc_fill_tile(sB_lo, Blo, c0);
     if (threadIdx.x < kTcN) {
       const int j = c0 + threadIdx.x;
       const float nb = j < nB ? nB_[j] : INFINITY;  // +inf: padded columns never win and never qualify
