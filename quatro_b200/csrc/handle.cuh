@@ -37,7 +37,8 @@ struct qb200_handle {
   float4* normals;            // [2S*V]
   float* spfh;                // [2S*V*36] rows padded to 36 floats
   float* desc_t;              // [2S*40*V] FPFH, dimension-major per cloud (row d = bin d over all points; rows 33..39 zero)
-  float *desc_hi, *desc_lo;   // [2S*40*V] TF32 split of desc_t (hi = top 19 bits, lo = TF32(x - hi)) for the tensor-core filter
+  float* desc_tiles;          // [2S*(V/128)*2*5120] TF32 hi / lo images of every 128-point block in the UMMA shared-memory layout
+  float* desc_rows;           // [2S*V*40] exact fp32 descriptors, point-major (exact re-rank)
   float* desc_norm;           // [2S*V] squared norms (fp32 fma chain)
   unsigned* norm_max;         // [2S] per-cloud max squared norm (float bits)
   float* approx_min;          // [2S*V] tensor-core approximate NN distance per point

@@ -7,8 +7,8 @@
 // are used as a FILTER with a rigorous error bound and the winners are re-ranked exactly:
 //
 //   split_desc_kernel   x -> hi (top 19 bits = a TF32 value), lo = TF32(x - hi); |x|^2; per-cloud max norm
-//   tc_match_kernel<0>  approximate row minima  m~_i = min_j d~(i,j)      (run for both orientations)
-//   tc_match_kernel<1>  every (i,j) with d~(i,j) <= m~_i + margin_i or <= m~_j + margin_j is queued
+//   tc_match_kernel<0>  upper bounds  U_i = min over every 4th column tile of d~(i,j)   (both orientations)
+//   tc_match_kernel<1>  every (i,j) with d~(i,j) <= U_i + margin_i or <= U_j + margin_j is queued
 //   rerank_kernel       exact fp32 chain distance of the queued pairs -> packed atomicMin into the
 //                       row / column minima (distance bits << 32 | index  => lowest-index ties)
 //
@@ -18,13 +18,14 @@
 // slack).  If a queue overflows (thousands of near-identical descriptors) the pair is redone by the
 // exact CUDA-core kernel of match.cu, so results never depend on the filter.
 //
-// Kernel anatomy (one CTA = 128 source rows, 2 CTAs per SM so one CTA's epilogue overlaps the other's
-// loads and MMAs):
-//   operands  : point-major TF32 hi/lo rows -> shared memory in the canonical K-major, no-swizzle UMMA layout
-//               (8 points x 16 B core matrices) by 16-byte cp.async; fence.proxy.async
-//   MMA       : one thread issues 15 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) into a
-//               128-column TMEM accumulator, tcgen05.commit -> mbarrier
-//   epilogue  : 8 warps, tcgen05.ld.32x32b.x32 (lane = row), fused  nb_j - 2 dot  + min / threshold test
+// Kernel anatomy (one CTA = 128 source rows, one CTA per SM):
+//   operands  : 128-point blocks are stored in global memory as ready-made shared-memory images (canonical K-major,
+//               no-swizzle UMMA layout), so a tile is ONE cp.async.bulk (TMA bulk copy) completing on an mbarrier;
+//               B tiles stream through a 2-stage ring
+//   MMA       : one thread issues 15 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) into one of two
+//               128-column TMEM accumulator stages, tcgen05.commit -> mbarrier
+//   epilogue  : 8 warps drain the OTHER TMEM stage meanwhile: tcgen05.ld.32x32b.x32 (lane = row), fused
+//               nb_j - 2 dot  + min / threshold test
 #include "handle.cuh"
 
 namespace qb {
@@ -38,21 +39,9 @@ constexpr int kSpinLimit = 400000;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void tc_cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-}
-
-// Canonical K-major / no-swizzle operand tile (validated by tools/tc_probe.cu on B200; MN-major TF32 without swizzle
-// yields zeros): core matrix = 8 points x 16 B (4 consecutive K values); [kc = K/4][point group = p/8][p % 8][4 floats],
-// i.e. byte offset kc*2048 + p*16.  The source is point-major (row p = 40 contiguous floats), so every 16-byte chunk
-// is one cp.async and consecutive threads write consecutive shared-memory addresses.
-__device__ __forceinline__ void tc_fill_tile(uint32_t dst_base, const float* __restrict__ src_rows /* [V][kDescK] */, int p0) {
-  for (int t = threadIdx.x; t < 128 * (kDescK / 4); t += kTcThreads) {
-    const int p = t & 127, kc = t >> 7;
-    tc_cp_async16(dst_base + kc * 2048 + p * 16, src_rows + (size_t)(p0 + p) * kDescK + kc * 4);
-  }
-}
-
+// Operand tiles use the canonical K-major / no-swizzle UMMA layout (validated by tools/tc_probe.cu on B200; MN-major
+// TF32 without swizzle yields zeros): core matrix = 8 points x 16 B (4 consecutive K values), byte offset
+// kc*2048 + p*16 for K chunk kc (4 dims) and point p of the 128-point block.
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
   // start address >> 4 | LBO = 2048 B (next 4-wide K chunk) | SBO = 128 B (next 8-point group) | version 1 (sm_100) | SWIZZLE_NONE
   return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
@@ -83,33 +72,45 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// squared norms, TF32 hi/lo split, per-cloud max norm
+// ------------------------------------------------------------------------------------------------
+// split_desc_kernel: per point  |x|^2 (fp32 fma chain), per-cloud max norm, and two re-layouts of the descriptor:
+//   rows  [cloud][V][40]            exact fp32, point-major (the re-rank reads 160 contiguous bytes per point)
+//   tiles [cloud][V/128][2][5120]   TF32 hi / lo images of each 128-point block, stored EXACTLY in the shared-memory
+//                                   operand layout (float index kc*512 + p*4 + e), so a tile is one 20/40 KB bulk copy
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileFloats = kDescK * 128;  // 5120
+
 __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V,
-                                                         float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ norm,
+                                                         float* __restrict__ tiles, float* __restrict__ rows, float* __restrict__ norm,
                                                          unsigned* __restrict__ norm_max) {
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = n_vox[cloud];
+  const int NB = V >> 7;
   float acc = 0.0f;
-  if (q < n) {
+  if (q < ((n + 127) & ~127)) {  // pad the last block with zeros so stale data never reaches the tensor core
     const size_t base = (size_t)cloud * kDescK * V + q;
-    float4* __restrict__ ho = reinterpret_cast<float4*>(hi + ((size_t)cloud * V + q) * kDescK);  // point-major rows of 40 floats
-    float4* __restrict__ lw = reinterpret_cast<float4*>(lo + ((size_t)cloud * V + q) * kDescK);
+    const int blk = q >> 7, p = q & 127;
+    float4* __restrict__ th = reinterpret_cast<float4*>(tiles + ((size_t)(cloud * NB + blk) * 2 + 0) * kTileFloats) + p;
+    float4* __restrict__ tl = reinterpret_cast<float4*>(tiles + ((size_t)(cloud * NB + blk) * 2 + 1) * kTileFloats) + p;
+    float4* __restrict__ rw = reinterpret_cast<float4*>(rows + ((size_t)cloud * V + q) * kDescK);
 #pragma unroll
-    for (int c4 = 0; c4 < kDescK / 4; ++c4) {
-      float hv[4], lv[4];
+    for (int kc = 0; kc < kDescK / 4; ++kc) {
+      float xv[4], hv[4], lv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int d = 4 * c4 + e;
-        const float x = d < kDescDim ? desc_t[base + (size_t)d * V] : 0.0f;
+        const int d = 4 * kc + e;
+        const float x = (d < kDescDim && q < n) ? desc_t[base + (size_t)d * V] : 0.0f;
+        xv[e] = x;
         hv[e] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
         lv[e] = __uint_as_float(__float_as_uint(x - hv[e]) & 0xFFFFE000u);
         if (d < kDescDim) acc = __fmaf_rn(x, x, acc);
       }
-      ho[c4] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      lw[c4] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+      th[kc * 128] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      tl[kc * 128] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+      rw[kc] = make_float4(xv[0], xv[1], xv[2], xv[3]);
     }
-    norm[(size_t)cloud * V + q] = acc;
+    if (q < n) norm[(size_t)cloud * V + q] = acc;
   }
   float m = (q < n && acc == acc) ? acc : 0.0f;
 #pragma unroll
@@ -117,17 +118,49 @@ __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict
   if (lane_id() == 0 && m > 0.0f) atomicMax(norm_max + cloud, __float_as_uint(m));
 }
 
-// MODE 0: approx_min[cloudA][i] = min_j d~(i,j).      MODE 1: queue candidates (rows = source cloud).
+// ---- mbarrier / bulk-copy helpers ---------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+// bounded wait: returns false if the barrier never completed (a descriptor bug must not hang the box)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  for (int spin = 0; spin < kSpinLimit; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+// MODE 0: approx_min[cloudA][i] = min over the SAMPLED column tiles of d~(i,j)  (an upper bound of the row minimum).
+// MODE 1: queue every (i,j) with d~ <= bound_i + margin_i or <= bound_j + margin_j   (rows = source cloud, all tiles).
 // MODE 2: MODE 0 + dump of the first 128 x 128 tile of d~ (validation hook).
+// Pipeline per CTA (128 rows): B tiles arrive by bulk copy into a 2-stage ring; MMA(k) into TMEM stage k&1 runs
+// while all 8 warps drain TMEM stage (k-1)&1.
 template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 2)
-tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict__ lo, const float* __restrict__ norm,
-                const unsigned* __restrict__ norm_max, const int* __restrict__ n_vox, int V, float* __restrict__ approx_min,
-                unsigned* __restrict__ cand_q, int* __restrict__ cand_n, int qcap, float* __restrict__ dbg_tile) {
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const float* __restrict__ norm, const unsigned* __restrict__ norm_max,
+                const int* __restrict__ n_vox, int V, float* __restrict__ approx_min, unsigned* __restrict__ cand_q,
+                int* __restrict__ cand_n, int qcap, float* __restrict__ dbg_tile) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_full[2], s_mma[2], s_afull;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_nb[kTcN], s_cj[kTcN], s_part[kTcM];
+  __shared__ float s_nb[2][kTcN], s_cj[2][kTcN], s_part[kTcM];
+  __shared__ int s_dead;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
   const int cloudA = swap ? 2 * pair + 1 : 2 * pair, cloudB = swap ? 2 * pair : 2 * pair + 1;
@@ -136,20 +169,27 @@ tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict_
   if (r0 >= nA || nB <= 0) return;  // uniform for the CTA, before any barrier / allocation
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t sA_hi = smem_u32(smem), sA_lo = sA_hi + kTcTileBytes, sB_hi = sA_lo + kTcTileBytes, sB_lo = sB_hi + kTcTileBytes;
-  const float* __restrict__ Ahi = hi + (size_t)cloudA * V * kDescK;  // point-major [V][40]
-  const float* __restrict__ Alo = lo + (size_t)cloudA * V * kDescK;
-  const float* __restrict__ Bhi = hi + (size_t)cloudB * V * kDescK;
-  const float* __restrict__ Blo = lo + (size_t)cloudB * V * kDescK;
+  const int NB = V >> 7;
+  constexpr uint32_t kPairBytes = 2 * kTcTileBytes;  // hi + lo image of one 128-point block
+  const uint32_t sA = smem_u32(smem), sB0 = sA + kPairBytes;
+  const float* __restrict__ tA = tiles + (size_t)cloudA * NB * 2 * kTileFloats;
+  const float* __restrict__ tB = tiles + (size_t)cloudB * NB * 2 * kTileFloats;
   const float* __restrict__ nA_ = norm + (size_t)cloudA * V;
   const float* __restrict__ nB_ = norm + (size_t)cloudB * V;
+  const uint32_t bar_full0 = smem_u32(&s_full[0]), bar_mma0 = smem_u32(&s_mma[0]), bar_a = smem_u32(&s_afull);
 
-  if (warp == 0) {  // TMEM: 128 fp32 columns x 128 lanes
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(kTcN) : "memory");
+  const int n_tiles = (nB + kTcN - 1) / kTcN;
+  const int step = tile_step < n_tiles ? tile_step : n_tiles;      // sampled passes visit every step-th tile
+  const int first = step > 1 ? (stripe % step) : 0;
+  const int ntl = (n_tiles - first + step - 1) / step;             // >= 1
+
+  if (warp == 0) {  // TMEM: 2 accumulator stages x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(2 * kTcN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&s_bar)) : "memory");
+    mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1); mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1); mbar_init(bar_a, 1);
+    s_dead = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -157,98 +197,103 @@ tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict_
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
 
-  tc_fill_tile(sA_hi, Ahi, r0);
-  tc_fill_tile(sA_lo, Alo, r0);
+  // per-tile column data (norms, and in MODE 1 the column thresholds) for ring stage s
+  const float nmaxA = __uint_as_float(norm_max[cloudA]), nmaxB = __uint_as_float(norm_max[cloudB]);
+  auto load_cols = [&](int s, int jt) {
+    if (threadIdx.x < kTcN) {
+      const int j = jt * kTcN + threadIdx.x;
+      const float nb = j < nB ? nB_[j] : INFINITY;  // +inf: padded columns never win and never qualify
+      s_nb[s][threadIdx.x] = nb;
+      if (MODE == 1) s_cj[s][threadIdx.x] = j < nB ? nb - (approx_min[(size_t)cloudB * V + j] + kTcKappa * (nb + nmaxA)) : INFINITY;
+    }
+  };
+  auto issue_tile = [&](int s, int jt) {  // one thread: 40 KB bulk copy of block jt of cloud B into ring stage s
+    mbar_expect_tx(bar_full0 + 8 * s, kPairBytes);
+    bulk_g2s(sB0 + s * kPairBytes, tB + (size_t)jt * 2 * kTileFloats, kPairBytes, bar_full0 + 8 * s);
+  };
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_a, kPairBytes);
+    bulk_g2s(sA, tA + (size_t)stripe * 2 * kTileFloats, kPairBytes, bar_a);
+    issue_tile(0, first);
+    if (ntl > 1) issue_tile(1, first + step);
+  }
+  load_cols(0, first);
+  if (ntl > 1) load_cols(1, first + step);
 
   // this thread's accumulator row and column half
   const int quad = warp & 3, chalf = warp >> 2;
   const int row = quad * 32 + lane, gi = r0 + row;
   const bool row_ok = gi < nA;
   const float na_i = row_ok ? nA_[gi] : 0.0f;
-  const float nmaxA = __uint_as_float(norm_max[cloudA]), nmaxB = __uint_as_float(norm_max[cloudB]);
-  float m = INFINITY;  // MODE 0: running min of nb_j - 2 dot
+  float m = INFINITY;  // MODE 0/2: running min of nb_j - 2 dot
   float Ri = 0.0f;     // MODE 1: row threshold on nb_j - 2 dot
   if (MODE == 1) Ri = row_ok ? (approx_min[(size_t)cloudA * V + gi] + kTcKappa * (na_i + nmaxB)) - na_i : -INFINITY;
   const float negna = -na_i;
-
   // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-  uint32_t parity = 0;
-  bool dead = false;
-  const int n_tiles = (nB + kTcN - 1) / kTcN;
+  __syncthreads();  // s_nb / s_cj of the first two tiles visible
 
-  for (int jt = 0; jt < n_tiles; ++jt) {
-    const int c0 = jt * kTcN;
-    tc_fill_tile(sB_hi, Bhi, c0);
-    tc_fill_tile(sB_lo, Blo, c0);
-    if (threadIdx.x < kTcN) {
-      const int j = c0 + threadIdx.x;
-      const float nb = j < nB ? nB_[j] : INFINITY;  // +inf: padded columns never win and never qualify
-      s_nb[threadIdx.x] = nb;
-      if (MODE == 1) s_cj[threadIdx.x] = j < nB ? nb - (approx_min[(size_t)cloudB * V + j] + kTcKappa * (nb + nmaxA)) : INFINITY;
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-    __syncthreads();
-
-    if (threadIdx.x == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      uint32_t acc = 0;
-#pragma unroll
-      for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
-        tc_mma_tf32(tmem, tc_smem_desc(sA_hi + kb * 4096), tc_smem_desc(sB_lo + kb * 4096), idesc, acc);
-        acc = 1;
-        tc_mma_tf32(tmem, tc_smem_desc(sA_lo + kb * 4096), tc_smem_desc(sB_hi + kb * 4096), idesc, 1);
-      }
-#pragma unroll
-      for (int kb = 0; kb < kTcKB; ++kb) tc_mma_tf32(tmem, tc_smem_desc(sA_hi + kb * 4096), tc_smem_desc(sB_hi + kb * 4096), idesc, 1);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&s_bar)) : "memory");
-    }
-    // wait for the accumulator (bounded spin: a descriptor bug must not hang the box)
-    {
-      int spin = 0;
-      uint32_t ok = 0;
-      while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(&s_bar)), "r"(parity)
-            : "memory");
-        if (!ok && ++spin > kSpinLimit) { dead = true; break; }
-      }
-    }
-    parity ^= 1;
+  auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile index first + k*step)
+    const int s = k & 1, jt = first + k * step;
+    if (!mbar_wait(bar_mma0 + 8 * s, (uint32_t)((k >> 1) & 1))) s_dead = 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-
-    if (!dead) {
+    const int c0 = jt * kTcN;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int cb = chalf * 64 + ch * 32;
-        uint32_t v[32];
-        tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)cb, v);
+    for (int ch = 0; ch < 2; ++ch) {
+      const int cb = chalf * 64 + ch * 32;
+      uint32_t v[32];
+      tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * kTcN + cb), v);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float dot = __uint_as_float(v[c]);
-          const float t = fmaf(-2.0f, dot, s_nb[cb + c]);
-          if (MODE != 1) {
-            m = fminf(m, t);
-            if (MODE == 2 && stripe == 0 && jt == 0) dbg_tile[(size_t)row * kTcN + cb + c] = na_i + t;
-          } else {
-            const float u = fmaf(-2.0f, dot, s_cj[cb + c]);
-            if (row_ok && ((t <= Ri) || (u <= negna))) {
-              const int slot = atomicAdd(cand_n + pair, 1);
-              if (slot < qcap) cand_q[(size_t)pair * qcap + slot] = ((unsigned)gi << 16) | (unsigned)(c0 + cb + c);
-            }
+      for (int c = 0; c < 32; ++c) {
+        const float dot = __uint_as_float(v[c]);
+        const float t = fmaf(-2.0f, dot, s_nb[s][cb + c]);
+        if (MODE != 1) {
+          m = fminf(m, t);
+          if (MODE == 2 && stripe == 0 && jt == 0) dbg_tile[(size_t)row * kTcN + cb + c] = na_i + t;
+        } else {
+          const float u = fmaf(-2.0f, dot, s_cj[s][cb + c]);
+          if (row_ok && ((t <= Ri) || (u <= negna))) {
+            const int slot = atomicAdd(cand_n + pair, 1);
+            if (slot < qcap) cand_q[(size_t)pair * qcap + slot] = ((unsigned)gi << 16) | (unsigned)(c0 + cb + c);
           }
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();  // TMEM and the B tiles are free again
+  };
+
+  for (int k = 0; k < ntl; ++k) {
+    const int s = k & 1;
+    if (threadIdx.x == 0) {
+      bool ok = true;
+      if (k == 0) ok = mbar_wait(bar_a, 0);
+      ok = ok && mbar_wait(bar_full0 + 8 * s, (uint32_t)((k >> 1) & 1));
+      if (!ok) s_dead = 1;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sB0 + s * kPairBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(s * kTcN);
+      uint32_t acc = 0;
+#pragma unroll
+      for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
+        tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bL + kb * 4096), idesc, acc);
+        acc = 1;
+        tc_mma_tf32(d, tc_smem_desc(aL + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
+      }
+#pragma unroll
+      for (int kb = 0; kb < kTcKB; ++kb) tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * s) : "memory");
+    }
+    __syncwarp();
+    if (k >= 1) epilogue(k - 1);  // overlaps the MMAs just issued
+    __syncthreads();              // TMEM stage s^1, s_nb[s^1] and (MMA k-1 being complete) B stage s^1 are free
+    if (k >= 1 && k + 1 < ntl) {
+      if (threadIdx.x == 0) issue_tile(s ^ 1, first + (k + 1) * step);
+      load_cols(s ^ 1, first + (k + 1) * step);  // read again only after the next barriers
+    }
+    if (s_dead) break;  // uniform: written before the barrier above
   }
+  if (!s_dead) epilogue(ntl - 1);
+  __syncthreads();
+  const bool dead = s_dead != 0;
 
   if (MODE != 1) {
     if (chalf == 1) s_part[row] = m;
@@ -260,7 +305,7 @@ tc_match_kernel(int swap, const float* __restrict__ hi, const float* __restrict_
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTcN) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * kTcN) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long tc_pack(float d, int idx) {
@@ -268,7 +313,7 @@ __device__ __forceinline__ unsigned long long tc_pack(float d, int idx) {
 }
 
 // exact canonical distance of every queued (src, tgt) pair; folds both directions
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V,
+__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ rows, const int* __restrict__ n_vox, int V,
                                                      const unsigned* __restrict__ cand_q, const int* __restrict__ cand_n, int qcap,
                                                      int* __restrict__ fallback, unsigned long long* __restrict__ rowbest,
                                                      unsigned long long* __restrict__ colbest) {
@@ -278,16 +323,20 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ d
     if (blockIdx.x == 0 && threadIdx.x == 0) fallback[pair] = 1;
     return;
   }
-  const float* __restrict__ A = desc_t + (size_t)(2 * pair) * kDescK * V;
-  const float* __restrict__ B = desc_t + (size_t)(2 * pair + 1) * kDescK * V;
+  const float4* __restrict__ A = reinterpret_cast<const float4*>(rows + (size_t)(2 * pair) * V * kDescK);
+  const float4* __restrict__ B = reinterpret_cast<const float4*>(rows + (size_t)(2 * pair + 1) * V * kDescK);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
     const unsigned e = cand_q[(size_t)pair * qcap + c];
     const int i = (int)(e >> 16), j = (int)(e & 0xFFFFu);
     float acc = 0.0f;
 #pragma unroll
-    for (int d = 0; d < kDescDim; ++d) {
-      const float diff = A[(size_t)d * V + i] - B[(size_t)d * V + j];
+    for (int c4 = 0; c4 < (kDescDim + 3) / 4; ++c4) {  // same d = 0..32 fma chain as the exact kernel
+      const float4 a = __ldg(A + (size_t)i * (kDescK / 4) + c4), b = __ldg(B + (size_t)j * (kDescK / 4) + c4);
+      float diff = a.x - b.x;
       acc = __fmaf_rn(diff, diff, acc);
+      if (4 * c4 + 1 < kDescDim) { diff = a.y - b.y; acc = __fmaf_rn(diff, diff, acc); }
+      if (4 * c4 + 2 < kDescDim) { diff = a.z - b.z; acc = __fmaf_rn(diff, diff, acc); }
+      if (4 * c4 + 3 < kDescDim) { diff = a.w - b.w; acc = __fmaf_rn(diff, diff, acc); }
     }
     if (acc == acc) {
       atomicMin(rowbest + (size_t)pair * V + i, tc_pack(acc, j));
@@ -299,13 +348,16 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ d
 // implemented in match.cu: exact kernels restricted to the pairs flagged in `only`
 int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);
 
+constexpr int kTcSampleStep = 4;  // the bound passes visit every 4th column tile
+
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
   static bool attr_set = false;
-  const size_t smem = 4 * (size_t)kTcTileBytes + 1024;
+  const size_t smem = 3 * (size_t)(2 * kTcTileBytes) + 1024;  // A + two B ring stages, hi and lo images each
   if (!attr_set) {
     QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
@@ -314,34 +366,34 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, (size_t)n_pairs * sizeof(int), h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->norm_max, 0, (size_t)2 * n_pairs * sizeof(unsigned), h->stream));
   const dim3 gsplit((V + 255) / 256, 2 * n_pairs);
-  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max);
+  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_tiles, h->desc_rows, h->desc_norm, h->norm_max);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
-  tc_match_kernel<0><<<g, kTcThreads, smem, h->stream>>>(0, h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
+  tc_match_kernel<0><<<g, kTcThreads, smem, h->stream>>>(0, kTcSampleStep, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
                                                          nullptr, nullptr, 0, nullptr);
-  tc_match_kernel<0><<<g, kTcThreads, smem, h->stream>>>(1, h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
+  tc_match_kernel<0><<<g, kTcThreads, smem, h->stream>>>(1, kTcSampleStep, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
                                                          nullptr, nullptr, 0, nullptr);
-  tc_match_kernel<1><<<g, kTcThreads, smem, h->stream>>>(0, h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
-                                                         h->cand_q, h->cand_n, h->qcap, nullptr);
+  tc_match_kernel<1><<<g, kTcThreads, smem, h->stream>>>(0, 1, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min, h->cand_q,
+                                                         h->cand_n, h->qcap, nullptr);
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
   const dim3 gr(64, n_pairs);
-  rerank_kernel<<<gr, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->cand_q, h->cand_n, h->qcap, h->tc_fallback, h->rowbest, h->colbest);
+  rerank_kernel<<<gr, 256, 0, h->stream>>>(h->desc_rows, h->ctr.n_vox, V, h->cand_q, h->cand_n, h->qcap, h->tc_fallback, h->rowbest, h->colbest);
   h->launches += 5;
   QB_CUDA_TRY(h, cudaGetLastError());
   return launch_match_exact(h, n_pairs, h->tc_fallback);
 }
 
-// debug/validation hook: approximate distances of the first 128 x 128 tile of pair 0 (after launch_match_nn inputs are in place)
+// debug/validation hook: approximate distances of the first 128 x 128 tile of pair 0 (descriptors already in desc_t)
 int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
-  const size_t smem = 4 * (size_t)kTcTileBytes + 1024;
+  const size_t smem = 3 * (size_t)(2 * kTcTileBytes) + 1024;
   QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->norm_max, 0, 2 * sizeof(unsigned), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
-  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max);
+  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_tiles, h->desc_rows, h->desc_norm, h->norm_max);
   const dim3 g(1, 1);
-  tc_match_kernel<2><<<g, kTcThreads, smem, h->stream>>>(0, h->desc_hi, h->desc_lo, h->desc_norm, h->norm_max, h->ctr.n_vox, h->V, h->approx_min,
-                                                         nullptr, nullptr, 0, d_out);
+  tc_match_kernel<2><<<g, kTcThreads, smem, h->stream>>>(0, 1, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, h->V, h->approx_min, nullptr,
+                                                         nullptr, 0, d_out);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
