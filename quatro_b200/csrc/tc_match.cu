@@ -7,7 +7,7 @@
 // are used as a FILTER with a rigorous error bound and the winners are re-ranked exactly:
 //
 //   split_desc_kernel   x -> hi (top 19 bits = a TF32 value), lo = TF32(x - hi); |x|^2; per-cloud max norm
-//   tc_match_kernel<0>  upper bounds  U_i = min over every 4th column tile of d~(i,j)   (both orientations)
+//   tc_match_kernel<0>  upper bounds  U_i = min over every 2nd column tile of d~(i,j)   (both orientations)
 //   tc_match_kernel<1>  every (i,j) with d~(i,j) <= U_i + margin_i or <= U_j + margin_j is queued
 //   rerank_kernel       exact fp32 chain distance of the queued pairs -> packed atomicMin into the
 //                       row / column minima (distance bits << 32 | index  => lowest-index ties)
@@ -151,16 +151,19 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 // MODE 2: MODE 0 + dump of the first 128 x 128 tile of d~ (validation hook).
 // Pipeline per CTA (128 rows): B tiles arrive by bulk copy into a 2-stage ring; MMA(k) into TMEM stage k&1 runs
 // while all 8 warps drain TMEM stage (k-1)&1.
+constexpr int kTcStages = 3;      // B-tile ring (prefetch distance 2)
+constexpr int kTcQueue = 8192;    // per-CTA shared-memory candidate queue (entries)
+
 template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const float* __restrict__ norm, const unsigned* __restrict__ norm_max,
                 const int* __restrict__ n_vox, int V, float* __restrict__ approx_min, unsigned* __restrict__ cand_q,
                 int* __restrict__ cand_n, int qcap, float* __restrict__ dbg_tile) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t s_full[2], s_mma[2], s_afull;
+  __shared__ uint64_t s_full[kTcStages], s_mma[2], s_afull;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_nb[2][kTcN], s_cj[2][kTcN], s_part[kTcM];
-  __shared__ int s_dead;
+  __shared__ float s_nb[kTcStages][kTcN], s_cj[kTcStages][kTcN], s_part[kTcM];
+  __shared__ int s_dead, s_qn, s_qbase;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
   const int cloudA = swap ? 2 * pair + 1 : 2 * pair, cloudB = swap ? 2 * pair : 2 * pair + 1;
@@ -172,6 +175,7 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
   const int NB = V >> 7;
   constexpr uint32_t kPairBytes = 2 * kTcTileBytes;  // hi + lo image of one 128-point block
   const uint32_t sA = smem_u32(smem), sB0 = sA + kPairBytes;
+  unsigned* s_q = reinterpret_cast<unsigned*>(smem + (1 + kTcStages) * kPairBytes);  // MODE 1 only
   const float* __restrict__ tA = tiles + (size_t)cloudA * NB * 2 * kTileFloats;
   const float* __restrict__ tB = tiles + (size_t)cloudB * NB * 2 * kTileFloats;
   const float* __restrict__ nA_ = norm + (size_t)cloudA * V;
@@ -188,8 +192,9 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (threadIdx.x == 0) {
-    mbar_init(bar_full0, 1); mbar_init(bar_full0 + 8, 1); mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1); mbar_init(bar_a, 1);
-    s_dead = 0;
+    for (int i = 0; i < kTcStages; ++i) mbar_init(bar_full0 + 8 * i, 1);
+    mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1); mbar_init(bar_a, 1);
+    s_dead = 0; s_qn = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -197,19 +202,19 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
 
-  // per-tile column data (norms, and in MODE 1 the column thresholds) for ring stage s
+  // per-tile column data (norms, and in MODE 1 the column thresholds) for ring stage st
   const float nmaxA = __uint_as_float(norm_max[cloudA]), nmaxB = __uint_as_float(norm_max[cloudB]);
-  auto load_cols = [&](int s, int jt) {
+  auto load_cols = [&](int st, int jt) {
     if (threadIdx.x < kTcN) {
       const int j = jt * kTcN + threadIdx.x;
       const float nb = j < nB ? nB_[j] : INFINITY;  // +inf: padded columns never win and never qualify
-      s_nb[s][threadIdx.x] = nb;
-      if (MODE == 1) s_cj[s][threadIdx.x] = j < nB ? nb - (approx_min[(size_t)cloudB * V + j] + kTcKappa * (nb + nmaxA)) : INFINITY;
+      s_nb[st][threadIdx.x] = nb;
+      if (MODE == 1) s_cj[st][threadIdx.x] = j < nB ? nb - (approx_min[(size_t)cloudB * V + j] + kTcKappa * (nb + nmaxA)) : INFINITY;
     }
   };
-  auto issue_tile = [&](int s, int jt) {  // one thread: 40 KB bulk copy of block jt of cloud B into ring stage s
-    mbar_expect_tx(bar_full0 + 8 * s, kPairBytes);
-    bulk_g2s(sB0 + s * kPairBytes, tB + (size_t)jt * 2 * kTileFloats, kPairBytes, bar_full0 + 8 * s);
+  auto issue_tile = [&](int st, int jt) {  // one thread: 40 KB bulk copy of block jt of cloud B into ring stage st
+    mbar_expect_tx(bar_full0 + 8 * st, kPairBytes);
+    bulk_g2s(sB0 + st * kPairBytes, tB + (size_t)jt * 2 * kTileFloats, kPairBytes, bar_full0 + 8 * st);
   };
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_a, kPairBytes);
@@ -228,33 +233,54 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
   float m = INFINITY;  // MODE 0/2: running min of nb_j - 2 dot
   float Ri = 0.0f;     // MODE 1: row threshold on nb_j - 2 dot
   if (MODE == 1) Ri = row_ok ? (approx_min[(size_t)cloudA * V + gi] + kTcKappa * (na_i + nmaxB)) - na_i : -INFINITY;
-  const float negna = -na_i;
+  const float negna = row_ok ? -na_i : -INFINITY;
   // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
   __syncthreads();  // s_nb / s_cj of the first two tiles visible
 
-  auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile index first + k*step)
-    const int s = k & 1, jt = first + k * step;
-    if (!mbar_wait(bar_mma0 + 8 * s, (uint32_t)((k >> 1) & 1))) s_dead = 1;
+  auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile index first + k*step, ring stage k%3)
+    const int ts = k & 1, st = k % kTcStages, jt = first + k * step;
+    if (!mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1))) s_dead = 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int c0 = jt * kTcN;
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       const int cb = chalf * 64 + ch * 32;
       uint32_t v[32];
-      tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * kTcN + cb), v);
+      tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
+      if (MODE != 1) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float dot = __uint_as_float(v[c]);
-        const float t = fmaf(-2.0f, dot, s_nb[s][cb + c]);
-        if (MODE != 1) {
+        for (int c = 0; c < 32; ++c) {
+          const float t = fmaf(-2.0f, __uint_as_float(v[c]), s_nb[st][cb + c]);
           m = fminf(m, t);
           if (MODE == 2 && stripe == 0 && jt == 0) dbg_tile[(size_t)row * kTcN + cb + c] = na_i + t;
-        } else {
-          const float u = fmaf(-2.0f, dot, s_cj[s][cb + c]);
-          if (row_ok && ((t <= Ri) || (u <= negna))) {
-            const int slot = atomicAdd(cand_n + pair, 1);
-            if (slot < qcap) cand_q[(size_t)pair * qcap + slot] = ((unsigned)gi << 16) | (unsigned)(c0 + cb + c);
+        }
+      } else {
+        // branch-free candidate mask of this lane's row over the 32 columns, then one warp-aggregated queue reservation
+        uint32_t mask = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float dot = __uint_as_float(v[c]);
+          const float t = fmaf(-2.0f, dot, s_nb[st][cb + c]);
+          const float u = fmaf(-2.0f, dot, s_cj[st][cb + c]);
+          mask |= ((t <= Ri) || (u <= negna) ? 1u : 0u) << c;
+        }
+        if (__any_sync(0xffffffffu, mask != 0)) {
+          int tot;
+          int off = warp_excl_scan(__popc(mask), &tot);
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_qn, tot);
+          off += __shfl_sync(0xffffffffu, base, 0);
+          while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const unsigned e = ((unsigned)gi << 16) | (unsigned)(c0 + cb + c);
+            if (off < kTcQueue) s_q[off] = e;
+            else {  // shared queue full (pathological ties): straight to the global queue
+              const int slot = atomicAdd(cand_n + pair, 1);
+              if (slot < qcap) cand_q[(size_t)pair * qcap + slot] = e;
+            }
+            ++off;
           }
         }
       }
@@ -263,14 +289,14 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
   };
 
   for (int k = 0; k < ntl; ++k) {
-    const int s = k & 1;
+    const int ts = k & 1, st = k % kTcStages;
     if (threadIdx.x == 0) {
       bool ok = true;
       if (k == 0) ok = mbar_wait(bar_a, 0);
-      ok = ok && mbar_wait(bar_full0 + 8 * s, (uint32_t)((k >> 1) & 1));
+      ok = ok && mbar_wait(bar_full0 + 8 * st, (uint32_t)((k / kTcStages) & 1));
       if (!ok) s_dead = 1;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sB0 + s * kPairBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(s * kTcN);
+      const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sB0 + st * kPairBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
       uint32_t acc = 0;
 #pragma unroll
       for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
@@ -280,14 +306,15 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
       }
 #pragma unroll
       for (int kb = 0; kb < kTcKB; ++kb) tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * s) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * ts) : "memory");
     }
     __syncwarp();
     if (k >= 1) epilogue(k - 1);  // overlaps the MMAs just issued
-    __syncthreads();              // TMEM stage s^1, s_nb[s^1] and (MMA k-1 being complete) B stage s^1 are free
-    if (k >= 1 && k + 1 < ntl) {
-      if (threadIdx.x == 0) issue_tile(s ^ 1, first + (k + 1) * step);
-      load_cols(s ^ 1, first + (k + 1) * step);  // read again only after the next barriers
+    __syncthreads();              // TMEM stage ts^1 drained; MMA k-1 complete => ring stage (k-1)%3 and its column data are free
+    if (k + 2 < ntl) {            // prefetch distance 2: tile k+2 goes into the stage tile k-1 just left
+      const int st2 = (k + 2) % kTcStages;
+      if (threadIdx.x == 0) issue_tile(st2, first + (k + 2) * step);
+      load_cols(st2, first + (k + 2) * step);  // read again only after the next barriers
     }
     if (s_dead) break;  // uniform: written before the barrier above
   }
@@ -300,8 +327,14 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
     __syncthreads();
     // a dead wait (should never happen) yields +inf: everything qualifies, the queue overflows, the exact kernel takes over
     if (chalf == 0 && row_ok) approx_min[(size_t)cloudA * V + gi] = dead ? INFINITY : fminf(m, s_part[row]) + na_i;
-  } else if (dead && threadIdx.x == 0) {
-    atomicAdd(cand_n + pair, qcap + 1);
+  } else {
+    // flush the shared-memory candidate queue with ONE global reservation
+    const int nq = s_qn < kTcQueue ? s_qn : kTcQueue;
+    if (threadIdx.x == 0) s_qbase = atomicAdd(cand_n + pair, dead ? qcap + 1 : nq);
+    __syncthreads();
+    const int gbase = s_qbase;
+    for (int t = threadIdx.x; t < nq; t += kTcThreads)
+      if (gbase + t < qcap) cand_q[(size_t)pair * qcap + gbase + t] = s_q[t];
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -348,12 +381,12 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ r
 // implemented in match.cu: exact kernels restricted to the pairs flagged in `only`
 int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);
 
-constexpr int kTcSampleStep = 4;  // the bound passes visit every 4th column tile
+constexpr int kTcSampleStep = 2;  // the bound passes visit every 2nd column tile
 
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
   static bool attr_set = false;
-  const size_t smem = 3 * (size_t)(2 * kTcTileBytes) + 1024;  // A + two B ring stages, hi and lo images each
+  const size_t smem = (size_t)(1 + kTcStages) * (2 * kTcTileBytes) + (size_t)kTcQueue * 4 + 1024;  // A + B ring (hi+lo images) + queue
   if (!attr_set) {
     QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -386,7 +419,7 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
 
 // debug/validation hook: approximate distances of the first 128 x 128 tile of pair 0 (descriptors already in desc_t)
 int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
-  const size_t smem = 3 * (size_t)(2 * kTcTileBytes) + 1024;
+  const size_t smem = (size_t)(1 + kTcStages) * (2 * kTcTileBytes) + (size_t)kTcQueue * 4 + 1024;
   QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->norm_max, 0, 2 * sizeof(unsigned), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
