@@ -37,8 +37,8 @@ struct qb200_handle {
   float4* normals;            // [2S*V]
   float* spfh;                // [2S*V*36] rows padded to 36 floats
   float* desc_t;              // [2S*40*V] FPFH, dimension-major per cloud (row d = bin d over all points; rows 33..39 zero)
-  float* desc_tiles;          // [2S*(V/128)*2*5120] TF32 hi / lo images of every 128-point block in the UMMA shared-memory layout
-  float* desc_rows;           // [2S*V*40] exact fp32 descriptors, point-major (exact re-rank)
+  float* desc_tiles;          // [2S*(V/128)*3*5120] per 128-point block: centred TF32 hi | lo | exact fp32 images in the UMMA
+                              // shared-memory operand layout (one bulk copy per tile)
   float* desc_norm;           // [2S*V] squared norms (fp32 fma chain)
   unsigned* norm_max;         // [2S] per-cloud max squared norm (float bits)
   float* approx_min;          // [2S*V] tensor-core approximate NN distance per point

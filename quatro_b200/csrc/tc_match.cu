@@ -1,45 +1,46 @@
-// tc_match.cu -- K6 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+// tc_match.cu -- K6 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.   Opt-in: QB200_MATCH_TC=1.
 //
-// The N_src x N_tgt x 33 descriptor-distance matrix is the one genuinely dense contraction of the
-// path (north_star): d(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j.  The reference does two exact 1-NN
-// searches (FLANN kd-trees, src/teaser_utils/feature_matcher.cc:97-125); the exact answer here is
-// defined by the fp32 fma chain of match.cu.  Tensor cores cannot reproduce that rounding, so they
-// are used as a FILTER with a rigorous error bound and the winners are re-ranked exactly:
+// The N_src x N_tgt x 33 descriptor-distance matrix is the one genuinely dense contraction of the path
+// (north_star): d(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j.  The reference does two exact 1-NN searches (FLANN kd-trees,
+// src/teaser_utils/feature_matcher.cc:97-125); the exact answer here is DEFINED by the fp32 fma chain of match.cu
+// (lowest-index ties).  Tensor cores cannot reproduce that rounding, so they act as a conservative FILTER and the
+// survivors are evaluated exactly inside the same kernel -- results are bit-identical to the exact kernel.
 //
-//   split_desc_kernel   x -> hi (top 19 bits = a TF32 value), lo = TF32(x - hi); |x|^2; per-cloud max norm
-//   tc_match_kernel<0>  upper bounds  U_i = min over every 2nd column tile of d~(i,j)   (both orientations)
-//   tc_match_kernel<1>  every (i,j) with d~(i,j) <= U_i + margin_i or <= U_j + margin_j is queued
-//   rerank_kernel       exact fp32 chain distance of the queued pairs -> packed atomicMin into the
-//                       row / column minima (distance bits << 32 | index  => lowest-index ties)
+//   split_desc_kernel : x' = x - mu  (mu = FPFH signature of a plane: 100 in bins 5, 16, 27 -- street scenes are dominated
+//                       by planar points whose descriptors are near-identical, centring makes THEIR dot products tiny and
+//                       therefore the filter's absolute error tiny exactly where near-ties are dense);
+//                       hi = TF32(x'), lo = TF32(x' - hi), |x'|^2;  128-point blocks are written as ready-made
+//                       shared-memory operand images (hi | lo | exact x), so a tile is ONE cp.async.bulk.
+//   tc_nn_kernel      : one pass over all (128-row stripe) x (128-column tile) blocks:
+//                         d~ = |a'|^2 + |b'|^2 - 2 (hi.hi + hi.lo + lo.hi)      3 x 5 tcgen05.mma.kind::tf32, fp32 in TMEM
+//                         |d~ - d| <= e_ij = c/2 (|a'_i|^2 + |b'_j|^2),  c = 6e-5   (split + accumulation + chain rounding)
+//                         (i,j) is evaluated EXACTLY (fp32 chain from the exact images) iff its lower bound d~ - e_ij
+//                         does not exceed the best exact distance known so far for row i or for column j;
+//                         row bests live in registers, column bests in global memory (atomicMin on packed
+//                         distance|index words; stripes start at staggered column tiles so bounds tighten quickly).
+//                       A pair whose stripes evaluate too many entries (massive exact ties) is flagged and redone by the
+//                       exact CUDA-core kernel, so results never depend on the filter.
 //
-// d~ uses three TF32 MMAs per K block (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM), i.e.
-// |d~ - d| <= ~2.3e-5 (|a|^2 + |b|^2); margin = 1e-4 (|a_i|^2 + max_j |b_j|^2) therefore always keeps
-// the exact arg-min in the queue (tests/test_gpu_parity.py::test_tc_filter_error_bound measures the
-// slack).  If a queue overflows (thousands of near-identical descriptors) the pair is redone by the
-// exact CUDA-core kernel of match.cu, so results never depend on the filter.
-//
-// Kernel anatomy (one CTA = 128 source rows, one CTA per SM):
-//   operands  : 128-point blocks are stored in global memory as ready-made shared-memory images (canonical K-major,
-//               no-swizzle UMMA layout), so a tile is ONE cp.async.bulk (TMA bulk copy) completing on an mbarrier;
-//               B tiles stream through a 2-stage ring
-//   MMA       : one thread issues 15 x tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) into one of two
-//               128-column TMEM accumulator stages, tcgen05.commit -> mbarrier
-//   epilogue  : 8 warps drain the OTHER TMEM stage meanwhile: tcgen05.ld.32x32b.x32 (lane = row), fused
-//               nb_j - 2 dot  + min / threshold test
+// Pipeline per CTA (one per SM): bulk copies fill a 3-stage ring of B images (prefetch distance 2); one thread issues
+// the 15 MMAs of tile k into TMEM stage k&1 and commits to an mbarrier; meanwhile all 8 warps drain stage (k-1)&1 with
+// tcgen05.ld.32x32b.x32 (lane = row) and run the filter / exact evaluation.
 #include "handle.cuh"
 
 namespace qb {
 
 constexpr int kTcM = 128, kTcN = 128;
 constexpr int kTcKB = kDescK / 8;                 // K blocks of 8 (TF32 MMA K)
-constexpr int kTcTileBytes = kDescK * 128 * 4;    // one operand tile (128 points x 40 dims) = 20480 B
+constexpr int kTcTileBytes = kDescK * 128 * 4;    // one operand image (128 points x 40 dims) = 20480 B
+constexpr int kTileFloats = kDescK * 128;         // 5120
+constexpr int kTcImages = 3;                      // hi | lo | exact
 constexpr int kTcThreads = 256;
-constexpr float kTcKappa = 1.0e-4f;               // margin = kappa * (|a_i|^2 + max_j |b_j|^2)
+constexpr int kTcStages = 3;                      // B ring (prefetch distance 2)
+constexpr float kTcC = 6.0e-5f;                   // |d~ - d| <= kTcC/2 * (|a'|^2 + |b'|^2)
 constexpr int kSpinLimit = 400000;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Operand tiles use the canonical K-major / no-swizzle UMMA layout (validated by tools/tc_probe.cu on B200; MN-major
+// Operand images use the canonical K-major / no-swizzle UMMA layout (validated by tools/tc_probe.cu on B200; MN-major
 // TF32 without swizzle yields zeros): core matrix = 8 points x 16 B (4 consecutive K values), byte offset
 // kc*2048 + p*16 for K chunk kc (4 dims) and point p of the 128-point block.
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
@@ -72,50 +73,39 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// ------------------------------------------------------------------------------------------------
-// split_desc_kernel: per point  |x|^2 (fp32 fma chain), per-cloud max norm, and two re-layouts of the descriptor:
-//   rows  [cloud][V][40]            exact fp32, point-major (the re-rank reads 160 contiguous bytes per point)
-//   tiles [cloud][V/128][2][5120]   TF32 hi / lo images of each 128-point block, stored EXACTLY in the shared-memory
-//                                   operand layout (float index kc*512 + p*4 + e), so a tile is one 20/40 KB bulk copy
-// ------------------------------------------------------------------------------------------------
-constexpr int kTileFloats = kDescK * 128;  // 5120
+__device__ __forceinline__ float tc_mu(int d) { return (d == 5 || d == 16 || d == 27) ? 100.0f : 0.0f; }
 
+// centred TF32 split + exact image + centred squared norm, written block-wise in the shared-memory operand layout
 __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V,
-                                                         float* __restrict__ tiles, float* __restrict__ rows, float* __restrict__ norm,
-                                                         unsigned* __restrict__ norm_max) {
+                                                         float* __restrict__ tiles, float* __restrict__ norm) {
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = n_vox[cloud];
   const int NB = V >> 7;
+  if (q >= ((n + 127) & ~127)) return;  // the last block is padded with zeros so stale data never reaches the tensor core
+  const size_t base = (size_t)cloud * kDescK * V + q;
+  const int blk = q >> 7, p = q & 127;
+  float4* __restrict__ img = reinterpret_cast<float4*>(tiles + (size_t)(cloud * NB + blk) * kTcImages * kTileFloats) + p;
   float acc = 0.0f;
-  if (q < ((n + 127) & ~127)) {  // pad the last block with zeros so stale data never reaches the tensor core
-    const size_t base = (size_t)cloud * kDescK * V + q;
-    const int blk = q >> 7, p = q & 127;
-    float4* __restrict__ th = reinterpret_cast<float4*>(tiles + ((size_t)(cloud * NB + blk) * 2 + 0) * kTileFloats) + p;
-    float4* __restrict__ tl = reinterpret_cast<float4*>(tiles + ((size_t)(cloud * NB + blk) * 2 + 1) * kTileFloats) + p;
-    float4* __restrict__ rw = reinterpret_cast<float4*>(rows + ((size_t)cloud * V + q) * kDescK);
 #pragma unroll
-    for (int kc = 0; kc < kDescK / 4; ++kc) {
-      float xv[4], hv[4], lv[4];
+  for (int kc = 0; kc < kDescK / 4; ++kc) {
+    float xv[4], hv[4], lv[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int d = 4 * kc + e;
-        const float x = (d < kDescDim && q < n) ? desc_t[base + (size_t)d * V] : 0.0f;
-        xv[e] = x;
-        hv[e] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-        lv[e] = __uint_as_float(__float_as_uint(x - hv[e]) & 0xFFFFE000u);
-        if (d < kDescDim) acc = __fmaf_rn(x, x, acc);
-      }
-      th[kc * 128] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      tl[kc * 128] = make_float4(lv[0], lv[1], lv[2], lv[3]);
-      rw[kc] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    for (int e = 0; e < 4; ++e) {
+      const int d = 4 * kc + e;
+      const bool live = d < kDescDim && q < n;
+      const float x = live ? desc_t[base + (size_t)d * V] : 0.0f;
+      const float xc = live ? x - tc_mu(d) : 0.0f;
+      xv[e] = x;
+      hv[e] = __uint_as_float(__float_as_uint(xc) & 0xFFFFE000u);
+      lv[e] = __uint_as_float(__float_as_uint(xc - hv[e]) & 0xFFFFE000u);
+      acc = __fmaf_rn(xc, xc, acc);
     }
-    if (q < n) norm[(size_t)cloud * V + q] = acc;
+    img[0 * (kTileFloats / 4) + kc * 128] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    img[1 * (kTileFloats / 4) + kc * 128] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    img[2 * (kTileFloats / 4) + kc * 128] = make_float4(xv[0], xv[1], xv[2], xv[3]);
   }
-  float m = (q < n && acc == acc) ? acc : 0.0f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane_id() == 0 && m > 0.0f) atomicMax(norm_max + cloud, __float_as_uint(m));
+  if (q < n) norm[(size_t)cloud * V + q] = acc;
 }
 
 // ---- mbarrier / bulk-copy helpers ---------------------------------------------------------------
@@ -146,46 +136,44 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return false;
 }
 
-// MODE 0: approx_min[cloudA][i] = min over the SAMPLED column tiles of d~(i,j)  (an upper bound of the row minimum).
-// MODE 1: queue every (i,j) with d~ <= bound_i + margin_i or <= bound_j + margin_j   (rows = source cloud, all tiles).
-// MODE 2: MODE 0 + dump of the first 128 x 128 tile of d~ (validation hook).
-// Pipeline per CTA (128 rows): B tiles arrive by bulk copy into a 2-stage ring; MMA(k) into TMEM stage k&1 runs
-// while all 8 warps drain TMEM stage (k-1)&1.
-constexpr int kTcStages = 3;      // B-tile ring (prefetch distance 2)
-constexpr int kTcQueue = 8192;    // per-CTA shared-memory candidate queue (entries)
+__device__ __forceinline__ unsigned long long tc_pack(float d, int idx) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
+}
 
-template <int MODE>
+// rows = source cloud (2*pair), columns = target cloud (2*pair+1).  dbg_tile != nullptr: additionally dump d~ of the
+// first tile of stripe 0 (validation hook).
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const float* __restrict__ norm, const unsigned* __restrict__ norm_max,
-                const int* __restrict__ n_vox, int V, float* __restrict__ approx_min, unsigned* __restrict__ cand_q,
-                int* __restrict__ cand_n, int qcap, float* __restrict__ dbg_tile) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, const int* __restrict__ n_vox, int V,
+             unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest, int* __restrict__ fallback,
+             float* __restrict__ dbg_tile) {
+  extern __shared__ __align__(128) unsigned char smem[];  // 220 KB of operand images; static + dynamic must stay <= 227 KB
   __shared__ uint64_t s_full[kTcStages], s_mma[2], s_afull;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_nb[kTcStages][kTcN], s_cj[kTcStages][kTcN], s_part[kTcM];
-  __shared__ int s_dead, s_qn, s_qbase;
+  __shared__ float s_nbm[kTcStages][kTcN], s_cj[kTcStages][kTcN];
+  __shared__ unsigned long long s_cb[kTcStages][kTcN];
+  __shared__ int s_dead, s_evals;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
-  const int cloudA = swap ? 2 * pair + 1 : 2 * pair, cloudB = swap ? 2 * pair : 2 * pair + 1;
+  const int cloudA = 2 * pair, cloudB = 2 * pair + 1;
   const int nA = n_vox[cloudA], nB = n_vox[cloudB];
   const int r0 = stripe * kTcM;
   if (r0 >= nA || nB <= 0) return;  // uniform for the CTA, before any barrier / allocation
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NB = V >> 7;
-  constexpr uint32_t kPairBytes = 2 * kTcTileBytes;  // hi + lo image of one 128-point block
-  const uint32_t sA = smem_u32(smem), sB0 = sA + kPairBytes;
-  unsigned* s_q = reinterpret_cast<unsigned*>(smem + (1 + kTcStages) * kPairBytes);  // MODE 1 only
-  const float* __restrict__ tA = tiles + (size_t)cloudA * NB * 2 * kTileFloats;
-  const float* __restrict__ tB = tiles + (size_t)cloudB * NB * 2 * kTileFloats;
+  constexpr uint32_t kABytes = 2 * kTcTileBytes;          // hi + lo of the A block
+  constexpr uint32_t kBBytes = kTcImages * kTcTileBytes;  // hi + lo + exact of a B block
+  const uint32_t sA = smem_u32(smem), sB0 = sA + kABytes;
+  const float* __restrict__ tA = tiles + (size_t)cloudA * NB * kTcImages * kTileFloats;
+  const float* __restrict__ tB = tiles + (size_t)cloudB * NB * kTcImages * kTileFloats;
   const float* __restrict__ nA_ = norm + (size_t)cloudA * V;
   const float* __restrict__ nB_ = norm + (size_t)cloudB * V;
+  unsigned long long* __restrict__ cbg = colbest + (size_t)pair * V;
   const uint32_t bar_full0 = smem_u32(&s_full[0]), bar_mma0 = smem_u32(&s_mma[0]), bar_a = smem_u32(&s_afull);
 
   const int n_tiles = (nB + kTcN - 1) / kTcN;
-  const int step = tile_step < n_tiles ? tile_step : n_tiles;      // sampled passes visit every step-th tile
-  const int first = step > 1 ? (stripe % step) : 0;
-  const int ntl = (n_tiles - first + step - 1) / step;             // >= 1
+  const int first = stripe % n_tiles;  // staggered start: concurrent stripes of a pair work on different column tiles
+  auto tile_of = [&](int k) { const int t = first + k; return t >= n_tiles ? t - n_tiles : t; };
 
   if (warp == 0) {  // TMEM: 2 accumulator stages x 128 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(2 * kTcN) : "memory");
@@ -194,7 +182,7 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcStages; ++i) mbar_init(bar_full0 + 8 * i, 1);
     mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1); mbar_init(bar_a, 1);
-    s_dead = 0; s_qn = 0;
+    s_dead = 0; s_evals = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -202,93 +190,108 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
 
-  // per-tile column data (norms, and in MODE 1 the column thresholds) for ring stage st
-  const float nmaxA = __uint_as_float(norm_max[cloudA]), nmaxB = __uint_as_float(norm_max[cloudB]);
-  auto load_cols = [&](int st, int jt) {
+  const float kLow = 1.0f - 0.5f * kTcC;  // d~ - e_ij = kLow (na' + nb') - 2 dot
+  auto load_cols = [&](int st, int jt) {  // per-column filter data of tile jt into ring stage st
     if (threadIdx.x < kTcN) {
       const int j = jt * kTcN + threadIdx.x;
-      const float nb = j < nB ? nB_[j] : INFINITY;  // +inf: padded columns never win and never qualify
-      s_nb[st][threadIdx.x] = nb;
-      if (MODE == 1) s_cj[st][threadIdx.x] = j < nB ? nb - (approx_min[(size_t)cloudB * V + j] + kTcKappa * (nb + nmaxA)) : INFINITY;
+      float nbm = INFINITY, cj = INFINITY;  // padded columns never qualify
+      unsigned long long cb = ~0ull;
+      if (j < nB) {
+        nbm = kLow * nB_[j];
+        cb = cbg[j];  // snapshot of the best exact (distance | source index) known for this column
+        const float dbest = cb == ~0ull ? INFINITY : __uint_as_float((unsigned)(cb >> 32));
+        cj = nbm - dbest;
+      }
+      s_nbm[st][threadIdx.x] = nbm; s_cj[st][threadIdx.x] = cj; s_cb[st][threadIdx.x] = cb;
     }
   };
-  auto issue_tile = [&](int st, int jt) {  // one thread: 40 KB bulk copy of block jt of cloud B into ring stage st
-    mbar_expect_tx(bar_full0 + 8 * st, kPairBytes);
-    bulk_g2s(sB0 + st * kPairBytes, tB + (size_t)jt * 2 * kTileFloats, kPairBytes, bar_full0 + 8 * st);
+  auto issue_tile = [&](int st, int jt) {  // one thread: 60 KB bulk copy of block jt of cloud B into ring stage st
+    mbar_expect_tx(bar_full0 + 8 * st, kBBytes);
+    bulk_g2s(sB0 + st * kBBytes, tB + (size_t)jt * kTcImages * kTileFloats, kBBytes, bar_full0 + 8 * st);
   };
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar_a, kPairBytes);
-    bulk_g2s(sA, tA + (size_t)stripe * 2 * kTileFloats, kPairBytes, bar_a);
-    issue_tile(0, first);
-    if (ntl > 1) issue_tile(1, first + step);
+    mbar_expect_tx(bar_a, kABytes);
+    bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
+    issue_tile(0, tile_of(0));
+    if (n_tiles > 1) issue_tile(1, tile_of(1));
   }
-  load_cols(0, first);
-  if (ntl > 1) load_cols(1, first + step);
+  load_cols(0, tile_of(0));
+  if (n_tiles > 1) load_cols(1, tile_of(1));
 
-  // this thread's accumulator row and column half
+  // this thread's accumulator row (TMEM lane) and column half; its exact source descriptor lives in registers
   const int quad = warp & 3, chalf = warp >> 2;
   const int row = quad * 32 + lane, gi = r0 + row;
   const bool row_ok = gi < nA;
-  const float na_i = row_ok ? nA_[gi] : 0.0f;
-  float m = INFINITY;  // MODE 0/2: running min of nb_j - 2 dot
-  float Ri = 0.0f;     // MODE 1: row threshold on nb_j - 2 dot
-  if (MODE == 1) Ri = row_ok ? (approx_min[(size_t)cloudA * V + gi] + kTcKappa * (na_i + nmaxB)) - na_i : -INFINITY;
-  const float negna = row_ok ? -na_i : -INFINITY;
+  float ax[kDescDim + 3];
+  {
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(tA + ((size_t)stripe * kTcImages + 2) * kTileFloats) + row;
+#pragma unroll
+    for (int kc = 0; kc < (kDescDim + 3) / 4; ++kc) {
+      const float4 t = __ldg(src + kc * 128);
+      ax[4 * kc] = t.x; ax[4 * kc + 1] = t.y; ax[4 * kc + 2] = t.z; ax[4 * kc + 3] = t.w;
+    }
+  }
+  const float nam = row_ok ? kLow * nA_[gi] : 0.0f;
+  const float negna = row_ok ? -nam : -INFINITY;   // column test:  kLow nb' - 2 dot - cbest_j <= -kLow na'
+  unsigned long long rbest = ~0ull;
+  float Ri = row_ok ? INFINITY : -INFINITY;        // row test:     kLow nb' - 2 dot <= best_i - kLow na'
+  int my_evals = 0;
   // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-  __syncthreads();  // s_nb / s_cj of the first two tiles visible
+  __syncthreads();  // column data of the first two tiles visible
 
-  auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile index first + k*step, ring stage k%3)
-    const int ts = k & 1, st = k % kTcStages, jt = first + k * step;
+  auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile tile_of(k), ring stage k%3)
+    const int ts = k & 1, st = k % kTcStages, jt = tile_of(k);
     if (!mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1))) s_dead = 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int c0 = jt * kTcN;
+    const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + st * kBBytes + 2 * kTcTileBytes);  // exact image
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       const int cb = chalf * 64 + ch * 32;
       uint32_t v[32];
       tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
-      if (MODE != 1) {
+      uint32_t mask = 0;  // branch-free candidate mask of this lane's row over the 32 columns
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float t = fmaf(-2.0f, __uint_as_float(v[c]), s_nb[st][cb + c]);
-          m = fminf(m, t);
-          if (MODE == 2 && stripe == 0 && jt == 0) dbg_tile[(size_t)row * kTcN + cb + c] = na_i + t;
-        }
-      } else {
-        // branch-free candidate mask of this lane's row over the 32 columns, then one warp-aggregated queue reservation
-        uint32_t mask = 0;
+      for (int c = 0; c < 32; ++c) {
+        const float dot = __uint_as_float(v[c]);
+        const float t = fmaf(-2.0f, dot, s_nbm[st][cb + c]);
+        const float u = fmaf(-2.0f, dot, s_cj[st][cb + c]);
+        mask |= ((t <= Ri) || (u <= negna) ? 1u : 0u) << c;
+        if (dbg_tile != nullptr && stripe == 0 && k == 0) dbg_tile[(size_t)row * kTcN + cb + c] = (nam + s_nbm[st][cb + c]) / kLow - 2.0f * dot;
+      }
+      while (mask) {  // exact fp32 chain for the survivors (thresholds are re-checked: they tighten as we go)
+        const int c = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float dot = __uint_as_float(v[c]);
+        if (!((fmaf(-2.0f, dot, s_nbm[st][cb + c]) <= Ri) || (fmaf(-2.0f, dot, s_cj[st][cb + c]) <= negna))) continue;
+        const int pcol = cb + c;
+        float acc = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float dot = __uint_as_float(v[c]);
-          const float t = fmaf(-2.0f, dot, s_nb[st][cb + c]);
-          const float u = fmaf(-2.0f, dot, s_cj[st][cb + c]);
-          mask |= ((t <= Ri) || (u <= negna) ? 1u : 0u) << c;
+        for (int kc = 0; kc < (kDescDim + 3) / 4; ++kc) {
+          const float4 b = bex[kc * 128 + pcol];
+          float diff = ax[4 * kc] - b.x;
+          acc = __fmaf_rn(diff, diff, acc);
+          if (4 * kc + 1 < kDescDim) { diff = ax[4 * kc + 1] - b.y; acc = __fmaf_rn(diff, diff, acc); }
+          if (4 * kc + 2 < kDescDim) { diff = ax[4 * kc + 2] - b.z; acc = __fmaf_rn(diff, diff, acc); }
+          if (4 * kc + 3 < kDescDim) { diff = ax[4 * kc + 3] - b.w; acc = __fmaf_rn(diff, diff, acc); }
         }
-        if (__any_sync(0xffffffffu, mask != 0)) {
-          int tot;
-          int off = warp_excl_scan(__popc(mask), &tot);
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s_qn, tot);
-          off += __shfl_sync(0xffffffffu, base, 0);
-          while (mask) {
-            const int c = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const unsigned e = ((unsigned)gi << 16) | (unsigned)(c0 + cb + c);
-            if (off < kTcQueue) s_q[off] = e;
-            else {  // shared queue full (pathological ties): straight to the global queue
-              const int slot = atomicAdd(cand_n + pair, 1);
-              if (slot < qcap) cand_q[(size_t)pair * qcap + slot] = e;
-            }
-            ++off;
-          }
+        ++my_evals;
+        if (acc == acc) {  // NaN never wins
+          const int j = c0 + pcol;
+          const unsigned long long pr = tc_pack(acc, j);
+          if (pr < rbest) { rbest = pr; Ri = acc - nam; }
+          const unsigned long long pc = tc_pack(acc, gi);
+          if (pc < s_cb[st][pcol]) atomicMin(cbg + j, pc);
         }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   };
 
-  for (int k = 0; k < ntl; ++k) {
+  bool aborted = false;
+  int k = 0;
+  for (; k < n_tiles; ++k) {
     const int ts = k & 1, st = k % kTcStages;
     if (threadIdx.x == 0) {
       bool ok = true;
@@ -296,7 +299,7 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
       ok = ok && mbar_wait(bar_full0 + 8 * st, (uint32_t)((k / kTcStages) & 1));
       if (!ok) s_dead = 1;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sB0 + st * kPairBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
+      const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sB0 + st * kBBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
       uint32_t acc = 0;
 #pragma unroll
       for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
@@ -309,124 +312,86 @@ tc_match_kernel(int swap, int tile_step, const float* __restrict__ tiles, const 
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * ts) : "memory");
     }
     __syncwarp();
-    if (k >= 1) epilogue(k - 1);  // overlaps the MMAs just issued
-    __syncthreads();              // TMEM stage ts^1 drained; MMA k-1 complete => ring stage (k-1)%3 and its column data are free
-    if (k + 2 < ntl) {            // prefetch distance 2: tile k+2 goes into the stage tile k-1 just left
-      const int st2 = (k + 2) % kTcStages;
-      if (threadIdx.x == 0) issue_tile(st2, first + (k + 2) * step);
-      load_cols(st2, first + (k + 2) * step);  // read again only after the next barriers
+    if (k >= 1) {
+      epilogue(k - 1);  // overlaps the MMAs just issued
+      const int ws = __reduce_add_sync(0xffffffffu, my_evals);
+      my_evals = 0;
+      if (lane == 0 && ws) atomicAdd(&s_evals, ws);
     }
-    if (s_dead) break;  // uniform: written before the barrier above
+    __syncthreads();  // TMEM stage ts^1 drained; MMA k-1 complete => ring stage (k-1)%3 and its column data are free
+    if (k + 2 < n_tiles) {  // prefetch distance 2: tile k+2 goes into the stage tile k-1 just left
+      const int st2 = (k + 2) % kTcStages;
+      if (threadIdx.x == 0) issue_tile(st2, tile_of(k + 2));
+      load_cols(st2, tile_of(k + 2));  // read again only after the next barriers
+    }
+    // massive ties: once more than 1/4 of the entries seen needed the exact chain, hand the pair to the exact kernel
+    if (s_dead || (k >= 3 && s_evals > k * (kTcM * kTcN / 4))) {  // uniform: both written before the barrier above
+      aborted = true;
+      break;
+    }
   }
-  if (!s_dead) epilogue(ntl - 1);
+  if (!aborted) {
+    epilogue(n_tiles - 1);
+  } else if (threadIdx.x == 0) {
+    // never leave the CTA with asynchronous work in flight: MMA(k) and the prefetched tiles k+1, k+2
+    mbar_wait(bar_mma0 + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
+    if (k + 1 < n_tiles) mbar_wait(bar_full0 + 8 * ((k + 1) % kTcStages), (uint32_t)(((k + 1) / kTcStages) & 1));
+    if (k + 2 < n_tiles) mbar_wait(bar_full0 + 8 * ((k + 2) % kTcStages), (uint32_t)(((k + 2) / kTcStages) & 1));
+  }
   __syncthreads();
-  const bool dead = s_dead != 0;
 
-  if (MODE != 1) {
-    if (chalf == 1) s_part[row] = m;
-    __syncthreads();
-    // a dead wait (should never happen) yields +inf: everything qualifies, the queue overflows, the exact kernel takes over
-    if (chalf == 0 && row_ok) approx_min[(size_t)cloudA * V + gi] = dead ? INFINITY : fminf(m, s_part[row]) + na_i;
+  if (aborted) {
+    if (threadIdx.x == 0) fallback[pair] = 1;
   } else {
-    // flush the shared-memory candidate queue with ONE global reservation
-    const int nq = s_qn < kTcQueue ? s_qn : kTcQueue;
-    if (threadIdx.x == 0) s_qbase = atomicAdd(cand_n + pair, dead ? qcap + 1 : nq);
+    unsigned long long* s_rowmerge = reinterpret_cast<unsigned long long*>(smem);  // the operand images are dead now
+    if (chalf == 1) s_rowmerge[row] = rbest;
     __syncthreads();
-    const int gbase = s_qbase;
-    for (int t = threadIdx.x; t < nq; t += kTcThreads)
-      if (gbase + t < qcap) cand_q[(size_t)pair * qcap + gbase + t] = s_q[t];
+    if (chalf == 0 && row_ok) {
+      const unsigned long long o = s_rowmerge[row];
+      rowbest[(size_t)pair * V + gi] = rbest < o ? rbest : o;
+    }
   }
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * kTcN) : "memory");
 }
 
-__device__ __forceinline__ unsigned long long tc_pack(float d, int idx) {
-  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
-}
-
-// exact canonical distance of every queued (src, tgt) pair; folds both directions
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ rows, const int* __restrict__ n_vox, int V,
-                                                     const unsigned* __restrict__ cand_q, const int* __restrict__ cand_n, int qcap,
-                                                     int* __restrict__ fallback, unsigned long long* __restrict__ rowbest,
-                                                     unsigned long long* __restrict__ colbest) {
-  const int pair = blockIdx.y;
-  const int n = cand_n[pair];
-  if (n > qcap) {  // overflow: the exact CUDA-core kernel redoes this pair
-    if (blockIdx.x == 0 && threadIdx.x == 0) fallback[pair] = 1;
-    return;
-  }
-  const float4* __restrict__ A = reinterpret_cast<const float4*>(rows + (size_t)(2 * pair) * V * kDescK);
-  const float4* __restrict__ B = reinterpret_cast<const float4*>(rows + (size_t)(2 * pair + 1) * V * kDescK);
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-    const unsigned e = cand_q[(size_t)pair * qcap + c];
-    const int i = (int)(e >> 16), j = (int)(e & 0xFFFFu);
-    float acc = 0.0f;
-#pragma unroll
-    for (int c4 = 0; c4 < (kDescDim + 3) / 4; ++c4) {  // same d = 0..32 fma chain as the exact kernel
-      const float4 a = __ldg(A + (size_t)i * (kDescK / 4) + c4), b = __ldg(B + (size_t)j * (kDescK / 4) + c4);
-      float diff = a.x - b.x;
-      acc = __fmaf_rn(diff, diff, acc);
-      if (4 * c4 + 1 < kDescDim) { diff = a.y - b.y; acc = __fmaf_rn(diff, diff, acc); }
-      if (4 * c4 + 2 < kDescDim) { diff = a.z - b.z; acc = __fmaf_rn(diff, diff, acc); }
-      if (4 * c4 + 3 < kDescDim) { diff = a.w - b.w; acc = __fmaf_rn(diff, diff, acc); }
-    }
-    if (acc == acc) {
-      atomicMin(rowbest + (size_t)pair * V + i, tc_pack(acc, j));
-      atomicMin(colbest + (size_t)pair * V + j, tc_pack(acc, i));
-    }
-  }
-}
-
-// implemented in match.cu: exact kernels restricted to the pairs flagged in `only`
-int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);
-
-constexpr int kTcSampleStep = 2;  // the bound passes visit every 2nd column tile
+static size_t tc_smem_bytes() { return 2 * (size_t)kTcTileBytes + (size_t)kTcStages * kTcImages * kTcTileBytes; }
 
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
   static bool attr_set = false;
-  const size_t smem = (size_t)(1 + kTcStages) * (2 * kTcTileBytes) + (size_t)kTcQueue * 4 + 1024;  // A + B ring (hi+lo images) + queue
+  const size_t smem = tc_smem_bytes();
   if (!attr_set) {
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->cand_n, 0, (size_t)n_pairs * sizeof(int), h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, (size_t)n_pairs * sizeof(int), h->stream));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->norm_max, 0, (size_t)2 * n_pairs * sizeof(unsigned), h->stream));
   const dim3 gsplit((V + 255) / 256, 2 * n_pairs);
-  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_tiles, h->desc_rows, h->desc_norm, h->norm_max);
+  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_tiles, h->desc_norm);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
-  tc_match_kernel<0><<<g, kTcThreads, smem, h->stream>>>(0, kTcSampleStep, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
-                                                         nullptr, nullptr, 0, nullptr);
-  tc_match_kernel<0><<<g, kTcThreads, smem, h->stream>>>(1, kTcSampleStep, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min,
-                                                         nullptr, nullptr, 0, nullptr);
-  tc_match_kernel<1><<<g, kTcThreads, smem, h->stream>>>(0, 1, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, V, h->approx_min, h->cand_q,
-                                                         h->cand_n, h->qcap, nullptr);
+  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, V, h->rowbest, h->colbest, h->tc_fallback, nullptr);
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
-  const dim3 gr(64, n_pairs);
-  rerank_kernel<<<gr, 256, 0, h->stream>>>(h->desc_rows, h->ctr.n_vox, V, h->cand_q, h->cand_n, h->qcap, h->tc_fallback, h->rowbest, h->colbest);
-  h->launches += 5;
+  h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return launch_match_exact(h, n_pairs, h->tc_fallback);
 }
 
-// debug/validation hook: approximate distances of the first 128 x 128 tile of pair 0 (descriptors already in desc_t)
+// debug/validation hook: approximate distances d~ of the first 128 x 128 tile of pair 0 (descriptors already in desc_t)
 int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
-  const size_t smem = (size_t)(1 + kTcStages) * (2 * kTcTileBytes) + (size_t)kTcQueue * 4 + 1024;
-  QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_match_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->norm_max, 0, 2 * sizeof(unsigned), h->stream));
+  const size_t smem = tc_smem_bytes();
+  QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)h->V * 8, h->stream));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)h->V * 8, h->stream));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, sizeof(int), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
-  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_tiles, h->desc_rows, h->desc_norm, h->norm_max);
+  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_tiles, h->desc_norm);
   const dim3 g(1, 1);
-  tc_match_kernel<2><<<g, kTcThreads, smem, h->stream>>>(0, 1, h->desc_tiles, h->desc_norm, h->norm_max, h->ctr.n_vox, h->V, h->approx_min, nullptr,
-                                                         nullptr, 0, d_out);
+  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, h->V, h->rowbest, h->colbest, h->tc_fallback, d_out);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
