@@ -151,6 +151,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   __shared__ uint32_t s_tmem;
   __shared__ float s_nbm[kTcStages][kTcN], s_cj[kTcStages][kTcN];
   __shared__ unsigned long long s_cb[kTcStages][kTcN];
+  __shared__ unsigned s_colub[kTcN];  // warm-up: per-column upper bound (ordered-uint keys) of a fresh tile
   __shared__ int s_dead, s_evals;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
@@ -240,11 +241,48 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
   __syncthreads();  // column data of the first two tiles visible
 
+  const float kHighOverLow = (1.0f + 0.5f * kTcC) / kLow;  // (1 + c/2) nb' from the stored kLow nb'
   auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile tile_of(k), ring stage k%3)
     const int ts = k & 1, st = k % kTcStages, jt = tile_of(k);
     if (!mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1))) s_dead = 1;
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int c0 = jt * kTcN;
+    // ---- warm-up on fresh tiles: with no exact bound yet every entry would qualify.  Upper bounds of the exact row /
+    // column minima come from the tile itself: UB_ij = d~_ij + e_ij = (1+c/2)(na'+nb') - 2 dot >= d_ij.
+    const int fresh_local = (k == 0) || (threadIdx.x < kTcN && c0 + (int)threadIdx.x < nB && s_cb[st][threadIdx.x] == ~0ull);
+    if (__syncthreads_or(fresh_local)) {
+      if (threadIdx.x < kTcN) s_colub[threadIdx.x] = 0xFFFFFFFFu;
+      __syncthreads();
+      const float nah = row_ok ? nam * kHighOverLow : INFINITY;
+      float rowub = INFINITY;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int cb = chalf * 64 + ch * 32;
+        uint32_t v[32];
+        tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
+        unsigned mine = 0xFFFFFFFFu;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float ub = fmaf(-2.0f, __uint_as_float(v[c]), s_nbm[st][cb + c] * kHighOverLow) + nah;
+          rowub = fminf(rowub, ub);
+          unsigned key = __float_as_uint(ub);
+          key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);  // order-preserving float -> uint
+          if (!(ub == ub)) key = 0xFFFFFFFFu;
+          const unsigned mn = __reduce_min_sync(0xffffffffu, key);   // min over the warp's 32 rows
+          if (lane == c) mine = mn;
+        }
+        atomicMin(&s_colub[cb + lane], mine);
+      }
+      __syncthreads();
+      if (threadIdx.x < kTcN) {
+        const unsigned key = s_colub[threadIdx.x];
+        const float colub = __uint_as_float((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key);
+        // tighten the column test: kLow nb' - 2 dot - min(best_j, UB_j) <= -kLow na'
+        if (key != 0xFFFFFFFFu) s_cj[st][threadIdx.x] = fmaxf(s_cj[st][threadIdx.x], s_nbm[st][threadIdx.x] - colub);
+      }
+      if (rbest == ~0ull && row_ok) Ri = fminf(Ri, rowub - nam);
+      __syncthreads();
+    }
     const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + st * kBBytes + 2 * kTcTileBytes);  // exact image
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
