@@ -33,7 +33,7 @@ constexpr int kTcKB = kDescK / 8;                 // K blocks of 8 (TF32 MMA K)
 constexpr int kTcTileBytes = kDescK * 128 * 4;    // one operand image (128 points x 40 dims) = 20480 B
 constexpr int kTileFloats = kDescK * 128;         // 5120
 constexpr int kTcImages = 3;                      // hi | lo | exact
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 512;                   // 16 warps: TMEM lane quadrant = warp & 3, column quarter = warp >> 2
 constexpr int kTcStages = 3;                      // B ring (prefetch distance 2)
 constexpr float kTcC = 6.0e-5f;                   // |d~ - d| <= kTcC/2 * (|a'|^2 + |b'|^2)
 constexpr int kSpinLimit = 400000;
@@ -219,8 +219,8 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   load_cols(0, tile_of(0));
   if (n_tiles > 1) load_cols(1, tile_of(1));
 
-  // this thread's accumulator row (TMEM lane) and column half; its exact source descriptor lives in registers
-  const int quad = warp & 3, chalf = warp >> 2;
+  // this thread's accumulator row (TMEM lane) and column quarter; its exact source descriptor lives in registers
+  const int quad = warp & 3, cq = warp >> 2;
   const int row = quad * 32 + lane, gi = r0 + row;
   const bool row_ok = gi < nA;
   float ax[kDescDim + 3];
@@ -255,9 +255,8 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       __syncthreads();
       const float nah = row_ok ? nam * kHighOverLow : INFINITY;
       float rowub = INFINITY;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int cb = chalf * 64 + ch * 32;
+      {
+        const int cb = cq * 32;
         uint32_t v[32];
         tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
         unsigned mine = 0xFFFFFFFFu;
@@ -284,9 +283,8 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       __syncthreads();
     }
     const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + st * kBBytes + 2 * kTcTileBytes);  // exact image
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int cb = chalf * 64 + ch * 32;
+    {
+      const int cb = cq * 32;
       uint32_t v[32];
       tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
       uint32_t mask = 0;  // branch-free candidate mask of this lane's row over the 32 columns
@@ -382,11 +380,16 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     if (threadIdx.x == 0) fallback[pair] = 1;
   } else {
     unsigned long long* s_rowmerge = reinterpret_cast<unsigned long long*>(smem);  // the operand images are dead now
-    if (chalf == 1) s_rowmerge[row] = rbest;
+    if (cq > 0) s_rowmerge[(cq - 1) * kTcM + row] = rbest;
     __syncthreads();
-    if (chalf == 0 && row_ok) {
-      const unsigned long long o = s_rowmerge[row];
-      rowbest[(size_t)pair * V + gi] = rbest < o ? rbest : o;
+    if (cq == 0 && row_ok) {
+      unsigned long long best = rbest;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const unsigned long long o = s_rowmerge[t * kTcM + row];
+        best = o < best ? o : best;
+      }
+      rowbest[(size_t)pair * V + gi] = best;
     }
   }
   __syncthreads();
