@@ -246,10 +246,10 @@ int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {
   h->cfg = cfg; h->device = cfg.device;
   h->S = cfg.max_batch_slots; h->R = cfg.max_raw_points; h->V = cfg.max_voxel_points; h->Lc = cfg.max_corr;
   h->W = h->Lc / 32; h->NS = h->V / kMatchTile;
-  // K6 implementation switch: the exact CUDA-core kernel is the default; QB200_MATCH_TC=1 selects the tcgen05 filter +
-  // exact re-rank (identical results; see DESIGN.md section 5 for the measured trade-off)
-  const char* fe = getenv("QB200_MATCH_TC");
-  h->force_exact_match = (fe && fe[0] == '1') ? 0 : 1;
+  // K6 implementation switch: the tcgen05 filter + in-kernel exact evaluation is the default; QB200_MATCH_EXACT=1 forces
+  // the exact CUDA-core kernel everywhere (identical results; A/B and triage)
+  const char* fe = getenv("QB200_MATCH_EXACT");
+  h->force_exact_match = (fe && fe[0] == '1') ? 1 : 0;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return QB200_ERR_CUDA; }
   h->stream = h->own_stream;
   const int rc = alloc_all(h);

@@ -46,7 +46,7 @@ struct qb200_handle {
   int* cand_n;                // [S]
   int* tc_fallback;           // [S] 1 = candidate queue overflowed: pair re-done by the exact fp32 kernel
   int qcap;
-  int force_exact_match;      // 1 (default): exact CUDA-core K6; 0 (QB200_MATCH_TC=1): tcgen05 filter + exact re-rank
+  int force_exact_match;      // 0 (default): tcgen05 filter + exact evaluation; 1 (QB200_MATCH_EXACT=1): exact CUDA-core K6 only
   // ---- matching ----
   unsigned long long* rowbest;// [S*V] packed (dist bits << 32 | tgt idx) per source point
   unsigned long long* colpart;// [S*NS*V] per-stripe partial column minima

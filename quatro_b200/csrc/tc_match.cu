@@ -1,4 +1,4 @@
-// tc_match.cu -- K6 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.   Opt-in: QB200_MATCH_TC=1.
+// tc_match.cu -- K6 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.   (QB200_MATCH_EXACT=1 bypasses it.)
 //
 // The N_src x N_tgt x 33 descriptor-distance matrix is the one genuinely dense contraction of the path
 // (north_star): d(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j.  The reference does two exact 1-NN searches (FLANN kd-trees,

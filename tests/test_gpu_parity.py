@@ -165,9 +165,9 @@ def test_tc_filter_error_bound(handle):
     assert worst < 2.5e-5, worst
 
 
-def test_match_tensor_core_path(oracle, scan_pair):
-    """QB200_MATCH_TC=1 selects the tcgen05 filter + exact re-rank for K6.  It must give the oracle's answer on real
-    descriptors, and on thousands of identical descriptors (candidate queue overflows -> exact-kernel fallback)."""
+def test_match_exact_kernel_and_tie_fallback(oracle, scan_pair):
+    """Default K6 = tcgen05 filter + in-kernel exact evaluation; thousands of identical descriptors make its stripes abort
+    to the exact CUDA-core kernel.  QB200_MATCH_EXACT=1 forces the exact kernel everywhere.  All must equal the oracle."""
     import os
     from quatro_b200.capi import Handle
     rng = np.random.default_rng(4)
@@ -180,7 +180,7 @@ def test_match_tensor_core_path(oracle, scan_pair):
     with Handle(max_batch_slots=2) as h:
         got = h.match(a, ad, b, bd, p)
         assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
-    os.environ["QB200_MATCH_TC"] = "1"
+    os.environ["QB200_MATCH_EXACT"] = "1"
     try:
         with Handle(max_batch_slots=2) as h:
             got = h.match(a, ad, b, bd, p)
@@ -190,7 +190,7 @@ def test_match_tensor_core_path(oracle, scan_pair):
             r_got, _ = h.register_pair(src, tgt, default_params())
             assert (r_got.n_mutual, r_got.n_corr, r_got.clique_size) == (r_ref.n_mutual, r_ref.n_corr, r_ref.clique_size)
     finally:
-        del os.environ["QB200_MATCH_TC"]
+        del os.environ["QB200_MATCH_EXACT"]
 
 
 def test_match_and_pack(handle, oracle, small_pair):
