@@ -13,7 +13,7 @@ pairs on 1 GPU; 8 ranks x 256 = configs[3]'s 2048 pairs).  Pairs are independent
           qb200_register_batch), CUDA events on the launching stream, max over ranks.
   e2e   : the same call with pinned HOST buffers -- H2D of every scan and D2H of the result records are
           inside the timed region.
-  roofline      : the dominant kernel (match_stripe_kernel, the N_src x N_tgt x 33 contraction) from CUDA events
+  roofline      : the dominant kernel (tc_nn_kernel, the N_src x N_tgt x 33 contraction on tcgen05) from CUDA events
                   recorded around it inside the timed steps.
   cpu_baseline  : the CPU oracle (restatement of the reference path; the reference binary itself cannot be
                   built here) timed on this box's host cores on a bounded sample of the same pairs.
@@ -38,6 +38,32 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "registrations/sec (64-ring pair)"
 UNIT = "registrations/s"
+
+
+def _host_threads() -> int:
+    """Threads for the CPU arm: usable cores (affinity, cgroup quota), one per physical core (SMT siblings only
+    oversubscribe the OpenMP loops)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            n = min(n, max(1, int(quota) // int(period)))
+    except (OSError, ValueError):
+        pass
+    try:
+        sib = Path("/sys/devices/system/cpu/cpu0/topology/thread_siblings_list").read_text().strip()
+        smt = len(sib.replace("-", ",").split(",")) if sib else 1
+        if "-" in sib:
+            a, b = sib.split("-")[:2]
+            smt = int(b) - int(a) + 1
+        if smt > 1 and n >= (os.cpu_count() or n):
+            n = max(1, n // smt)
+    except (OSError, ValueError):
+        pass
+    return n
 
 
 def load_peaks():
@@ -105,7 +131,7 @@ def run_reference(args, rank, world):
     from oracle import Oracle
     from quatro_b200.capi import default_params
     o = Oracle()
-    cores = o.set_num_threads(0)
+    cores = o.set_num_threads(_host_threads())   # torchrun exports OMP_NUM_THREADS=1: ask for every usable host core explicitly
     p = default_params()
     per_step = args.ref_pairs_per_step
     pairs = gen_pairs(range(per_step))
@@ -264,7 +290,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import Oracle
             o = Oracle()
-            cores = o.set_num_threads(0)
+            cores = o.set_num_threads(_host_threads())
             o.register_pair(pairs[0][0], pairs[0][1], p)  # warm-up
             t0 = time.perf_counter(); n = 0
             checked = 0

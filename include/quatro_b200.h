@@ -212,6 +212,12 @@ int qb200_get_kernel_ms(qb200_handle* h, float* ms, int32_t* launches, int32_t n
  * never depend on these values (exact fp32 re-rank); tests use this to measure the filter's error margin. */
 int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, const float* b33, int32_t nb, float* out);
 
+
+/* Diagnostics: cumulative counters of the tensor-core matcher since creation / the last reset:
+ * out4[0] = descriptor pairs that went through the exact fp32 chain, [1] = 128 x 128 tiles drained,
+ * [2] = warm-up passes, [3] = stripes handed to the exact kernel.  Synchronises the handle's stream. */
+int qb200_debug_match_stats(qb200_handle* h, uint64_t* out4, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

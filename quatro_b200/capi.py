@@ -124,6 +124,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_get_stage_ms": (i32, [vp, vp, i32]),
         "qb200_get_kernel_ms": (i32, [vp, vp, vp, i32]),
         "qb200_debug_tc_distances": (i32, [vp, vp, i32, vp, i32, vp]),
+        "qb200_debug_match_stats": (i32, [vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
@@ -140,6 +141,7 @@ EXPORTED_SYMBOLS = [
     "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
+    "qb200_debug_match_stats",
 ]
 
 
@@ -337,6 +339,11 @@ class Handle:
         self._check(self.lib.qb200_get_last_correspondences(self.h, _ptr(corr), _ptr(sm), _ptr(tm), cap, C.byref(n)),
                     "qb200_get_last_correspondences")
         return corr[: n.value].copy(), sm[: n.value].copy(), tm[: n.value].copy()
+
+    def debug_match_stats(self, reset: bool = True) -> dict:
+        out = np.zeros(4, np.uint64)
+        self._check(self.lib.qb200_debug_match_stats(self.h, _ptr(out), int(reset)), "qb200_debug_match_stats")
+        return {"exact_evals": int(out[0]), "tiles": int(out[1]), "warmups": int(out[2]), "aborted_stripes": int(out[3])}
 
     def debug_tc_distances(self, a33, b33) -> np.ndarray:
         a33, b33 = _f32(a33, 33), _f32(b33, 33)

@@ -48,6 +48,12 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_cloud_n, C * sizeof(int)));
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_raw_off, (C + 1) * sizeof(int)));
   QB_ALLOC(h, h->raw_stage, C * R);
+  QB_ALLOC(h, h->raw_stage2, C * R);
+  QB_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_rawfree[i], cudaEventDisableTiming));
+  }
   QB_ALLOC(h, h->key_a, C * R);
   QB_ALLOC(h, h->key_b, C * R);
   QB_ALLOC(h, h->val_a, C * R);
@@ -65,12 +71,9 @@ int alloc_all(qb200_handle* h) {
   QB_ALLOC(h, h->desc_tiles, C * kDescK * V * 3);
   QB_CUDA_TRY(h, cudaMemset(h->desc_tiles, 0, C * kDescK * V * 3 * sizeof(float)));
   QB_ALLOC(h, h->desc_norm, C * V);
-  QB_ALLOC(h, h->norm_max, C);
-  QB_ALLOC(h, h->approx_min, C * V);
-  h->qcap = 32 * (int)V;
-  QB_ALLOC(h, h->cand_q, S * (size_t)h->qcap);
-  QB_ALLOC(h, h->cand_n, S);
   QB_ALLOC(h, h->tc_fallback, S);
+  QB_ALLOC(h, h->tc_stats, 4);
+  QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 4 * sizeof(unsigned long long)));
   QB_ALLOC(h, h->rowbest, S * V);
   QB_ALLOC(h, h->colpart, S * h->NS * V);
   QB_ALLOC(h, h->colbest, S * V);
@@ -267,9 +270,9 @@ void qb200_destroy(qb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
+  void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->raw_stage2, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->desc_t, h->rowbest, h->colpart, h->colbest,
-                      h->desc_tiles, h->desc_norm, h->norm_max, h->approx_min, h->cand_q, h->cand_n, h->tc_fallback,
+                      h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
                       h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
                       h->ctr_block};
@@ -283,6 +286,11 @@ void qb200_destroy(qb200_handle* h) {
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 4; ++i)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_rawfree[i]) cudaEventDestroy(h->ev_rawfree[i]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -526,12 +534,43 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
   for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
   const float cell = lattice_cell(*p);
-  for (int w0 = 0; w0 < n_pairs; w0 += h->S) {
+  // Host inputs: the H2D copy of wave w+1 is issued on a second stream into the other staging buffer before wave w is
+  // computed, so PCIe transfers hide behind the kernels (the buffer is recycled once the voxel stage that read it is done).
+  auto stage_wave = [&](int w0, int buf) -> int {  // enqueue the H2D copies of the wave starting at pair w0
+    const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
+    float4* base = buf ? h->raw_stage2 : h->raw_stage;
+    QB_CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_rawfree[buf], 0));
+    size_t total = 0;
+    for (int s = 0; s < np; ++s) {
+      const qb200_pair& pr = pairs[w0 + s];
+      if (pr.n_src > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(base + total, pr.src, (size_t)pr.n_src * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
+      total += pr.n_src;
+      if (pr.n_tgt > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(base + total, pr.tgt, (size_t)pr.n_tgt * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
+      total += pr.n_tgt;
+    }
+    QB_CUDA_TRY(h, cudaEventRecord(h->ev_copied[buf], h->copy_stream));
+    return QB200_OK;
+  };
+  if (kind == QB200_MEM_HOST) {
+    // both staging buffers are free: every earlier batch was synchronised before it returned
+    QB_CUDA_TRY(h, cudaEventRecord(h->ev_rawfree[0], h->stream));
+    QB_CUDA_TRY(h, cudaEventRecord(h->ev_rawfree[1], h->stream));
+    const int rc0 = stage_wave(0, 0);
+    if (rc0) return rc0;
+  }
+  int wave = 0;
+  for (int w0 = 0; w0 < n_pairs; w0 += h->S, ++wave) {
     const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
     const int ncl = 2 * np;
+    const int buf = wave & 1;
     int rc;
     cudaEventRecord(h->ev[0], h->stream);
+    if (kind == QB200_MEM_HOST) {
+      if (w0 + h->S < n_pairs && (rc = stage_wave(w0 + h->S, buf ^ 1))) return rc;  // prefetch the next wave
+      QB_CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[buf], 0));
+    }
     int total = 0;
+    const float4* base = buf ? h->raw_stage2 : h->raw_stage;
     for (int s = 0; s < np; ++s) {
       const qb200_pair& pr = pairs[w0 + s];
       const float* ptr[2] = {pr.src, pr.tgt};
@@ -540,13 +579,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
         const int cloud = 2 * s + k;
         h->h_raw_off[cloud] = total;
         h->h_cloud_n[cloud] = cnt[k];
-        if (kind == QB200_MEM_HOST) {
-          float4* dst = h->raw_stage + (size_t)total;
-          if (cnt[k] > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(dst, ptr[k], (size_t)cnt[k] * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-          h->h_cloud_ptr[cloud] = dst;
-        } else {
-          h->h_cloud_ptr[cloud] = reinterpret_cast<const float4*>(ptr[k]);
-        }
+        h->h_cloud_ptr[cloud] = kind == QB200_MEM_HOST ? base + total : reinterpret_cast<const float4*>(ptr[k]);
         total += cnt[k];
       }
     }
@@ -557,6 +590,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
     if ((rc = wave_reset(h, ncl))) return rc;
     cudaEventRecord(h->ev[1], h->stream);
     if ((rc = launch_voxel(h, ncl, total, p->voxel_size, p->skip_flagged))) return rc;
+    if (kind == QB200_MEM_HOST) QB_CUDA_TRY(h, cudaEventRecord(h->ev_rawfree[buf], h->stream));  // raw scans are dead after K1
     cudaEventRecord(h->ev[2], h->stream);
     if ((rc = launch_fpfh(h, ncl, p->normal_radius, p->fpfh_radius, cell))) return rc;
     cudaEventRecord(h->ev[3], h->stream);
@@ -583,6 +617,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
     }
     // the wave's own reads of h_cloud_* / h_raw_off are complete after the synchronize above
   }
+  if (kind == QB200_MEM_HOST) QB_CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
   if (n_pairs == 1) {
     h->last_n_corr = results[0].n_corr;
     h->last_n_clique = results[0].clique_size;
@@ -641,6 +676,15 @@ int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_ma
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n) {
   if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->stage_ms[i];
+  return QB200_OK;
+}
+
+int qb200_debug_match_stats(qb200_handle* h, uint64_t* out4, int32_t reset) {
+  if (!h || !out4) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  QB_CUDA_TRY(h, cudaMemcpy(out4, h->tc_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 4 * sizeof(unsigned long long)));
   return QB200_OK;
 }
 

@@ -20,9 +20,10 @@ struct qb200_handle {
   int* d_cloud_n;             // [2S]
   int* d_raw_off;             // [2S+1] offsets into the concatenated sort arrays
   const float4** h_cloud_ptr; int* h_cloud_n; int* h_raw_off;  // pinned mirrors
-  float4* raw_stage;          // [2S*R] staging for host inputs
-  float4* h_stage;            // pinned host staging [2S*R] (allocated on first host-batch call)
-  size_t h_stage_elems;
+  float4* raw_stage;          // [2S*R] staging for host inputs (wave w uses buffer w & 1)
+  float4* raw_stage2;         // second staging buffer: H2D of wave w+1 overlaps the compute of wave w
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copied[2], ev_rawfree[2];
 
   // ---- sort workspace (voxel sort, then lattice sort) ----
   uint64_t *key_a, *key_b;    // [2S*R]
@@ -40,12 +41,8 @@ struct qb200_handle {
   float* desc_tiles;          // [2S*(V/128)*3*5120] per 128-point block: centred TF32 hi | lo | exact fp32 images in the UMMA
                               // shared-memory operand layout (one bulk copy per tile)
   float* desc_norm;           // [2S*V] squared norms (fp32 fma chain)
-  unsigned* norm_max;         // [2S] per-cloud max squared norm (float bits)
-  float* approx_min;          // [2S*V] tensor-core approximate NN distance per point
-  unsigned* cand_q;           // [S*QCAP] candidate (src << 16 | tgt) pairs for the exact re-rank
-  int* cand_n;                // [S]
-  int* tc_fallback;           // [S] 1 = candidate queue overflowed: pair re-done by the exact fp32 kernel
-  int qcap;
+  int* tc_fallback;           // [S] 1 = too many exact ties for the filter to pay off: pair re-done by the exact fp32 kernel
+  unsigned long long* tc_stats; // [4] diagnostics, cumulative: exact evaluations, tiles drained, warm-up passes, aborted stripes
   int force_exact_match;      // 0 (default): tcgen05 filter + exact evaluation; 1 (QB200_MATCH_EXACT=1): exact CUDA-core K6 only
   // ---- matching ----
   unsigned long long* rowbest;// [S*V] packed (dist bits << 32 | tgt idx) per source point

@@ -33,7 +33,8 @@ constexpr int kTcKB = kDescK / 8;                 // K blocks of 8 (TF32 MMA K)
 constexpr int kTcTileBytes = kDescK * 128 * 4;    // one operand image (128 points x 40 dims) = 20480 B
 constexpr int kTileFloats = kDescK * 128;         // 5120
 constexpr int kTcImages = 3;                      // hi | lo | exact
-constexpr int kTcThreads = 512;                   // 16 warps: TMEM lane quadrant = warp & 3, column quarter = warp >> 2
+constexpr int kTcEpiWarps = 16;                   // filter / evaluation warps: TMEM lane quadrant = warp & 3, column quarter = warp >> 2
+constexpr int kTcThreads = (kTcEpiWarps + 1) * 32;  // + 1 copy / MMA warp
 constexpr int kTcStages = 3;                      // B ring (prefetch distance 2)
 constexpr float kTcC = 6.0e-5f;                   // |d~ - d| <= kTcC/2 * (|a'|^2 + |b'|^2)
 constexpr int kSpinLimit = 400000;
@@ -103,8 +104,10 @@ __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict
     }
     img[0 * (kTileFloats / 4) + kc * 128] = make_float4(hv[0], hv[1], hv[2], hv[3]);
     img[1 * (kTileFloats / 4) + kc * 128] = make_float4(lv[0], lv[1], lv[2], lv[3]);
-    img[2 * (kTileFloats / 4) + kc * 128] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    if (kc < kDescK / 4 - 1) img[2 * (kTileFloats / 4) + kc * 128] = make_float4(xv[0], xv[1], xv[2], xv[3]);
   }
+  // the exact image has no data in dims 36..39: slot 36 carries the column's filter term kLow |x'|^2 (+inf = padding)
+  img[2 * (kTileFloats / 4) + (kDescK / 4 - 1) * 128] = make_float4(q < n ? (1.0f - 0.5f * kTcC) * acc : INFINITY, 0.0f, 0.0f, 0.0f);
   if (q < n) norm[(size_t)cloud * V + q] = acc;
 }
 
@@ -140,19 +143,38 @@ __device__ __forceinline__ unsigned long long tc_pack(float d, int idx) {
   return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned tc_fkey(float f) {  // order-preserving float -> uint, NaN last
+  unsigned key = __float_as_uint(f);
+  key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+  return f == f ? key : 0xFFFFFFFFu;
+}
+__device__ __forceinline__ float tc_fkey_inv(unsigned key) { return __uint_as_float((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key); }
+
 // rows = source cloud (2*pair), columns = target cloud (2*pair+1).  dbg_tile != nullptr: additionally dump d~ of the
 // first tile of stripe 0 (validation hook).
+//
+// Warp roles (no CTA-wide barrier inside the tile loop, everything is handed over through mbarriers):
+//   warp 16      : one elected lane issues the bulk copies (3-stage ring, prefetch distance 2) and the 15 MMAs per tile
+//   warps 0..15  : warp w owns TMEM lanes 32 (w & 3) .. +31 (rows) and columns 32 (w >> 2) .. +31 of every tile:
+//                  tcgen05.ld -> release the TMEM stage -> branch-free filter -> the warp's survivors are compacted
+//                  into batches of 32 and evaluated exactly, ONE CANDIDATE PER LANE (the source descriptor of another
+//                  lane's row comes over warp shuffles, the target descriptor from the exact image in shared memory)
+//                  -> release the ring stage.
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, const int* __restrict__ n_vox, int V,
              unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest, int* __restrict__ fallback,
-             float* __restrict__ dbg_tile) {
+             unsigned long long* __restrict__ stats, float* __restrict__ dbg_tile) {
   extern __shared__ __align__(128) unsigned char smem[];  // 220 KB of operand images; static + dynamic must stay <= 227 KB
-  __shared__ uint64_t s_full[kTcStages], s_mma[2], s_afull;
+  __shared__ uint64_t s_fullx[kTcStages], s_sfree[kTcStages], s_fullhl[2], s_mma[2], s_tfree[2], s_afull;
   __shared__ uint32_t s_tmem;
-  __shared__ float s_nbm[kTcStages][kTcN], s_cj[kTcStages][kTcN];
-  __shared__ unsigned long long s_cb[kTcStages][kTcN];
-  __shared__ unsigned s_colub[kTcN];  // warm-up: per-column upper bound (ordered-uint keys) of a fresh tile
-  __shared__ int s_dead, s_evals;
+  __shared__ unsigned long long s_rbest[kTcM];                 // best exact (distance | target index) per row of the stripe
+  __shared__ __align__(16) float s_wnbm[kTcEpiWarps][32];      // per warp: kLow |b'_j|^2 of its 32 columns
+  __shared__ __align__(16) float s_wcj[kTcEpiWarps][32];       //           kLow |b'_j|^2 - (best exact distance of column j)
+  __shared__ unsigned short s_queue[kTcEpiWarps][32];          //           one batch of candidates (row lane << 5 | column)
+  __shared__ int s_dead, s_abort, s_evals, s_warm;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
   const int cloudA = 2 * pair, cloudB = 2 * pair + 1;
@@ -162,15 +184,17 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NB = V >> 7;
-  constexpr uint32_t kABytes = 2 * kTcTileBytes;          // hi + lo of the A block
-  constexpr uint32_t kBBytes = kTcImages * kTcTileBytes;  // hi + lo + exact of a B block
-  const uint32_t sA = smem_u32(smem), sB0 = sA + kABytes;
+  // shared-memory map: A block (hi | lo | exact) | 2 stages of B (hi | lo) | 3 stages of B exact images.  The operand images
+  // are dead as soon as the MMAs of their tile completed, the exact image only when every warp evaluated the tile.
+  constexpr uint32_t kABytes = kTcImages * kTcTileBytes;
+  constexpr uint32_t kHLBytes = 2 * kTcTileBytes;
+  constexpr uint32_t kXBytes = kTcTileBytes;
+  const uint32_t sA = smem_u32(smem), sHL0 = sA + kABytes, sX0 = sHL0 + 2 * kHLBytes;
   const float* __restrict__ tA = tiles + (size_t)cloudA * NB * kTcImages * kTileFloats;
   const float* __restrict__ tB = tiles + (size_t)cloudB * NB * kTcImages * kTileFloats;
-  const float* __restrict__ nA_ = norm + (size_t)cloudA * V;
-  const float* __restrict__ nB_ = norm + (size_t)cloudB * V;
   unsigned long long* __restrict__ cbg = colbest + (size_t)pair * V;
-  const uint32_t bar_full0 = smem_u32(&s_full[0]), bar_mma0 = smem_u32(&s_mma[0]), bar_a = smem_u32(&s_afull);
+  const uint32_t bar_fullx0 = smem_u32(&s_fullx[0]), bar_sfree0 = smem_u32(&s_sfree[0]), bar_fullhl0 = smem_u32(&s_fullhl[0]),
+                 bar_mma0 = smem_u32(&s_mma[0]), bar_tfree0 = smem_u32(&s_tfree[0]), bar_a = smem_u32(&s_afull);
 
   const int n_tiles = (nB + kTcN - 1) / kTcN;
   const int first = stripe % n_tiles;  // staggered start: concurrent stripes of a pair work on different column tiles
@@ -181,223 +205,228 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kTcStages; ++i) mbar_init(bar_full0 + 8 * i, 1);
-    mbar_init(bar_mma0, 1); mbar_init(bar_mma0 + 8, 1); mbar_init(bar_a, 1);
-    s_dead = 0; s_evals = 0;
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(bar_fullx0 + 8 * i, 1); mbar_init(bar_sfree0 + 8 * i, kTcEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_fullhl0 + 8 * i, 1); mbar_init(bar_mma0 + 8 * i, 1); mbar_init(bar_tfree0 + 8 * i, kTcEpiWarps); }
+    mbar_init(bar_a, 1);
+    s_dead = 0; s_abort = 0; s_evals = 0; s_warm = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  if (threadIdx.x < kTcM) s_rbest[threadIdx.x] = ~0ull;
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
+  volatile int* v_dead = &s_dead;
+  volatile int* v_abort = &s_abort;
 
-  const float kLow = 1.0f - 0.5f * kTcC;  // d~ - e_ij = kLow (na' + nb') - 2 dot
-  auto load_cols = [&](int st, int jt) {  // per-column filter data of tile jt into ring stage st
-    if (threadIdx.x < kTcN) {
-      const int j = jt * kTcN + threadIdx.x;
-      float nbm = INFINITY, cj = INFINITY;  // padded columns never qualify
-      unsigned long long cb = ~0ull;
-      if (j < nB) {
-        nbm = kLow * nB_[j];
-        cb = cbg[j];  // snapshot of the best exact (distance | source index) known for this column
-        const float dbest = cb == ~0ull ? INFINITY : __uint_as_float((unsigned)(cb >> 32));
-        cj = nbm - dbest;
-      }
-      s_nbm[st][threadIdx.x] = nbm; s_cj[st][threadIdx.x] = cj; s_cb[st][threadIdx.x] = cb;
+  if (warp == kTcEpiWarps) {
+    // ================= copy / MMA warp =================
+    // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+    auto issue_hl = [&](int k) {  // operand images (hi | lo, 40 KB) of tile k -> stage k & 1
+      const uint32_t bar = bar_fullhl0 + 8 * (k & 1);
+      mbar_expect_tx(bar, kHLBytes);
+      bulk_g2s(sHL0 + (k & 1) * kHLBytes, tB + (size_t)tile_of(k) * kTcImages * kTileFloats, kHLBytes, bar);
+    };
+    auto issue_x = [&](int k) {  // exact image (20 KB) of tile k -> stage k % 3
+      const uint32_t bar = bar_fullx0 + 8 * (k % kTcStages);
+      mbar_expect_tx(bar, kXBytes);
+      bulk_g2s(sX0 + (k % kTcStages) * kXBytes, tB + ((size_t)tile_of(k) * kTcImages + 2) * kTileFloats, kXBytes, bar);
+    };
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, kABytes);
+      bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
+      issue_hl(0); issue_x(0);
+      if (n_tiles > 1) { issue_hl(1); issue_x(1); }
     }
-  };
-  auto issue_tile = [&](int st, int jt) {  // one thread: 60 KB bulk copy of block jt of cloud B into ring stage st
-    mbar_expect_tx(bar_full0 + 8 * st, kBBytes);
-    bulk_g2s(sB0 + st * kBBytes, tB + (size_t)jt * kTcImages * kTileFloats, kBBytes, bar_full0 + 8 * st);
-  };
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar_a, kABytes);
-    bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
-    issue_tile(0, tile_of(0));
-    if (n_tiles > 1) issue_tile(1, tile_of(1));
-  }
-  load_cols(0, tile_of(0));
-  if (n_tiles > 1) load_cols(1, tile_of(1));
-
-  // this thread's accumulator row (TMEM lane) and column quarter; its exact source descriptor lives in registers
-  const int quad = warp & 3, cq = warp >> 2;
-  const int row = quad * 32 + lane, gi = r0 + row;
-  const bool row_ok = gi < nA;
-  float ax[kDescDim + 3];
-  {
-    const float4* __restrict__ src = reinterpret_cast<const float4*>(tA + ((size_t)stripe * kTcImages + 2) * kTileFloats) + row;
-#pragma unroll
-    for (int kc = 0; kc < (kDescDim + 3) / 4; ++kc) {
-      const float4 t = __ldg(src + kc * 128);
-      ax[4 * kc] = t.x; ax[4 * kc + 1] = t.y; ax[4 * kc + 2] = t.z; ax[4 * kc + 3] = t.w;
-    }
-  }
-  const float nam = row_ok ? kLow * nA_[gi] : 0.0f;
-  const float negna = row_ok ? -nam : -INFINITY;   // column test:  kLow nb' - 2 dot - cbest_j <= -kLow na'
-  unsigned long long rbest = ~0ull;
-  float Ri = row_ok ? INFINITY : -INFINITY;        // row test:     kLow nb' - 2 dot <= best_i - kLow na'
-  int my_evals = 0;
-  // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-  __syncthreads();  // column data of the first two tiles visible
-
-  const float kHighOverLow = (1.0f + 0.5f * kTcC) / kLow;  // (1 + c/2) nb' from the stored kLow nb'
-  auto epilogue = [&](int k) {  // drain TMEM stage k&1 (tile tile_of(k), ring stage k%3)
-    const int ts = k & 1, st = k % kTcStages, jt = tile_of(k);
-    if (!mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1))) s_dead = 1;
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int c0 = jt * kTcN;
-    // ---- warm-up on fresh tiles: with no exact bound yet every entry would qualify.  Upper bounds of the exact row /
-    // column minima come from the tile itself: UB_ij = d~_ij + e_ij = (1+c/2)(na'+nb') - 2 dot >= d_ij.
-    const int fresh_local = (k == 0) || (threadIdx.x < kTcN && c0 + (int)threadIdx.x < nB && s_cb[st][threadIdx.x] == ~0ull);
-    if (__syncthreads_or(fresh_local)) {
-      if (threadIdx.x < kTcN) s_colub[threadIdx.x] = 0xFFFFFFFFu;
-      __syncthreads();
-      const float nah = row_ok ? nam * kHighOverLow : INFINITY;
-      float rowub = INFINITY;
-      {
-        const int cb = cq * 32;
-        uint32_t v[32];
-        tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
-        unsigned mine = 0xFFFFFFFFu;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float ub = fmaf(-2.0f, __uint_as_float(v[c]), s_nbm[st][cb + c] * kHighOverLow) + nah;
-          rowub = fminf(rowub, ub);
-          unsigned key = __float_as_uint(ub);
-          key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);  // order-preserving float -> uint
-          if (!(ub == ub)) key = 0xFFFFFFFFu;
-          const unsigned mn = __reduce_min_sync(0xffffffffu, key);   // min over the warp's 32 rows
-          if (lane == c) mine = mn;
-        }
-        atomicMin(&s_colub[cb + lane], mine);
-      }
-      __syncthreads();
-      if (threadIdx.x < kTcN) {
-        const unsigned key = s_colub[threadIdx.x];
-        const float colub = __uint_as_float((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key);
-        // tighten the column test: kLow nb' - 2 dot - min(best_j, UB_j) <= -kLow na'
-        if (key != 0xFFFFFFFFu) s_cj[st][threadIdx.x] = fmaxf(s_cj[st][threadIdx.x], s_nbm[st][threadIdx.x] - colub);
-      }
-      if (rbest == ~0ull && row_ok) Ri = fminf(Ri, rowub - nam);
-      __syncthreads();
-    }
-    const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + st * kBBytes + 2 * kTcTileBytes);  // exact image
-    {
-      const int cb = cq * 32;
-      uint32_t v[32];
-      tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
-      uint32_t mask = 0;  // branch-free candidate mask of this lane's row over the 32 columns
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float dot = __uint_as_float(v[c]);
-        const float t = fmaf(-2.0f, dot, s_nbm[st][cb + c]);
-        const float u = fmaf(-2.0f, dot, s_cj[st][cb + c]);
-        mask |= ((t <= Ri) || (u <= negna) ? 1u : 0u) << c;
-        if (dbg_tile != nullptr && stripe == 0 && k == 0) dbg_tile[(size_t)row * kTcN + cb + c] = (nam + s_nbm[st][cb + c]) / kLow - 2.0f * dot;
-      }
-      while (mask) {  // exact fp32 chain for the survivors (thresholds are re-checked: they tighten as we go)
-        const int c = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float dot = __uint_as_float(v[c]);
-        if (!((fmaf(-2.0f, dot, s_nbm[st][cb + c]) <= Ri) || (fmaf(-2.0f, dot, s_cj[st][cb + c]) <= negna))) continue;
-        const int pcol = cb + c;
-        float acc = 0.0f;
-#pragma unroll
-        for (int kc = 0; kc < (kDescDim + 3) / 4; ++kc) {
-          const float4 b = bex[kc * 128 + pcol];
-          float diff = ax[4 * kc] - b.x;
-          acc = __fmaf_rn(diff, diff, acc);
-          if (4 * kc + 1 < kDescDim) { diff = ax[4 * kc + 1] - b.y; acc = __fmaf_rn(diff, diff, acc); }
-          if (4 * kc + 2 < kDescDim) { diff = ax[4 * kc + 2] - b.z; acc = __fmaf_rn(diff, diff, acc); }
-          if (4 * kc + 3 < kDescDim) { diff = ax[4 * kc + 3] - b.w; acc = __fmaf_rn(diff, diff, acc); }
-        }
-        ++my_evals;
-        if (acc == acc) {  // NaN never wins
-          const int j = c0 + pcol;
-          const unsigned long long pr = tc_pack(acc, j);
-          if (pr < rbest) { rbest = pr; Ri = acc - nam; }
-          const unsigned long long pc = tc_pack(acc, gi);
-          if (pc < s_cb[st][pcol]) atomicMin(cbg + j, pc);
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-  };
-
-  bool aborted = false;
-  int k = 0;
-  for (; k < n_tiles; ++k) {
-    const int ts = k & 1, st = k % kTcStages;
-    if (threadIdx.x == 0) {
-      bool ok = true;
-      if (k == 0) ok = mbar_wait(bar_a, 0);
-      ok = ok && mbar_wait(bar_full0 + 8 * st, (uint32_t)((k / kTcStages) & 1));
-      if (!ok) s_dead = 1;
+    bool ok = mbar_wait(bar_a, 0);
+    for (int k = 0; k < n_tiles && ok; ++k) {
+      const int ts = k & 1;
+      ok = mbar_wait(bar_fullhl0 + 8 * ts, (uint32_t)((k >> 1) & 1));
+      if (ok && k >= 2) ok = mbar_wait(bar_tfree0 + 8 * ts, (uint32_t)(((k >> 1) - 1) & 1));  // TMEM stage drained (tile k-2)
+      if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sB0 + st * kBBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
-      uint32_t acc = 0;
+      if (lane == 0) {
+        const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sHL0 + ts * kHLBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
+        uint32_t acc = 0;
 #pragma unroll
-      for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
-        tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bL + kb * 4096), idesc, acc);
-        acc = 1;
-        tc_mma_tf32(d, tc_smem_desc(aL + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
+        for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
+          tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bL + kb * 4096), idesc, acc);
+          acc = 1;
+          tc_mma_tf32(d, tc_smem_desc(aL + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
+        }
+#pragma unroll
+        for (int kb = 0; kb < kTcKB; ++kb) tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * ts) : "memory");
       }
-#pragma unroll
-      for (int kb = 0; kb < kTcKB; ++kb) tc_mma_tf32(d, tc_smem_desc(aH + kb * 4096), tc_smem_desc(bH + kb * 4096), idesc, 1);
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * ts) : "memory");
+      __syncwarp();
+      if (k + 2 < n_tiles) {  // prefetch distance 2
+        ok = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1));  // MMAs of tile k done: its operand stage is free
+        if (ok && lane == 0) issue_hl(k + 2);
+        // the exact image of tile k+2 replaces that of tile k-1: wait until every warp evaluated tile k-1
+        if (ok && k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 2) % kTcStages), (uint32_t)(((k - 1) / kTcStages) & 1));
+        if (ok && lane == 0) issue_x(k + 2);
+      }
     }
-    __syncwarp();
-    if (k >= 1) {
-      epilogue(k - 1);  // overlaps the MMAs just issued
-      const int ws = __reduce_add_sync(0xffffffffu, my_evals);
-      my_evals = 0;
-      if (lane == 0 && ws) atomicAdd(&s_evals, ws);
-    }
-    __syncthreads();  // TMEM stage ts^1 drained; MMA k-1 complete => ring stage (k-1)%3 and its column data are free
-    if (k + 2 < n_tiles) {  // prefetch distance 2: tile k+2 goes into the stage tile k-1 just left
-      const int st2 = (k + 2) % kTcStages;
-      if (threadIdx.x == 0) issue_tile(st2, tile_of(k + 2));
-      load_cols(st2, tile_of(k + 2));  // read again only after the next barriers
-    }
-    // massive ties: once more than 1/4 of the entries seen needed the exact chain, hand the pair to the exact kernel
-    if (s_dead || (k >= 3 && s_evals > k * (kTcM * kTcN / 4))) {  // uniform: both written before the barrier above
-      aborted = true;
-      break;
-    }
-  }
-  if (!aborted) {
-    epilogue(n_tiles - 1);
-  } else if (threadIdx.x == 0) {
-    // never leave the CTA with asynchronous work in flight: MMA(k) and the prefetched tiles k+1, k+2
-    mbar_wait(bar_mma0 + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
-    if (k + 1 < n_tiles) mbar_wait(bar_full0 + 8 * ((k + 1) % kTcStages), (uint32_t)(((k + 1) / kTcStages) & 1));
-    if (k + 2 < n_tiles) mbar_wait(bar_full0 + 8 * ((k + 2) % kTcStages), (uint32_t)(((k + 2) / kTcStages) & 1));
-  }
-  __syncthreads();
-
-  if (aborted) {
-    if (threadIdx.x == 0) fallback[pair] = 1;
+    if (!ok) *v_dead = 1;
   } else {
-    unsigned long long* s_rowmerge = reinterpret_cast<unsigned long long*>(smem);  // the operand images are dead now
-    if (cq > 0) s_rowmerge[(cq - 1) * kTcM + row] = rbest;
-    __syncthreads();
-    if (cq == 0 && row_ok) {
-      unsigned long long best = rbest;
-#pragma unroll
-      for (int t = 0; t < 3; ++t) {
-        const unsigned long long o = s_rowmerge[t * kTcM + row];
-        best = o < best ? o : best;
+    // ================= filter / evaluation warps =================
+    const int quad = warp & 3, cq = warp >> 2, cb = cq * 32;
+    const int row = quad * 32 + lane, gi = r0 + row;
+    const bool row_ok = gi < nA;
+    const float4* __restrict__ aex = reinterpret_cast<const float4*>(smem + 2 * kTcTileBytes) + quad * 32;  // exact image of the A block
+    const float kLow = 1.0f - 0.5f * kTcC;                   // d~ - e_ij = kLow (na' + nb') - 2 dot
+    const float kHighOverLow = (1.0f + 0.5f * kTcC) / kLow;  // (1 + c/2) x from the stored kLow x
+    const float nam = row_ok ? kLow * norm[(size_t)cloudA * V + gi] : 0.0f;
+    const float negna = row_ok ? -nam : -INFINITY;           // column test:  kLow nb' - 2 dot - cbest_j <= -kLow na'
+    float Ri_ub = row_ok ? INFINITY : -INFINITY;             // row test:     kLow nb' - 2 dot <= best_i - kLow na'
+    float* wnbm = s_wnbm[warp];
+    float* wcj = s_wcj[warp];
+    unsigned short* wq = s_queue[warp];
+    volatile unsigned long long* v_rbest = s_rbest;
+    int evals_w = 0;
+    bool alive = mbar_wait(bar_a, 0);
+    unsigned long long cb_next = ~0ull;  // snapshot of colbest for this lane's column of the NEXT tile (hides the L2 latency)
+    {
+      const int j = tile_of(0) * kTcN + cb + lane;
+      if (j < nB) cb_next = __ldcg(cbg + j);
+    }
+    for (int k = 0; k < n_tiles; ++k) {
+      const int ts = k & 1, st = k % kTcStages, jt = tile_of(k), c0 = jt * kTcN;
+      const unsigned long long cb_cur = cb_next;
+      cb_next = ~0ull;
+      if (k + 1 < n_tiles) {
+        const int j = tile_of(k + 1) * kTcN + cb + lane;
+        if (j < nB) cb_next = __ldcg(cbg + j);
       }
-      rowbest[(size_t)pair * V + gi] = best;
+      if (alive) alive = mbar_wait(bar_fullx0 + 8 * st, (uint32_t)((k / kTcStages) & 1));  // the exact image is read below
+      if (alive) alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1));
+      if (!alive) *v_dead = 1;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const bool skip = __any_sync(0xffffffffu, (*v_abort | *v_dead) != 0);
+      uint32_t v[32];
+      if (!skip) tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tfree0 + 8 * ts);  // accumulators are in registers: the MMA of tile k+2 may overwrite them
+      if (!skip) {
+        const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + 2 * kHLBytes + st * kXBytes);  // exact image
+        // ---- per-column filter data of this warp's 32 columns (lane = column)
+        const float nbm = bex[9 * 128 + cb + lane].x;  // kLow |b'_j|^2, +inf for padded columns (split_desc_kernel)
+        const float dbest = cb_cur == ~0ull ? INFINITY : __uint_as_float((unsigned)(cb_cur >> 32));
+        float cj = nbm == INFINITY ? INFINITY : nbm - dbest;  // -inf while the column has no exact distance yet
+        const unsigned long long rb = v_rbest[row];
+        float Ri = fminf(Ri_ub, rb == ~0ull ? INFINITY : __uint_as_float((unsigned)(rb >> 32)) - nam);
+        wnbm[lane] = nbm;
+        __syncwarp();
+        const float4* __restrict__ wn4 = reinterpret_cast<const float4*>(wnbm);
+        const float4* __restrict__ wc4 = reinterpret_cast<const float4*>(wcj);
+        // ---- warm-up: a row / column without any exact distance would let every entry through.  Upper bounds of the
+        // exact minima come from the tile itself: UB_ij = d~_ij + e_ij = (1+c/2)(na'+nb') - 2 dot >= d_ij.
+        if (__any_sync(0xffffffffu, (row_ok && Ri == INFINITY) || (cb_cur == ~0ull && nbm != INFINITY))) {
+          if (lane == 0) atomicAdd(&s_warm, 1);
+          const float nah = row_ok ? nam * kHighOverLow : INFINITY;
+          float rowub = INFINITY;
+          unsigned mine = 0xFFFFFFFFu;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 w = wn4[c4];
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = 4 * c4 + e;
+              const float ub = fmaf(-2.0f, __uint_as_float(v[c]), wv[e] * kHighOverLow) + nah;
+              rowub = fminf(rowub, ub);
+              const unsigned mn = __reduce_min_sync(0xffffffffu, tc_fkey(ub));  // min over the warp's 32 rows
+              if (lane == c) mine = mn;
+            }
+          }
+          if (mine != 0xFFFFFFFFu && nbm != INFINITY) cj = fmaxf(cj, nbm - tc_fkey_inv(mine));
+          if (row_ok) { Ri_ub = fminf(Ri_ub, rowub - nam); Ri = fminf(Ri, Ri_ub); }
+        }
+        wcj[lane] = cj;
+        __syncwarp();
+        // ---- branch-free filter of this lane's row over the 32 columns
+        uint32_t mask = 0;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 w = wn4[c4], x = wc4[c4];
+          const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * c4 + e;
+            const float dot = __uint_as_float(v[c]);
+            const float t = fmaf(-2.0f, dot, wv[e]);
+            const float u = fmaf(-2.0f, dot, xv[e]);
+            if ((t <= Ri) || (u <= negna)) mask |= 1u << c;
+            if (dbg_tile != nullptr && stripe == 0 && k == 0) dbg_tile[(size_t)row * kTcN + cb + c] = (nam + wv[e]) / kLow - 2.0f * dot;
+          }
+        }
+        // ---- exact evaluation, one candidate per lane, 32 per round
+        int remaining = __reduce_add_sync(0xffffffffu, __popc(mask));
+        evals_w += remaining;
+        while (remaining > 0) {  // warp-uniform
+          int tot;
+          int p = warp_excl_scan(__popc(mask), &tot);
+          while (mask && p < 32) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1;
+            wq[p++] = (unsigned short)((lane << 5) | c);
+          }
+          __syncwarp();
+          const int nb = tot < 32 ? tot : 32;
+          const int q = lane < nb ? wq[lane] : 0;
+          const int rl = q >> 5, c = q & 31;
+          const int pcol = cb + c;
+          float acc = 0.0f;
+#pragma unroll
+          for (int kc = 0; kc < (kDescDim + 3) / 4; ++kc) {
+            const float4 a = aex[kc * 128 + rl], b = bex[kc * 128 + pcol];
+            float diff = a.x - b.x;
+            acc = __fmaf_rn(diff, diff, acc);
+            if (4 * kc + 1 < kDescDim) { diff = a.y - b.y; acc = __fmaf_rn(diff, diff, acc); }
+            if (4 * kc + 2 < kDescDim) { diff = a.z - b.z; acc = __fmaf_rn(diff, diff, acc); }
+            if (4 * kc + 3 < kDescDim) { diff = a.w - b.w; acc = __fmaf_rn(diff, diff, acc); }
+          }
+          const float dbc = __shfl_sync(0xffffffffu, dbest, c);
+          if (lane < nb && acc == acc) {  // NaN never wins
+            const int rr = quad * 32 + rl, j = c0 + pcol;
+            const unsigned long long pr = tc_pack(acc, j);
+            if (pr < v_rbest[rr]) atomicMin(&s_rbest[rr], pr);
+            if (acc <= dbc) atomicMin(cbg + j, tc_pack(acc, r0 + rr));
+          }
+          __syncwarp();
+          remaining = tot - nb;
+        }
+        // massive ties: once more than half of the entries seen needed the exact chain, hand the pair to the exact kernel
+        if (lane == 0) {
+          const int seen = atomicAdd(&s_evals, evals_w) + evals_w;
+          if (k >= 7 && seen > (k + 1) * (kTcM * kTcN / 2)) *v_abort = 1;
+        }
+        evals_w = 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree0 + 8 * st);  // ring stage st may be refilled
     }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  const bool aborted = (s_abort | s_dead) != 0;
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + 0, (unsigned long long)s_evals);
+    atomicAdd(stats + 1, (unsigned long long)n_tiles);
+    atomicAdd(stats + 2, (unsigned long long)s_warm);
+    if (aborted) {
+      atomicAdd(stats + 3, 1ull);
+      fallback[pair] = 1;
+    }
+  }
+  if (!aborted && threadIdx.x < kTcM && r0 + (int)threadIdx.x < nA) rowbest[(size_t)pair * V + r0 + threadIdx.x] = s_rbest[threadIdx.x];
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * kTcN) : "memory");
 }
 
-static size_t tc_smem_bytes() { return 2 * (size_t)kTcTileBytes + (size_t)kTcStages * kTcImages * kTcTileBytes; }
+static size_t tc_smem_bytes() { return (size_t)kTcImages * kTcTileBytes + 2 * 2 * (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes; }
 
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
@@ -414,7 +443,7 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_tiles, h->desc_norm);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
-  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, V, h->rowbest, h->colbest, h->tc_fallback, nullptr);
+  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, nullptr);
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
   h->launches += 2;
@@ -432,7 +461,7 @@ int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
   const dim3 gsplit((h->V + 255) / 256, 2);
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_tiles, h->desc_norm);
   const dim3 g(1, 1);
-  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, h->V, h->rowbest, h->colbest, h->tc_fallback, d_out);
+  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, h->V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, d_out);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
