@@ -34,8 +34,9 @@ constexpr int kTcTileBytes = kDescK * 128 * 4;    // one operand image (128 poin
 constexpr int kTileFloats = kDescK * 128;         // 5120
 constexpr int kTcImages = 3;                      // hi | lo | exact
 constexpr int kTcEpiWarps = 16;                   // filter / evaluation warps: TMEM lane quadrant = warp & 3, column quarter = warp >> 2
-constexpr int kTcThreads = (kTcEpiWarps + 1) * 32;  // + 1 copy / MMA warp
-constexpr int kTcStages = 3;                      // B ring (prefetch distance 2)
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;  // + MMA warp + copy warp
+constexpr int kTcAcc = 4;                          // TMEM accumulator stages (4 x 128 columns = all of TMEM)
+constexpr int kTcStages = 4;                      // ring of exact B images (prefetch distance 3); operand images: 2 stages
 constexpr float kTcC = 6.0e-5f;                   // |d~ - d| <= kTcC/2 * (|a'|^2 + |b'|^2)
 constexpr int kSpinLimit = 400000;
 
@@ -163,12 +164,13 @@ __device__ __forceinline__ float tc_fkey_inv(unsigned key) { return __uint_as_fl
 //                  into batches of 32 and evaluated exactly, ONE CANDIDATE PER LANE (the source descriptor of another
 //                  lane's row comes over warp shuffles, the target descriptor from the exact image in shared memory)
 //                  -> release the ring stage.
+template <bool kDbg>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, const int* __restrict__ n_vox, int V,
              unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest, int* __restrict__ fallback,
              unsigned long long* __restrict__ stats, float* __restrict__ dbg_tile) {
   extern __shared__ __align__(128) unsigned char smem[];  // 220 KB of operand images; static + dynamic must stay <= 227 KB
-  __shared__ uint64_t s_fullx[kTcStages], s_sfree[kTcStages], s_fullhl[2], s_mma[2], s_tfree[2], s_afull;
+  __shared__ uint64_t s_fullx[kTcStages], s_sfree[kTcStages], s_fullhl[2], s_mma[kTcAcc], s_tfree[kTcAcc], s_afull;
   __shared__ uint32_t s_tmem;
   __shared__ unsigned long long s_rbest[kTcM];                 // best exact (distance | target index) per row of the stripe
   __shared__ __align__(16) float s_wnbm[kTcEpiWarps][32];      // per warp: kLow |b'_j|^2 of its 32 columns
@@ -200,13 +202,14 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   const int first = stripe % n_tiles;  // staggered start: concurrent stripes of a pair work on different column tiles
   auto tile_of = [&](int k) { const int t = first + k; return t >= n_tiles ? t - n_tiles : t; };
 
-  if (warp == 0) {  // TMEM: 2 accumulator stages x 128 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(2 * kTcN) : "memory");
+  if (warp == 0) {  // TMEM: 4 accumulator stages x 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(kTcAcc * kTcN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcStages; ++i) { mbar_init(bar_fullx0 + 8 * i, 1); mbar_init(bar_sfree0 + 8 * i, kTcEpiWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_fullhl0 + 8 * i, 1); mbar_init(bar_mma0 + 8 * i, 1); mbar_init(bar_tfree0 + 8 * i, kTcEpiWarps); }
+    for (int i = 0; i < 2; ++i) mbar_init(bar_fullhl0 + 8 * i, 1);
+    for (int i = 0; i < kTcAcc; ++i) { mbar_init(bar_mma0 + 8 * i, 1); mbar_init(bar_tfree0 + 8 * i, kTcEpiWarps); }
     mbar_init(bar_a, 1);
     s_dead = 0; s_abort = 0; s_evals = 0; s_warm = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -220,34 +223,18 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   volatile int* v_abort = &s_abort;
 
   if (warp == kTcEpiWarps) {
-    // ================= copy / MMA warp =================
+    // ================= MMA warp =================
     // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-    auto issue_hl = [&](int k) {  // operand images (hi | lo, 40 KB) of tile k -> stage k & 1
-      const uint32_t bar = bar_fullhl0 + 8 * (k & 1);
-      mbar_expect_tx(bar, kHLBytes);
-      bulk_g2s(sHL0 + (k & 1) * kHLBytes, tB + (size_t)tile_of(k) * kTcImages * kTileFloats, kHLBytes, bar);
-    };
-    auto issue_x = [&](int k) {  // exact image (20 KB) of tile k -> stage k % 3
-      const uint32_t bar = bar_fullx0 + 8 * (k % kTcStages);
-      mbar_expect_tx(bar, kXBytes);
-      bulk_g2s(sX0 + (k % kTcStages) * kXBytes, tB + ((size_t)tile_of(k) * kTcImages + 2) * kTileFloats, kXBytes, bar);
-    };
-    if (lane == 0) {
-      mbar_expect_tx(bar_a, kABytes);
-      bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
-      issue_hl(0); issue_x(0);
-      if (n_tiles > 1) { issue_hl(1); issue_x(1); }
-    }
     bool ok = mbar_wait(bar_a, 0);
     for (int k = 0; k < n_tiles && ok; ++k) {
-      const int ts = k & 1;
-      ok = mbar_wait(bar_fullhl0 + 8 * ts, (uint32_t)((k >> 1) & 1));
-      if (ok && k >= 2) ok = mbar_wait(bar_tfree0 + 8 * ts, (uint32_t)(((k >> 1) - 1) & 1));  // TMEM stage drained (tile k-2)
+      const int ts = k & (kTcAcc - 1), hs = k & 1;
+      ok = mbar_wait(bar_fullhl0 + 8 * hs, (uint32_t)((k >> 1) & 1));
+      if (ok && k >= kTcAcc) ok = mbar_wait(bar_tfree0 + 8 * ts, (uint32_t)(((k >> 2) - 1) & 1));  // accumulator stage drained (tile k-4)
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (lane == 0) {
-        const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sHL0 + ts * kHLBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
+        const uint32_t aH = sA, aL = sA + kTcTileBytes, bH = sHL0 + hs * kHLBytes, bL = bH + kTcTileBytes, d = tmem + (uint32_t)(ts * kTcN);
         uint32_t acc = 0;
 #pragma unroll
         for (int kb = 0; kb < kTcKB; ++kb) {  // small cross terms first, then hi.hi
@@ -260,13 +247,37 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * ts) : "memory");
       }
       __syncwarp();
-      if (k + 2 < n_tiles) {  // prefetch distance 2
-        ok = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1));  // MMAs of tile k done: its operand stage is free
+    }
+    if (!ok) *v_dead = 1;
+  } else if (warp == kTcEpiWarps + 1) {
+    // ================= copy warp =================
+    auto issue_hl = [&](int k) {  // operand images (hi | lo, 40 KB) of tile k -> stage k & 1
+      const uint32_t bar = bar_fullhl0 + 8 * (k & 1);
+      mbar_expect_tx(bar, kHLBytes);
+      bulk_g2s(sHL0 + (k & 1) * kHLBytes, tB + (size_t)tile_of(k) * kTcImages * kTileFloats, kHLBytes, bar);
+    };
+    auto issue_x = [&](int k) {  // exact image (20 KB) of tile k -> stage k & 3
+      const uint32_t bar = bar_fullx0 + 8 * (k & (kTcStages - 1));
+      mbar_expect_tx(bar, kXBytes);
+      bulk_g2s(sX0 + (k & (kTcStages - 1)) * kXBytes, tB + ((size_t)tile_of(k) * kTcImages + 2) * kTileFloats, kXBytes, bar);
+    };
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, kABytes);
+      bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
+      for (int k = 0; k < 2 && k < n_tiles; ++k) issue_hl(k);
+      for (int k = 0; k < 3 && k < n_tiles; ++k) issue_x(k);
+    }
+    bool ok = true;
+    for (int k = 0; k < n_tiles && ok; ++k) {
+      if (k + 2 < n_tiles) {  // operand stage k & 1 is free once the MMAs of tile k completed
+        ok = mbar_wait(bar_mma0 + 8 * (k & (kTcAcc - 1)), (uint32_t)((k >> 2) & 1));
         if (ok && lane == 0) issue_hl(k + 2);
-        // the exact image of tile k+2 replaces that of tile k-1: wait until every warp evaluated tile k-1
-        if (ok && k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 2) % kTcStages), (uint32_t)(((k - 1) / kTcStages) & 1));
-        if (ok && lane == 0) issue_x(k + 2);
       }
+      if (ok && k + 3 < n_tiles) {  // the exact image of tile k+3 replaces that of tile k-1: every warp must have evaluated it
+        if (k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 3) & (kTcStages - 1)), (uint32_t)(((k - 1) >> 2) & 1));
+        if (ok && lane == 0) issue_x(k + 3);
+      }
+      __syncwarp();
     }
     if (!ok) *v_dead = 1;
   } else {
@@ -292,15 +303,15 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       if (j < nB) cb_next = __ldcg(cbg + j);
     }
     for (int k = 0; k < n_tiles; ++k) {
-      const int ts = k & 1, st = k % kTcStages, jt = tile_of(k), c0 = jt * kTcN;
+      const int ts = k & (kTcAcc - 1), st = k & (kTcStages - 1), jt = tile_of(k), c0 = jt * kTcN;
       const unsigned long long cb_cur = cb_next;
       cb_next = ~0ull;
       if (k + 1 < n_tiles) {
         const int j = tile_of(k + 1) * kTcN + cb + lane;
         if (j < nB) cb_next = __ldcg(cbg + j);
       }
-      if (alive) alive = mbar_wait(bar_fullx0 + 8 * st, (uint32_t)((k / kTcStages) & 1));  // the exact image is read below
-      if (alive) alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 1) & 1));
+      if (alive) alive = mbar_wait(bar_fullx0 + 8 * st, (uint32_t)((k >> 2) & 1));  // the exact image is read below
+      if (alive) alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 2) & 1));
       if (!alive) *v_dead = 1;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const bool skip = __any_sync(0xffffffffu, (*v_abort | *v_dead) != 0);
@@ -358,8 +369,13 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
             const float dot = __uint_as_float(v[c]);
             const float t = fmaf(-2.0f, dot, wv[e]);
             const float u = fmaf(-2.0f, dot, xv[e]);
-            if ((t <= Ri) || (u <= negna)) mask |= 1u << c;
-            if (dbg_tile != nullptr && stripe == 0 && k == 0) dbg_tile[(size_t)row * kTcN + cb + c] = (nam + wv[e]) / kLow - 2.0f * dot;
+            asm("{\n\t.reg .pred p, q;\n\t"
+                "setp.le.f32 p, %1, %2;\n\t"
+                "setp.le.or.f32 q, %3, %4, p;\n\t"
+                "@q or.b32 %0, %0, %5;\n\t}\n"
+                : "+r"(mask)
+                : "f"(u), "f"(negna), "f"(t), "f"(Ri), "r"(1u << c));
+            if (kDbg && stripe == 0 && k == 0) dbg_tile[(size_t)row * kTcN + cb + c] = (nam + wv[e]) / kLow - 2.0f * dot;
           }
         }
         // ---- exact evaluation, one candidate per lane, 32 per round
@@ -423,17 +439,17 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   }
   if (!aborted && threadIdx.x < kTcM && r0 + (int)threadIdx.x < nA) rowbest[(size_t)pair * V + r0 + threadIdx.x] = s_rbest[threadIdx.x];
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(2 * kTcN) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(kTcAcc * kTcN) : "memory");
 }
 
-static size_t tc_smem_bytes() { return (size_t)kTcImages * kTcTileBytes + 2 * 2 * (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes; }
+static size_t tc_smem_bytes() { return (size_t)kTcImages * kTcTileBytes + 2 * 2 * (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes; }  // 220 KB
 
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
   static bool attr_set = false;
   const size_t smem = tc_smem_bytes();
   if (!attr_set) {
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
@@ -443,7 +459,7 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_tiles, h->desc_norm);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
-  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, nullptr);
+  tc_nn_kernel<false><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, nullptr);
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
   h->launches += 2;
@@ -454,14 +470,14 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
 // debug/validation hook: approximate distances d~ of the first 128 x 128 tile of pair 0 (descriptors already in desc_t)
 int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
   const size_t smem = tc_smem_bytes();
-  QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)h->V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)h->V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, sizeof(int), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_tiles, h->desc_norm);
   const dim3 g(1, 1);
-  tc_nn_kernel<<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, h->V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, d_out);
+  tc_nn_kernel<true><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, h->V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, d_out);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
