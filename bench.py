@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
-    ap.add_argument("--slots", type=int, default=128, help="pairs per device wave")
+    ap.add_argument("--slots", type=int, default=64, help="pairs per device wave (two lanes of this size alternate)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

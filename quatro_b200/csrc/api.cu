@@ -48,12 +48,7 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_cloud_n, C * sizeof(int)));
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_raw_off, (C + 1) * sizeof(int)));
   QB_ALLOC(h, h->raw_stage, C * R);
-  QB_ALLOC(h, h->raw_stage2, C * R);
-  QB_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
-    QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
-    QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_rawfree[i], cudaEventDisableTiming));
-  }
+  QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   QB_ALLOC(h, h->key_a, C * R);
   QB_ALLOC(h, h->key_b, C * R);
   QB_ALLOC(h, h->val_a, C * R);
@@ -253,6 +248,8 @@ int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {
   // the exact CUDA-core kernel everywhere (identical results; A/B and triage)
   const char* fe = getenv("QB200_MATCH_EXACT");
   h->force_exact_match = (fe && fe[0] == '1') ? 1 : 0;
+  const char* ln = getenv("QB200_LANES");
+  h->max_lanes = (ln && ln[0] >= '1' && ln[0] <= '4') ? ln[0] - '0' : 4;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return QB200_ERR_CUDA; }
   h->stream = h->own_stream;
   const int rc = alloc_all(h);
@@ -270,7 +267,7 @@ void qb200_destroy(qb200_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->raw_stage2, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
+  void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->desc_t, h->rowbest, h->colpart, h->colbest,
                       h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
@@ -286,11 +283,9 @@ void qb200_destroy(qb200_handle* h) {
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 4; ++i)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
-  for (int i = 0; i < 2; ++i) {
-    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
-    if (h->ev_rawfree[i]) cudaEventDestroy(h->ev_rawfree[i]);
-  }
-  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 3; ++i)
+    if (h->lane[i]) qb200_destroy(h->lane[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -302,7 +297,13 @@ int qb200_set_stream(qb200_handle* h, void* cuda_stream) {
 }
 
 const char* qb200_last_error(const qb200_handle* h) { return h ? h->err : "null handle"; }
-int64_t qb200_launch_count(const qb200_handle* h) { return h ? h->launches : 0; }
+int64_t qb200_launch_count(const qb200_handle* h) {
+  if (!h) return 0;
+  int64_t n = h->launches;
+  for (int i = 0; i < 3; ++i)
+    if (h->lane[i]) n += h->lane[i]->launches;
+  return n;
+}
 
 // ---- stage: voxelize ----------------------------------------------------------------------------
 int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, int32_t skip_flagged, float* out4, int32_t cap,
@@ -519,6 +520,77 @@ int qb200_solve_correspondences(qb200_handle* h, const float* a4, const float* b
 }
 
 // ---- raw scans -> pose ------------------------------------------------------------------------------
+// enqueue one wave (np <= S pairs) on lane L: H2D of the scans (host kind), K1..K11, D2H of the result records.  No sync.
+static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np, qb200_mem_kind kind, const qb200_params* p, float cell) {
+  const int ncl = 2 * np;
+  int rc;
+  cudaEventRecord(L->ev[0], L->stream);
+  int total = 0;
+  for (int s = 0; s < np; ++s) {
+    const qb200_pair& pr = pairs[w0 + s];
+    const float* ptr[2] = {pr.src, pr.tgt};
+    const int cnt[2] = {pr.n_src, pr.n_tgt};
+    for (int k = 0; k < 2; ++k) {
+      const int cloud = 2 * s + k;
+      L->h_raw_off[cloud] = total;
+      L->h_cloud_n[cloud] = cnt[k];
+      if (kind == QB200_MEM_HOST) {
+        L->h_cloud_ptr[cloud] = L->raw_stage + total;
+        if (cnt[k] > 0)
+          QB_CUDA_TRY(L, cudaMemcpyAsync(L->raw_stage + total, ptr[k], (size_t)cnt[k] * sizeof(float4), cudaMemcpyHostToDevice, L->stream));
+      } else {
+        L->h_cloud_ptr[cloud] = reinterpret_cast<const float4*>(ptr[k]);
+      }
+      total += cnt[k];
+    }
+  }
+  L->h_raw_off[ncl] = total;
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_ptr, L->h_cloud_ptr, (size_t)ncl * sizeof(float4*), cudaMemcpyHostToDevice, L->stream));
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_n, L->h_cloud_n, (size_t)ncl * sizeof(int), cudaMemcpyHostToDevice, L->stream));
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_raw_off, L->h_raw_off, (size_t)(ncl + 1) * sizeof(int), cudaMemcpyHostToDevice, L->stream));
+  if ((rc = wave_reset(L, ncl))) return rc;
+  cudaEventRecord(L->ev[1], L->stream);
+  if ((rc = launch_voxel(L, ncl, total, p->voxel_size, p->skip_flagged))) return rc;
+  cudaEventRecord(L->ev[2], L->stream);
+  if ((rc = launch_fpfh(L, ncl, p->normal_radius, p->fpfh_radius, cell))) return rc;
+  cudaEventRecord(L->ev[3], L->stream);
+  if ((rc = launch_match(L, np, *p))) return rc;
+  cudaEventRecord(L->ev[4], L->stream);
+  cudaEventRecord(L->ev[5], L->stream);  // re-recorded inside run_solver when the graph stage runs
+  if ((rc = run_solver(L, np, *p, 1))) return rc;
+  cudaEventRecord(L->ev[7], L->stream);
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->h_results, L->d_results, (size_t)np * sizeof(qb200_result), cudaMemcpyDeviceToHost, L->stream));
+  cudaEventRecord(L->ev[8], L->stream);
+  L->pend_w0 = w0;
+  L->pend_np = np;
+  return QB200_OK;
+}
+
+// wait for the wave in flight on lane L, hand out its records and add its stage / kernel times to the public handle h
+static int wave_collect(qb200_handle* h, qb200_handle* L, qb200_result* results) {
+  if (L->pend_np == 0) return QB200_OK;
+  const int np = L->pend_np;
+  L->pend_np = 0;
+  if (cudaStreamSynchronize(L->stream) != cudaSuccess) {
+    h->fail(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
+    return QB200_ERR_CUDA;
+  }
+  memcpy(results + L->pend_w0, L->h_results, (size_t)np * sizeof(qb200_result));
+  for (int i = 0; i < 8; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, L->ev[i], L->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
+  }
+  for (int k = 0; k < 2; ++k) {
+    float ms = 0.f;
+    if (L->kev_armed[k] && cudaEventElapsedTime(&ms, L->kev[2 * k], L->kev[2 * k + 1]) == cudaSuccess) {
+      h->kernel_ms[k] += ms;
+      h->kernel_calls[k] += 1;
+    }
+    L->kev_armed[k] = 0;
+  }
+  return QB200_OK;
+}
+
 int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_mem_kind kind,
                          qb200_result* results) {
   if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
@@ -534,90 +606,39 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
   for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
   const float cell = lattice_cell(*p);
-  // Host inputs: the H2D copy of wave w+1 is issued on a second stream into the other staging buffer before wave w is
-  // computed, so PCIe transfers hide behind the kernels (the buffer is recycled once the voxel stage that read it is done).
-  auto stage_wave = [&](int w0, int buf) -> int {  // enqueue the H2D copies of the wave starting at pair w0
-    const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
-    float4* base = buf ? h->raw_stage2 : h->raw_stage;
-    QB_CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_rawfree[buf], 0));
-    size_t total = 0;
-    for (int s = 0; s < np; ++s) {
-      const qb200_pair& pr = pairs[w0 + s];
-      if (pr.n_src > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(base + total, pr.src, (size_t)pr.n_src * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
-      total += pr.n_src;
-      if (pr.n_tgt > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(base + total, pr.tgt, (size_t)pr.n_tgt * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
-      total += pr.n_tgt;
-    }
-    QB_CUDA_TRY(h, cudaEventRecord(h->ev_copied[buf], h->copy_stream));
-    return QB200_OK;
-  };
-  if (kind == QB200_MEM_HOST) {
-    // both staging buffers are free: every earlier batch was synchronised before it returned
-    QB_CUDA_TRY(h, cudaEventRecord(h->ev_rawfree[0], h->stream));
-    QB_CUDA_TRY(h, cudaEventRecord(h->ev_rawfree[1], h->stream));
-    const int rc0 = stage_wave(0, 0);
-    if (rc0) return rc0;
-  }
-  int wave = 0;
-  for (int w0 = 0; w0 < n_pairs; w0 += h->S, ++wave) {
-    const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
-    const int ncl = 2 * np;
-    const int buf = wave & 1;
-    int rc;
-    cudaEventRecord(h->ev[0], h->stream);
-    if (kind == QB200_MEM_HOST) {
-      if (w0 + h->S < n_pairs && (rc = stage_wave(w0 + h->S, buf ^ 1))) return rc;  // prefetch the next wave
-      QB_CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_copied[buf], 0));
-    }
-    int total = 0;
-    const float4* base = buf ? h->raw_stage2 : h->raw_stage;
-    for (int s = 0; s < np; ++s) {
-      const qb200_pair& pr = pairs[w0 + s];
-      const float* ptr[2] = {pr.src, pr.tgt};
-      const int cnt[2] = {pr.n_src, pr.n_tgt};
-      for (int k = 0; k < 2; ++k) {
-        const int cloud = 2 * s + k;
-        h->h_raw_off[cloud] = total;
-        h->h_cloud_n[cloud] = cnt[k];
-        h->h_cloud_ptr[cloud] = kind == QB200_MEM_HOST ? base + total : reinterpret_cast<const float4*>(ptr[k]);
-        total += cnt[k];
+  // More than one wave: rotate over the lanes so that one wave's PCIe copies and single-warp solver tail run under the
+  // other waves' dense kernels.  Results do not depend on the lane (no state is shared between waves).
+  const int n_waves = (n_pairs + h->S - 1) / h->S;
+  const int n_lanes = n_waves < h->max_lanes ? (n_waves < 1 ? 1 : n_waves) : h->max_lanes;
+  qb200_handle* lanes[4] = {h, h, h, h};
+  for (int l = 1; l < n_lanes; ++l) {
+    if (!h->lane[l - 1]) {
+      const int rc = qb200_create(&h->cfg, &h->lane[l - 1]);
+      if (rc != QB200_OK) {
+        h->fail(__FILE__, __LINE__, "cannot allocate another lane");
+        return rc;
       }
+      h->lane[l - 1]->max_lanes = 1;
     }
-    h->h_raw_off[ncl] = total;
-    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_ptr, h->h_cloud_ptr, (size_t)ncl * sizeof(float4*), cudaMemcpyHostToDevice, h->stream));
-    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_n, h->h_cloud_n, (size_t)ncl * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_raw_off, h->h_raw_off, (size_t)(ncl + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if ((rc = wave_reset(h, ncl))) return rc;
-    cudaEventRecord(h->ev[1], h->stream);
-    if ((rc = launch_voxel(h, ncl, total, p->voxel_size, p->skip_flagged))) return rc;
-    if (kind == QB200_MEM_HOST) QB_CUDA_TRY(h, cudaEventRecord(h->ev_rawfree[buf], h->stream));  // raw scans are dead after K1
-    cudaEventRecord(h->ev[2], h->stream);
-    if ((rc = launch_fpfh(h, ncl, p->normal_radius, p->fpfh_radius, cell))) return rc;
-    cudaEventRecord(h->ev[3], h->stream);
-    if ((rc = launch_match(h, np, *p))) return rc;
-    cudaEventRecord(h->ev[4], h->stream);
-    cudaEventRecord(h->ev[5], h->stream);  // re-recorded inside run_solver when the graph stage runs
-    if ((rc = run_solver(h, np, *p, 1))) return rc;
-    cudaEventRecord(h->ev[7], h->stream);
-    QB_CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results, (size_t)np * sizeof(qb200_result), cudaMemcpyDeviceToHost, h->stream));
-    cudaEventRecord(h->ev[8], h->stream);
-    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    memcpy(results + w0, h->h_results, (size_t)np * sizeof(qb200_result));
-    for (int i = 0; i < 8; ++i) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
-    }
-    for (int k = 0; k < 2; ++k) {
-      float ms = 0.f;
-      if (h->kev_armed[k] && cudaEventElapsedTime(&ms, h->kev[2 * k], h->kev[2 * k + 1]) == cudaSuccess) {
-        h->kernel_ms[k] += ms;
-        h->kernel_calls[k] += 1;
-      }
-      h->kev_armed[k] = 0;
-    }
-    // the wave's own reads of h_cloud_* / h_raw_off are complete after the synchronize above
+    lanes[l] = h->lane[l - 1];
+    // the lane starts after whatever the caller queued on this handle's stream
+    if (l == 1) QB_CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+    QB_CUDA_TRY(h, cudaStreamWaitEvent(lanes[l]->stream, h->ev_fork, 0));
   }
-  if (kind == QB200_MEM_HOST) QB_CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+  int rc = QB200_OK, wave = 0;
+  for (int w0 = 0; w0 < n_pairs && rc == QB200_OK; w0 += h->S, ++wave) {
+    qb200_handle* L = lanes[wave % n_lanes];
+    const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
+    if ((rc = wave_collect(h, L, results))) break;  // the lane's previous wave (its pinned tables are reused)
+    rc = wave_submit(L, pairs, w0, np, kind, p, cell);
+    if (rc != QB200_OK && L != h) h->fail(__FILE__, __LINE__, L->err);
+  }
+  // drain in submission order; on an error still wait for everything in flight (the copies read caller memory)
+  for (int i = 0; i < n_lanes; ++i) {
+    const int rc2 = wave_collect(h, lanes[(wave + i) % n_lanes], results);
+    if (rc == QB200_OK) rc = rc2;
+  }
+  if (rc != QB200_OK) return rc;
   if (n_pairs == 1) {
     h->last_n_corr = results[0].n_corr;
     h->last_n_clique = results[0].clique_size;
@@ -685,6 +706,13 @@ int qb200_debug_match_stats(qb200_handle* h, uint64_t* out4, int32_t reset) {
   QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   QB_CUDA_TRY(h, cudaMemcpy(out4, h->tc_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (reset) QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 4 * sizeof(unsigned long long)));
+  for (int l = 0; l < 3; ++l) {
+    if (!h->lane[l]) continue;
+    uint64_t o2[4];
+    const int rc = qb200_debug_match_stats(h->lane[l], o2, reset);
+    if (rc) return rc;
+    for (int i = 0; i < 4; ++i) out4[i] += o2[i];
+  }
   return QB200_OK;
 }
 

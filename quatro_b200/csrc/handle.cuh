@@ -20,10 +20,13 @@ struct qb200_handle {
   int* d_cloud_n;             // [2S]
   int* d_raw_off;             // [2S+1] offsets into the concatenated sort arrays
   const float4** h_cloud_ptr; int* h_cloud_n; int* h_raw_off;  // pinned mirrors
-  float4* raw_stage;          // [2S*R] staging for host inputs (wave w uses buffer w & 1)
-  float4* raw_stage2;         // second staging buffer: H2D of wave w+1 overlaps the compute of wave w
-  cudaStream_t copy_stream;
-  cudaEvent_t ev_copied[2], ev_rawfree[2];
+  float4* raw_stage;          // [2S*R] staging for host inputs
+  // Multi-wave batches rotate over this handle and up to 3 more lanes (own stream and buffers, created on first use):
+  // the H2D copies and the latency-bound solver tail of one wave overlap the dense kernels of the others.
+  qb200_handle* lane[3];
+  int max_lanes;              // 1..4 (QB200_LANES, default 4)
+  int pend_w0, pend_np;       // wave in flight on this lane (pend_np == 0: none)
+  cudaEvent_t ev_fork;
 
   // ---- sort workspace (voxel sort, then lattice sort) ----
   uint64_t *key_a, *key_b;    // [2S*R]

@@ -361,6 +361,18 @@ def test_register_batch_matches_single_and_oracle(handle, oracle):
     # order / batch composition must not change any pair's result
     out2 = handle.register_batch(pairs[::-1], p)
     assert out2[::-1].tobytes() == out.tobytes()
+    # three waves alternating between the two lanes, and the single-lane path (QB200_LANES=1): same records
+    import os
+    from quatro_b200.capi import Handle
+    with Handle(max_batch_slots=4) as h4:
+        assert h4.register_batch(pairs, p).tobytes() == out.tobytes()
+        assert h4.register_batch(pairs, p).tobytes() == out.tobytes()      # lanes are reusable
+    os.environ["QB200_LANES"] = "1"
+    try:
+        with Handle(max_batch_slots=4) as h1:
+            assert h1.register_batch(pairs, p).tobytes() == out.tobytes()
+    finally:
+        del os.environ["QB200_LANES"]
 
 
 def test_register_batch_device_resident_inputs(handle, oracle):
