@@ -731,7 +731,7 @@ int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, cons
   float* scratch2 = scratch + (size_t)128 * kDescDim;
   QB_CUDA_TRY(h, cudaMemcpyAsync(scratch2, b33, (size_t)nb * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   if ((rc = launch_desc_from_aos(h, 1, nb, scratch2))) return rc;
-  float* d_out = scratch2 + (size_t)128 * kDescDim;
+  float* d_out = h->spfh;  // not the sort scratch: K6 sorts the descriptors by norm first
   QB_CUDA_TRY(h, cudaMemsetAsync(d_out, 0, 128 * 128 * sizeof(float), h->stream));
   if ((rc = launch_tc_debug_tile(h, d_out))) return rc;
   QB_CUDA_TRY(h, cudaMemcpyAsync(out, d_out, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -25,6 +25,7 @@
 // the 15 MMAs of tile k into TMEM stage k&1 and commits to an mbarrier; meanwhile all 8 warps drain stage (k-1)&1 with
 // tcgen05.ld.32x32b.x32 (lane = row) and run the filter / exact evaluation.
 #include "handle.cuh"
+#include <cstdlib>
 
 namespace qb {
 
@@ -77,15 +78,40 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 __device__ __forceinline__ float tc_mu(int d) { return (d == 5 || d == 16 || d == 27) ? 100.0f : 0.0f; }
 
-// centred TF32 split + exact image + centred squared norm, written block-wise in the shared-memory operand layout
+// centred squared norm of every descriptor (the fp32 chain split_desc_kernel repeats) as the sort key cloud | norm bits:
+// K6 processes the points of a cloud in ascending-norm order, which turns the reverse triangle inequality
+// d(a,b) >= (|a'| - |b'|)^2 into a tile-level lower bound (whole 128 x 128 blocks are skipped without being loaded).
+__global__ void __launch_bounds__(256) norm_key_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V,
+                                                       uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= V) return;
+  uint32_t bits = 0xFFFFFFFFu;  // padding sorts last
+  if (q < n_vox[cloud]) {
+    const size_t base = (size_t)cloud * kDescK * V + q;
+    float acc = 0.0f;
+#pragma unroll
+    for (int d = 0; d < kDescDim; ++d) {
+      const float xc = desc_t[base + (size_t)d * V] - tc_mu(d);
+      acc = __fmaf_rn(xc, xc, acc);
+    }
+    bits = acc == acc ? __float_as_uint(acc) : 0xFFFFFFFEu;  // squared norms are >= 0: the bit pattern orders them
+  }
+  keys[(size_t)cloud * V + q] = ((uint64_t)cloud << 32) | bits;
+  vals[(size_t)cloud * V + q] = (uint32_t)q;
+}
+
+// centred TF32 split + exact image + centred squared norm, written block-wise in the shared-memory operand layout;
+// rank r of the cloud (ascending norm, ties by index) is point perm[r]
 __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V,
-                                                         float* __restrict__ tiles, float* __restrict__ norm) {
+                                                         const uint32_t* __restrict__ perm, float* __restrict__ tiles,
+                                                         float* __restrict__ norm) {
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = n_vox[cloud];
   const int NB = V >> 7;
   if (q >= ((n + 127) & ~127)) return;  // the last block is padded with zeros so stale data never reaches the tensor core
-  const size_t base = (size_t)cloud * kDescK * V + q;
+  const size_t base = (size_t)cloud * kDescK * V + (q < n ? perm[(size_t)cloud * V + q] : 0u);
   const int blk = q >> 7, p = q & 127;
   float4* __restrict__ img = reinterpret_cast<float4*>(tiles + (size_t)(cloud * NB + blk) * kTcImages * kTileFloats) + p;
   float acc = 0.0f;
@@ -109,7 +135,59 @@ __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict
   }
   // the exact image has no data in dims 36..39: slot 36 carries the column's filter term kLow |x'|^2 (+inf = padding)
   img[2 * (kTileFloats / 4) + (kDescK / 4 - 1) * 128] = make_float4(q < n ? (1.0f - 0.5f * kTcC) * acc : INFINITY, 0.0f, 0.0f, 0.0f);
-  if (q < n) norm[(size_t)cloud * V + q] = acc;
+  if (q < n) norm[(size_t)cloud * V + q] = acc;  // rank order
+}
+
+// Exact duplicates.  Street scenes contain hundreds of points with bit-identical descriptors (the histogram of a perfect
+// plane, ...): every pair of them ties at distance 0 and would have to go through the exact chain.  Identical descriptors
+// have identical norms, so after the norm sort they are neighbours: each run is collapsed to its first rank (the stable
+// sort makes that the LOWEST point index, exactly the tie-break of the reference search), K6 runs on the unique
+// descriptors only and broadcast_best_kernel hands the class result to every member.  One CTA per cloud.
+__global__ void __launch_bounds__(1024) dedup_kernel(const float* __restrict__ desc_t, const int* __restrict__ n_vox, int V,
+                                                     const uint64_t* __restrict__ sorted_keys, const uint32_t* __restrict__ perm, int enable,
+                                                     uint32_t* __restrict__ uperm, uint32_t* __restrict__ class_of, int* __restrict__ n_unique) {
+  __shared__ int scan_smem[33];
+  const int cloud = blockIdx.x;
+  const int n = n_vox[cloud];
+  const float* __restrict__ D = desc_t + (size_t)cloud * kDescK * V;
+  const uint32_t* __restrict__ pm = perm + (size_t)cloud * V;
+  const uint64_t* __restrict__ sk = sorted_keys + (size_t)cloud * V;
+  int base = 0;
+  for (int start = 0; start < n; start += blockDim.x) {
+    const int r = start + threadIdx.x;
+    int flag = 0;
+    if (r < n) {
+      flag = 1;
+      if (enable && r > 0 && sk[r] == sk[r - 1]) {  // same norm bits: compare the descriptors bit by bit
+        const uint32_t a = pm[r], b = pm[r - 1];
+        bool same = true;
+        for (int d = 0; d < kDescDim && same; ++d) same = __float_as_uint(D[(size_t)d * V + a]) == __float_as_uint(D[(size_t)d * V + b]);
+        flag = same ? 0 : 1;
+      }
+    }
+    int total;
+    const int ex = block_excl_scan(flag, scan_smem, &total);
+    if (r < n) {
+      const int u = base + ex + flag - 1;  // a duplicate belongs to the class opened by the closest earlier rank
+      class_of[(size_t)cloud * V + r] = (uint32_t)u;
+      if (flag) uperm[(size_t)cloud * V + u] = pm[r];
+    }
+    base += total;
+  }
+  if (threadIdx.x == 0) n_unique[cloud] = base;
+}
+
+// class results (unique-rank order) -> every point of the class, in point order for the mutual-NN stage
+__global__ void __launch_bounds__(256) broadcast_best_kernel(const unsigned long long* __restrict__ rowbest_u,
+                                                             const unsigned long long* __restrict__ colbest_u, const int* __restrict__ n_vox,
+                                                             int V, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ class_of,
+                                                             unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest) {
+  const int cloud = blockIdx.y, pair = cloud >> 1;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_vox[cloud]) return;
+  const uint32_t u = class_of[(size_t)cloud * V + r], q = perm[(size_t)cloud * V + r];
+  if (cloud & 1) colbest[(size_t)pair * V + q] = colbest_u[(size_t)pair * V + u];
+  else rowbest[(size_t)pair * V + q] = rowbest_u[(size_t)pair * V + u];
 }
 
 // ---- mbarrier / bulk-copy helpers ---------------------------------------------------------------
@@ -154,21 +232,24 @@ __device__ __forceinline__ unsigned tc_fkey(float f) {  // order-preserving floa
 }
 __device__ __forceinline__ float tc_fkey_inv(unsigned key) { return __uint_as_float((key & 0x80000000u) ? (key & 0x7FFFFFFFu) : ~key); }
 
-// rows = source cloud (2*pair), columns = target cloud (2*pair+1).  dbg_tile != nullptr: additionally dump d~ of the
-// first tile of stripe 0 (validation hook).
+// rows = source cloud (2*pair), columns = target cloud (2*pair+1): their UNIQUE descriptors in ascending-norm (rank) order;
+// n_vox / perm are the per-cloud unique counts and the point index of every unique rank.  rowbest / colbest_r are indexed by
+// unique rank (broadcast_best_kernel maps them back).  kDbg: additionally
+// dump d~ of the first tile of stripe 0 (validation hook).
 //
 // Warp roles (no CTA-wide barrier inside the tile loop, everything is handed over through mbarriers):
-//   warp 16      : one elected lane issues the bulk copies (3-stage ring, prefetch distance 2) and the 15 MMAs per tile
+//   warp 17      : copy + schedule warp.  Picks the stripe's next column tile, nearest norm range first, and SKIPS a tile when
+//                  its lower bound (gap between the norm ranges)^2 exceeds every current best of the stripe's rows and of
+//                  the tile's columns; issues the bulk copies (2 operand stages, 4 exact-image stages)
+//   warp 16      : one elected lane issues the 15 MMAs per tile into one of 4 TMEM accumulator stages
 //   warps 0..15  : warp w owns TMEM lanes 32 (w & 3) .. +31 (rows) and columns 32 (w >> 2) .. +31 of every tile:
 //                  tcgen05.ld -> release the TMEM stage -> branch-free filter -> the warp's survivors are compacted
-//                  into batches of 32 and evaluated exactly, ONE CANDIDATE PER LANE (the source descriptor of another
-//                  lane's row comes over warp shuffles, the target descriptor from the exact image in shared memory)
-//                  -> release the ring stage.
+//                  into batches of 32 and evaluated exactly, ONE CANDIDATE PER LANE -> release the exact-image stage.
 template <bool kDbg>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, const int* __restrict__ n_vox, int V,
-             unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest, int* __restrict__ fallback,
-             unsigned long long* __restrict__ stats, float* __restrict__ dbg_tile) {
+             const uint32_t* __restrict__ perm, unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest_r,
+             int* __restrict__ fallback, unsigned long long* __restrict__ stats, float* __restrict__ dbg_tile, int no_prune) {
   extern __shared__ __align__(128) unsigned char smem[];  // 220 KB of operand images; static + dynamic must stay <= 227 KB
   __shared__ uint64_t s_fullx[kTcStages], s_sfree[kTcStages], s_fullhl[2], s_mma[kTcAcc], s_tfree[kTcAcc], s_afull;
   __shared__ uint32_t s_tmem;
@@ -176,7 +257,8 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   __shared__ __align__(16) float s_wnbm[kTcEpiWarps][32];      // per warp: kLow |b'_j|^2 of its 32 columns
   __shared__ __align__(16) float s_wcj[kTcEpiWarps][32];       //           kLow |b'_j|^2 - (best exact distance of column j)
   __shared__ unsigned short s_queue[kTcEpiWarps][32];          //           one batch of candidates (row lane << 5 | column)
-  __shared__ int s_dead, s_abort, s_evals, s_warm;
+  __shared__ int s_seq[8];                                     // column tile of sequence position n (ring), -1 = end of the stripe
+  __shared__ int s_dead, s_abort, s_evals, s_warm, s_npos;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
   const int cloudA = 2 * pair, cloudB = 2 * pair + 1;
@@ -186,7 +268,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NB = V >> 7;
-  // shared-memory map: A block (hi | lo | exact) | 2 stages of B (hi | lo) | 3 stages of B exact images.  The operand images
+  // shared-memory map: A block (hi | lo | exact) | 2 stages of B (hi | lo) | 4 stages of B exact images.  The operand images
   // are dead as soon as the MMAs of their tile completed, the exact image only when every warp evaluated the tile.
   constexpr uint32_t kABytes = kTcImages * kTcTileBytes;
   constexpr uint32_t kHLBytes = 2 * kTcTileBytes;
@@ -194,13 +276,14 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   const uint32_t sA = smem_u32(smem), sHL0 = sA + kABytes, sX0 = sHL0 + 2 * kHLBytes;
   const float* __restrict__ tA = tiles + (size_t)cloudA * NB * kTcImages * kTileFloats;
   const float* __restrict__ tB = tiles + (size_t)cloudB * NB * kTcImages * kTileFloats;
-  unsigned long long* __restrict__ cbg = colbest + (size_t)pair * V;
+  const float* __restrict__ nrmA = norm + (size_t)cloudA * V;   // rank order, ascending
+  const float* __restrict__ nrmB = norm + (size_t)cloudB * V;
+  const uint32_t* __restrict__ permA = perm + (size_t)cloudA * V;
+  const uint32_t* __restrict__ permB = perm + (size_t)cloudB * V;
+  unsigned long long* __restrict__ cbg = colbest_r + (size_t)pair * V;
   const uint32_t bar_fullx0 = smem_u32(&s_fullx[0]), bar_sfree0 = smem_u32(&s_sfree[0]), bar_fullhl0 = smem_u32(&s_fullhl[0]),
                  bar_mma0 = smem_u32(&s_mma[0]), bar_tfree0 = smem_u32(&s_tfree[0]), bar_a = smem_u32(&s_afull);
-
   const int n_tiles = (nB + kTcN - 1) / kTcN;
-  const int first = stripe % n_tiles;  // staggered start: concurrent stripes of a pair work on different column tiles
-  auto tile_of = [&](int k) { const int t = first + k; return t >= n_tiles ? t - n_tiles : t; };
 
   if (warp == 0) {  // TMEM: 4 accumulator stages x 128 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(kTcAcc * kTcN) : "memory");
@@ -211,7 +294,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     for (int i = 0; i < 2; ++i) mbar_init(bar_fullhl0 + 8 * i, 1);
     for (int i = 0; i < kTcAcc; ++i) { mbar_init(bar_mma0 + 8 * i, 1); mbar_init(bar_tfree0 + 8 * i, kTcEpiWarps); }
     mbar_init(bar_a, 1);
-    s_dead = 0; s_abort = 0; s_evals = 0; s_warm = 0;
+    s_dead = 0; s_abort = 0; s_evals = 0; s_warm = 0; s_npos = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (threadIdx.x < kTcM) s_rbest[threadIdx.x] = ~0ull;
@@ -221,16 +304,19 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   const uint32_t tmem = s_tmem;
   volatile int* v_dead = &s_dead;
   volatile int* v_abort = &s_abort;
+  volatile int* v_seq = s_seq;
+  volatile unsigned long long* v_rbest = s_rbest;
 
   if (warp == kTcEpiWarps) {
     // ================= MMA warp =================
     // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
     bool ok = mbar_wait(bar_a, 0);
-    for (int k = 0; k < n_tiles && ok; ++k) {
+    for (int k = 0; ok; ++k) {
       const int ts = k & (kTcAcc - 1), hs = k & 1;
       ok = mbar_wait(bar_fullhl0 + 8 * hs, (uint32_t)((k >> 1) & 1));
-      if (ok && k >= kTcAcc) ok = mbar_wait(bar_tfree0 + 8 * ts, (uint32_t)(((k >> 2) - 1) & 1));  // accumulator stage drained (tile k-4)
+      if (!ok || v_seq[k & 7] < 0) break;
+      if (k >= kTcAcc) ok = mbar_wait(bar_tfree0 + 8 * ts, (uint32_t)(((k >> 2) - 1) & 1));  // accumulator stage drained (position k-4)
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (lane == 0) {
@@ -250,36 +336,113 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     }
     if (!ok) *v_dead = 1;
   } else if (warp == kTcEpiWarps + 1) {
-    // ================= copy warp =================
-    auto issue_hl = [&](int k) {  // operand images (hi | lo, 40 KB) of tile k -> stage k & 1
-      const uint32_t bar = bar_fullhl0 + 8 * (k & 1);
-      mbar_expect_tx(bar, kHLBytes);
-      bulk_g2s(sHL0 + (k & 1) * kHLBytes, tB + (size_t)tile_of(k) * kTcImages * kTileFloats, kHLBytes, bar);
+    // ================= copy + schedule warp =================
+    // norm range of the stripe's rows and of a column tile (ranks are sorted by norm: first / last valid entry)
+    const float amin = sqrtf(nrmA[r0]), amax = sqrtf(nrmA[(r0 + kTcM < nA ? r0 + kTcM : nA) - 1]);
+    auto tile_lb = [&](int t) -> float {  // lower bound of every exact distance between the stripe and column tile t
+      const float bmin = sqrtf(nrmB[t * kTcN]), bmax = sqrtf(nrmB[(t * kTcN + kTcN < nB ? t * kTcN + kTcN : nB) - 1]);
+      const float gap = fmaxf(amin - bmax, bmin - amax) - 2.0e-3f;  // slack: rounding of the norm chains and square roots
+      if (!(amin <= amax && bmin <= bmax)) return 0.0f;               // NaN norms: never skip
+      return gap > 0.0f ? gap * gap * 0.9999f : 0.0f;
     };
-    auto issue_x = [&](int k) {  // exact image (20 KB) of tile k -> stage k & 3
-      const uint32_t bar = bar_fullx0 + 8 * (k & (kTcStages - 1));
+    // start at the tile whose norm range is closest to the stripe's, then walk outwards on both sides
+    int t0 = 0;
+    {
+      float best = INFINITY;
+      for (int t = lane; t < n_tiles; t += 32) {
+        const float g = tile_lb(t);
+        if (g < best) { best = g; t0 = t; }
+      }
+      const unsigned key = __reduce_min_sync(0xffffffffu, tc_fkey(best));
+      const unsigned who = __ballot_sync(0xffffffffu, tc_fkey(best) == key);
+      t0 = __shfl_sync(0xffffffffu, t0, __ffs(who) - 1);
+    }
+    int lo = t0 - 1, hi = t0 + 1;
+    bool first = true, done = false;
+    auto next_tile = [&]() -> int {  // warp-uniform
+      if (first) { first = false; return t0; }
+      while (true) {
+        if ((lo < 0 && hi >= n_tiles) || *v_abort || *v_dead) return -1;
+        const float gl = lo >= 0 ? tile_lb(lo) : INFINITY, gh = hi < n_tiles ? tile_lb(hi) : INFINITY;
+        const bool left = gl <= gh;
+        const int t = left ? lo : hi;
+        const float lb = left ? gl : gh;
+        if (left) --lo; else ++hi;
+        if (lb <= 0.0f || no_prune) return t;
+        // current worst row best of the stripe / worst column best of the tile (+inf while any is unknown)
+        unsigned rmax = 0, cmax = 0;
+#pragma unroll
+        for (int i = 0; i < kTcM / 32; ++i) {
+          const int row = lane + 32 * i;
+          if (r0 + row < nA) {
+            const unsigned long long rb = v_rbest[row];
+            rmax = max(rmax, rb == ~0ull ? 0x7F800000u : (unsigned)(rb >> 32));
+          }
+        }
+        rmax = __reduce_max_sync(0xffffffffu, rmax);  // distances are >= 0: the bit patterns order them
+        if (!(lb > __uint_as_float(rmax))) return t;
+#pragma unroll
+        for (int i = 0; i < kTcN / 32; ++i) {
+          const int j = t * kTcN + lane + 32 * i;
+          if (j < nB) {
+            const unsigned long long cb = __ldcg(cbg + j);
+            cmax = max(cmax, cb == ~0ull ? 0x7F800000u : (unsigned)(cb >> 32));
+          }
+        }
+        cmax = __reduce_max_sync(0xffffffffu, cmax);
+        if (!(lb > __uint_as_float(cmax))) return t;
+        // every entry of the tile is farther than all current bests (strictly: ties go to the lower index): skipped for good
+      }
+    };
+    int n_issued = 0;
+    auto decide = [&](int n) {  // fix the tile of sequence position n
+      int t = -1;
+      if (!done) {
+        t = next_tile();
+        if (t < 0) done = true; else ++n_issued;
+      }
+      if (lane == 0) v_seq[n & 7] = t;
+      __syncwarp();
+      return t;
+    };
+    auto issue_hl = [&](int n) {  // operand images (hi | lo, 40 KB) of position n -> stage n & 1; end marker: plain arrive
+      const int t = v_seq[n & 7];
+      if (lane != 0) return;
+      const uint32_t bar = bar_fullhl0 + 8 * (n & 1);
+      if (t < 0) { mbar_arrive(bar); return; }
+      mbar_expect_tx(bar, kHLBytes);
+      bulk_g2s(sHL0 + (n & 1) * kHLBytes, tB + (size_t)t * kTcImages * kTileFloats, kHLBytes, bar);
+    };
+    auto issue_x = [&](int n) {  // exact image (20 KB) of position n -> stage n & 3
+      const int t = v_seq[n & 7];
+      if (lane != 0) return;
+      const uint32_t bar = bar_fullx0 + 8 * (n & (kTcStages - 1));
+      if (t < 0) { mbar_arrive(bar); return; }
       mbar_expect_tx(bar, kXBytes);
-      bulk_g2s(sX0 + (k & (kTcStages - 1)) * kXBytes, tB + ((size_t)tile_of(k) * kTcImages + 2) * kTileFloats, kXBytes, bar);
+      bulk_g2s(sX0 + (n & (kTcStages - 1)) * kXBytes, tB + ((size_t)t * kTcImages + 2) * kTileFloats, kXBytes, bar);
     };
     if (lane == 0) {
       mbar_expect_tx(bar_a, kABytes);
       bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
-      for (int k = 0; k < 2 && k < n_tiles; ++k) issue_hl(k);
-      for (int k = 0; k < 3 && k < n_tiles; ++k) issue_x(k);
     }
+    for (int n = 0; n < 3; ++n) decide(n);
+    issue_hl(0); issue_hl(1);
+    issue_x(0); issue_x(1); issue_x(2);
     bool ok = true;
-    for (int k = 0; k < n_tiles && ok; ++k) {
-      if (k + 2 < n_tiles) {  // operand stage k & 1 is free once the MMAs of tile k completed
-        ok = mbar_wait(bar_mma0 + 8 * (k & (kTcAcc - 1)), (uint32_t)((k >> 2) & 1));
-        if (ok && lane == 0) issue_hl(k + 2);
-      }
-      if (ok && k + 3 < n_tiles) {  // the exact image of tile k+3 replaces that of tile k-1: every warp must have evaluated it
-        if (k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 3) & (kTcStages - 1)), (uint32_t)(((k - 1) >> 2) & 1));
-        if (ok && lane == 0) issue_x(k + 3);
-      }
-      __syncwarp();
+    for (int k = 0; ok; ++k) {
+      if (v_seq[k & 7] < 0) break;
+      // operand stage k & 1 is free once the MMAs of position k completed
+      ok = mbar_wait(bar_mma0 + 8 * (k & (kTcAcc - 1)), (uint32_t)((k >> 2) & 1));
+      if (!ok) break;
+      issue_hl(k + 2);
+      // the exact image of position k+3 replaces that of position k-1: every warp must have evaluated it
+      if (k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 3) & (kTcStages - 1)), (uint32_t)(((k - 1) >> 2) & 1));
+      if (!ok) break;
+      decide(k + 3);
+      issue_x(k + 3);
     }
     if (!ok) *v_dead = 1;
+    if (lane == 0) s_npos = n_issued;
   } else {
     // ================= filter / evaluation warps =================
     const int quad = warp & 3, cq = warp >> 2, cb = cq * 32;
@@ -288,38 +451,40 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     const float4* __restrict__ aex = reinterpret_cast<const float4*>(smem + 2 * kTcTileBytes) + quad * 32;  // exact image of the A block
     const float kLow = 1.0f - 0.5f * kTcC;                   // d~ - e_ij = kLow (na' + nb') - 2 dot
     const float kHighOverLow = (1.0f + 0.5f * kTcC) / kLow;  // (1 + c/2) x from the stored kLow x
-    const float nam = row_ok ? kLow * norm[(size_t)cloudA * V + gi] : 0.0f;
+    const float nam = row_ok ? kLow * nrmA[gi] : 0.0f;
     const float negna = row_ok ? -nam : -INFINITY;           // column test:  kLow nb' - 2 dot - cbest_j <= -kLow na'
+    const unsigned oa = row_ok ? permA[gi] : 0u;             // point index of this lane's row
     float Ri_ub = row_ok ? INFINITY : -INFINITY;             // row test:     kLow nb' - 2 dot <= best_i - kLow na'
     float* wnbm = s_wnbm[warp];
     float* wcj = s_wcj[warp];
     unsigned short* wq = s_queue[warp];
-    volatile unsigned long long* v_rbest = s_rbest;
     int evals_w = 0;
     bool alive = mbar_wait(bar_a, 0);
-    unsigned long long cb_next = ~0ull;  // snapshot of colbest for this lane's column of the NEXT tile (hides the L2 latency)
-    {
-      const int j = tile_of(0) * kTcN + cb + lane;
-      if (j < nB) cb_next = __ldcg(cbg + j);
-    }
-    for (int k = 0; k < n_tiles; ++k) {
-      const int ts = k & (kTcAcc - 1), st = k & (kTcStages - 1), jt = tile_of(k), c0 = jt * kTcN;
-      const unsigned long long cb_cur = cb_next;
-      cb_next = ~0ull;
-      if (k + 1 < n_tiles) {
-        const int j = tile_of(k + 1) * kTcN + cb + lane;
-        if (j < nB) cb_next = __ldcg(cbg + j);
-      }
+    for (int k = 0;; ++k) {
+      const int ts = k & (kTcAcc - 1), st = k & (kTcStages - 1);
       if (alive) alive = mbar_wait(bar_fullx0 + 8 * st, (uint32_t)((k >> 2) & 1));  // the exact image is read below
-      if (alive) alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 2) & 1));
-      if (!alive) *v_dead = 1;
+      alive = __all_sync(0xffffffffu, alive);
+      if (!alive) { *v_dead = 1; break; }
+      const int jt = v_seq[k & 7];
+      if (jt < 0) break;
+      const int c0 = jt * kTcN;
+      // snapshot of the column's best and its point index (lane = column); the load overlaps the wait for the MMAs
+      unsigned long long cb_cur = ~0ull;
+      unsigned ob = 0;
+      if (c0 + cb + lane < nB) {
+        cb_cur = __ldcg(cbg + c0 + cb + lane);
+        ob = permB[c0 + cb + lane];
+      }
+      alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 2) & 1));
+      alive = __all_sync(0xffffffffu, alive);
+      if (!alive) { *v_dead = 1; break; }
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const bool skip = __any_sync(0xffffffffu, (*v_abort | *v_dead) != 0);
       uint32_t v[32];
       if (!skip) tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ts * kTcN + cb), v);
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tfree0 + 8 * ts);  // accumulators are in registers: the MMA of tile k+2 may overwrite them
+      if (lane == 0) mbar_arrive(bar_tfree0 + 8 * ts);  // accumulators are in registers: the stage may be overwritten
       if (!skip) {
         const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + 2 * kHLBytes + st * kXBytes);  // exact image
         // ---- per-column filter data of this warp's 32 columns (lane = column)
@@ -375,9 +540,17 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
                 "@q or.b32 %0, %0, %5;\n\t}\n"
                 : "+r"(mask)
                 : "f"(u), "f"(negna), "f"(t), "f"(Ri), "r"(1u << c));
-            if (kDbg && stripe == 0 && k == 0) dbg_tile[(size_t)row * kTcN + cb + c] = (nam + wv[e]) / kLow - 2.0f * dot;
+            if (kDbg) {
+              const unsigned oc = __shfl_sync(0xffffffffu, ob, c);
+              if (stripe == 0 && k == 0 && row_ok && c0 + cb + c < nB) dbg_tile[(size_t)oa * kTcN + oc] = (nam + wv[e]) / kLow - 2.0f * dot;
+            }
           }
         }
+        // padding never competes: a padded row (-inf thresholds) would pass the column test of a column without a best
+        // (-inf <= -inf), a padded column (+inf terms) the row test of a row without one -- and their zero images look
+        // like the all-zero descriptor of an isolated point
+        mask &= __ballot_sync(0xffffffffu, c0 + cb + lane < nB);
+        if (!row_ok) mask = 0;
         // ---- exact evaluation, one candidate per lane, 32 per round
         int remaining = __reduce_add_sync(0xffffffffu, __popc(mask));
         evals_w += remaining;
@@ -405,11 +578,13 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
             if (4 * kc + 3 < kDescDim) { diff = a.w - b.w; acc = __fmaf_rn(diff, diff, acc); }
           }
           const float dbc = __shfl_sync(0xffffffffu, dbest, c);
+          const unsigned oc = __shfl_sync(0xffffffffu, ob, c);   // point index of the candidate's column
+          const unsigned orow = __shfl_sync(0xffffffffu, oa, rl);  // ... and of its row
           if (lane < nb && acc == acc) {  // NaN never wins
-            const int rr = quad * 32 + rl, j = c0 + pcol;
-            const unsigned long long pr = tc_pack(acc, j);
+            const int rr = quad * 32 + rl;
+            const unsigned long long pr = tc_pack(acc, (int)oc);
             if (pr < v_rbest[rr]) atomicMin(&s_rbest[rr], pr);
-            if (acc <= dbc) atomicMin(cbg + j, tc_pack(acc, r0 + rr));
+            if (acc <= dbc) atomicMin(cbg + c0 + pcol, tc_pack(acc, (int)orow));
           }
           __syncwarp();
           remaining = tot - nb;
@@ -422,7 +597,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         evals_w = 0;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree0 + 8 * st);  // ring stage st may be refilled
+      if (lane == 0) mbar_arrive(bar_sfree0 + 8 * st);  // the exact-image stage may be refilled
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -430,7 +605,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   const bool aborted = (s_abort | s_dead) != 0;
   if (threadIdx.x == 0) {
     atomicAdd(stats + 0, (unsigned long long)s_evals);
-    atomicAdd(stats + 1, (unsigned long long)n_tiles);
+    atomicAdd(stats + 1, (unsigned long long)s_npos);
     atomicAdd(stats + 2, (unsigned long long)s_warm);
     if (aborted) {
       atomicAdd(stats + 3, 1ull);
@@ -444,6 +619,25 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
 
 static size_t tc_smem_bytes() { return (size_t)kTcImages * kTcTileBytes + 2 * 2 * (size_t)kTcTileBytes + (size_t)kTcStages * kTcTileBytes; }  // 220 KB
 
+// norm keys -> one radix sort for all clouds (h->val_b = rank -> point) -> duplicate classes.
+// Scratch (free once the sort consumed its inputs): val_a = unique rank -> point, key_a = [class of rank | unique counts].
+static int sort_and_dedup(qb200_handle* h, int n_clouds, int dedup) {
+  const int V = h->V;
+  const dim3 g((V + 255) / 256, n_clouds);
+  norm_key_kernel<<<g, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->key_a, h->val_a);
+  h->launches += 1;
+  int bits = 0;
+  while ((1 << bits) < n_clouds) ++bits;
+  const int rc = sort_pairs(h, n_clouds * V, 32 + bits);
+  if (rc) return rc;
+  uint32_t* class_of = reinterpret_cast<uint32_t*>(h->key_a);
+  int* n_unique = reinterpret_cast<int*>(class_of + (size_t)2 * h->S * V);
+  dedup_kernel<<<n_clouds, 1024, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->key_b, h->val_b, dedup, h->val_a, class_of, n_unique);
+  h->launches += 1;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
   static bool attr_set = false;
@@ -452,32 +646,52 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
     QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  // triage switches (results are identical either way): QB200_TC_NODEDUP=1 keeps duplicate descriptors, QB200_TC_NOPRUNE=1
+  // visits every column tile
+  static const int no_dedup = (getenv("QB200_TC_NODEDUP") && getenv("QB200_TC_NODEDUP")[0] == '1') ? 1 : 0;
+  static const int no_prune = (getenv("QB200_TC_NOPRUNE") && getenv("QB200_TC_NOPRUNE")[0] == '1') ? 1 : 0;
+  int rc = sort_and_dedup(h, 2 * n_pairs, no_dedup ? 0 : 1);
+  if (rc) return rc;
+  const uint32_t* uperm = h->val_a;
+  const uint32_t* class_of = reinterpret_cast<const uint32_t*>(h->key_a);
+  const int* n_unique = reinterpret_cast<const int*>(class_of + (size_t)2 * h->S * V);
+  // class results, indexed by unique rank (colpart is scratch of the exact kernel, which runs later)
+  unsigned long long* colbest_u = h->colpart;
+  unsigned long long* rowbest_u = h->colpart + (size_t)h->S * V;
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, (size_t)2 * h->S * V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, (size_t)n_pairs * sizeof(int), h->stream));
   const dim3 gsplit((V + 255) / 256, 2 * n_pairs);
-  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->desc_tiles, h->desc_norm);
+  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, n_unique, V, uperm, h->desc_tiles, h->desc_norm);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
-  tc_nn_kernel<false><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, nullptr);
+  tc_nn_kernel<false><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, V, uperm, rowbest_u, colbest_u,
+                                                          h->tc_fallback, h->tc_stats, nullptr, no_prune);
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
-  h->launches += 2;
+  broadcast_best_kernel<<<gsplit, 256, 0, h->stream>>>(rowbest_u, colbest_u, h->ctr.n_vox, V, h->val_b, class_of, h->rowbest, h->colbest);
+  h->launches += 3;
   QB_CUDA_TRY(h, cudaGetLastError());
   return launch_match_exact(h, n_pairs, h->tc_fallback);
 }
 
-// debug/validation hook: approximate distances d~ of the first 128 x 128 tile of pair 0 (descriptors already in desc_t)
+// debug/validation hook: approximate distances d~ of the first 128 x 128 tile of pair 0 (descriptors already in desc_t;
+// duplicates are kept so that every (row, column) of the dump is filled)
 int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
   const size_t smem = tc_smem_bytes();
   QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)h->V * 8, h->stream));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)h->V * 8, h->stream));
+  int rc = sort_and_dedup(h, 2, 0);
+  if (rc) return rc;
+  const uint32_t* uperm = h->val_a;
+  const int* n_unique = reinterpret_cast<const int*>(reinterpret_cast<const uint32_t*>(h->key_a) + (size_t)2 * h->S * h->V);
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, (size_t)2 * h->S * h->V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, sizeof(int), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
-  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, h->ctr.n_vox, h->V, h->desc_tiles, h->desc_norm);
+  split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, n_unique, h->V, uperm, h->desc_tiles, h->desc_norm);
   const dim3 g(1, 1);
-  tc_nn_kernel<true><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, h->ctr.n_vox, h->V, h->rowbest, h->colbest, h->tc_fallback, h->tc_stats, d_out);
+  tc_nn_kernel<true><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, h->V, uperm, h->colpart + (size_t)h->S * h->V,
+                                                         h->colpart, h->tc_fallback, h->tc_stats, d_out, 0);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;

@@ -145,6 +145,22 @@ def _fpfh_like(rng, n):
     return d.astype(np.float32)
 
 
+def test_match_isolated_points_and_padding(handle, oracle):
+    """All-zero descriptors (FPFH of a point without neighbours) are bit-identical to the zero padding of the last
+    128-point block: padded rows / columns must never enter the exact evaluation (regression: they once won ties)."""
+    rng = np.random.default_rng(21)
+    for na, nb in ((300, 290), (129, 257), (640, 513)):
+        a, b = P4(rng.uniform(-30, 30, (na, 3))), P4(rng.uniform(-30, 30, (nb, 3)))
+        ad, bd = _fpfh_like(rng, na), _fpfh_like(rng, nb)
+        ad[[7, na // 2, na - 1]] = 0.0
+        bd[[3, nb - 2]] = 0.0
+        ad[na // 3] = ad[5]; bd[nb // 3] = ad[5]                 # a duplicate class that is not the zero vector
+        p = default_params(); p.use_tuple_test = 0
+        ref = oracle.match(a, ad, b, bd, p)
+        got = handle.match(a, ad, b, bd, p)
+        assert np.array_equal(got[0], ref[0]) and got[1] == ref[1], (na, nb)
+
+
 def test_tc_filter_error_bound(handle):
     """The tensor-core (tcgen05, 3xTF32) approximate distances must stay well inside the margin the candidate
     filter assumes: |d~ - d| <= kappa/4 * (|a|^2 + |b|^2) with kappa = 1e-4 (csrc/tc_match.cu)."""
