@@ -43,34 +43,38 @@ static int clog2(int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1a: raw point -> (cloud | voxel cell) key.  128-bit loads, one pass over the raw scan.
+// K1a: bounding box of the kept raw points (one pass, 128-bit loads), then raw point -> (cloud | voxel) key.
+// The voxel key is PCL's own linear index  (i - min_i) + (j - min_j) dx + (k - min_k) dx dy  ([EXT] pcl::VoxelGrid,
+// called from include/quatro.hpp:49-57), which the library requires to fit an int: 31 key bits + the cloud id, so the
+// radix sort of the whole wave needs 5 passes instead of the 8 an absolute (k, j, i) lattice key would take.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
-                                                         const int* __restrict__ raw_off, float inv_leaf, int skip_flagged,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int* __restrict__ bbox,
+constexpr int kVoxShift = 31;
+constexpr uint64_t kVoxMask = (1ull << kVoxShift) - 1;
+constexpr uint64_t kVoxInvalid = kVoxMask;  // dx dy dz <= INT_MAX: a valid index is at most 2^31 - 2
+
+__device__ __forceinline__ bool raw_point_kept(const float4 p, int skip_flagged) {
+  return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(skip_flagged && p.w < 0.0f);
+}
+
+__global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
+                                                         float inv_leaf, int skip_flagged, int* __restrict__ bbox,
                                                          int* __restrict__ n_valid, int* __restrict__ cloud_status) {
   const int cloud = blockIdx.y;
-  const int n = cloud_n[cloud], off = raw_off[cloud];
+  const int n = cloud_n[cloud];
   const float4* __restrict__ pts = cloud_ptr[cloud];
   int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN, cnt = 0, bad = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = __ldg(pts + i);
-    bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(skip_flagged && p.w < 0.0f);
-    uint64_t cell = kCellInvalid;
-    if (ok) {
-      const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
-      if (cell_ok(ci, cj, ck)) {
-        cell = cell_key(ci, cj, ck);
-        const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
-        mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
-        mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
-        ++cnt;
-      } else {
-        bad = 1;  // outside the representable lattice: PCL's index would overflow as well
-      }
+    if (!raw_point_kept(p, skip_flagged)) continue;
+    const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
+    if (cell_ok(ci, cj, ck)) {
+      const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
+      mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+      mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+      ++cnt;
+    } else {
+      bad = 1;  // outside the representable lattice: PCL's index would overflow as well
     }
-    keys[off + i] = ((uint64_t)cloud << kCloudShift) | cell;
-    vals[off + i] = (uint32_t)i;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -87,6 +91,38 @@ __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __
       atomicAdd(n_valid + cloud, cnt);
     }
     if (bad) cloud_status[cloud] = QB200_ERR_VOXEL_OVERFLOW;
+  }
+}
+
+__global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
+                                                         const int* __restrict__ raw_off, float inv_leaf, int skip_flagged,
+                                                         const int* __restrict__ bbox, const int* __restrict__ n_valid,
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int cloud = blockIdx.y;
+  const int n = cloud_n[cloud], off = raw_off[cloud];
+  const float4* __restrict__ pts = cloud_ptr[cloud];
+  // min_b / div_b of pcl::VoxelGrid::applyFilter
+  long long m0 = 0, m1 = 0, m2 = 0, d0 = 1, d1 = 1, d2 = 1;
+  if (n_valid[cloud] > 0) {
+    const int* b = bbox + cloud * 6;
+    m0 = (long long)floorf(ordered_float(b[0]) * inv_leaf); m1 = (long long)floorf(ordered_float(b[1]) * inv_leaf);
+    m2 = (long long)floorf(ordered_float(b[2]) * inv_leaf);
+    d0 = (long long)floorf(ordered_float(b[3]) * inv_leaf) - m0 + 1; d1 = (long long)floorf(ordered_float(b[4]) * inv_leaf) - m1 + 1;
+    d2 = (long long)floorf(ordered_float(b[5]) * inv_leaf) - m2 + 1;
+  }
+  (void)d2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(pts + i);
+    uint64_t cell = kVoxInvalid;
+    if (raw_point_kept(p, skip_flagged)) {
+      const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
+      if (cell_ok(ci, cj, ck)) {
+        const long long lin = ((long long)ci - m0) + ((long long)cj - m1) * d0 + ((long long)ck - m2) * d0 * d1;
+        if (lin >= 0 && lin < (long long)kVoxInvalid) cell = (uint64_t)lin;  // otherwise the cloud is refused (overflow) anyway
+      }
+    }
+    keys[off + i] = ((uint64_t)cloud << kVoxShift) | cell;
+    vals[off + i] = (uint32_t)i;
   }
 }
 
@@ -135,7 +171,7 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
     bool valid = false;
     if (p < n) {
       k = keys[off + p];
-      valid = (k & kCellMask) != kCellInvalid;
+      valid = mode == 0 ? (k & kVoxMask) != kVoxInvalid : (k & kCellMask) != kCellInvalid;
       if (p > 0) kprev = keys[off + p - 1];
     }
     const int head = (valid && (p == 0 || k != kprev)) ? 1 : 0;
@@ -280,15 +316,41 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
   normals[(size_t)cloud * V + q] = make_float4(out[0], out[1], out[2], out[3]);
 }
 
+// K4 / K5 walk the same neighbourhoods.  A thread first COLLECTS its neighbour indices (cheap distance tests, divergent)
+// into a shared-memory list and then processes the list in a dense loop, so the expensive per-neighbour work (pair
+// features, 33-bin gathers) runs with most lanes of the warp active instead of whenever any lane found a neighbour.
+// Neighbourhoods larger than the list are handled window by window (ordinals [base, base + cap)), order preserved.
+constexpr int kNbrThreads = 128;
+constexpr int kNbrCap = 96;
+
+template <class Process>
+__device__ __forceinline__ int for_each_neighbor_listed(const LatticeView& L, const float4 pq, int m, float r2,
+                                                        unsigned short (*nbr)[kNbrThreads], Process&& process) {
+  int k_total = 0;
+  for (int base = 0;; base += kNbrCap) {
+    int k = 0;
+    for_each_neighbor(L, pq, m, r2, [&](int p, float, const float4) {
+      if (k >= base && k < base + kNbrCap) nbr[k - base][threadIdx.x] = (unsigned short)p;
+      ++k;
+    });
+    k_total = k;
+    const int kl = k_total - base < kNbrCap ? k_total - base : kNbrCap;
+    for (int t = 0; t < kl; ++t) process((int)nbr[t][threadIdx.x]);
+    if (base + kNbrCap >= k_total) break;
+  }
+  return k_total;
+}
+
 // K4: SPFH.  Bin COUNTS are order-free; the float histogram value is rebuilt by repeated addition
 // of the same increment, which is what the sequential reference loop produces.
-constexpr int kSpfhThreads = 128;
+constexpr int kSpfhThreads = kNbrThreads;
 __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __restrict__ pts, const float4* __restrict__ normals,
                                                             const int* __restrict__ n_pts, int V, const uint64_t* __restrict__ cell_key,
                                                             const int* __restrict__ cell_start, const uint32_t* __restrict__ order,
                                                             const int* __restrict__ n_cells, float inv, int m, float r2,
                                                             float* __restrict__ spfh) {
   __shared__ unsigned short cnts[kDescDim][kSpfhThreads];
+  __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_pts[cloud]) return;
@@ -298,10 +360,9 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
   const float4 nq = nrm[q];
 #pragma unroll
   for (int b = 0; b < kDescDim; ++b) cnts[b][threadIdx.x] = 0;
-  int k = 0;
-  for_each_neighbor(L, pq, m, r2, [&](int p, float, const float4 pp) {
-    ++k;
+  const int k = for_each_neighbor_listed(L, pq, m, r2, nbr, [&](int p) {
     if (p == q) return;
+    const float4 pp = L.pts[p];
     const float4 np = nrm[p];
     float f1, f2, f3;
     if (!qb_pair_features(pq.x, pq.y, pq.z, nq.x, nq.y, nq.z, pp.x, pp.y, pp.z, np.x, np.y, np.z, &f1, &f2, &f3)) return;
@@ -324,10 +385,11 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
 
 // K5: FPFH = per-third renormalised sum of neighbour SPFHs weighted by 1/d^2, neighbours in lattice
 // order.  Output is written dimension-major (desc_t[d][q]) for the matching kernel's tile loads.
-__global__ void __launch_bounds__(128) fpfh_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
-                                                   const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
-                                                   const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv, int m,
-                                                   float r2, const float* __restrict__ spfh, float* __restrict__ desc_t) {
+__global__ void __launch_bounds__(kNbrThreads) fpfh_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                           const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
+                                                           const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv,
+                                                           int m, float r2, const float* __restrict__ spfh, float* __restrict__ desc_t) {
+  __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_pts[cloud]) return;
@@ -338,7 +400,10 @@ __global__ void __launch_bounds__(128) fpfh_kernel(const float4* __restrict__ pt
 #pragma unroll
   for (int b = 0; b < kDescDim; ++b) o[b] = 0.0f;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for_each_neighbor(L, pq, m, r2, [&](int p, float d2, const float4) {
+  for_each_neighbor_listed(L, pq, m, r2, nbr, [&](int p) {
+    const float4 pp = L.pts[p];
+    const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
+    const float d2 = (dx * dx + dy * dy) + dz * dz;  // the same expression as the neighbour test: bit-identical
     if (d2 == 0.0f) return;
     const float weight = 1.0f / d2;
     float s[kDescPad];
@@ -388,10 +453,11 @@ int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int s
   if (n_clouds <= 0) return QB200_OK;
   const float inv = 1.0f / leaf;
   const dim3 gk(64, n_clouds);
-  voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->key_a, h->val_a, h->ctr.bbox,
-                                               h->ctr.n_valid, h->ctr.cloud_status);
-  h->launches++;
-  const int rc = sort_pairs(h, total_raw, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
+  voxel_bbox_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid, h->ctr.cloud_status);
+  voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid,
+                                               h->key_a, h->val_a);
+  h->launches += 2;
+  const int rc = sort_pairs(h, total_raw, kVoxShift + clog2(n_clouds > 1 ? n_clouds : 2));
   if (rc) return rc;
   run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(0, h->key_b, h->d_raw_off, h->d_cloud_n, h->V, inv, h->ctr.bbox, h->ctr.n_valid,
                                                      h->vox_start, nullptr, h->ctr.n_vox, nullptr, h->ctr.cloud_status);
@@ -420,7 +486,7 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
                                             h->normals);
   spfh_kernel<<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
                                                   h->ctr.n_cells, inv, mf, rf2, h->spfh);
-  fpfh_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf, rf2,
+  fpfh_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf, rf2,
                                          h->spfh, h->desc_t);
   h->launches += 4;
   QB_CUDA_TRY(h, cudaGetLastError());
