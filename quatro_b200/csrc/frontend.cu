@@ -249,34 +249,87 @@ struct LatticeView {
   float inv;
 };
 
+// candidates of the occupied cells [c0, c1): loads are issued four points at a time (index -> point are dependent loads;
+// independent candidates overlap their latency), tests and callbacks stay in (cell, index) order
+template <class F>
+__device__ __forceinline__ void walk_cells(const LatticeView& L, const float4 pq, float r2, int c0, int c1, F&& f) {
+  if (c0 >= c1) return;
+  const int t1 = L.cstart[c1];
+  for (int t = L.cstart[c0]; t < t1; t += 4) {
+    int p[4];
+    float4 pp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[e] = t + e < t1 ? (int)L.order[t + e] : -1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pp[e] = p[e] >= 0 ? L.pts[p[e]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (p[e] < 0) continue;
+      const float dx = pq.x - pp[e].x, dy = pq.y - pp[e].y, dz = pq.z - pp[e].z;
+      const float d2 = (dx * dx + dy * dy) + dz * dz;
+      if (d2 < r2) f(p[e], d2, pp[e]);
+    }
+  }
+}
+
 template <class F>
 __device__ __forceinline__ void for_each_neighbor(const LatticeView& L, const float4 pq, int m, float r2, F&& f) {
   if (!(isfinite(pq.x) && isfinite(pq.y) && isfinite(pq.z))) return;
   const int ci = (int)floorf(pq.x * L.inv), cj = (int)floorf(pq.y * L.inv), ck = (int)floorf(pq.z * L.inv);
   if (!cell_ok(ci, cj, ck)) return;
+  const int ilo = max(ci - m, -kOffIJ), ihi = min(ci + m, kOffIJ - 2);
+  if (m == 1) {
+    // the usual case (cell >= radius): the 9 (k, j) rows are located by 9 binary searches that advance in lockstep, so
+    // their loads are independent (one round trip per step instead of nine), and each row is one contiguous cell range
+    uint64_t lo[9], hi[9];
+    int a[9], b[9], e[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int k = ck + r / 3 - 1, j = cj + r % 3 - 1;
+      const bool ok = !(k < -kOffK || k >= kOffK - 1 || j < -kOffIJ || j >= kOffIJ - 1);
+      lo[r] = ok ? cell_key(ilo, j, k) : 1;
+      hi[r] = ok ? cell_key(ihi, j, k) : 0;
+      a[r] = 0; b[r] = ok ? L.n_cells : 0;
+      e[r] = 0;
+    }
+    const int steps = 33 - __clz(L.n_cells | 1);
+    for (int s = 0; s < steps; ++s) {
+#pragma unroll
+      for (int r = 0; r < 9; ++r) {
+        if (a[r] < b[r]) {
+          const int mid = (a[r] + b[r]) >> 1;
+          if (L.ckeys[mid] < lo[r]) a[r] = mid + 1; else b[r] = mid;
+        }
+      }
+    }
+    // end of each row's range: at most 3 cells (i - 1, i, i + 1)
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      int c = a[r];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (c < L.n_cells && hi[r] >= lo[r] && L.ckeys[c] <= hi[r]) ++c;
+      e[r] = c;
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) walk_cells(L, pq, r2, a[r], e[r], f);
+    return;
+  }
   for (int dk = -m; dk <= m; ++dk) {
     const int k = ck + dk;
     if (k < -kOffK || k >= kOffK - 1) continue;
     for (int dj = -m; dj <= m; ++dj) {
       const int j = cj + dj;
       if (j < -kOffIJ || j >= kOffIJ - 1) continue;
-      const int ilo = max(ci - m, -kOffIJ), ihi = min(ci + m, kOffIJ - 2);
       const uint64_t lo = cell_key(ilo, j, k), hi = cell_key(ihi, j, k);
       int a = 0, b = L.n_cells;
       while (a < b) {
         const int mid = (a + b) >> 1;
         if (L.ckeys[mid] < lo) a = mid + 1; else b = mid;
       }
-      for (int c = a; c < L.n_cells && L.ckeys[c] <= hi; ++c) {
-        const int t1 = L.cstart[c + 1];
-        for (int t = L.cstart[c]; t < t1; ++t) {
-          const int p = (int)L.order[t];
-          const float4 pp = L.pts[p];
-          const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
-          const float d2 = (dx * dx + dy * dy) + dz * dz;
-          if (d2 < r2) f(p, d2, pp);
-        }
-      }
+      int c = a;
+      while (c < L.n_cells && L.ckeys[c] <= hi) ++c;
+      walk_cells(L, pq, r2, a, c, f);
     }
   }
 }
