@@ -249,7 +249,8 @@ template <bool kDbg>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, const int* __restrict__ n_vox, int V,
              const uint32_t* __restrict__ perm, unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest_r,
-             int* __restrict__ fallback, unsigned long long* __restrict__ stats, float* __restrict__ dbg_tile, int no_prune) {
+             unsigned* __restrict__ tile_cmax, int* __restrict__ fallback, unsigned long long* __restrict__ stats,
+             float* __restrict__ dbg_tile, int no_prune) {
   extern __shared__ __align__(128) unsigned char smem[];  // 220 KB of operand images; static + dynamic must stay <= 227 KB
   __shared__ uint64_t s_fullx[kTcStages], s_sfree[kTcStages], s_fullhl[2], s_mma[kTcAcc], s_tfree[kTcAcc], s_afull;
   __shared__ uint32_t s_tmem;
@@ -258,6 +259,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   __shared__ __align__(16) float s_wcj[kTcEpiWarps][32];       //           kLow |b'_j|^2 - (best exact distance of column j)
   __shared__ unsigned short s_queue[kTcEpiWarps][32];          //           one batch of candidates (row lane << 5 | column)
   __shared__ int s_seq[8];                                     // column tile of sequence position n (ring), -1 = end of the stripe
+  __shared__ float s_tlb[128];                                 // lower bound of every distance between the stripe and column tile t
   __shared__ int s_dead, s_abort, s_evals, s_warm, s_npos;
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
@@ -345,32 +347,37 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       if (!(amin <= amax && bmin <= bmax)) return 0.0f;               // NaN norms: never skip
       return gap > 0.0f ? gap * gap * 0.9999f : 0.0f;
     };
-    // start at the tile whose norm range is closest to the stripe's, then walk outwards on both sides
+    // lower bounds of all column tiles (at most 128: V <= 16384 ... 65536 / 128 = 512 tiles are covered by the loop stride),
+    // kept in shared memory; start at the tile whose norm range is closest to the stripe's, then walk outwards on both sides
     int t0 = 0;
     {
       float best = INFINITY;
       for (int t = lane; t < n_tiles; t += 32) {
         const float g = tile_lb(t);
+        if (t < 128) s_tlb[t] = g;
         if (g < best) { best = g; t0 = t; }
       }
       const unsigned key = __reduce_min_sync(0xffffffffu, tc_fkey(best));
       const unsigned who = __ballot_sync(0xffffffffu, tc_fkey(best) == key);
       t0 = __shfl_sync(0xffffffffu, t0, __ffs(who) - 1);
+      __syncwarp();
     }
+    auto tlb = [&](int t) -> float { return t < 128 ? s_tlb[t] : tile_lb(t); };
+    unsigned* __restrict__ tcm = tile_cmax + (size_t)pair * (V >> 7);  // per column tile: a recent max of its column bests
     int lo = t0 - 1, hi = t0 + 1;
     bool first = true, done = false;
     auto next_tile = [&]() -> int {  // warp-uniform
       if (first) { first = false; return t0; }
       while (true) {
         if ((lo < 0 && hi >= n_tiles) || *v_abort || *v_dead) return -1;
-        const float gl = lo >= 0 ? tile_lb(lo) : INFINITY, gh = hi < n_tiles ? tile_lb(hi) : INFINITY;
+        const float gl = lo >= 0 ? tlb(lo) : INFINITY, gh = hi < n_tiles ? tlb(hi) : INFINITY;
         const bool left = gl <= gh;
         const int t = left ? lo : hi;
         const float lb = left ? gl : gh;
         if (left) --lo; else ++hi;
         if (lb <= 0.0f || no_prune) return t;
-        // current worst row best of the stripe / worst column best of the tile (+inf while any is unknown)
-        unsigned rmax = 0, cmax = 0;
+        // current worst row best of the stripe (+inf while any row is unknown)
+        unsigned rmax = 0;
 #pragma unroll
         for (int i = 0; i < kTcM / 32; ++i) {
           const int row = lane + 32 * i;
@@ -381,6 +388,11 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         }
         rmax = __reduce_max_sync(0xffffffffu, rmax);  // distances are >= 0: the bit patterns order them
         if (!(lb > __uint_as_float(rmax))) return t;
+        // worst column best of the tile: first the shared per-tile value (an upper bound: bests only shrink), and only if
+        // that does not settle it the 128 current column bests themselves, whose max refreshes the shared value
+        unsigned cmax = __ldcg(tcm + t);
+        if (lb > __uint_as_float(cmax)) continue;
+        cmax = 0;
 #pragma unroll
         for (int i = 0; i < kTcN / 32; ++i) {
           const int j = t * kTcN + lane + 32 * i;
@@ -390,6 +402,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
           }
         }
         cmax = __reduce_max_sync(0xffffffffu, cmax);
+        if (lane == 0) atomicMin(tcm + t, cmax);
         if (!(lb > __uint_as_float(cmax))) return t;
         // every entry of the tile is farther than all current bests (strictly: ties go to the lower index): skipped for good
       }
@@ -435,10 +448,11 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       ok = mbar_wait(bar_mma0 + 8 * (k & (kTcAcc - 1)), (uint32_t)((k >> 2) & 1));
       if (!ok) break;
       issue_hl(k + 2);
-      // the exact image of position k+3 replaces that of position k-1: every warp must have evaluated it
+      // the exact image of position k+3 replaces that of position k-1: every warp must have evaluated it.  The tile is
+      // chosen BEFORE the wait (the choice needs no free stage; its L2 round trips hide behind the evaluation of tile k-1)
+      decide(k + 3);
       if (k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 3) & (kTcStages - 1)), (uint32_t)(((k - 1) >> 2) & 1));
       if (!ok) break;
-      decide(k + 3);
       issue_x(k + 3);
     }
     if (!ok) *v_dead = 1;
@@ -590,7 +604,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
           remaining = tot - nb;
         }
         // massive ties: once more than half of the entries seen needed the exact chain, hand the pair to the exact kernel
-        if (lane == 0) {
+        if (lane == 0 && evals_w) {
           const int seen = atomicAdd(&s_evals, evals_w) + evals_w;
           if (k >= 7 && seen > (k + 1) * (kTcM * kTcN / 2)) *v_abort = 1;
         }
@@ -658,16 +672,17 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
   // class results, indexed by unique rank (colpart is scratch of the exact kernel, which runs later)
   unsigned long long* colbest_u = h->colpart;
   unsigned long long* rowbest_u = h->colpart + (size_t)h->S * V;
+  unsigned* tile_cmax = reinterpret_cast<unsigned*>(h->colpart + (size_t)2 * h->S * V);  // [S][V/128] float bits, starts at "+inf"
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, (size_t)2 * h->S * V * 8, h->stream));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, ((size_t)2 * h->S * V + (size_t)h->S * (V >> 7) / 2 + 1) * 8, h->stream));  // 0xFFFFFFFF > +inf bits
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, (size_t)n_pairs * sizeof(int), h->stream));
   const dim3 gsplit((V + 255) / 256, 2 * n_pairs);
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, n_unique, V, uperm, h->desc_tiles, h->desc_norm);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
   tc_nn_kernel<false><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, V, uperm, rowbest_u, colbest_u,
-                                                          h->tc_fallback, h->tc_stats, nullptr, no_prune);
+                                                          tile_cmax, h->tc_fallback, h->tc_stats, nullptr, no_prune);
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
   broadcast_best_kernel<<<gsplit, 256, 0, h->stream>>>(rowbest_u, colbest_u, h->ctr.n_vox, V, h->val_b, class_of, h->rowbest, h->colbest);
@@ -685,13 +700,13 @@ int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
   if (rc) return rc;
   const uint32_t* uperm = h->val_a;
   const int* n_unique = reinterpret_cast<const int*>(reinterpret_cast<const uint32_t*>(h->key_a) + (size_t)2 * h->S * h->V);
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, (size_t)2 * h->S * h->V * 8, h->stream));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, ((size_t)2 * h->S * h->V + (size_t)h->S * (h->V >> 7) / 2 + 1) * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, sizeof(int), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, n_unique, h->V, uperm, h->desc_tiles, h->desc_norm);
   const dim3 g(1, 1);
   tc_nn_kernel<true><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, h->V, uperm, h->colpart + (size_t)h->S * h->V,
-                                                         h->colpart, h->tc_fallback, h->tc_stats, d_out, 0);
+                                                         h->colpart, reinterpret_cast<unsigned*>(h->colpart + (size_t)2 * h->S * h->V), h->tc_fallback, h->tc_stats, d_out, 0);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
