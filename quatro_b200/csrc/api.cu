@@ -608,7 +608,26 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   const float cell = lattice_cell(*p);
   // More than one wave: rotate over the lanes so that one wave's PCIe copies and single-warp solver tail run under the
   // other waves' dense kernels.  Results do not depend on the lane (no state is shared between waves).
-  const int n_waves = (n_pairs + h->S - 1) / h->S;
+  // Wave plan.  Host inputs: nothing can run before the first wave's scans crossed PCIe, so the batch opens with a quarter
+  // wave (its copy is the only one that is not hidden) followed by the remaining three quarters; all other waves are full.
+  int wave_n[64], n_waves = 0;
+  {
+    int left = n_pairs;
+    if (kind == QB200_MEM_HOST && n_pairs > h->S && h->S >= 8 && h->max_lanes > 1) {
+      wave_n[n_waves++] = h->S / 4;
+      wave_n[n_waves++] = h->S - h->S / 4;
+      left -= h->S;
+    }
+    while (left > 0 && n_waves < 63) {
+      wave_n[n_waves] = left < h->S ? left : h->S;
+      left -= wave_n[n_waves++];
+    }
+    if (left > 0) {  // more than ~60 waves: no special opening, walk the rest uniformly below
+      n_waves = 0;
+    }
+  }
+  const bool planned = n_waves > 0;
+  if (!planned) n_waves = (n_pairs + h->S - 1) / h->S;
   const int n_lanes = n_waves < h->max_lanes ? (n_waves < 1 ? 1 : n_waves) : h->max_lanes;
   qb200_handle* lanes[4] = {h, h, h, h};
   for (int l = 1; l < n_lanes; ++l) {
@@ -626,12 +645,14 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
     QB_CUDA_TRY(h, cudaStreamWaitEvent(lanes[l]->stream, h->ev_fork, 0));
   }
   int rc = QB200_OK, wave = 0;
-  for (int w0 = 0; w0 < n_pairs && rc == QB200_OK; w0 += h->S, ++wave) {
+  for (int w0 = 0; w0 < n_pairs && rc == QB200_OK; ++wave) {
     qb200_handle* L = lanes[wave % n_lanes];
-    const int np = (n_pairs - w0 < h->S) ? n_pairs - w0 : h->S;
+    int np = planned ? wave_n[wave] : h->S;
+    if (np > n_pairs - w0) np = n_pairs - w0;
     if ((rc = wave_collect(h, L, results))) break;  // the lane's previous wave (its pinned tables are reused)
     rc = wave_submit(L, pairs, w0, np, kind, p, cell);
     if (rc != QB200_OK && L != h) h->fail(__FILE__, __LINE__, L->err);
+    w0 += np;
   }
   // drain in submission order; on an error still wait for everything in flight (the copies read caller memory)
   for (int i = 0; i < n_lanes; ++i) {
