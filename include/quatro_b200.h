@@ -65,7 +65,7 @@ typedef struct qb200_params {
   float voxel_size;              /* 0.3   voxelize leaf                      params.yaml:22 */
   float normal_radius;           /* 0.5                                      params.yaml:24 */
   float fpfh_radius;             /* 0.75                                     params.yaml:25 */
-  float grid_cell;               /* 0 -> fpfh_radius. Cell of the neighbour-search lattice; the neighbour SETS do not
+  float grid_cell;               /* 0 -> (1 + 2^-9) fpfh_radius. Cell of the neighbour-search lattice; the neighbour SETS do not
                                     depend on it, only the (cell,index) order in which they are accumulated. */
   float tuple_scale;             /* 0.95                                     fpfh_manager.hpp:127 */
   int32_t use_crosscheck;        /* 1 */

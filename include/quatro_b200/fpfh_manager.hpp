@@ -26,7 +26,7 @@ class FPFHManager {
     normal_radius_ = normal_radius; fpfh_radius_ = fpfh_radius; interval_ = interval;
   }
   void clearInputs() { is_initial_ = true; corr.clear(); }
-  // lattice cell of the neighbour search (only fixes the accumulation order); 0 = library default (fpfh_radius)
+  // lattice cell of the neighbour search (only fixes the accumulation order); 0 = library default ((1 + 2^-9) fpfh_radius)
   void setGridCell(float cell) { grid_cell_ = cell; }
   void setSeed(uint64_t seed) { seed_ = seed; }  // tuple-test RNG (the reference seeds with time(NULL))
 

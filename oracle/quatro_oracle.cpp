@@ -1112,7 +1112,7 @@ int qo_solve_correspondences(const float* a4, const float* b4, int L, const qb20
 int qo_match_and_pack(const float* src4, int n_src, const float* tgt4, int n_tgt, const qb200_params* prm, int* corr,
                       float* src_matched4, float* tgt_matched4, int cap, int* n_corr, int* n_mutual) {
   if (prm->normal_radius > prm->fpfh_radius) return QB200_ERR_BAD_ARG;
-  const float cell = prm->grid_cell > 0 ? prm->grid_cell : prm->fpfh_radius;
+  const float cell = prm->grid_cell > 0 ? prm->grid_cell : prm->fpfh_radius * 1.001953125f;  // (1 + 2^-9) r: a 3 x 3 x 3 cell walk is then provably enough
   std::vector<float> sd((size_t)n_src * 33), td((size_t)n_tgt * 33);
   qo_compute_fpfh(src4, n_src, prm->normal_radius, prm->fpfh_radius, cell, nullptr, sd.data(), nullptr);
   qo_compute_fpfh(tgt4, n_tgt, prm->normal_radius, prm->fpfh_radius, cell, nullptr, td.data(), nullptr);
@@ -1150,7 +1150,7 @@ int qo_register_pair(const float* src4, int n_src, const float* tgt4, int n_tgt,
   ts[1] = now_s() - t0; t0 = now_s();
   r.n_src_vox = (int)sv.size(); r.n_tgt_vox = (int)tv.size();
   if (sv.empty() || tv.empty()) { r.status = QB200_DEGENERATE_INPUT; *res = r; return r.status; }
-  const float cell = prm->grid_cell > 0 ? prm->grid_cell : prm->fpfh_radius;
+  const float cell = prm->grid_cell > 0 ? prm->grid_cell : prm->fpfh_radius * 1.001953125f;  // (1 + 2^-9) r: a 3 x 3 x 3 cell walk is then provably enough
   std::vector<float> sd((size_t)sv.size() * 33), td((size_t)tv.size() * 33);
   qo_compute_fpfh(&sv[0].x, (int)sv.size(), prm->normal_radius, prm->fpfh_radius, cell, nullptr, sd.data(), nullptr);
   qo_compute_fpfh(&tv[0].x, (int)tv.size(), prm->normal_radius, prm->fpfh_radius, cell, nullptr, td.data(), nullptr);

@@ -150,7 +150,9 @@ bool params_ok(const qb200_params* p) {
   return true;
 }
 
-float lattice_cell(const qb200_params& p) { return p.grid_cell > 0 ? p.grid_cell : p.fpfh_radius; }
+// default cell = (1 + 2^-9) fpfh_radius: with the cell a hair larger than the radius, |x' - x| < r keeps the cell index of a
+// neighbour within +-1 even after the float rounding of x / cell, so the walk covers 27 cells instead of 125
+float lattice_cell(const qb200_params& p) { return p.grid_cell > 0 ? p.grid_cell : p.fpfh_radius * 1.001953125f; }
 
 // graph -> clique -> pose for pairs [0, n) whose matched points / n_corr are already on the device
 int run_solver(qb200_handle* h, int n_pairs, const qb200_params& p, int have_frontend) {
