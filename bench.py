@@ -263,6 +263,20 @@ def main():
     value = world * P * args.steps / (dev_ms * 1e-3)
     e2e_value = world * P * args.steps / (e2e_ms * 1e-3)
 
+    # BASELINE configs[1] (one pair on one GPU): latency of a single registration through the same call, host buffers
+    single_ms = None
+    if rank == 0:
+        lat = []
+        for i in range(12):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            handle.register_batch_raw(pa_host, 1, p, MEM_HOST, out)
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                lat.append(a0.elapsed_time(a1))
+        single_ms = float(np.median(lat))
+
     if rank == 0:
         peaks = load_peaks()
         nA, nB, L = res_dev["n_src_vox"].astype(np.float64), res_dev["n_tgt_vox"].astype(np.float64), res_dev["n_corr"].astype(np.float64)
@@ -315,6 +329,7 @@ def main():
             "stages_ms_per_step": {k: float(v / args.steps) for k, v in zip(["h2d", "voxel", "fpfh", "match", "graph", "clique", "pose", "d2h"], sms)},
             "valid_pairs": int(res_dev["valid"].sum()), "mean_n_vox": float((nA.mean() + nB.mean()) / 2), "mean_L": float(L.mean()),
             "mean_clique": float(res_dev["clique_size"].mean()),
+            "single_pair_latency_ms": single_ms,
         }
         print(json.dumps(line))
     handle.close()
