@@ -36,6 +36,15 @@ int sort_pairs(qb200_handle* h, int n_items, int end_bit) {
   return QB200_OK;
 }
 
+// keys only (the payload rides in the low key bits below begin_bit: 8 instead of 12 bytes per item and pass)
+int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit) {
+  if (n_items <= 0) return QB200_OK;
+  size_t bytes = h->cub_bytes;
+  QB_CUDA_TRY(h, cub::DeviceRadixSort::SortKeys(h->cub_temp, bytes, h->key_a, h->key_b, n_items, begin_bit, end_bit, h->stream));
+  h->launches += 1 + (end_bit - begin_bit + 7) / 8;
+  return QB200_OK;
+}
+
 static int clog2(int n) {
   int b = 0;
   while ((1 << b) < n) ++b;
@@ -96,8 +105,8 @@ __global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __
 
 __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
                                                          const int* __restrict__ raw_off, float inv_leaf, int skip_flagged,
-                                                         const int* __restrict__ bbox, const int* __restrict__ n_valid,
-                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                         const int* __restrict__ bbox, const int* __restrict__ n_valid, int idx_bits,
+                                                         uint64_t* __restrict__ keys) {
   const int cloud = blockIdx.y;
   const int n = cloud_n[cloud], off = raw_off[cloud];
   const float4* __restrict__ pts = cloud_ptr[cloud];
@@ -121,8 +130,7 @@ __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __
         if (lin >= 0 && lin < (long long)kVoxInvalid) cell = (uint64_t)lin;  // otherwise the cloud is refused (overflow) anyway
       }
     }
-    keys[off + i] = ((uint64_t)cloud << kVoxShift) | cell;
-    vals[off + i] = (uint32_t)i;
+    keys[off + i] = ((((uint64_t)cloud << kVoxShift) | cell) << idx_bits) | (uint64_t)i;  // stable sort on the bits above idx_bits
   }
 }
 
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __
 //   mode 1 (cells):  segment = [cloud*V, cloud*V + V),     writes starts[] and cell keys
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_t* __restrict__ keys, const int* __restrict__ seg_off,
-                                                         const int* __restrict__ seg_n, int V, float inv_leaf, const int* __restrict__ bbox,
+                                                         const int* __restrict__ seg_n, int V, int key_shift, float inv_leaf, const int* __restrict__ bbox,
                                                          const int* __restrict__ n_valid_in, int* __restrict__ starts,
                                                          uint64_t* __restrict__ cell_keys, int* __restrict__ n_out, int* __restrict__ n_valid_out,
                                                          int* __restrict__ cloud_status) {
@@ -170,9 +178,9 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
     uint64_t k = 0, kprev = 0;
     bool valid = false;
     if (p < n) {
-      k = keys[off + p];
+      k = keys[off + p] >> key_shift;  // mode 0: the low bits carry the point index
       valid = mode == 0 ? (k & kVoxMask) != kVoxInvalid : (k & kCellMask) != kCellInvalid;
-      if (p > 0) kprev = keys[off + p - 1];
+      if (p > 0) kprev = keys[off + p - 1] >> key_shift;
     }
     const int head = (valid && (p == 0 || k != kprev)) ? 1 : 0;
     int tot, vtot;
@@ -202,8 +210,9 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
 // K1c: centroid of each voxel, summed in original point order (stable sort) -> identical to the
 // sequential CPU sum.  One thread per voxel; points are gathered through the sorted index.
 __global__ void __launch_bounds__(128) voxel_centroid_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ raw_off,
-                                                             const uint32_t* __restrict__ sorted_idx, const int* __restrict__ starts,
-                                                             const int* __restrict__ n_vox, int V, float4* __restrict__ vox_pts) {
+                                                             const uint64_t* __restrict__ sorted_keys, uint64_t idx_mask,
+                                                             const int* __restrict__ starts, const int* __restrict__ n_vox, int V,
+                                                             float4* __restrict__ vox_pts) {
   const int cloud = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_vox[cloud]) return;
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(128) voxel_centroid_kernel(const float4* const
   const int a = starts[(size_t)cloud * (V + 1) + r], b = starts[(size_t)cloud * (V + 1) + r + 1];
   float sx = 0.f, sy = 0.f, sz = 0.f;
   for (int t = a; t < b; ++t) {
-    const float4 p = __ldg(pts + sorted_idx[off + t]);
+    const float4 p = __ldg(pts + (sorted_keys[off + t] & idx_mask));
     sx += p.x; sy += p.y; sz += p.z;
   }
   const float cnt = (float)(b - a);
@@ -507,15 +516,17 @@ int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int s
   const float inv = 1.0f / leaf;
   const dim3 gk(64, n_clouds);
   voxel_bbox_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid, h->ctr.cloud_status);
+  const int idx_bits = clog2(h->R > 2 ? h->R : 2);  // point index inside its scan
   voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid,
-                                               h->key_a, h->val_a);
+                                               idx_bits, h->key_a);
   h->launches += 2;
-  const int rc = sort_pairs(h, total_raw, kVoxShift + clog2(n_clouds > 1 ? n_clouds : 2));
+  const int rc = sort_keys(h, total_raw, idx_bits, idx_bits + kVoxShift + clog2(n_clouds > 1 ? n_clouds : 2));
   if (rc) return rc;
-  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(0, h->key_b, h->d_raw_off, h->d_cloud_n, h->V, inv, h->ctr.bbox, h->ctr.n_valid,
+  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(0, h->key_b, h->d_raw_off, h->d_cloud_n, h->V, idx_bits, inv, h->ctr.bbox, h->ctr.n_valid,
                                                      h->vox_start, nullptr, h->ctr.n_vox, nullptr, h->ctr.cloud_status);
   const dim3 gc((h->V + 127) / 128, n_clouds);
-  voxel_centroid_kernel<<<gc, 128, 0, h->stream>>>(h->d_cloud_ptr, h->d_raw_off, h->val_b, h->vox_start, h->ctr.n_vox, h->V, h->vox_pts);
+  voxel_centroid_kernel<<<gc, 128, 0, h->stream>>>(h->d_cloud_ptr, h->d_raw_off, h->key_b, (1ull << idx_bits) - 1, h->vox_start, h->ctr.n_vox, h->V,
+                                                   h->vox_pts);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
@@ -532,7 +543,7 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
   h->launches++;
   const int rc = sort_pairs(h, n_clouds * V, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
   if (rc) return rc;
-  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, V, inv, nullptr, nullptr, h->cell_start, h->cell_key,
+  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, V, 0, inv, nullptr, nullptr, h->cell_start, h->cell_key,
                                                      h->ctr.n_cells, h->ctr.n_lat, h->ctr.cloud_status);
   const dim3 gp((V + 127) / 128, n_clouds);
   normals_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mn, rn2,

@@ -105,5 +105,6 @@ int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33);
 int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33);
 size_t sort_temp_bytes(int max_items);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);
+int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit);
 
 }  // namespace qb

@@ -215,10 +215,23 @@ __global__ void __launch_bounds__(32) cloud_mean_kernel(const float4* __restrict
   const int n = n_pts[cloud];
   const float4* __restrict__ p = pts + (size_t)cloud * V;
   float mx = 0.f, my = 0.f, mz = 0.f;
+  // software-pipelined: four chunks of 32 points are in flight while the current one is summed (the additions are a
+  // serial chain by definition, the loads need not be)
+  constexpr int kAhead = 4;
+  float4 buf[kAhead];
+#pragma unroll
+  for (int a = 0; a < kAhead; ++a) {
+    const int i = a * 32 + (int)lane_id();
+    buf[a] = i < n ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int base = 0; base < n; base += 32) {
-    const int i = base + (int)lane_id();
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < n) v = p[i];
+    const float4 v = buf[0];
+#pragma unroll
+    for (int a = 0; a + 1 < kAhead; ++a) buf[a] = buf[a + 1];
+    {
+      const int i = base + kAhead * 32 + (int)lane_id();
+      buf[kAhead - 1] = i < n ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int lim = min(32, n - base);
     for (int l = 0; l < lim; ++l) {
       mx = mx + __shfl_sync(0xffffffffu, v.x, l);
