@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
+    ap.add_argument("--graph-L", type=int, default=3000, help="correspondences per set of the K8 roofline pass (0 = skip)")
     ap.add_argument("--slots", type=int, default=64, help="pairs per device wave (two lanes of this size alternate)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=8)
@@ -187,6 +188,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from quatro_b200 import synth
     from quatro_b200.capi import Handle, Pair, default_params, RESULT_DTYPE, MEM_HOST, MEM_DEVICE
 
     torch.cuda.set_device(local_rank)
@@ -303,6 +305,32 @@ def main():
                           "frac": graph_gbs / peaks["hbm_gbs"], "traffic": None, "launch_ms": graph_ms_launch,
                           "bytes_per_launch": graph_bytes_step / max(kcalls[1] / args.steps, 1), "mean_L": float(L.mean()),
                           "note": "fp32-pipe bound at algorithmic-minimum bytes (SURVEY.md 8d): ~30 instr per pair test vs 0.27 B per pair"}
+        # K8 at the size BASELINE's configs name (~3k correspondences per pair): 32 precomputed correspondence sets through
+        # qb200_solve_batch (device-resident), tim_graph_kernel timed with CUDA events inside the call
+        roofline_graph_3k = None
+        if args.graph_L > 0:
+            gsets, keep = [], []
+            for i in range(32):
+                a4, b4, _, _ = synth.matched_pairs(7000 + i, args.graph_L, inlier_ratio=0.03, noise=0.04)
+                ta, tb = torch.from_numpy(np.ascontiguousarray(a4)).to(dev), torch.from_numpy(np.ascontiguousarray(b4)).to(dev)
+                keep.append((ta, tb))
+                gsets.append((ta.data_ptr(), tb.data_ptr(), len(a4)))
+            torch.cuda.synchronize(dev)
+            handle.solve_batch(gsets, p, kind=MEM_DEVICE)  # warm-up
+            gms, gcalls = 0.0, 0
+            for _ in range(5):
+                rg = handle.solve_batch(gsets, p, kind=MEM_DEVICE)
+                m, c = handle.kernel_ms()
+                gms += float(m[1]); gcalls += int(c[1])
+            Lg = float(args.graph_L)
+            g_bytes = 32 * (2 * Lg * 16 + Lg * np.ceil(Lg / 32) * 4 + 4 * Lg)
+            g_ms = gms / max(gcalls, 1)
+            g_pairs = 32 * Lg * (Lg - 1) / 2
+            roofline_graph_3k = {"kernel": "tim_graph_kernel (K8)", "bound": "hbm", "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "launch_ms": g_ms,
+                                 "L": int(Lg), "sets_per_launch": 32, "bytes_per_launch": g_bytes, "pair_tests_per_s": g_pairs / (g_ms * 1e-3),
+                                 "valid_sets": int(rg["valid"].sum()),
+                                 "note": "algorithmic-minimum bytes (0.27 B per pair test) against ~30 fp32 instructions per pair test: the kernel is bound by the fp32 pipe, pair_tests_per_s is the meaningful rate"}
         cpu = None
         if not args.no_cpu_baseline:
             from oracle import Oracle
@@ -325,7 +353,8 @@ def main():
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (front end, match, graph filter) / f64 (graph boundary, GNC, COTE)",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_graph": roofline_graph, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_graph": roofline_graph,
+            "roofline_graph_3k": roofline_graph_3k, "cpu_baseline": cpu,
             "stages_ms_per_step": {k: float(v / args.steps) for k, v in zip(["h2d", "voxel", "fpfh", "match", "graph", "clique", "pose", "d2h"], sms)},
             "valid_pairs": int(res_dev["valid"].sum()), "mean_n_vox": float((nA.mean() + nB.mean()) / 2), "mean_L": float(L.mean()),
             "mean_clique": float(res_dev["clique_size"].mean()),

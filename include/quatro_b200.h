@@ -183,6 +183,19 @@ int qb200_match_and_pack(qb200_handle* h, const float* src4, int32_t n_src, cons
                          int32_t n_tgt, const qb200_params* p, int32_t* corr, float* src_matched4,
                          float* tgt_matched4, int32_t cap, int32_t* n_corr);
 
+/* Batch of precomputed correspondence sets (matched point pairs a[i] <-> b[i], xyzw records): graph -> max clique ->
+ * GNC-TLS yaw + COTE for every set, = Quatro::computeTransformation (include/quatro.hpp:769-936) called once per set
+ * with setInputSource / setInputTarget already given matched clouds.  Sets are processed in waves of
+ * max_batch_slots; kind says where a / b live; results is a host array of n records. */
+typedef struct qb200_corr_set {
+  const float* a;   /* L x 4 floats (source side) */
+  const float* b;   /* L x 4 floats (target side) */
+  int32_t L;        /* <= max_corr */
+  int32_t reserved;
+} qb200_corr_set;
+int qb200_solve_batch(qb200_handle* h, const qb200_corr_set* sets, int32_t n_sets, const qb200_params* p,
+                      qb200_mem_kind kind, qb200_result* results);
+
 /* raw scans in -> pose out. */
 int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4,
                         int32_t n_tgt, const qb200_params* p, qb200_result* res);

@@ -62,6 +62,10 @@ class Pair(C.Structure):
     _fields_ = [("src", C.c_void_p), ("tgt", C.c_void_p), ("n_src", C.c_int32), ("n_tgt", C.c_int32)]
 
 
+class CorrSet(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("L", C.c_int32), ("reserved", C.c_int32)]
+
+
 RESULT_DTYPE = np.dtype([
     ("valid", "<i4"), ("status", "<i4"), ("n_src_vox", "<i4"), ("n_tgt_vox", "<i4"), ("n_mutual", "<i4"),
     ("n_corr", "<i4"), ("max_core", "<i4"), ("clique_size", "<i4"), ("gnc_iters", "<i4"), ("n_rot_inliers", "<i4"),
@@ -125,6 +129,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_get_kernel_ms": (i32, [vp, vp, vp, i32]),
         "qb200_debug_tc_distances": (i32, [vp, vp, i32, vp, i32, vp]),
         "qb200_debug_match_stats": (i32, [vp, vp, i32]),
+        "qb200_solve_batch": (i32, [vp, vp, i32, vp, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
@@ -142,6 +147,7 @@ EXPORTED_SYMBOLS = [
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
     "qb200_debug_match_stats",
+    "qb200_solve_batch",
 ]
 
 
@@ -313,6 +319,24 @@ class Handle:
                 arr[i].src, arr[i].n_src, arr[i].tgt, arr[i].n_tgt = pr[0], pr[1], pr[2], pr[3]
         out = np.zeros(n, RESULT_DTYPE)
         self._check(self.lib.qb200_register_batch(self.h, arr, n, C.byref(params), kind, _ptr(out)), "qb200_register_batch")
+        return out
+
+    def solve_batch(self, sets: Sequence, params: Params, kind: int = MEM_HOST) -> np.ndarray:
+        """sets: sequence of (a4, b4) matched point arrays (MEM_HOST: numpy (L,4) float32; MEM_DEVICE: (a_ptr, b_ptr, L)).
+        Graph -> clique -> pose for every set; returns a RESULT_DTYPE array."""
+        n = len(sets)
+        arr = (CorrSet * n)()
+        keep = []
+        for i, st in enumerate(sets):
+            if kind == MEM_HOST:
+                a, b = _f32(st[0], 4), _f32(st[1], 4)
+                assert len(a) == len(b)
+                keep.append((a, b))
+                arr[i].a, arr[i].b, arr[i].L = a.ctypes.data, b.ctypes.data, len(a)
+            else:
+                arr[i].a, arr[i].b, arr[i].L = st[0], st[1], st[2]
+        out = np.zeros(n, RESULT_DTYPE)
+        self._check(self.lib.qb200_solve_batch(self.h, arr, n, C.byref(params), kind, _ptr(out)), "qb200_solve_batch")
         return out
 
     def register_batch_raw(self, pair_array, n: int, params: Params, kind: int, out: np.ndarray):

@@ -521,6 +521,58 @@ int qb200_solve_correspondences(qb200_handle* h, const float* a4, const float* b
   return fetch_result(h, res);
 }
 
+// ---- batches of precomputed correspondences -> poses ------------------------------------------------------
+int qb200_solve_batch(qb200_handle* h, const qb200_corr_set* sets, int32_t n_sets, const qb200_params* p, qb200_mem_kind kind,
+                      qb200_result* results) {
+  if (!h || n_sets < 0 || (n_sets > 0 && (!sets || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
+  if (p->inlier_selection_mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
+  for (int i = 0; i < n_sets; ++i)
+    if (sets[i].L < 0 || sets[i].L > h->Lc || (sets[i].L > 0 && (!sets[i].a || !sets[i].b))) {
+      h->fail(__FILE__, __LINE__, "correspondence set is null or exceeds max_corr");
+      return QB200_ERR_BAD_ARG;
+    }
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
+  for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
+  const cudaMemcpyKind ck = kind == QB200_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  for (int w0 = 0; w0 < n_sets; w0 += h->S) {
+    const int np = n_sets - w0 < h->S ? n_sets - w0 : h->S;
+    int rc = wave_reset(h, 2 * np);
+    if (rc) return rc;
+    for (int s = 0; s < np; ++s) {
+      const qb200_corr_set& cs = sets[w0 + s];
+      h->h_cloud_n[s] = cs.L;
+      if (cs.L > 0) {
+        QB_CUDA_TRY(h, cudaMemcpyAsync(h->ma + (size_t)s * h->Lc, cs.a, (size_t)cs.L * sizeof(float4), ck, h->stream));
+        QB_CUDA_TRY(h, cudaMemcpyAsync(h->mb + (size_t)s * h->Lc, cs.b, (size_t)cs.L * sizeof(float4), ck, h->stream));
+      }
+    }
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->ctr.n_corr, h->h_cloud_n, (size_t)np * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    cudaEventRecord(h->ev[4], h->stream);
+    cudaEventRecord(h->ev[5], h->stream);
+    if ((rc = run_solver(h, np, *p, 0))) return rc;
+    cudaEventRecord(h->ev[7], h->stream);
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results, (size_t)np * sizeof(qb200_result), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(results + w0, h->h_results, (size_t)np * sizeof(qb200_result));
+    for (int i = 4; i < 7; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
+    }
+    if (h->kev_armed[1]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->kev[2], h->kev[3]) == cudaSuccess) { h->kernel_ms[1] += ms; h->kernel_calls[1] += 1; }
+      h->kev_armed[1] = 0;
+    }
+  }
+  if (n_sets == 1) {
+    h->last_n_corr = results[0].n_corr;
+    h->last_n_clique = results[0].clique_size;
+    h->last_n_final = results[0].n_final_inliers;
+  }
+  return QB200_OK;
+}
+
 // ---- raw scans -> pose ------------------------------------------------------------------------------
 // enqueue one wave (np <= S pairs) on lane L: H2D of the scans (host kind), K1..K11, D2H of the result records.  No sync.
 static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np, qb200_mem_kind kind, const qb200_params* p, float cell) {

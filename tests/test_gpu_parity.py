@@ -345,6 +345,31 @@ def test_solve_correspondences_and_degenerate(handle, oracle):
     assert np.allclose(r_got.matrix(), r_ref.matrix(), atol=1e-9)
 
 
+def test_solve_batch_matches_single_and_oracle(handle, oracle):
+    """qb200_solve_batch = computeTransformation per correspondence set; 11 sets > 8 slots (two waves), ragged sizes."""
+    p = default_params()
+    sets = []
+    for i, L in enumerate((40, 3, 160, 700, 0, 1, 33, 320, 1500, 64, 2)):
+        a4, b4, _, _ = synth.matched_pairs(300 + i, max(L, 1), inlier_ratio=0.3, noise=0.03)
+        sets.append((a4[:L], b4[:L]))
+    out = handle.solve_batch(sets, p)
+    assert len(out) == len(sets)
+    for (a4, b4), g in zip(sets, out):
+        if len(a4) == 0:
+            assert g["valid"] == 0
+            continue
+        r_ref, st_ref = oracle.solve_correspondences(a4, b4, p)
+        r_one, st_one = handle.solve_correspondences(a4, b4, p)
+        for k in ("valid", "status", "n_corr", "n_edges", "max_core", "clique_size", "gnc_iters", "n_rot_inliers", "n_final_inliers"):
+            assert g[k] == getattr(r_ref, k) == getattr(r_one, k), (k, len(a4))
+        assert np.allclose(np.asarray(g["T"]).reshape(4, 4).T, r_ref.matrix(), atol=1e-9)
+    import torch
+    dev = [(torch.from_numpy(np.ascontiguousarray(a)).cuda(), torch.from_numpy(np.ascontiguousarray(b)).cuda()) for a, b in sets]
+    torch.cuda.synchronize()
+    out_d = handle.solve_batch([(a.data_ptr() if len(a) else 0, b.data_ptr() if len(b) else 0, len(a)) for a, b in dev], p, kind=1)
+    assert out_d.tobytes() == out.tobytes()
+
+
 # ---- end to end ----------------------------------------------------------------------------------------
 def _same_record(g, r):
     for k in ("valid", "status", "n_src_vox", "n_tgt_vox", "n_mutual", "n_corr", "n_edges", "max_core", "clique_size", "gnc_iters",
