@@ -580,6 +580,16 @@ static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np,
   int rc;
   cudaEventRecord(L->ev[0], L->stream);
   int total = 0;
+  // host scans that lie back to back in the caller's memory (one big pinned buffer is the usual case) go over PCIe as one
+  // copy: far fewer DMA descriptors than one per scan
+  const float* run_src = nullptr;
+  int run_dst = 0, run_n = 0;
+  auto flush_run = [&]() -> int {
+    if (run_n > 0)
+      QB_CUDA_TRY(L, cudaMemcpyAsync(L->raw_stage + run_dst, run_src, (size_t)run_n * sizeof(float4), cudaMemcpyHostToDevice, L->stream));
+    run_n = 0;
+    return QB200_OK;
+  };
   for (int s = 0; s < np; ++s) {
     const qb200_pair& pr = pairs[w0 + s];
     const float* ptr[2] = {pr.src, pr.tgt};
@@ -590,14 +600,21 @@ static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np,
       L->h_cloud_n[cloud] = cnt[k];
       if (kind == QB200_MEM_HOST) {
         L->h_cloud_ptr[cloud] = L->raw_stage + total;
-        if (cnt[k] > 0)
-          QB_CUDA_TRY(L, cudaMemcpyAsync(L->raw_stage + total, ptr[k], (size_t)cnt[k] * sizeof(float4), cudaMemcpyHostToDevice, L->stream));
+        if (cnt[k] > 0) {
+          if (run_n > 0 && ptr[k] == run_src + (size_t)run_n * 4 && run_n < (1 << 26)) {
+            run_n += cnt[k];
+          } else {
+            if ((rc = flush_run())) return rc;
+            run_src = ptr[k]; run_dst = total; run_n = cnt[k];
+          }
+        }
       } else {
         L->h_cloud_ptr[cloud] = reinterpret_cast<const float4*>(ptr[k]);
       }
       total += cnt[k];
     }
   }
+  if ((rc = flush_run())) return rc;
   L->h_raw_off[ncl] = total;
   QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_ptr, L->h_cloud_ptr, (size_t)ncl * sizeof(float4*), cudaMemcpyHostToDevice, L->stream));
   QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_n, L->h_cloud_n, (size_t)ncl * sizeof(int), cudaMemcpyHostToDevice, L->stream));
@@ -664,6 +681,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   // other waves' dense kernels.  Results do not depend on the lane (no state is shared between waves).
   // Wave plan.  Host inputs: nothing can run before the first wave's scans crossed PCIe, so the batch opens with a quarter
   // wave (its copy is the only one that is not hidden) followed by the remaining three quarters; all other waves are full.
+  // (Closing with small waves as well does not pay: every wave carries the same single-warp solver tail.)
   int wave_n[64], n_waves = 0;
   {
     int left = n_pairs;
@@ -676,9 +694,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
       wave_n[n_waves] = left < h->S ? left : h->S;
       left -= wave_n[n_waves++];
     }
-    if (left > 0) {  // more than ~60 waves: no special opening, walk the rest uniformly below
-      n_waves = 0;
-    }
+    if (left > 0) n_waves = 0;  // more than ~60 waves: no special opening, walk uniformly below
   }
   const bool planned = n_waves > 0;
   if (!planned) n_waves = (n_pairs + h->S - 1) / h->S;

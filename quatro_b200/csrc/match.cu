@@ -208,44 +208,36 @@ __global__ void __launch_bounds__(1024) match_mutual_kernel(const unsigned long 
   }
 }
 
-// Matcher::normalizePoints: float mean accumulated in index order (one warp per cloud; every lane
-// performs the same sequential additions, loads are coalesced 32 points at a time).
+// Matcher::normalizePoints: float mean accumulated in index order.  One warp per cloud: chunks of 32 points are staged in
+// shared memory with coalesced loads (two chunks ahead); lanes 0..2 each own one coordinate and run its serial addition
+// chain from shared memory (a 4-cycle dependent add per point instead of a shuffle round trip).
 __global__ void __launch_bounds__(32) cloud_mean_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V, float* __restrict__ mean) {
-  const int cloud = blockIdx.x;
+  __shared__ float buf[2][3][32];
+  const int cloud = blockIdx.x, lane = (int)lane_id();
   const int n = n_pts[cloud];
   const float4* __restrict__ p = pts + (size_t)cloud * V;
-  float mx = 0.f, my = 0.f, mz = 0.f;
-  // software-pipelined: four chunks of 32 points are in flight while the current one is summed (the additions are a
-  // serial chain by definition, the loads need not be)
-  constexpr int kAhead = 4;
-  float4 buf[kAhead];
-#pragma unroll
-  for (int a = 0; a < kAhead; ++a) {
-    const int i = a * 32 + (int)lane_id();
-    buf[a] = i < n ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int base = 0; base < n; base += 32) {
-    const float4 v = buf[0];
-#pragma unroll
-    for (int a = 0; a + 1 < kAhead; ++a) buf[a] = buf[a + 1];
-    {
-      const int i = base + kAhead * 32 + (int)lane_id();
-      buf[kAhead - 1] = i < n ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  float acc = 0.f;
+  float4 nxt = lane < n ? p[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = 0, it = 0; base < n; base += 32, ++it) {
+    const int b = it & 1;
+    buf[b][0][lane] = nxt.x; buf[b][1][lane] = nxt.y; buf[b][2][lane] = nxt.z;
+    const int i = base + 32 + lane;
+    nxt = i < n ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);  // in flight while this chunk is summed
+    __syncwarp();
     const int lim = min(32, n - base);
-    for (int l = 0; l < lim; ++l) {
-      mx = mx + __shfl_sync(0xffffffffu, v.x, l);
-      my = my + __shfl_sync(0xffffffffu, v.y, l);
-      mz = mz + __shfl_sync(0xffffffffu, v.z, l);
+    if (lane < 3) {
+      const float* __restrict__ src = buf[b][lane];
+      if (lim == 32) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l) acc = acc + src[l];
+      } else {
+        for (int l = 0; l < lim; ++l) acc = acc + src[l];
+      }
     }
+    // the other buffer is rewritten next iteration; this one only after another __syncwarp
   }
-  if (lane_id() == 0 && n > 0) {
-    const float fn = (float)n;
-    mean[cloud * 4 + 0] = mx / fn;
-    mean[cloud * 4 + 1] = my / fn;
-    mean[cloud * 4 + 2] = mz / fn;
-    mean[cloud * 4 + 3] = 0.f;
-  }
+  if (lane < 3 && n > 0) mean[cloud * 4 + lane] = acc / (float)n;
+  if (lane == 3 && n > 0) mean[cloud * 4 + 3] = 0.f;
 }
 
 __device__ __forceinline__ void philox4x32_10(unsigned long long seed, unsigned long long ctr, unsigned out[4]) {
