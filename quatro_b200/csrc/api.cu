@@ -251,7 +251,7 @@ int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {
   const char* fe = getenv("QB200_MATCH_EXACT");
   h->force_exact_match = (fe && fe[0] == '1') ? 1 : 0;
   const char* ln = getenv("QB200_LANES");
-  h->max_lanes = (ln && ln[0] >= '1' && ln[0] <= '4') ? ln[0] - '0' : 4;
+  h->max_lanes = (ln && ln[0] >= '1' && ln[0] <= '8') ? ln[0] - '0' : 4;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return QB200_ERR_CUDA; }
   h->stream = h->own_stream;
   const int rc = alloc_all(h);
@@ -286,7 +286,7 @@ void qb200_destroy(qb200_handle* h) {
   for (int i = 0; i < 4; ++i)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 7; ++i)
     if (h->lane[i]) qb200_destroy(h->lane[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
@@ -302,7 +302,7 @@ const char* qb200_last_error(const qb200_handle* h) { return h ? h->err : "null 
 int64_t qb200_launch_count(const qb200_handle* h) {
   if (!h) return 0;
   int64_t n = h->launches;
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 7; ++i)
     if (h->lane[i]) n += h->lane[i]->launches;
   return n;
 }
@@ -699,7 +699,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   const bool planned = n_waves > 0;
   if (!planned) n_waves = (n_pairs + h->S - 1) / h->S;
   const int n_lanes = n_waves < h->max_lanes ? (n_waves < 1 ? 1 : n_waves) : h->max_lanes;
-  qb200_handle* lanes[4] = {h, h, h, h};
+  qb200_handle* lanes[8] = {h, h, h, h, h, h, h, h};
   for (int l = 1; l < n_lanes; ++l) {
     if (!h->lane[l - 1]) {
       const int rc = qb200_create(&h->cfg, &h->lane[l - 1]);
@@ -797,7 +797,7 @@ int qb200_debug_match_stats(qb200_handle* h, uint64_t* out4, int32_t reset) {
   QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   QB_CUDA_TRY(h, cudaMemcpy(out4, h->tc_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (reset) QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 4 * sizeof(unsigned long long)));
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < 7; ++l) {
     if (!h->lane[l]) continue;
     uint64_t o2[4];
     const int rc = qb200_debug_match_stats(h->lane[l], o2, reset);

@@ -362,11 +362,10 @@ int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
   const int cache_words = 14336;
   const size_t sm_kcore = (size_t)4 * Lc * sizeof(unsigned short) + (size_t)(Lc + 2) * sizeof(int) + (size_t)cache_words * 4;
   const size_t sm_clique = (size_t)Lc * sizeof(unsigned short) + (size_t)W * sizeof(uint32_t) + (size_t)cache_words * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(h->func_attr_set & 1u)) {  // per handle: the opt-in is a per-device property of the function
     QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_kcore));
     QB_CUDA_TRY(h, cudaFuncSetAttribute(clique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_clique));
-    attr_set = true;
+    h->func_attr_set |= 1u;
   }
   kcore_kernel<<<n_pairs, 32, sm_kcore, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, cache_words, h->kcore, h->korder, h->rank_of,
                                                      h->by_rank, h->kbin, h->ctr.max_core);

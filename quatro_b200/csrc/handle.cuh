@@ -21,10 +21,11 @@ struct qb200_handle {
   int* d_raw_off;             // [2S+1] offsets into the concatenated sort arrays
   const float4** h_cloud_ptr; int* h_cloud_n; int* h_raw_off;  // pinned mirrors
   float4* raw_stage;          // [2S*R] staging for host inputs
-  // Multi-wave batches rotate over this handle and up to 3 more lanes (own stream and buffers, created on first use):
+  // Multi-wave batches rotate over this handle and up to 7 more lanes (own stream and buffers, created on first use):
   // the H2D copies and the latency-bound solver tail of one wave overlap the dense kernels of the others.
-  qb200_handle* lane[3];
-  int max_lanes;              // 1..4 (QB200_LANES, default 4)
+  qb200_handle* lane[7];
+  int max_lanes;              // 1..8 (QB200_LANES, default 4)
+  unsigned func_attr_set;     // which kernels already got their dynamic shared-memory opt-in on this handle's device
   int pend_w0, pend_np;       // wave in flight on this lane (pend_np == 0: none)
   cudaEvent_t ev_fork;
 

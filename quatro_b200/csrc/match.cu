@@ -351,11 +351,10 @@ size_t match_smem_bytes() { return 3 * sizeof(float) * kDescDim * kMT + 8 * kMT 
 // pairs flagged in only[] (the tensor-core filter's overflow fallback).
 int launch_match_exact(qb200_handle* h, int n_pairs, const int* only) {
   const int V = h->V;
-  static bool attr_set = false;
   const size_t smem = match_smem_bytes();
-  if (!attr_set) {
+  if (!(h->func_attr_set & 2u)) {  // per handle: the opt-in is a per-device property of the function
     QB_CUDA_TRY(h, cudaFuncSetAttribute(match_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    h->func_attr_set |= 2u;
   }
   const dim3 gs(h->NS, n_pairs);
   if (only == nullptr) cudaEventRecord(h->kev[0], h->stream);

@@ -654,11 +654,10 @@ static int sort_and_dedup(qb200_handle* h, int n_clouds, int dedup) {
 
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
-  static bool attr_set = false;
   const size_t smem = tc_smem_bytes();
-  if (!attr_set) {
+  if (!(h->func_attr_set & 8u)) {  // per handle: the opt-in is a per-device property of the function
     QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    h->func_attr_set |= 8u;
   }
   // triage switches (results are identical either way): QB200_TC_NODEDUP=1 keeps duplicate descriptors, QB200_TC_NOPRUNE=1
   // visits every column tile
