@@ -22,16 +22,9 @@ namespace qb {
 
 constexpr int kMaxWordsPerLane = 4;  // Lc <= 4096  ->  W <= 128 words per row
 
-__device__ __forceinline__ int warp_max(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+// one REDUX instead of five dependent shuffles: these sit on the serial chain of the single-warp kernels below
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 // stable counting sort of vertices by key[v] (ids ascending inside a bucket); bin[d] ends up as the
 // START of bucket d (d = 0..maxkey), bin[maxkey+1] = n.  One warp.
@@ -309,19 +302,31 @@ __global__ void __launch_bounds__(32) clique_kernel(const uint32_t* __restrict__
       psize = warp_sum(psize);
       if (psize <= mc) continue;
       int sz = 1;
-      for (;;) {
-        // highest set bit of P across the warp
-        int top = -1;
+      if (nwl == 1) {
+        // L <= 1024 (the usual case): one adjacency word per lane, the step is clz -> REDUX -> one row word -> AND
+        uint32_t p0 = P[0];
+        for (;;) {
+          const int top = warp_max(p0 ? lane * 32 + 31 - __clz(p0) : -1);  // highest set bit of P across the warp
+          if (top < 0) break;
+          if (lane == 0) chain[sz - 1] = (unsigned short)top;
+          ++sz;
+          p0 &= row_word(top, lane);
+        }
+      } else {
+        for (;;) {
+          // highest set bit of P across the warp
+          int top = -1;
 #pragma unroll
-        for (int k = 0; k < kMaxWordsPerLane; ++k)
-          if (k < nwl && P[k]) top = max(top, (lane + 32 * k) * 32 + 31 - __clz(P[k]));
-        top = warp_max(top);
-        if (top < 0) break;
-        if (lane == 0) chain[sz - 1] = (unsigned short)top;
-        ++sz;
+          for (int k = 0; k < kMaxWordsPerLane; ++k)
+            if (k < nwl && P[k]) top = max(top, (lane + 32 * k) * 32 + 31 - __clz(P[k]));
+          top = warp_max(top);
+          if (top < 0) break;
+          if (lane == 0) chain[sz - 1] = (unsigned short)top;
+          ++sz;
 #pragma unroll
-        for (int k = 0; k < kMaxWordsPerLane; ++k)
-          if (k < nwl) P[k] &= row_word(top, lane + 32 * k);
+          for (int k = 0; k < kMaxWordsPerLane; ++k)
+            if (k < nwl) P[k] &= row_word(top, lane + 32 * k);
+        }
       }
       if (sz > mc) {
         mc = sz;
