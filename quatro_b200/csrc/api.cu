@@ -61,6 +61,8 @@ int alloc_all(qb200_handle* h) {
   QB_ALLOC(h, h->cell_start, C * (V + 1));
   QB_ALLOC(h, h->normals, C * V);
   QB_ALLOC(h, h->spfh, C * V * kDescPad);
+  QB_ALLOC(h, h->nbr_list, C * kNbrGlobalCap * V);
+  QB_ALLOC(h, h->nbr_cnt, C * V);
   QB_ALLOC(h, h->desc_t, C * kDescK * V);
   QB_CUDA_TRY(h, cudaMemset(h->desc_t, 0, C * kDescK * V * sizeof(float)));
   QB_ALLOC(h, h->desc_tiles, C * kDescK * V * 3);
@@ -270,7 +272,7 @@ void qb200_destroy(qb200_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
-                      h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->desc_t, h->rowbest, h->colpart, h->colbest,
+                      h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t, h->rowbest, h->colpart, h->colbest,
                       h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
                       h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,

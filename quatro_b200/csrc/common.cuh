@@ -34,6 +34,7 @@ constexpr int kDescPad = 36;   // floats per SPFH row (16-byte multiple: float4 
 constexpr int kDescK = 40;     // rows (K extent) of the dimension-major FPFH matrices: 33 bins + zero padding to a multiple of
                                // the TF32 tensor-core K step (8)
 constexpr int kMatchTile = 128;
+constexpr int kNbrGlobalCap = 80;  // neighbour indices per point handed from K4 (SPFH) to K5 (FPFH)
 
 // Per-cloud / per-pair counters that live on the device for a whole wave (no host round trips
 // between stages).  Arrays are indexed by cloud (2 per pair: 2*s = source, 2*s+1 = target) or slot.

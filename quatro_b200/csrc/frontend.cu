@@ -385,9 +385,11 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
 constexpr int kNbrThreads = 128;
 constexpr int kNbrCap = 96;
 
+// glist != nullptr: the first kNbrGlobalCap indices are also written to glist[t * gstride] (K5 reuses them)
 template <class Process>
 __device__ __forceinline__ int for_each_neighbor_listed(const LatticeView& L, const float4 pq, int m, float r2,
-                                                        unsigned short (*nbr)[kNbrThreads], Process&& process) {
+                                                        unsigned short (*nbr)[kNbrThreads], Process&& process,
+                                                        unsigned short* __restrict__ glist = nullptr, size_t gstride = 0) {
   int k_total = 0;
   for (int base = 0;; base += kNbrCap) {
     int k = 0;
@@ -397,6 +399,10 @@ __device__ __forceinline__ int for_each_neighbor_listed(const LatticeView& L, co
     });
     k_total = k;
     const int kl = k_total - base < kNbrCap ? k_total - base : kNbrCap;
+    if (glist != nullptr && base == 0) {
+      const int kg = kl < kNbrGlobalCap ? kl : kNbrGlobalCap;
+      for (int t = 0; t < kg; ++t) glist[(size_t)t * gstride] = nbr[t][threadIdx.x];  // coalesced across the CTA's points
+    }
     for (int t = 0; t < kl; ++t) process((int)nbr[t][threadIdx.x]);
     if (base + kNbrCap >= k_total) break;
   }
@@ -410,7 +416,8 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
                                                             const int* __restrict__ n_pts, int V, const uint64_t* __restrict__ cell_key,
                                                             const int* __restrict__ cell_start, const uint32_t* __restrict__ order,
                                                             const int* __restrict__ n_cells, float inv, int m, float r2,
-                                                            float* __restrict__ spfh) {
+                                                            float* __restrict__ spfh, unsigned short* __restrict__ nbr_list,
+                                                            int* __restrict__ nbr_cnt) {
   __shared__ unsigned short cnts[kDescDim][kSpfhThreads];
   __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
   const int cloud = blockIdx.y;
@@ -433,7 +440,8 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
     cnts[b1][threadIdx.x]++;
     cnts[11 + b2][threadIdx.x]++;
     cnts[22 + b3][threadIdx.x]++;
-  });
+  }, nbr_list + (size_t)cloud * kNbrGlobalCap * V + q, (size_t)V);
+  nbr_cnt[(size_t)cloud * V + q] = k;
   float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescPad;  // rows padded to 36 floats: 16-byte gathers in K5
   const float incr = k >= 2 ? 100.0f / (float)(k - 1) : 0.0f;
   for (int b = 0; b < kDescDim; ++b) {
@@ -450,7 +458,9 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
 __global__ void __launch_bounds__(kNbrThreads) fpfh_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
                                                            const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
                                                            const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv,
-                                                           int m, float r2, const float* __restrict__ spfh, float* __restrict__ desc_t) {
+                                                           int m, float r2, const float* __restrict__ spfh,
+                                                           const unsigned short* __restrict__ nbr_list, const int* __restrict__ nbr_cnt,
+                                                           float* __restrict__ desc_t) {
   __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(kNbrThreads) fpfh_kernel(const float4* __restr
 #pragma unroll
   for (int b = 0; b < kDescDim; ++b) o[b] = 0.0f;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for_each_neighbor_listed(L, pq, m, r2, nbr, [&](int p) {
+  auto accumulate = [&](int p) {
     const float4 pp = L.pts[p];
     const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
     const float d2 = (dx * dx + dy * dy) + dz * dz;  // the same expression as the neighbour test: bit-identical
@@ -480,7 +490,16 @@ __global__ void __launch_bounds__(kNbrThreads) fpfh_kernel(const float4* __restr
     for (int b = 11; b < 22; ++b) { const float v = s[b] * weight; s1 += v; o[b] += v; }
 #pragma unroll
     for (int b = 22; b < 33; ++b) { const float v = s[b] * weight; s2 += v; o[b] += v; }
-  });
+  };
+  // K4 walked the same neighbourhood (same radius, same lattice): reuse its list, in the same (cell, index) order.
+  // The lattice walk is repeated only for the rare point with more than kNbrGlobalCap neighbours (uniform per thread).
+  const int kq = nbr_cnt[(size_t)cloud * V + q];
+  if (kq <= kNbrGlobalCap) {
+    const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
+    for (int t = 0; t < kq; ++t) accumulate((int)gl[(size_t)t * V]);
+  } else {
+    for_each_neighbor_listed(L, pq, m, r2, nbr, accumulate);
+  }
   if (s0 != 0.0) s0 = 100.0 / s0;
   if (s1 != 0.0) s1 = 100.0 / s1;
   if (s2 != 0.0) s2 = 100.0 / s2;
@@ -549,9 +568,9 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
   normals_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mn, rn2,
                                             h->normals);
   spfh_kernel<<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
-                                                  h->ctr.n_cells, inv, mf, rf2, h->spfh);
+                                                  h->ctr.n_cells, inv, mf, rf2, h->spfh, h->nbr_list, h->nbr_cnt);
   fpfh_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf, rf2,
-                                         h->spfh, h->desc_t);
+                                         h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t);
   h->launches += 4;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;

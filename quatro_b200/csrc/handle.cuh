@@ -41,6 +41,8 @@ struct qb200_handle {
   int* cell_start;            // [2S*(V+1)]
   float4* normals;            // [2S*V]
   float* spfh;                // [2S*V*36] rows padded to 36 floats
+  unsigned short* nbr_list;   // [2S][kNbrGlobalCap][V] neighbour indices found by K4 (lattice order), reused by K5
+  int* nbr_cnt;               // [2S*V] neighbour count (self included); > kNbrGlobalCap: K5 walks the lattice itself
   float* desc_t;              // [2S*40*V] FPFH, dimension-major per cloud (row d = bin d over all points; rows 33..39 zero)
   float* desc_tiles;          // [2S*(V/128)*3*5120] per 128-point block: centred TF32 hi | lo | exact fp32 images in the UMMA
                               // shared-memory operand layout (one bulk copy per tile)
