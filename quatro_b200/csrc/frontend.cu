@@ -355,29 +355,6 @@ __device__ __forceinline__ LatticeView make_view(int cloud, int V, const float4*
   return L;
 }
 
-// K3: normals.  One thread per point, sequential float accumulation in lattice order.
-__global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
-                                                      const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
-                                                      const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv, int m,
-                                                      float r2, float4* __restrict__ normals) {
-  const int cloud = blockIdx.y;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_pts[cloud]) return;
-  const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
-  const float4 pq = L.pts[q];
-  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int cnt = 0;
-  for_each_neighbor(L, pq, m, r2, [&](int, float, const float4 pp) {
-    accu[0] += pp.x * pp.x; accu[1] += pp.x * pp.y; accu[2] += pp.x * pp.z;
-    accu[3] += pp.y * pp.y; accu[4] += pp.y * pp.z; accu[5] += pp.z * pp.z;
-    accu[6] += pp.x; accu[7] += pp.y; accu[8] += pp.z;
-    ++cnt;
-  });
-  float out[4];
-  qb_normal_from_accu(accu, cnt, pq.x, pq.y, pq.z, out);
-  normals[(size_t)cloud * V + q] = make_float4(out[0], out[1], out[2], out[3]);
-}
-
 // K4 / K5 walk the same neighbourhoods.  A thread first COLLECTS its neighbour indices (cheap distance tests, divergent)
 // into a shared-memory list and then processes the list in a dense loop, so the expensive per-neighbour work (pair
 // features, 33-bin gathers) runs with most lanes of the warp active instead of whenever any lane found a neighbour.
@@ -385,11 +362,9 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
 constexpr int kNbrThreads = 128;
 constexpr int kNbrCap = 96;
 
-// glist != nullptr: the first kNbrGlobalCap indices are also written to glist[t * gstride] (K5 reuses them)
 template <class Process>
 __device__ __forceinline__ int for_each_neighbor_listed(const LatticeView& L, const float4 pq, int m, float r2,
-                                                        unsigned short (*nbr)[kNbrThreads], Process&& process,
-                                                        unsigned short* __restrict__ glist = nullptr, size_t gstride = 0) {
+                                                        unsigned short (*nbr)[kNbrThreads], Process&& process) {
   int k_total = 0;
   for (int base = 0;; base += kNbrCap) {
     int k = 0;
@@ -399,14 +374,68 @@ __device__ __forceinline__ int for_each_neighbor_listed(const LatticeView& L, co
     });
     k_total = k;
     const int kl = k_total - base < kNbrCap ? k_total - base : kNbrCap;
-    if (glist != nullptr && base == 0) {
-      const int kg = kl < kNbrGlobalCap ? kl : kNbrGlobalCap;
-      for (int t = 0; t < kg; ++t) glist[(size_t)t * gstride] = nbr[t][threadIdx.x];  // coalesced across the CTA's points
-    }
     for (int t = 0; t < kl; ++t) process((int)nbr[t][threadIdx.x]);
     if (base + kNbrCap >= k_total) break;
   }
   return k_total;
+}
+
+// K2c: the fpfh_radius neighbourhood of every point, found ONCE: indices in lattice (cell, index) order, written
+// [t][point] so that the stores of a CTA's points coalesce.  K3 (smaller radius: a subsequence of the same order), K4 and K5
+// consume the list; a point with more than kNbrGlobalCap neighbours makes its consumers walk the lattice themselves.
+__global__ void __launch_bounds__(kNbrThreads) nbr_list_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                               const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
+                                                               const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv,
+                                                               int m, float r2, unsigned short* __restrict__ nbr_list,
+                                                               int* __restrict__ nbr_cnt) {
+  const int cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_pts[cloud]) return;
+  const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
+  unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
+  int k = 0;
+  for_each_neighbor(L, L.pts[q], m, r2, [&](int p, float, const float4) {
+    if (k < kNbrGlobalCap) gl[(size_t)k * V] = (unsigned short)p;
+    ++k;
+  });
+  nbr_cnt[(size_t)cloud * V + q] = k;
+}
+
+// K3: normals.  One thread per point, sequential float accumulation in lattice order over the points within
+// normal_radius: the subsequence of the K2c list that passes the (bit-identical) distance test.
+__global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                      const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
+                                                      const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv, int m,
+                                                      float r2, const unsigned short* __restrict__ nbr_list, const int* __restrict__ nbr_cnt,
+                                                      int list_usable, float4* __restrict__ normals) {
+  const int cloud = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_pts[cloud]) return;
+  const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
+  const float4 pq = L.pts[q];
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int cnt = 0;
+  auto add = [&](const float4 pp) {
+    accu[0] += pp.x * pp.x; accu[1] += pp.x * pp.y; accu[2] += pp.x * pp.z;
+    accu[3] += pp.y * pp.y; accu[4] += pp.y * pp.z; accu[5] += pp.z * pp.z;
+    accu[6] += pp.x; accu[7] += pp.y; accu[8] += pp.z;
+    ++cnt;
+  };
+  const int kq = nbr_cnt[(size_t)cloud * V + q];
+  if (list_usable && kq <= kNbrGlobalCap) {
+    const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
+    for (int t = 0; t < kq; ++t) {
+      const float4 pp = L.pts[gl[(size_t)t * V]];
+      const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
+      const float d2 = (dx * dx + dy * dy) + dz * dz;  // same expression as the lattice walk
+      if (d2 < r2) add(pp);
+    }
+  } else {
+    for_each_neighbor(L, pq, m, r2, [&](int, float, const float4 pp) { add(pp); });
+  }
+  float out[4];
+  qb_normal_from_accu(accu, cnt, pq.x, pq.y, pq.z, out);
+  normals[(size_t)cloud * V + q] = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 // K4: SPFH.  Bin COUNTS are order-free; the float histogram value is rebuilt by repeated addition
@@ -416,8 +445,8 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
                                                             const int* __restrict__ n_pts, int V, const uint64_t* __restrict__ cell_key,
                                                             const int* __restrict__ cell_start, const uint32_t* __restrict__ order,
                                                             const int* __restrict__ n_cells, float inv, int m, float r2,
-                                                            float* __restrict__ spfh, unsigned short* __restrict__ nbr_list,
-                                                            int* __restrict__ nbr_cnt) {
+                                                            float* __restrict__ spfh, const unsigned short* __restrict__ nbr_list,
+                                                            const int* __restrict__ nbr_cnt) {
   __shared__ unsigned short cnts[kDescDim][kSpfhThreads];
   __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
   const int cloud = blockIdx.y;
@@ -429,7 +458,7 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
   const float4 nq = nrm[q];
 #pragma unroll
   for (int b = 0; b < kDescDim; ++b) cnts[b][threadIdx.x] = 0;
-  const int k = for_each_neighbor_listed(L, pq, m, r2, nbr, [&](int p) {
+  auto feature = [&](int p) {
     if (p == q) return;
     const float4 pp = L.pts[p];
     const float4 np = nrm[p];
@@ -440,8 +469,14 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
     cnts[b1][threadIdx.x]++;
     cnts[11 + b2][threadIdx.x]++;
     cnts[22 + b3][threadIdx.x]++;
-  }, nbr_list + (size_t)cloud * kNbrGlobalCap * V + q, (size_t)V);
-  nbr_cnt[(size_t)cloud * V + q] = k;
+  };
+  int k = nbr_cnt[(size_t)cloud * V + q];
+  if (k <= kNbrGlobalCap) {
+    const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
+    for (int t = 0; t < k; ++t) feature((int)gl[(size_t)t * V]);
+  } else {
+    k = for_each_neighbor_listed(L, pq, m, r2, nbr, feature);
+  }
   float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescPad;  // rows padded to 36 floats: 16-byte gathers in K5
   const float incr = k >= 2 ? 100.0f / (float)(k - 1) : 0.0f;
   for (int b = 0; b < kDescDim; ++b) {
@@ -565,12 +600,18 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
   run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, V, 0, inv, nullptr, nullptr, h->cell_start, h->cell_key,
                                                      h->ctr.n_cells, h->ctr.n_lat, h->ctr.cloud_status);
   const dim3 gp((V + 127) / 128, n_clouds);
+  nbr_list_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf,
+                                                     rf2, h->nbr_list, h->nbr_cnt);
+  // the list serves K3 when the normal neighbourhood is a subset visited in the same order: radius <= fpfh radius (checked
+  // by the callers) and the same lattice reach for both walks
+  const int list_usable = (mn <= mf && rn2 <= rf2) ? 1 : 0;
   normals_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mn, rn2,
-                                            h->normals);
+                                            h->nbr_list, h->nbr_cnt, list_usable, h->normals);
   spfh_kernel<<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
                                                   h->ctr.n_cells, inv, mf, rf2, h->spfh, h->nbr_list, h->nbr_cnt);
   fpfh_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf, rf2,
                                          h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t);
+  h->launches += 1;
   h->launches += 4;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
