@@ -474,6 +474,11 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     unsigned short* wq = s_queue[warp];
     int evals_w = 0;
     bool alive = mbar_wait(bar_a, 0);
+    // column snapshot (best | point index) of the NEXT tile, fetched while the current one is processed when the scheduler
+    // has already published it (pf_tile = tile the prefetch belongs to, -1 = none)
+    int pf_tile = -1;
+    unsigned long long pf_cb = ~0ull;
+    unsigned pf_ob = 0;
     for (int k = 0;; ++k) {
       const int ts = k & (kTcAcc - 1), st = k & (kTcStages - 1);
       if (alive) alive = mbar_wait(bar_fullx0 + 8 * st, (uint32_t)((k >> 2) & 1));  // the exact image is read below
@@ -485,9 +490,32 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       // snapshot of the column's best and its point index (lane = column); the load overlaps the wait for the MMAs
       unsigned long long cb_cur = ~0ull;
       unsigned ob = 0;
-      if (c0 + cb + lane < nB) {
+      if (pf_tile == jt) {
+        cb_cur = pf_cb; ob = pf_ob;
+      } else if (c0 + cb + lane < nB) {
         cb_cur = __ldcg(cbg + c0 + cb + lane);
         ob = permB[c0 + cb + lane];
+      }
+      pf_tile = -1;
+      {  // one non-blocking look at the next position: if its exact image is already announced, start its snapshot loads
+        uint32_t ready;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ready)
+            : "r"(bar_fullx0 + 8 * ((k + 1) & (kTcStages - 1))), "r"((uint32_t)(((k + 1) >> 2) & 1))
+            : "memory");
+        if (__all_sync(0xffffffffu, ready != 0)) {
+          const int jn = v_seq[(k + 1) & 7];
+          if (jn >= 0) {
+            pf_tile = jn; pf_cb = ~0ull; pf_ob = 0;
+            if (jn * kTcN + cb + lane < nB) {
+              pf_cb = __ldcg(cbg + jn * kTcN + cb + lane);
+              pf_ob = permB[jn * kTcN + cb + lane];
+            }
+          }
+        }
       }
       alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 2) & 1));
       alive = __all_sync(0xffffffffu, alive);
