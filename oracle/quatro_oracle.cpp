@@ -27,7 +27,9 @@
 //   D6 NaN Darboux features -> histogram bin 0 (reference: UB cast, lands on bin 0 on x86)
 //   D7 atan2f/acosf/sinf/cosf -> fixed-order float32 kernels of oracle/qo_math.h (< 2 ulp of libm)
 //   D8 neighbour accumulation order = ascending (lattice cell (k,j,i), point index); PCL's is
-//      kd-tree distance order.  Dot products / norms are evaluated left to right.
+//      kd-tree distance order.  Dot products / norms are evaluated left to right.  The lattice cell defaults to
+//      (1 + 2^-9) * fpfh_radius (params.grid_cell overrides it): the neighbour SETS never depend on the cell,
+//      the accumulation order does, so the CUDA library uses the same default.
 //   D9 2x2 rotation: own two-sided Jacobi SVD (Eigen::JacobiSVD unavailable); fp64 sums in index order
 // =====================================================================================
 #include <algorithm>
