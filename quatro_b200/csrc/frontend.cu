@@ -183,9 +183,10 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
       if (p > 0) kprev = keys[off + p - 1] >> key_shift;
     }
     const int head = (valid && (p == 0 || k != kprev)) ? 1 : 0;
-    int tot, vtot;
-    const int ex = block_excl_scan(head, sm, &tot);
-    (void)block_excl_scan(valid ? 1 : 0, sm, &vtot);
+    // one scan for both counts: heads in the low half, valid points in the high half (<= 1024 each per chunk)
+    int both;
+    const int exb = block_excl_scan(head | ((valid ? 1 : 0) << 16), sm, &both);
+    const int ex = exb & 0xFFFF, tot = both & 0xFFFF, vtot = both >> 16;
     const int rank = carry + ex;
     if (head && rank <= V) {
       starts[(size_t)cloud * (V + 1) + rank] = p;

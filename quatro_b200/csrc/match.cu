@@ -260,11 +260,17 @@ __device__ __forceinline__ float tri_side(const float4 a, const float4 b, const 
   return sqrtf((dx * dx + dy * dy) + dz * dz);
 }
 
-// tuple (triangle side-ratio) test, feature_matcher.cc:187-247: one thread per trial, counter-based RNG
-__global__ void __launch_bounds__(256) tuple_test_kernel(const float4* __restrict__ vox_pts, int V, const int* __restrict__ mut_i,
-                                                         const int* __restrict__ mut_j, const int* __restrict__ n_mutual,
-                                                         const int* __restrict__ swapped, const float* __restrict__ mean, float scale,
-                                                         int trials_per_corr, unsigned long long seed, unsigned char* __restrict__ mark) {
+// tuple (triangle side-ratio) test, feature_matcher.cc:187-247: one thread per trial, counter-based RNG.  Every trial reads six
+// random matched points: a CTA first stages the pair's matched points (both clouds, xyz) in shared memory when they fit
+// (<= kTupleStage mutual pairs, the usual case), so the random reads stay on chip.
+constexpr int kTupleStage = 1536;
+constexpr int kTupleThreads = 1024;
+constexpr int kTupleCtasPerPair = 8;
+__global__ void __launch_bounds__(kTupleThreads) tuple_test_kernel(const float4* __restrict__ vox_pts, int V, const int* __restrict__ mut_i,
+                                                                   const int* __restrict__ mut_j, const int* __restrict__ n_mutual,
+                                                                   const int* __restrict__ swapped, const float* __restrict__ mean, float scale,
+                                                                   int trials_per_corr, unsigned long long seed, unsigned char* __restrict__ mark) {
+  __shared__ float sp[2][kTupleStage][3];
   const int pair = blockIdx.y;
   const int ncorr = n_mutual[pair];
   if (ncorr <= 0) return;
@@ -279,12 +285,25 @@ __global__ void __launch_bounds__(256) tuple_test_kernel(const float4* __restric
   const int* __restrict__ li = mut_i + (size_t)pair * V;
   const int* __restrict__ lj = mut_j + (size_t)pair * V;
   unsigned char* __restrict__ mk = mark + (size_t)pair * V;
+  const bool staged = ncorr <= kTupleStage;  // uniform for the CTA
+  if (staged) {
+    for (int e = threadIdx.x; e < ncorr; e += blockDim.x) {
+      const float4 a = pi[li[e]], b = pj[lj[e]];
+      sp[0][e][0] = a.x; sp[0][e][1] = a.y; sp[0][e][2] = a.z;
+      sp[1][e][0] = b.x; sp[1][e][1] = b.y; sp[1][e][2] = b.z;
+    }
+    __syncthreads();
+  }
+  auto point = [&](int side, int r) -> float4 {
+    if (staged) return make_float4(sp[side][r][0], sp[side][r][1], sp[side][r][2], 0.f);
+    return side == 0 ? pi[li[r]] : pj[lj[r]];
+  };
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < trials; t += (long long)gridDim.x * blockDim.x) {
     unsigned r[4];
     philox4x32_10(seed, (unsigned long long)t, r);
     const int r0 = (int)(r[0] % (unsigned)ncorr), r1 = (int)(r[1] % (unsigned)ncorr), r2 = (int)(r[2] % (unsigned)ncorr);
-    const float4 a0 = pi[li[r0]], a1 = pi[li[r1]], a2 = pi[li[r2]];
-    const float4 b0 = pj[lj[r0]], b1 = pj[lj[r1]], b2 = pj[lj[r2]];
+    const float4 a0 = point(0, r0), a1 = point(0, r1), a2 = point(0, r2);
+    const float4 b0 = point(1, r0), b1 = point(1, r1), b2 = point(1, r2);
     const float li0 = tri_side(a0, a1, mi), li1 = tri_side(a1, a2, mi), li2 = tri_side(a2, a0, mi);
     const float lj0 = tri_side(b0, b1, mj), lj1 = tri_side(b1, b2, mj), lj2 = tri_side(b2, b0, mj);
     if ((li0 * scale < lj0) && (lj0 < li0 / scale) && (li1 * scale < lj1) && (lj1 < li1 / scale) && (li2 * scale < lj2) &&
@@ -381,8 +400,8 @@ int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p) {
   const int use_tuple = (p.use_tuple_test && p.tuple_scale != 0.0f) ? 1 : 0;
   if (use_tuple) {
     cloud_mean_kernel<<<2 * n_pairs, 32, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->mean);
-    const dim3 gt(296, n_pairs);
-    tuple_test_kernel<<<gt, 256, 0, h->stream>>>(h->vox_pts, V, h->mut_i, h->mut_j, h->ctr.n_mutual, h->ctr.swapped, h->mean, p.tuple_scale,
+    const dim3 gt(kTupleCtasPerPair, n_pairs);
+    tuple_test_kernel<<<gt, kTupleThreads, 0, h->stream>>>(h->vox_pts, V, h->mut_i, h->mut_j, h->ctr.n_mutual, h->ctr.swapped, h->mean, p.tuple_scale,
                                                  p.tuple_trials_per_corr, (unsigned long long)p.seed, h->mark);
     h->launches += 2;
   }
