@@ -368,6 +368,26 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     bool first = true, done = false;
     auto next_tile = [&]() -> int {  // warp-uniform
       if (first) { first = false; return t0; }
+      // One choice walks over several skipped tiles; its inputs are fetched once: the current worst row best of the stripe
+      // (+inf while any row is unknown) and the shared per-tile column maxima of the first 128 tiles (4 per lane, one L2
+      // round trip for the whole walk instead of one per candidate).
+      unsigned rmax = 0;
+#pragma unroll
+      for (int i = 0; i < kTcM / 32; ++i) {
+        const int row = lane + 32 * i;
+        if (r0 + row < nA) {
+          const unsigned long long rb = v_rbest[row];
+          rmax = max(rmax, rb == ~0ull ? 0x7F800000u : (unsigned)(rb >> 32));
+        }
+      }
+      const float rmaxf = __uint_as_float(__reduce_max_sync(0xffffffffu, rmax));  // distances are >= 0: the bit patterns order them
+      unsigned tc0 = 0xFFFFFFFFu, tc1 = 0xFFFFFFFFu, tc2 = 0xFFFFFFFFu, tc3 = 0xFFFFFFFFu;
+      if (!no_prune) {
+        if (lane < n_tiles) tc0 = __ldcg(tcm + lane);
+        if (lane + 32 < n_tiles) tc1 = __ldcg(tcm + lane + 32);
+        if (lane + 64 < n_tiles) tc2 = __ldcg(tcm + lane + 64);
+        if (lane + 96 < n_tiles) tc3 = __ldcg(tcm + lane + 96);
+      }
       while (true) {
         if ((lo < 0 && hi >= n_tiles) || *v_abort || *v_dead) return -1;
         const float gl = lo >= 0 ? tlb(lo) : INFINITY, gh = hi < n_tiles ? tlb(hi) : INFINITY;
@@ -376,21 +396,17 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         const float lb = left ? gl : gh;
         if (left) --lo; else ++hi;
         if (lb <= 0.0f || no_prune) return t;
-        // current worst row best of the stripe (+inf while any row is unknown)
-        unsigned rmax = 0;
-#pragma unroll
-        for (int i = 0; i < kTcM / 32; ++i) {
-          const int row = lane + 32 * i;
-          if (r0 + row < nA) {
-            const unsigned long long rb = v_rbest[row];
-            rmax = max(rmax, rb == ~0ull ? 0x7F800000u : (unsigned)(rb >> 32));
-          }
-        }
-        rmax = __reduce_max_sync(0xffffffffu, rmax);  // distances are >= 0: the bit patterns order them
-        if (!(lb > __uint_as_float(rmax))) return t;
+        if (!(lb > rmaxf)) return t;
         // worst column best of the tile: first the shared per-tile value (an upper bound: bests only shrink), and only if
         // that does not settle it the 128 current column bests themselves, whose max refreshes the shared value
-        unsigned cmax = __ldcg(tcm + t);
+        unsigned cmax;
+        if (t < 128) {
+          const int sl = t >> 5;
+          const unsigned mine = sl == 0 ? tc0 : sl == 1 ? tc1 : sl == 2 ? tc2 : tc3;
+          cmax = __shfl_sync(0xffffffffu, mine, t & 31);
+        } else {
+          cmax = __ldcg(tcm + t);
+        }
         if (lb > __uint_as_float(cmax)) continue;
         cmax = 0;
 #pragma unroll
