@@ -295,12 +295,12 @@ def main():
         roofline = {"kernel": "tc_nn_kernel (K6: tcgen05 3xTF32 filter of the N_src x N_tgt x 33 distance matrix + in-kernel exact fp32 evaluation)",
                     "bound": "tensor", "achieved": match_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": match_tflops / peaks["bf16_tflops"],
-                    "traffic": 3.988e8 * (match_flops_step / launches_per_step) / 2.05e11,  # ncu: 398.8 MB for a 64-pair launch (profiles/r01_ncu_summary.md), scaled by the launch's work
+                    "traffic": 3.978e8 * (match_flops_step / launches_per_step) / 2.05e11,  # ncu: 397.8 MB for a 64-pair launch (profiles/r01_ncu_summary.md), scaled by the launch's work
                     "traffic_unit": "bytes per launch (dram read + write, ncu --set full capture of the same launch geometry)",
                     "peak_source": peaks["source"] + ", burst bf16",
                     "launch_ms": match_ms_launch, "launches_per_step": launches_per_step, "share_of_step": float(kms[0] / args.steps / step_ms),
                     "flops_per_launch": match_flops_step / launches_per_step,
-                    "note": "achieved = 66 flop per descriptor pair (algorithmic, all n_src x n_tgt pairs) / launch time measured with CUDA events inside the timed steps (other lanes' kernels share the SMs meanwhile); the kernel skips ~72% of the tiles by a norm lower bound and runs 3xTF32 on K padded to 40 on the rest; ncu: tensor pipe 11%, issue 32%, bound by the tile scheduler and the exact evaluation (DESIGN.md 5.1)"}
+                    "note": "achieved = 66 flop per descriptor pair (algorithmic, all n_src x n_tgt pairs) / launch time measured with CUDA events inside the timed steps (other lanes' kernels share the SMs meanwhile); the kernel skips ~72% of the tiles by a norm lower bound and runs 3xTF32 on K padded to 40 on the rest; ncu: tensor pipe 15%, issue 43%, bound by the exact evaluation of the survivors (DESIGN.md 5.1)"}
         roofline_graph = {"kernel": "tim_graph_kernel (K8)", "bound": "hbm", "achieved": graph_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": graph_gbs / peaks["hbm_gbs"], "traffic": None, "launch_ms": graph_ms_launch,
                           "bytes_per_launch": graph_bytes_step / max(kcalls[1] / args.steps, 1), "mean_L": float(L.mean()),
