@@ -6,24 +6,28 @@
 // (lowest-index ties).  Tensor cores cannot reproduce that rounding, so they act as a conservative FILTER and the
 // survivors are evaluated exactly inside the same kernel -- results are bit-identical to the exact kernel.
 //
-//   split_desc_kernel : x' = x - mu  (mu = FPFH signature of a plane: 100 in bins 5, 16, 27 -- street scenes are dominated
-//                       by planar points whose descriptors are near-identical, centring makes THEIR dot products tiny and
-//                       therefore the filter's absolute error tiny exactly where near-ties are dense);
-//                       hi = TF32(x'), lo = TF32(x' - hi), |x'|^2;  128-point blocks are written as ready-made
-//                       shared-memory operand images (hi | lo | exact x), so a tile is ONE cp.async.bulk.
-//   tc_nn_kernel      : one pass over all (128-row stripe) x (128-column tile) blocks:
+//   norm_key_kernel   : |x - mu|^2 by the fp32 chain (mu = FPFH signature of a plane: 100 in bins 5, 16, 27 -- street scenes
+//                       are dominated by planar points, centring makes THEIR dot products tiny and therefore the filter's
+//                       absolute error tiny exactly where near-ties are dense) -> one radix sort orders every cloud by norm
+//   dedup_kernel      : runs of bit-identical descriptors (adjacent after the sort) collapse to their first rank = lowest index
+//   split_desc_kernel : hi = TF32(x'), lo = TF32(x' - hi), exact x, per block of 128 unique descriptors as ready-made
+//                       shared-memory operand images (hi | lo | exact), so an image is ONE cp.async.bulk
+//   tc_nn_kernel      : per 128-row stripe, column tiles in nearest-norm-first order; a tile whose lower bound
+//                       (gap of the norm ranges)^2 exceeds every current best of the stripe's rows and of its columns is
+//                       skipped unloaded; otherwise
 //                         d~ = |a'|^2 + |b'|^2 - 2 (hi.hi + hi.lo + lo.hi)      3 x 5 tcgen05.mma.kind::tf32, fp32 in TMEM
 //                         |d~ - d| <= e_ij = c/2 (|a'_i|^2 + |b'_j|^2),  c = 6e-5   (split + accumulation + chain rounding)
 //                         (i,j) is evaluated EXACTLY (fp32 chain from the exact images) iff its lower bound d~ - e_ij
 //                         does not exceed the best exact distance known so far for row i or for column j;
-//                         row bests live in registers, column bests in global memory (atomicMin on packed
-//                         distance|index words; stripes start at staggered column tiles so bounds tighten quickly).
-//                       A pair whose stripes evaluate too many entries (massive exact ties) is flagged and redone by the
+//                         row bests live in shared memory, column bests in global memory (atomicMin on packed
+//                         distance|index words).
+//                       A stripe that evaluates too many entries (massive near-ties) flags its pair, which is redone by the
 //                       exact CUDA-core kernel, so results never depend on the filter.
+//   broadcast_best_kernel : class results -> every member, in point order for the mutual-NN stage
 //
-// Pipeline per CTA (one per SM): bulk copies fill a 3-stage ring of B images (prefetch distance 2); one thread issues
-// the 15 MMAs of tile k into TMEM stage k&1 and commits to an mbarrier; meanwhile all 8 warps drain stage (k-1)&1 with
-// tcgen05.ld.32x32b.x32 (lane = row) and run the filter / exact evaluation.
+// tc_nn_kernel, one CTA per SM, 18 warps, mbarrier hand-offs only: warp 17 chooses tiles and issues the bulk copies
+// (2 operand stages, 4 exact-image stages), warp 16 issues the 15 MMAs per tile into one of 4 TMEM accumulator stages,
+// warps 0..15 drain them with tcgen05.ld.32x32b.x32 (lane = row) and run the filter / exact evaluation.
 #include "handle.cuh"
 #include <cstdlib>
 
