@@ -66,6 +66,32 @@ def test_neighbors_match_bruteforce(oracle):
 
 
 # ---- KAT-2 normals ---------------------------------------------------------------------------------
+def test_default_lattice_cell_covers_the_radius_with_27_cells(oracle):
+    """D8: the default cell (1 + 2^-9) r makes a 3 x 3 x 3 cell walk sufficient even when x / cell rounds across a cell
+    boundary.  Adversarial clouds: points within a few ulps of cell boundaries, at KITTI-scale coordinates, pairs at
+    distances just inside / outside the radius; the lattice walk must return exactly the brute-force set {d2 < r2}."""
+    rng = np.random.default_rng(7)
+    r = np.float32(0.75)
+    cell = np.float32(r * np.float32(1.001953125))
+    r2 = np.float32(np.float64(r) * np.float64(r))
+    n = 4000
+    base = rng.integers(-160, 160, (n, 3)).astype(np.float32) * cell          # exactly on cell boundaries ...
+    jitter = rng.choice(np.array([0.0, 1e-6, -1e-6, 1e-4, -1e-4, 0.3, -0.3, 0.7499, -0.7499, 0.7501], np.float32), (n, 3))
+    pts = (base + jitter).astype(np.float32)
+    # a dense cluster so that many pairs sit right at the radius
+    c0 = np.array([37, -12, 2], np.float32) * cell
+    ring = rng.normal(size=(600, 3)).astype(np.float32)
+    ring = c0 + ring / np.linalg.norm(ring, axis=1, keepdims=True) * rng.choice(np.array([0.7499995, 0.75, 0.7500005, 0.4], np.float32), (600, 1))
+    pts = np.vstack([pts, c0[None], ring]).astype(np.float32)
+    p4 = np.concatenate([pts, np.ones((len(pts), 1), np.float32)], 1)
+    for q in list(rng.integers(0, len(pts), 60)) + [n]:                            # n = the cluster centre
+        idx, d2 = oracle.neighbors(p4, float(cell), int(q), float(r), cap=len(pts))
+        d = pts[q][None, :] - pts
+        bf = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + (d[:, 2] * d[:, 2]).astype(np.float32)   # the walk's own expression
+        want = np.nonzero(bf < r2)[0]
+        assert np.array_equal(np.sort(idx), want), (q, len(idx), len(want))
+
+
 def test_kat2_plane_normals(oracle):
     g = np.arange(-2, 2.01, 0.25)
     xx, yy = np.meshgrid(g, g)
