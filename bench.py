@@ -193,6 +193,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: whatever NCCL logs (its version banner under NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     p = default_params()
