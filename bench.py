@@ -3,11 +3,19 @@
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle restatement) on host cores
+  python bench.py --scene dense ...                        # the back end at BASELINE's correspondence count (L ~ 3 k)
 
 A "step" is one pass of the whole hot path (voxel -> FPFH -> match -> TIM graph -> max clique ->
 GNC-TLS + COTE) over one batch of `--pairs` synthetic 64-ring pairs per GPU (BASELINE configs[2]: 256
 pairs on 1 GPU; 8 ranks x 256 = configs[3]'s 2048 pairs).  Pairs are independent, so ranks shard them
 (weak scaling) and the only collective is one NCCL all_gather of the fixed-size result records.
+
+Workloads (`--scene`):
+  street  config/params.yaml defaults on the street scene: ~111 k returns -> ~6.9 k voxel points -> ~1.8 k mutual
+          nearest neighbours -> ~300 correspondences after the tuple test (the default; the headline line).
+  dense   the same scans with voxel 0.22 m and the tuple test off (qb200_params.use_tuple_test = 0): ~10 k voxel points and
+          L ~ 3 k correspondences per pair, the size BASELINE.json quotes for the back end (K8 graph, K9 clique, K10 pose).
+          The default run measures it too, as the `dense` object of the one JSON line.
 
   value : whole-job registrations/s with the raw scans already resident in HBM (device pointers through
           qb200_register_batch), CUDA events on the launching stream, max over ranks.
@@ -38,6 +46,22 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "registrations/sec (64-ring pair)"
 UNIT = "registrations/s"
+
+SCENES = {
+    "street": {"params": {}, "cfg": {},
+               "what": "config/params.yaml defaults (voxel 0.3, normal_r 0.5, fpfh_r 0.75, noise_bound 0.3, PMC_HEU, median COTE)"},
+    "dense": {"params": {"voxel_size": 0.22, "use_tuple_test": 0}, "cfg": {"max_corr": 8192},
+              "what": "voxel 0.22 m, tuple test off (every mutual nearest neighbour is a correspondence): L ~ 3 k per pair; "
+                      "other parameters = config/params.yaml"},
+}
+
+
+def scene_params(scene):
+    from quatro_b200.capi import default_params
+    p = default_params()
+    for k, v in SCENES[scene]["params"].items():
+        setattr(p, k, v)
+    return p
 
 
 def _host_threads() -> int:
@@ -73,6 +97,13 @@ def load_peaks():
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def load_ncu_facts():
+    """Per-launch DRAM traffic of the roofline kernels, read from the committed summary of the round's ncu --set full capture
+    (profiles/r02_ncu_facts.json, written by tools/ncu_facts.py from the .ncu-rep); None when the file is absent."""
+    f = ROOT / "profiles" / "r02_ncu_facts.json"
+    return json.loads(f.read_text()) if f.exists() else None
 
 
 def gen_pairs(seeds):
@@ -124,15 +155,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_pair_parallel(pairs, p, cores, seconds):
+    """Best-case CPU line: `cores` pairs in flight, one single-threaded oracle call each (the reference itself is
+    not re-entrant, so this is what one process per core would reach).  Returns (registrations/s, pairs done)."""
+    from oracle import Oracle
+    o = Oracle()
+    done = [0] * cores
+    stop_at = time.perf_counter() + seconds
+
+    def work(k):
+        o.set_num_threads(1)  # OpenMP ICV of this host thread
+        i = k
+        while time.perf_counter() < stop_at:
+            s, t = pairs[i % len(pairs)]
+            o.register_pair(s, t, p)
+            done[k] += 1
+            i += cores
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(work, range(cores)))
+    dt = time.perf_counter() - t0
+    return sum(done) / dt, sum(done)
+
+
 def run_reference(args, rank, world):
     """The reference's CPU path (oracle restatement) on the host cores; rank 0 only."""
     if rank != 0:
         return
     from oracle import Oracle
-    from quatro_b200.capi import default_params
     o = Oracle()
     cores = o.set_num_threads(_host_threads())   # torchrun exports OMP_NUM_THREADS=1: ask for every usable host core explicitly
-    p = default_params()
+    p = scene_params(args.scene)
     per_step = args.ref_pairs_per_step
     pairs = gen_pairs(range(per_step))
     for _ in range(max(args.warmup, 1)):
@@ -145,21 +199,29 @@ def run_reference(args, rank, world):
             done += 1
     dt = time.perf_counter() - t0
     val = done / dt
-    sample = f"{per_step} pairs per step x {args.steps} steps, sequential pairs, OpenMP inside each stage"
+    best, best_n = cpu_pair_parallel(pairs, p, cores, min(10.0, max(3.0, dt)))
+    sample = (f"{per_step} of the workload's pairs per step x {args.steps} steps (bounded sample of the {args.pairs}-pair batch), sequential pairs "
+              f"like the reference process, OpenMP({cores}) inside each stage")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
         "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_best_case": {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
+                          "sample": f"{best_n} registrations, {cores} pairs in flight, one single-threaded oracle call per core"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_sample_pairs_per_step": per_step,
         "note": "CPU restatement of the reference path (oracle/); the PCL/FLANN/pmc binary cannot be built in this image",
     }))
 
 
 def workload_config(args, world):
-    return {"workload": f"batch of {args.pairs} synthetic 64-ring pairs per GPU (BASELINE configs[2]; {world}x{args.pairs} global, 8 GPUs = configs[3])",
+    what = {"street": f"batch of {args.pairs} synthetic 64-ring pairs per GPU (BASELINE configs[2]; {world}x{args.pairs} global, 8 GPUs = configs[3])",
+            "dense": f"batch of {args.pairs} synthetic 64-ring pairs per GPU, dense preset (L ~ 3 k correspondences per pair: the back end at "
+                     f"BASELINE's stated size; {world}x{args.pairs} global)"}[args.scene]
+    return {"workload": what, "scene": args.scene,
             "pairs_per_gpu": args.pairs, "global_pairs": args.pairs * world, "scan": "64 rings x 1800 azimuths, ~111k returns, ground flagged",
-            "params": "config/params.yaml defaults (voxel 0.3, normal_r 0.5, fpfh_r 0.75, noise_bound 0.3, PMC_HEU, median COTE)",
+            "params": SCENES[args.scene]["what"],
             "l2": "inputs larger than L2 (~0.9 GB of raw scans per GPU per step vs 126 MB)",
             "parallelism": f"dp{world}: independent pairs sharded across ranks, one NCCL all_gather of result records per step"}
 
@@ -170,12 +232,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="street", choices=sorted(SCENES))
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step")
     ap.add_argument("--graph-L", type=int, default=3000, help="correspondences per set of the K8 roofline pass (0 = skip)")
-    ap.add_argument("--slots", type=int, default=64, help="pairs per device wave (two lanes of this size alternate)")
+    ap.add_argument("--slots", type=int, default=64, help="pairs per device wave (the lanes rotate over waves of this size)")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense sub-measurement of the default (street) run")
+    ap.add_argument("--cross-rank-pairs", type=int, default=8, help="pairs of the next rank every rank re-registers and compares (N > 1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -189,7 +254,7 @@ def main():
     import torch
     import torch.distributed as dist
     from quatro_b200 import synth
-    from quatro_b200.capi import Handle, Pair, default_params, RESULT_DTYPE, MEM_HOST, MEM_DEVICE
+    from quatro_b200.capi import Handle, Pair, RESULT_DTYPE, MEM_HOST, MEM_DEVICE
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -197,54 +262,63 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    p = default_params()
     P = args.pairs
+    stream = torch.cuda.current_stream(dev)
 
     # ---- synthetic inputs: pinned host copy (e2e) and device-resident copy (value) ----
-    pairs = gen_pairs(range(rank * P, rank * P + P))
-    total_pts = sum(len(s) + len(t) for s, t in pairs)
-    host = torch.empty((total_pts, 4), dtype=torch.float32).pin_memory()
-    hv = host.numpy()
-    offs, o = [], 0
-    for s, t in pairs:
-        hv[o:o + len(s)] = s; offs.append((o, len(s))); o += len(s)
-        hv[o:o + len(t)] = t; offs.append((o, len(t))); o += len(t)
-    dvc = host.to(dev, non_blocking=False)
-    pa_host, pa_dev = (Pair * P)(), (Pair * P)()
-    for i in range(P):
-        (so, sn), (to, tn) = offs[2 * i], offs[2 * i + 1]
-        pa_host[i].src, pa_host[i].n_src, pa_host[i].tgt, pa_host[i].n_tgt = host.data_ptr() + so * 16, sn, host.data_ptr() + to * 16, tn
-        pa_dev[i].src, pa_dev[i].n_src, pa_dev[i].tgt, pa_dev[i].n_tgt = dvc.data_ptr() + so * 16, sn, dvc.data_ptr() + to * 16, tn
+    def build_inputs(seeds):
+        prs = gen_pairs(seeds)
+        total = sum(len(s) + len(t) for s, t in prs)
+        host = torch.empty((total, 4), dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        offs, o = [], 0
+        for s, t in prs:
+            hv[o:o + len(s)] = s; offs.append((o, len(s))); o += len(s)
+            hv[o:o + len(t)] = t; offs.append((o, len(t))); o += len(t)
+        dvc = host.to(dev, non_blocking=False)
+        n = len(prs)
+        pa_h, pa_d = (Pair * n)(), (Pair * n)()
+        for i in range(n):
+            (so, sn), (to, tn) = offs[2 * i], offs[2 * i + 1]
+            pa_h[i].src, pa_h[i].n_src, pa_h[i].tgt, pa_h[i].n_tgt = host.data_ptr() + so * 16, sn, host.data_ptr() + to * 16, tn
+            pa_d[i].src, pa_d[i].n_src, pa_d[i].tgt, pa_d[i].n_tgt = dvc.data_ptr() + so * 16, sn, dvc.data_ptr() + to * 16, tn
+        return prs, host, dvc, pa_h, pa_d, total
+
+    pairs, host, dvc, pa_host, pa_dev, total_pts = build_inputs(range(rank * P, rank * P + P))
     h2d_bytes = total_pts * 16
     d2h_bytes = P * RESULT_DTYPE.itemsize
 
-    handle = Handle(device=local_rank, max_batch_slots=min(args.slots, P))
-    stream = torch.cuda.current_stream(dev)
-    handle.set_stream(stream.cuda_stream)
+    def make_handle(scene):
+        hd = Handle(device=local_rank, max_batch_slots=min(args.slots, P), **SCENES[scene]["cfg"])
+        hd.set_stream(stream.cuda_stream)
+        return hd
+
+    handle = make_handle(args.scene)
+    p = scene_params(args.scene)
     out = np.zeros(P, RESULT_DTYPE)
     out_t = torch.zeros((P, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     gathered = [torch.empty_like(out_t) for _ in range(world)] if world > 1 else None
 
-    def step(pa, kind):
-        handle.register_batch_raw(pa, P, p, kind, out)
+    def step(hd, prm, pa, kind):
+        hd.register_batch_raw(pa, P, prm, kind, out)
         if world > 1:  # the path's only collective: gather the per-pair result records
             out_t.copy_(torch.from_numpy(out.view(np.uint8).reshape(P, -1)), non_blocking=True)
             dist.all_gather(gathered, out_t)
 
-    def timed(pa, kind, steps, sampler=None):
+    def timed(hd, prm, pa, kind, steps, sampler=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = handle.launch_count()
+        l0 = hd.launch_count()
         kms, kcalls, sms = np.zeros(2), np.zeros(2), np.zeros(8)
         e0.record(stream)
         for _ in range(steps):
-            step(pa, kind)
-            m, c = handle.kernel_ms()
-            kms += m; kcalls += c; sms += handle.stage_ms()
+            step(hd, prm, pa, kind)
+            m, c = hd.kernel_ms()
+            kms += m; kcalls += c; sms += hd.stage_ms()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -253,36 +327,109 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), handle.launch_count() - l0, kms, kcalls, sms, clocks
+        return float(ms.item()), hd.launch_count() - l0, kms, kcalls, sms, clocks
+
+    def single_pair_latency(hd, prm):
+        lat = []
+        for i in range(12):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            hd.register_batch_raw(pa_host, 1, prm, MEM_HOST, out)
+            a1.record(stream)
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                lat.append(a0.elapsed_time(a1))
+        return float(np.median(lat))
+
+    def oracle_check(prm, res, seconds, max_pairs=64):
+        """time the CPU oracle on the first pairs of this rank's batch and require identical records"""
+        from oracle import Oracle
+        o = Oracle()
+        cores = o.set_num_threads(_host_threads())
+        o.register_pair(pairs[0][0], pairs[0][1], prm)  # warm-up
+        t0 = time.perf_counter(); n = 0
+        while n < min(P, max_pairs) and time.perf_counter() - t0 < seconds:
+            r, _ = o.register_pair(pairs[n][0], pairs[n][1], prm)
+            g = res[n]
+            assert (r.n_corr, r.clique_size, r.n_edges, r.max_core) == (g["n_corr"], g["clique_size"], g["n_edges"], g["max_core"]), \
+                f"pair {n}: GPU result differs from the CPU oracle: {(r.n_corr, r.clique_size, r.n_edges, r.max_core)} vs {g}"
+            assert np.allclose(np.asarray(g["T"]), np.array(r.T[:]), atol=1e-9), f"pair {n}: pose differs from the CPU oracle"
+            n += 1
+        return n / (time.perf_counter() - t0), n, cores
 
     for _ in range(args.warmup):
-        step(pa_dev, MEM_DEVICE)
-    dev_ms, launches, kms, kcalls, sms, clocks = timed(pa_dev, MEM_DEVICE, args.steps, ClockSampler(local_rank) if rank == 0 else None)
+        step(handle, p, pa_dev, MEM_DEVICE)
+    dev_ms, launches, kms, kcalls, sms, clocks = timed(handle, p, pa_dev, MEM_DEVICE, args.steps, ClockSampler(local_rank) if rank == 0 else None)
     res_dev = out.copy()
     for _ in range(max(1, args.warmup // 2)):
-        step(pa_host, MEM_HOST)
-    e2e_ms, _, _, _, _, _ = timed(pa_host, MEM_HOST, args.steps)
+        step(handle, p, pa_host, MEM_HOST)
+    e2e_ms, _, _, _, _, _ = timed(handle, p, pa_host, MEM_HOST, args.steps)
     assert out.tobytes() == res_dev.tobytes(), "host-buffer and device-buffer runs disagree"
 
     value = world * P * args.steps / (dev_ms * 1e-3)
     e2e_value = world * P * args.steps / (e2e_ms * 1e-3)
 
+    # ---- N > 1: every rank re-registers the first k pairs of the NEXT rank and compares the bytes of the records ----
+    cross = None
+    if world > 1:
+        k = max(1, min(args.cross_rank_pairs, P))
+        nxt = (rank + 1) % world
+        _, h2, d2, _, pa2, _ = build_inputs(range(nxt * P, nxt * P + k))
+        mine = np.zeros(k, RESULT_DTYPE)
+        handle.register_batch_raw(pa2, k, p, MEM_DEVICE, mine)
+        theirs = torch.from_numpy(res_dev[:k].copy().view(np.uint8).reshape(k, -1)).to(dev)
+        allrec = [torch.empty_like(theirs) for _ in range(world)]
+        dist.all_gather(allrec, theirs)
+        same = bool(allrec[nxt].cpu().numpy().tobytes() == mine.tobytes())
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        cross = {"pairs_per_rank": k, "identical_on_all_ranks": bool(flag.item() == 1),
+                 "what": "rank r re-registered the first k pairs of rank (r+1) mod N and compared the result records byte for byte"}
+        assert cross["identical_on_all_ranks"], "results depend on the rank that computed them"
+
     # BASELINE configs[1] (one pair on one GPU): latency of a single registration through the same call, host buffers
-    single_ms = None
-    if rank == 0:
-        lat = []
-        for i in range(12):
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record(stream)
-            handle.register_batch_raw(pa_host, 1, p, MEM_HOST, out)
-            a1.record(stream)
-            torch.cuda.synchronize(dev)
-            if i >= 2:
-                lat.append(a0.elapsed_time(a1))
-        single_ms = float(np.median(lat))
+    single_ms = single_pair_latency(handle, p) if rank == 0 else None
+
+    # ---- the dense workload (L ~ 3 k) as a sub-measurement of the default run: 1 GPU only, device-resident inputs ----
+    dense = None
+    if args.scene == "street" and world == 1 and not args.no_dense:
+        pd = scene_params("dense")
+        hd = make_handle("dense")
+        for _ in range(2):
+            step(hd, pd, pa_dev, MEM_DEVICE)
+        d_ms, _, _, _, d_sms, _ = timed(hd, pd, pa_dev, MEM_DEVICE, 3)
+        d_res = out.copy()
+        d_single = single_pair_latency(hd, pd)
+        hd.close()
+        # one wave on one lane: the per-stage device times without overlap from other waves
+        os.environ["QB200_LANES"] = "1"
+        h1 = make_handle("dense")
+        del os.environ["QB200_LANES"]
+        n1 = min(args.slots, P)
+        o1 = np.zeros(n1, RESULT_DTYPE)
+        for _ in range(2):
+            h1.register_batch_raw(pa_dev, n1, pd, MEM_DEVICE, o1)
+        serial = h1.stage_ms().copy()
+        h1.close()
+        d_cpu = None
+        if not args.no_cpu_baseline:
+            v, n, cores = oracle_check(pd, d_res, min(args.cpu_baseline_seconds, 10.0), 32)
+            d_cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                     "sample": f"first {n} pairs, sequential, OpenMP({cores}) inside stages; all {n} matched the GPU records (counters exact, pose <= 1e-9)"}
+        names = ["h2d", "voxel", "fpfh", "match", "graph", "clique", "pose", "d2h"]
+        dL = d_res["n_corr"].astype(np.float64)
+        dense = {"config": {"workload": f"batch of {P} synthetic 64-ring pairs, dense preset", "params": SCENES["dense"]["what"]},
+                 "value": P * 3 / (d_ms * 1e-3), "unit": UNIT, "ms_per_step": d_ms / 3, "steps": 3, "warmup": 2,
+                 "mean_L": float(dL.mean()), "max_L": int(dL.max()), "mean_n_vox": float((d_res["n_src_vox"].mean() + d_res["n_tgt_vox"].mean()) / 2),
+                 "mean_edges": float(d_res["n_edges"].mean()), "mean_clique": float(d_res["clique_size"].mean()),
+                 "valid_pairs": int(d_res["valid"].sum()), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(d_res["status"], return_counts=True))},
+                 "stages_ms_per_step": {k: float(v / 3) for k, v in zip(names, d_sms)},
+                 "stages_ms_one_wave_one_lane": {"pairs": n1, **{k: float(v) for k, v in zip(names, serial)}},
+                 "single_pair_latency_ms": d_single, "cpu_baseline": d_cpu}
 
     if rank == 0:
         peaks = load_peaks()
+        facts = load_ncu_facts()
         nA, nB, L = res_dev["n_src_vox"].astype(np.float64), res_dev["n_tgt_vox"].astype(np.float64), res_dev["n_corr"].astype(np.float64)
         # K6: 66 flop per (src,tgt) descriptor pair (the 2*33 of the ||a||^2+||b||^2-2ab contraction, SURVEY.md 8d)
         match_flops_step = float((66.0 * nA * nB).sum())
@@ -294,19 +441,29 @@ def main():
         graph_ms_launch = kms[1] / max(kcalls[1], 1)
         graph_gbs = graph_bytes_step / (kcalls[1] / args.steps) / (graph_ms_launch * 1e-3) / 1e9 if graph_ms_launch > 0 else 0.0
         step_ms = dev_ms / args.steps
+        flops_launch = match_flops_step / max(launches_per_step, 1)
+        tc_fact = (facts or {}).get("tc_nn_kernel")
+        traffic = None
+        if tc_fact:  # bytes per launch of the captured 64-pair launch, scaled by this run's work per launch
+            traffic = tc_fact["dram_bytes_per_launch"] * flops_launch / tc_fact["algorithmic_flops_per_launch"]
+        tf32_peak = peaks["bf16_tflops"] / 2.0
         roofline = {"kernel": "tc_nn_kernel (K6: tcgen05 3xTF32 filter of the N_src x N_tgt x 33 distance matrix + in-kernel exact fp32 evaluation)",
                     "bound": "tensor", "achieved": match_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": match_tflops / peaks["bf16_tflops"],
-                    "traffic": 3.978e8 * (match_flops_step / launches_per_step) / 2.05e11,  # ncu: 397.8 MB for a 64-pair launch (profiles/r01_ncu_summary.md), scaled by the launch's work
-                    "traffic_unit": "bytes per launch (dram read + write, ncu --set full capture of the same launch geometry)",
+                    "frac_of_tf32_peak": match_tflops / tf32_peak,
+                    "tf32_peak": tf32_peak, "tf32_peak_source": "half of the measured bf16 peak (the kernel's MMAs are kind::tf32; nominal dense tf32 = bf16 / 2)",
+                    "traffic": traffic,
+                    "traffic_source": ("profiles/r02_ncu_facts.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch, scaled "
+                                       "by this run's algorithmic flops per launch") if tc_fact else "no ncu capture committed for this round",
+                    "algorithmic_bytes_per_launch": float(((nA + nB) * 132.0).sum()) / max(launches_per_step, 1),
                     "peak_source": peaks["source"] + ", burst bf16",
                     "launch_ms": match_ms_launch, "launches_per_step": launches_per_step, "share_of_step": float(kms[0] / args.steps / step_ms),
-                    "flops_per_launch": match_flops_step / launches_per_step,
-                    "note": "achieved = 66 flop per descriptor pair (algorithmic, all n_src x n_tgt pairs) / launch time measured with CUDA events inside the timed steps (other lanes' kernels share the SMs meanwhile); the kernel skips ~72% of the tiles by a norm lower bound and runs 3xTF32 on K padded to 40 on the rest; ncu: tensor pipe 15%, issue 43%, bound by the exact evaluation of the survivors (DESIGN.md 5.1)"}
+                    "flops_per_launch": flops_launch,
+                    "note": "achieved = 66 flop per descriptor pair (algorithmic, all n_src x n_tgt pairs) / launch time measured with CUDA events inside the timed steps (other lanes' kernels share the SMs meanwhile); the kernel skips most tiles by a norm lower bound and runs 3xTF32 on K padded to 40 on the rest (DESIGN.md 5.1)"}
         roofline_graph = {"kernel": "tim_graph_kernel (K8)", "bound": "hbm", "achieved": graph_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": graph_gbs / peaks["hbm_gbs"], "traffic": None, "launch_ms": graph_ms_launch,
                           "bytes_per_launch": graph_bytes_step / max(kcalls[1] / args.steps, 1), "mean_L": float(L.mean()),
-                          "note": "fp32-pipe bound at algorithmic-minimum bytes (SURVEY.md 8d): ~30 instr per pair test vs 0.27 B per pair"}
+                          "note": "fp32-pipe bound at algorithmic-minimum bytes (SURVEY.md 8d): ~18 instructions per pair test vs 0.27 B per pair"}
         # K8 at the size BASELINE's configs name (~3k correspondences per pair): 32 precomputed correspondence sets through
         # qb200_solve_batch (device-resident), tim_graph_kernel timed with CUDA events inside the call
         roofline_graph_3k = None
@@ -318,45 +475,49 @@ def main():
                 keep.append((ta, tb))
                 gsets.append((ta.data_ptr(), tb.data_ptr(), len(a4)))
             torch.cuda.synchronize(dev)
-            handle.solve_batch(gsets, p, kind=MEM_DEVICE)  # warm-up
-            gms, gcalls = 0.0, 0
+            hg = Handle(device=local_rank, max_batch_slots=32)
+            hg.set_stream(stream.cuda_stream)
+            hg.solve_batch(gsets, p, kind=MEM_DEVICE)  # warm-up
+            gms, gcalls, gst = 0.0, 0, np.zeros(8)
             for _ in range(5):
-                rg = handle.solve_batch(gsets, p, kind=MEM_DEVICE)
-                m, c = handle.kernel_ms()
-                gms += float(m[1]); gcalls += int(c[1])
+                rg = hg.solve_batch(gsets, p, kind=MEM_DEVICE)
+                m, c = hg.kernel_ms()
+                gms += float(m[1]); gcalls += int(c[1]); gst += hg.stage_ms()
+            hg.close()
             Lg = float(args.graph_L)
             g_bytes = 32 * (2 * Lg * 16 + Lg * np.ceil(Lg / 32) * 4 + 4 * Lg)
             g_ms = gms / max(gcalls, 1)
             g_pairs = 32 * Lg * (Lg - 1) / 2
-            roofline_graph_3k = {"kernel": "tim_graph_kernel (K8)", "bound": "hbm", "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                 "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "launch_ms": g_ms,
+            # fp32 view: 14 fma-pipe operations (9 FFMA + 5 FADD) per pair test against 148 SMs x 128 lanes x clock (1 op/lane/clk)
+            fp32_ops_peak = 148 * 128 * 1.965e9
+            g_fact = (facts or {}).get("tim_graph_kernel")
+            roofline_graph_3k = {"kernel": "tim_graph_kernel (K8)", "bound": "fp32 pipe (named bound); hbm fraction reported as BASELINE asks",
+                                 "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                                 "unit": "GB/s", "frac": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                 "traffic": g_fact["dram_bytes_per_launch"] if g_fact else None,
+                                 "traffic_source": "profiles/r02_ncu_facts.json (same 32 x L=3000 launch under ncu --set full)" if g_fact else None,
+                                 "launch_ms": g_ms,
                                  "L": int(Lg), "sets_per_launch": 32, "bytes_per_launch": g_bytes, "pair_tests_per_s": g_pairs / (g_ms * 1e-3),
+                                 "fp32_frac": 14.0 * g_pairs / (g_ms * 1e-3) / fp32_ops_peak,
+                                 "fp32_frac_note": "14 fma-pipe operations per pair test (9 FFMA + 5 FADD; 18.5 issued instructions) x pair tests/s / (148 SMs x 128 lanes x 1.965 GHz)",
+                                 "solve_batch_stage_ms": {"graph": float(gst[4] / 5), "clique": float(gst[5] / 5), "pose": float(gst[6] / 5)},
                                  "valid_sets": int(rg["valid"].sum()),
-                                 "note": "algorithmic-minimum bytes (0.27 B per pair test) against ~30 fp32 instructions per pair test: the kernel is bound by the fp32 pipe, pair_tests_per_s is the meaningful rate"}
-        cpu = None
+                                 "note": "algorithmic-minimum bytes (0.27 B per pair test) against ~18 fp32 instructions per pair test: the kernel is bound by the fp32 pipe, pair_tests_per_s is the meaningful rate"}
+        cpu = best = None
         if not args.no_cpu_baseline:
-            from oracle import Oracle
-            o = Oracle()
-            cores = o.set_num_threads(_host_threads())
-            o.register_pair(pairs[0][0], pairs[0][1], p)  # warm-up
-            t0 = time.perf_counter(); n = 0
-            checked = 0
-            while n < min(P, 64) and time.perf_counter() - t0 < args.cpu_baseline_seconds:
-                r, _ = o.register_pair(pairs[n][0], pairs[n][1], p)
-                g = res_dev[n]
-                assert (r.n_corr, r.clique_size, r.n_edges) == (g["n_corr"], g["clique_size"], g["n_edges"]), f"pair {n}: GPU result differs from the CPU oracle"
-                assert np.allclose(np.asarray(g["T"]), np.array(r.T[:]), atol=1e-9)
-                checked += 1; n += 1
-            dt = time.perf_counter() - t0
-            cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {n} pairs of rank 0's batch, sequential pairs, OpenMP({cores}) inside stages; all {checked} matched the GPU records"}
+            v, n, cores = oracle_check(p, res_dev, args.cpu_baseline_seconds)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {n} pairs of rank 0's batch, sequential pairs, OpenMP({cores}) inside stages; all {n} matched the GPU records"}
+            bv, bn = cpu_pair_parallel(pairs[:64], p, cores, min(8.0, args.cpu_baseline_seconds))
+            best = {"value": bv, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{bn} registrations, {cores} pairs in flight, one single-threaded oracle call per core (best-case CPU, SURVEY.md 8d)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (front end, match, graph filter) / f64 (graph boundary, GNC, COTE)",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_graph": roofline_graph,
-            "roofline_graph_3k": roofline_graph_3k, "cpu_baseline": cpu,
+            "roofline_graph_3k": roofline_graph_3k, "cpu_baseline": cpu, "cpu_best_case": best, "dense": dense, "cross_rank_check": cross,
             "stages_ms_per_step": {k: float(v / args.steps) for k, v in zip(["h2d", "voxel", "fpfh", "match", "graph", "clique", "pose", "d2h"], sms)},
             "valid_pairs": int(res_dev["valid"].sum()), "mean_n_vox": float((nA.mean() + nB.mean()) / 2), "mean_L": float(L.mean()),
             "mean_clique": float(res_dev["clique_size"].mean()),

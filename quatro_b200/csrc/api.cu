@@ -49,11 +49,15 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_raw_off, (C + 1) * sizeof(int)));
   QB_ALLOC(h, h->raw_stage, C * R);
   QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  QB_ALLOC(h, h->key_a, C * R);
-  QB_ALLOC(h, h->key_b, C * R);
-  QB_ALLOC(h, h->val_a, C * R);
-  QB_ALLOC(h, h->val_b, C * R);
-  h->cub_bytes = sort_temp_bytes((int)(C * R));
+  // the sort workspace serves the voxel sort (C*R items), the lattice / norm sorts (C*V items) and, afterwards, the duplicate-class
+  // tables of K6 (2S*V + 2S words in key_a): size it for the largest user
+  const size_t n_sort = C * (R > V ? R : V) + 64;
+  QB_ALLOC(h, h->key_a, n_sort);
+  QB_ALLOC(h, h->key_b, n_sort);
+  QB_ALLOC(h, h->val_a, n_sort);
+  QB_ALLOC(h, h->val_b, n_sort);
+  QB_ALLOC(h, h->aos_scratch, 2 * V * kDescDim);
+  h->cub_bytes = sort_temp_bytes((int)n_sort);
   QB_CUDA_TRY(h, cudaMalloc(&h->cub_temp, h->cub_bytes));
   QB_ALLOC(h, h->vox_start, C * (V + 1));
   QB_ALLOC(h, h->vox_pts, C * V);
@@ -72,7 +76,10 @@ int alloc_all(qb200_handle* h) {
   QB_ALLOC(h, h->tc_stats, 4);
   QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 4 * sizeof(unsigned long long)));
   QB_ALLOC(h, h->rowbest, S * V);
-  QB_ALLOC(h, h->colpart, S * h->NS * V);
+  {  // two layouts share colpart: [S][NS][V] stripe partials (exact kernel) and [2][S][V] class results + tile cache (tc_match.cu)
+    const size_t a = S * h->NS * V, b = 2 * S * V + S * (V >> 7) / 2 + 1;
+    QB_ALLOC(h, h->colpart, a > b ? a : b);
+  }
   QB_ALLOC(h, h->colbest, S * V);
   QB_ALLOC(h, h->mut_i, S * V);
   QB_ALLOC(h, h->mut_j, S * V);
@@ -237,7 +244,8 @@ int qb200_create(const qb200_config* cfg_in, qb200_handle** out) {
   if (cfg_in) cfg = *cfg_in; else qb200_default_config(&cfg);
   if (cfg.max_batch_slots < 1 || cfg.max_batch_slots > 2048 || cfg.max_raw_points < 1 || cfg.max_voxel_points < kMatchTile ||
       cfg.max_voxel_points % kMatchTile != 0 || cfg.max_voxel_points > 65536 || cfg.max_corr < 32 || cfg.max_corr % 32 != 0 ||
-      cfg.max_corr > 4096 || (long long)cfg.max_batch_slots * 2 * cfg.max_raw_points > 2000000000LL)
+      cfg.max_corr > 8192 || (long long)cfg.max_batch_slots * 2 * cfg.max_raw_points > 2000000000LL ||
+      (long long)cfg.max_batch_slots * 2 * cfg.max_voxel_points > 2000000000LL)
     return QB200_ERR_BAD_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg.device < 0 || cfg.device >= ndev) return QB200_ERR_NO_DEVICE;
@@ -273,7 +281,7 @@ void qb200_destroy(qb200_handle* h) {
   cudaDeviceSynchronize();
   void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t, h->rowbest, h->colpart, h->colbest,
-                      h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats,
+                      h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats, h->aos_scratch,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
                       h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
                       h->ctr_block};
@@ -363,7 +371,7 @@ int qb200_compute_fpfh(qb200_handle* h, const float* pts4, int32_t n, float norm
   if ((rc = launch_fpfh(h, 1, normal_radius, fpfh_radius, grid_cell))) return rc;
   if (normals4) QB_CUDA_TRY(h, cudaMemcpyAsync(normals4, h->normals, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
   if (desc33) {
-    float* scratch = reinterpret_cast<float*>(h->key_a);  // sort input is dead after the lattice sort
+    float* scratch = h->aos_scratch;
     if ((rc = launch_desc_to_aos(h, 0, n, scratch))) return rc;
     QB_CUDA_TRY(h, cudaMemcpyAsync(desc33, scratch, (size_t)n * kDescDim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   }
@@ -409,7 +417,7 @@ int qb200_match(qb200_handle* h, const float* src4, int32_t n_src, const float* 
   if (rc) return rc;
   if ((rc = upload_cloud_as_voxels(h, 0, src4, n_src))) return rc;
   if ((rc = upload_cloud_as_voxels(h, 1, tgt4, n_tgt))) return rc;
-  float* scratch = reinterpret_cast<float*>(h->key_a);
+  float* scratch = h->aos_scratch;
   QB_CUDA_TRY(h, cudaMemcpyAsync(scratch, src_desc33, (size_t)n_src * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   if ((rc = launch_desc_from_aos(h, 0, n_src, scratch))) return rc;
   float* scratch2 = scratch + (size_t)h->V * kDescDim;
@@ -493,7 +501,8 @@ int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t wo
 // ---- stage: pose given the clique -------------------------------------------------------------------
 int qb200_solve_pose(qb200_handle* h, const float* a4, const float* b4, int32_t L, const int32_t* clique, int32_t n_clique,
                      const qb200_params* p, qb200_result* res, uint8_t* rot_inlier_mask, uint8_t* trans_inlier_mask) {
-  if (!h || !res || !params_ok(p) || L < 0 || n_clique < 0 || n_clique > L || (n_clique > 0 && !clique)) return QB200_ERR_BAD_ARG;
+  if (!h || !res || !params_ok(p) || L < 0 || (L > 0 && (!a4 || !b4)) || n_clique < 0 || n_clique > L || (n_clique > 0 && !clique))
+    return QB200_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   int rc = upload_matched(h, a4, b4, L);
   if (rc) return rc;
@@ -678,6 +687,14 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
   cudaSetDevice(h->device);
   for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
   for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
+  // the rotation noise bound latches on the PUBLIC handle (quatro.hpp:469-470) and every lane gets the resolved value, so a pair's
+  // GNC bound never depends on the wave / lane it lands on
+  qb200_params p_resolved = *p;
+  if (!(p_resolved.rot_noise_bound > 0)) {
+    if (h->rot_noise_bound_latched <= 0) h->rot_noise_bound_latched = 2.0 * p->noise_bound;
+    p_resolved.rot_noise_bound = h->rot_noise_bound_latched;
+  }
+  p = &p_resolved;
   const float cell = lattice_cell(*p);
   // More than one wave: rotate over the lanes so that one wave's PCIe copies and single-warp solver tail run under the
   // other waves' dense kernels.  Results do not depend on the lane (no state is shared between waves).
@@ -818,7 +835,7 @@ int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, cons
   if (rc) return rc;
   if ((rc = set_counter(h, h->ctr.n_vox + 0, na))) return rc;
   if ((rc = set_counter(h, h->ctr.n_vox + 1, nb))) return rc;
-  float* scratch = reinterpret_cast<float*>(h->key_a);
+  float* scratch = h->aos_scratch;
   QB_CUDA_TRY(h, cudaMemcpyAsync(scratch, a33, (size_t)na * kDescDim * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   if ((rc = launch_desc_from_aos(h, 0, na, scratch))) return rc;
   float* scratch2 = scratch + (size_t)128 * kDescDim;

@@ -6,22 +6,29 @@
 // pair) and then inserts edges one by one; here a pair (i,j) is tested straight from
 // the two matched point sets and only the bit-packed symmetric adjacency matrix is written.
 //
-// Work unit: one warp owns a 32 x 32 block of the upper triangle.  Lane = column j; the 32 rows are
-// broadcast from shared memory.  __ballot_sync gives the row word of the block, and each lane ORs
-// its own test bit into the word of the TRANSPOSED block, so both halves of the symmetric matrix
-// come out of one evaluation of the M pair tests.
+// Arithmetic.  The reference's mask is abs(db/da - 1) <= beta/da && abs(da/db - 1) <= beta/db in fp64
+// (quatro.hpp:363-385), i.e. |da - db| <= beta up to rounding.  With A = da^2, B = db^2, s' = A + B - beta^2,
+// D = A - B, g = beta^2 (2 s' + beta^2) and t = D^2 - g (= (A + B - beta^2)^2 - 4AB):
+//        edge  <=>  t <= 0  or  s' <= 0.
+// The kernel evaluates this in fp32 with A, B in Gram form (|a_i|^2 + |a_j|^2 - 2 a_i.a_j: 4 instead of 6 operations per
+// distance) -- ~18 instructions per pair test -- together with a RIGOROUS bound of its own rounding error:
+//        |t_c - t| <= 36u M |D_c| + 1500 u^2 M^2 + 46 u beta^2 M =: q,   u = 2^-24,  M >= |a_i|^2+|b_i|^2+|a_j|^2+|b_j|^2 + 2 beta^2
+// (derivation in DESIGN.md 5.2).  Only pairs with |t_c| <= q -- a band of ~1e-4 relative width around the threshold --
+// or with both distances ~0 (the literal expression is NaN -> false for coincident duplicates) evaluate the literal fp64
+// expression, so the adjacency is bit-identical to the fp64 reference.
 //
-// Arithmetic: the reference's mask is abs(db/da - 1) <= beta/da  &&  abs(da/db - 1) <= beta/db in
-// fp64 (quatro.hpp:363-385), i.e. |db - da| <= beta up to rounding.  The kernel first decides in fp32
-// with the sqrt-free form  u = da^2 + db^2 - beta^2;  edge <=> u <= 0 or u^2 <= 4 da^2 db^2  and a
-// rigorous rounding-error bound; only pairs inside the bound (~1e-4 of them) evaluate the literal
-// fp64 expression, so the result is bit-identical to the fp64 reference while >99.9 % of the pairs
-// cost ~30 fp32 instructions.
+// Work decomposition.  A CTA work item is 256 rows x 512 columns of the upper triangle; the 256 row points are staged in
+// shared memory as (-2a, |a|^2 - beta^2/4 | -2b, |b|^2 - beta^2/4), each lane keeps FOUR columns in registers (one
+// broadcast row load feeds 4 tests).  Result bits are shifted in from the SIGN BITS of t, s' and |t| - q with funnel
+// shifts (no compare / select per test); a warp shuffle transpose turns the per-column words into the row-major half,
+// so both halves of the symmetric matrix come out of one evaluation of the M pair tests.
 #include "handle.cuh"
 
 namespace qb {
 
-constexpr int kGraphWarps = 8;  // 8 column blocks (256 columns) per CTA, one row block
+constexpr int kGW = 4;    // warps per CTA
+constexpr int kGC = 4;    // columns per lane: a warp covers 4 x 32 columns
+constexpr int kGRB = 8;   // 32-row blocks per work item
 
 // the literal reference expression (fp64, no FMA contraction: library is built with -fmad=false)
 __device__ __noinline__ bool tim_consistent_fp64(const float4 ai, const float4 aj, const float4 bi, const float4 bj, double beta) {
@@ -38,66 +45,159 @@ __device__ __noinline__ bool tim_consistent_fp64(const float4 ai, const float4 a
   return in_f && in_r;
 }
 
-__global__ void __launch_bounds__(kGraphWarps * 32) tim_graph_kernel(const float4* __restrict__ ma, const float4* __restrict__ mb,
-                                                                      const int* __restrict__ n_corr, int Lc, int W, double beta,
-                                                                      uint32_t* __restrict__ adj) {
-  __shared__ float4 ra[32], rb[32];
+// 32 x 32 bit transpose across a warp: lane l holds row l; afterwards lane l holds column l
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t mask = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? (((y >> s) & mask) | (x & ~mask)) : ((x & mask) | ((y & mask) << s));
+  }
+  return x;
+}
+
+struct GraphConst {
+  float b2, hb2q, twob2, b4;   // beta^2, beta^2/4, 2 beta^2, beta^4 (fp32)
+  float c1, c2, c3;            // q = c1 M |D| + (c2 M + c3) M
+  float two_b2_slack;          // 2 beta^2 (1 + 1e-5): part of M
+  double beta;
+};
+
+__global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __restrict__ ma, const float4* __restrict__ mb,
+                                                             const int* __restrict__ n_corr, int Lc, int W, GraphConst gc,
+                                                             uint32_t* __restrict__ adj) {
+  __shared__ float4 s_ra[kGRB * 32], s_rb[kGRB * 32];
+  __shared__ float s_rm[kGRB * 32];
+  __shared__ float s_mmax[kGRB];
   const int pair = blockIdx.y;
   const int L = n_corr[pair];
   if (L <= 0) return;
-  const int nb = (L + 31) >> 5;                       // 32-wide blocks per side
-  const int ng = (nb + kGraphWarps - 1) / kGraphWarps; // column groups of 8 blocks
+  const int nb = (L + 31) >> 5;                                 // 32-wide blocks per side
+  const int ncg = (nb + kGW * kGC - 1) / (kGW * kGC);           // column groups of 16 blocks
+  const int nrg = (nb + kGRB - 1) / kGRB;                       // row groups of 8 blocks
   const float4* __restrict__ A = ma + (size_t)pair * Lc;
   const float4* __restrict__ B = mb + (size_t)pair * Lc;
   uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float beta2 = (float)(beta * beta);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int tile = blockIdx.x; tile < nb * ng; tile += gridDim.x) {
-    const int bi = tile / ng, g = tile % ng;
-    if (g * kGraphWarps + kGraphWarps - 1 < bi) continue;  // entirely below the diagonal (uniform per CTA)
+  for (int item = blockIdx.x; item < nrg * ncg; item += gridDim.x) {
+    const int rg = item / ncg, cg = item % ncg;
+    if (cg * (kGW * kGC) + kGW * kGC - 1 < rg * kGRB) continue;  // entirely below the diagonal (uniform per CTA)
     __syncthreads();
-    if (threadIdx.x < 32) {
-      const int i = bi * 32 + threadIdx.x;
-      ra[threadIdx.x] = i < L ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      rb[threadIdx.x] = i < L ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = tid; idx < kGRB * 32; idx += kGW * 32) {
+      const int i = rg * (kGRB * 32) + idx;
+      const bool v = i < L;
+      const float4 pa = v ? A[i] : zero4, pb = v ? B[i] : zero4;
+      const float na = fmaf(pa.z, pa.z, fmaf(pa.y, pa.y, pa.x * pa.x));
+      const float nbn = fmaf(pb.z, pb.z, fmaf(pb.y, pb.y, pb.x * pb.x));
+      s_ra[idx] = make_float4(-2.0f * pa.x, -2.0f * pa.y, -2.0f * pa.z, na - gc.hb2q);
+      s_rb[idx] = make_float4(-2.0f * pb.x, -2.0f * pb.y, -2.0f * pb.z, nbn - gc.hb2q);
+      s_rm[idx] = na + nbn;
     }
     __syncthreads();
-    const int bj = g * kGraphWarps + warp;
-    if (bj < bi || bj >= nb) continue;  // warp-uniform
-    const int j = bj * 32 + lane;
-    const bool vj = j < L;
-    const float4 ca = vj ? A[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 cb = vj ? B[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t mine = 0, roww = 0;
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const int i = bi * 32 + r;
-      const float4 pa = ra[r], pb = rb[r];
-      const float dax = ca.x - pa.x, day = ca.y - pa.y, daz = ca.z - pa.z;
-      const float dbx = cb.x - pb.x, dby = cb.y - pb.y, dbz = cb.z - pb.z;
-      const float da2 = fmaf(daz, daz, fmaf(day, day, dax * dax));
-      const float db2 = fmaf(dbz, dbz, fmaf(dby, dby, dbx * dbx));
-      const float u = (da2 + db2) - beta2;
-      const float v4 = 4.0f * da2 * db2;
-      const float uu = u * u;
-      const float S = u + 2.0f * beta2;  // = da2 + db2 + beta2
-      bool edge = (u <= 0.0f) || (uu <= v4);
-      // rigorous fp32 error bound of (uu - v4) and of u; inside it (or for coincident points) ask fp64
-      const bool amb = (fabsf(uu - v4) <= 1.0e-6f * fmaf(fabsf(u), S, v4)) || (fabsf(u) <= 1.0e-6f * S) || (da2 == 0.0f) || (db2 == 0.0f);
-      const bool live = vj && (i < L) && (i != j);
-      if (__any_sync(0xffffffffu, amb && live)) {
-        if (amb && live) edge = tim_consistent_fp64(pa, ca, pb, cb, beta);
+    for (int rb = warp; rb < kGRB; rb += kGW) {
+      float m = s_rm[rb * 32 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) s_mmax[rb] = m;
+    }
+    __syncthreads();
+    const int cb0 = cg * (kGW * kGC) + warp * kGC;
+    if (cb0 >= nb) continue;  // warp-uniform; the barriers above are at the top of the item loop
+    float4 ca[kGC], cb[kGC];
+    float cm[kGC];
+    bool cv[kGC];
+#pragma unroll
+    for (int c = 0; c < kGC; ++c) {
+      const int j = (cb0 + c) * 32 + lane;
+      cv[c] = j < L;
+      const float4 pa = cv[c] ? A[j] : zero4, pb = cv[c] ? B[j] : zero4;
+      const float na = fmaf(pa.z, pa.z, fmaf(pa.y, pa.y, pa.x * pa.x));
+      const float nbn = fmaf(pb.z, pb.z, fmaf(pb.y, pb.y, pb.x * pb.x));
+      ca[c] = make_float4(pa.x, pa.y, pa.z, na - gc.hb2q);
+      cb[c] = make_float4(pb.x, pb.y, pb.z, nbn - gc.hb2q);
+      cm[c] = na + nbn;
+    }
+    for (int rbl = 0; rbl < kGRB; ++rbl) {
+      const int bi = rg * kGRB + rbl;
+      if (bi >= nb) break;
+      if (cb0 + kGC - 1 < bi) continue;  // all four column blocks below the diagonal (warp-uniform)
+      const float mm = s_mmax[rbl];
+      float qa[kGC], qk[kGC], Mj[kGC];
+#pragma unroll
+      for (int c = 0; c < kGC; ++c) {
+        Mj[c] = (mm + cm[c] + gc.two_b2_slack) * 1.00001f;
+        qa[c] = gc.c1 * Mj[c];
+        qk[c] = (gc.c2 * Mj[c] + gc.c3) * Mj[c];
       }
-      edge = edge && live;
-      const uint32_t word = __ballot_sync(0xffffffffu, edge);
-      if (lane == r) roww = word;
-      mine |= (edge ? 1u : 0u) << r;
+      uint32_t wt[kGC] = {0u, 0u, 0u, 0u}, ws[kGC] = {0u, 0u, 0u, 0u}, wa[kGC] = {0u, 0u, 0u, 0u};
+      float smin[kGC] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+      const float4* __restrict__ ra_p = s_ra + rbl * 32;
+      const float4* __restrict__ rb_p = s_rb + rbl * 32;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float4 ra = ra_p[r], rb = rb_p[r];
+#pragma unroll
+        for (int c = 0; c < kGC; ++c) {
+          const float Ap = fmaf(ra.x, ca[c].x, fmaf(ra.y, ca[c].y, fmaf(ra.z, ca[c].z, ra.w + ca[c].w)));
+          const float Bp = fmaf(rb.x, cb[c].x, fmaf(rb.y, cb[c].y, fmaf(rb.z, cb[c].z, rb.w + cb[c].w)));
+          const float D = Ap - Bp, sp = Ap + Bp;
+          const float g = fmaf(gc.twob2, sp, gc.b4);
+          const float t = fmaf(D, D, -g);
+          const float w = fabsf(t) - fmaf(fabsf(D), qa[c], qk[c]);
+          wt[c] = __funnelshift_l(__float_as_uint(t), wt[c], 1);    // sign(t):  t < 0
+          ws[c] = __funnelshift_l(__float_as_uint(sp), ws[c], 1);   // sign(s'): s' < 0
+          wa[c] = __funnelshift_l(__float_as_uint(w), wa[c], 1);    // |t| inside the error band
+          smin[c] = fminf(smin[c], sp);
+        }
+      }
+      const int nvalid = L - bi * 32;
+      const uint32_t rows_ok = nvalid >= 32 ? ~0u : ((1u << nvalid) - 1u);
+#pragma unroll
+      for (int c = 0; c < kGC; ++c) {
+        const int cbk = cb0 + c;
+        if (cbk < bi || cbk >= nb) continue;  // warp-uniform
+        uint32_t e = __brev(wt[c] | ws[c]);   // row 0 was shifted in first
+        uint32_t am = __brev(wa[c]);
+        uint32_t live = cv[c] ? rows_ok : 0u;
+        if (cbk == bi) live &= ~(1u << lane);  // i == j
+        // both squared distances ~0 (s' ~ -beta^2): the literal expression is 0/0 for coincident duplicates -> ask it
+        float sm = smin[c];
+        if (cbk == bi) {  // the diagonal pairs (i == j) sit at s' = -beta^2 themselves: redo the minimum without them
+          sm = 3.0e38f;
+#pragma unroll 1
+          for (int r = 0; r < 32; ++r) {
+            const float4 ra = ra_p[r], rb = rb_p[r];
+            const float Ap = fmaf(ra.x, ca[c].x, fmaf(ra.y, ca[c].y, fmaf(ra.z, ca[c].z, ra.w + ca[c].w)));
+            const float Bp = fmaf(rb.x, cb[c].x, fmaf(rb.y, cb[c].y, fmaf(rb.z, cb[c].z, rb.w + cb[c].w)));
+            if (r != lane) sm = fminf(sm, Ap + Bp);
+          }
+        }
+        if (sm <= fmaf(64.0f * 5.9604645e-8f, Mj[c], -gc.b2)) am = ~0u;
+        am &= live;
+        if (am) {
+          const int j = cbk * 32 + lane;
+          const float4 aj = A[j], bj = B[j];
+          while (am) {
+            const int r = __ffs(am) - 1;
+            am &= am - 1;
+            const int i = bi * 32 + r;
+            const bool ok = tim_consistent_fp64(A[i], aj, B[i], bj, gc.beta);
+            e = ok ? (e | (1u << r)) : (e & ~(1u << r));
+          }
+        }
+        e &= live;
+        // transposed half: row j, word bi.   row-major half: row (bi*32 + lane), word cbk.
+        if (cv[c]) G[(size_t)(cbk * 32 + lane) * W + bi] = e;
+        if (cbk != bi) {
+          const uint32_t tr = warp_transpose32(e);
+          const int irow = bi * 32 + lane;
+          if (irow < L) G[(size_t)irow * W + cbk] = tr;
+        }
+      }
     }
-    // row-major half: row (bi*32 + lane), word bj.   transposed half: row j, word bi.
-    const int irow = bi * 32 + lane;
-    if (irow < L) G[(size_t)irow * W + bj] = roww;
-    if (bj != bi && vj) G[(size_t)j * W + bi] = mine;
   }
 }
 
@@ -135,9 +235,23 @@ int launch_degree(qb200_handle* h, int n_pairs) {
 int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2) {
   if (n_pairs <= 0) return QB200_OK;
   const double beta = 2 * noise_bound * sqrt(cbar2);  // quatro.hpp:367
-  const dim3 g(148, n_pairs);
+  const double u = 5.9604644775390625e-8;             // 2^-24
+  GraphConst gc;
+  gc.beta = beta;
+  gc.b2 = (float)(beta * beta);
+  gc.hb2q = 0.25f * gc.b2;
+  gc.twob2 = 2.0f * gc.b2;
+  gc.b4 = gc.b2 * gc.b2;
+  gc.c1 = (float)(36.0 * u * 1.02);
+  gc.c2 = (float)(1500.0 * u * u * 1.02);
+  gc.c3 = (float)(46.0 * u * beta * beta * 1.02);
+  gc.two_b2_slack = (float)(2.0 * beta * beta * 1.00001);
+  // capacity-sized grid: Lc/256 x Lc/512 work items per pair; few pairs -> more CTAs per pair
+  int gx = 2 * 148 / n_pairs;
+  gx = gx < 8 ? 8 : (gx > 128 ? 128 : gx);
+  const dim3 g(gx, n_pairs);
   cudaEventRecord(h->kev[2], h->stream);
-  tim_graph_kernel<<<g, kGraphWarps * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, h->Lc, h->W, beta, h->adj);
+  tim_graph_kernel<<<g, kGW * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, h->Lc, h->W, gc, h->adj);
   cudaEventRecord(h->kev[3], h->stream);
   h->kev_armed[1] = 1;
   const dim3 gd((h->Lc + 7) / 8, n_pairs);

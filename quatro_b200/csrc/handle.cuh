@@ -33,6 +33,7 @@ struct qb200_handle {
   uint64_t *key_a, *key_b;    // [2S*R]
   uint32_t *val_a, *val_b;    // [2S*R]
   void* cub_temp; size_t cub_bytes;
+  float* aos_scratch;         // [2*V*33] AoS descriptors of the stage entry points (qb200_compute_fpfh / qb200_match)
 
   // ---- front end ----
   int* vox_start;             // [2S*(V+1)] position (in the sorted raw array) of each voxel's first point

@@ -107,6 +107,17 @@ __global__ void __launch_bounds__(kPoseThreads) pose_kernel(const float4* __rest
     return;
   }
 
+  if (c > Lp) {  // the solver workspace holds 4096 clique members (max_corr may be 8192): report, do not truncate
+    if (tid == 0) {
+      res->valid = 0;
+      res->status = QB200_CAPACITY_EXCEEDED;
+      res->clique_size = c; res->gnc_iters = 0; res->n_rot_inliers = 0; res->n_final_inliers = 0; res->cost = 0.0;
+      for (int i = 0; i < 16; ++i) res->T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+      n_final[pair] = 0;
+    }
+    return;
+  }
+
   // ---- GNC-TLS on the XY rows of the chain TIMs ----
   for (int j = tid; j < c; j += kPoseThreads) wX[j] = 1.0;
   double noise_bound_sq = pp.rot_noise_bound * pp.rot_noise_bound;
@@ -366,7 +377,7 @@ int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p) {
   pp.use_rot_inliers = p.using_rot_inliers_when_estimating_cote;
   pp.use_RyRx = p.use_pre_estimated_RyRx;
   for (int i = 0; i < 9; ++i) pp.RyRx[i] = p.RyRx[i];
-  const int Lp = next_pow2(h->Lc);
+  const int Lp = next_pow2(h->Lc < 4096 ? h->Lc : 4096);
   const size_t smem = pose_smem_bytes(Lp);
   if (!(h->func_attr_set & 4u)) {  // per handle: the opt-in is a per-device property of the function
     QB_CUDA_TRY(h, cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

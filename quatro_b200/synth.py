@@ -22,19 +22,33 @@ def _lib():
         lib.qb200_synth_outdoor_pair.restype = C.c_int
         lib.qb200_synth_outdoor_pair.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                                  C.POINTER(C.c_int), C.c_int, C.c_void_p]
+        lib.qb200_synth_outdoor_pair_ex.restype = C.c_int
+        lib.qb200_synth_outdoor_pair_ex.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(Scene), C.c_void_p, C.POINTER(C.c_int),
+                                                    C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]
         _LIB = lib
     return _LIB
 
 
-def outdoor_pair(seed: int, rings: int = 64, azimuths: int = 1800):
+class Scene(C.Structure):
+    """struct qb200_synth_scene of synth.cpp."""
+    _fields_ = [("n_build", C.c_int), ("n_pole", C.c_int), ("n_car", C.c_int), ("extent", C.c_double), ("max_dist", C.c_double),
+                ("sigma", C.c_double), ("n_clutter", C.c_int)]
+
+
+STREET = (30, 50, 15, 70.0, 10.0, 0.02, 0)       # BASELINE configs[1..3]: the street scene (mean L ~ 300 after the tuple test)
+
+
+def outdoor_pair(seed: int, rings: int = 64, azimuths: int = 1800, scene=STREET):
     """Returns (src (n,4) float32, tgt (m,4) float32, T_gt 4x4 float64) with p_tgt = T_gt @ p_src.
-    w = -1 marks ground returns."""
+    w = -1 marks ground returns.  scene = (n_build, n_pole, n_car, extent, max_dist, sigma, n_clutter)."""
     cap = rings * azimuths
     src = np.zeros((cap, 4), np.float32)
     tgt = np.zeros((cap, 4), np.float32)
     ns, nt = C.c_int(0), C.c_int(0)
     T = np.zeros(16, np.float64)
-    _lib().qb200_synth_outdoor_pair(seed, rings, azimuths, src.ctypes.data, C.byref(ns), tgt.ctypes.data, C.byref(nt), cap, T.ctypes.data)
+    sc = Scene(*scene)
+    _lib().qb200_synth_outdoor_pair_ex(seed, rings, azimuths, C.byref(sc), src.ctypes.data, C.byref(ns), tgt.ctypes.data, C.byref(nt), cap,
+                                       T.ctypes.data)
     return src[: ns.value].copy(), tgt[: nt.value].copy(), T.reshape(4, 4).T.copy()
 
 

@@ -73,7 +73,7 @@ double footprint_dist(const Box& b, double x, double y) {
   return std::sqrt(dx * dx + dy * dy);
 }
 
-Scene make_outdoor_scene(Rng& g, const double sensors[2][2], int n_build, int n_pole, int n_car, double extent) {
+Scene make_outdoor_scene(Rng& g, const double sensors[2][2], int n_build, int n_pole, int n_car, double extent, int n_clutter) {
   Scene s;
   auto clear_of_sensors = [&](const Box& b, double margin) {
     for (int k = 0; k < 2; ++k)
@@ -105,6 +105,15 @@ Scene make_outdoor_scene(Rng& g, const double sensors[2][2], int n_build, int n_
     for (int k = 0; k < 2; ++k)
       if (std::hypot(c.cx - sensors[k][0], c.cy - sensors[k][1]) < 2.0) ok = false;
     if (ok) s.cyls.push_back(c);
+  }
+  const int n_bc = (int)s.boxes.size();
+  guard = 0;
+  while ((int)s.boxes.size() < n_bc + n_clutter && guard++ < 1000000) {
+    const double cx = g.uni(-extent, extent), cy = g.uni(-extent, extent);
+    const double hx = g.uni(0.1, 0.6), hy = g.uni(0.1, 0.6);
+    Box b{{cx - hx, cy - hy, 0.0}, {cx + hx, cy + hy, g.uni(0.2, 2.5)}};
+    if (!clear_of_sensors(b, 2.0)) continue;
+    s.boxes.push_back(b);
   }
   return s;
 }
@@ -184,20 +193,31 @@ int scan(const Scene& s, const Pose& P, uint64_t noise_seed, int rings, int azim
 
 extern "C" {
 
+// Scene / motion knobs of the outdoor generator.  {30, 50, 15, 70, 10, 0.02} is the street scene of BASELINE configs[1..3];
+// the "dense" preset (more clutter, a revisit within ~1 m, see synth.py) yields the ~3 k correspondences per pair that
+// BASELINE.json quotes for the back end.
+struct qb200_synth_scene {
+  int n_build, n_pole, n_car;
+  double extent;      // half size of the square the objects are placed in [m]
+  double max_dist;    // |t_xy| ~ U(0, max_dist)
+  double sigma;       // range noise [m]
+  int n_clutter;      // small boxes (0.2 .. 1.2 m footprints, up to 2.5 m high): shrubs, bins, street furniture
+};
+
 // Outdoor 64-ring pair.  rings/azimuths let tests ask for a smaller sensor (e.g. 16 x 450).
 // T_gt: column-major 4x4 with p_tgt = T_gt * p_src.  Returns 0, or 1 if cap was too small.
-int qb200_synth_outdoor_pair(uint64_t seed, int rings, int azimuths, float* src4, int* n_src, float* tgt4, int* n_tgt, int cap,
-                             double* T_gt) {
+int qb200_synth_outdoor_pair_ex(uint64_t seed, int rings, int azimuths, const qb200_synth_scene* sc, float* src4, int* n_src, float* tgt4,
+                                int* n_tgt, int cap, double* T_gt) {
   Rng g(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull);
   const double h = 1.723;
-  const double yaw = g.uni(-M_PI, M_PI), dist = g.uni(0.0, 10.0), dir = g.uni(-M_PI, M_PI);
+  const double yaw = g.uni(-M_PI, M_PI), dist = g.uni(0.0, sc->max_dist), dir = g.uni(-M_PI, M_PI);
   const double roll = g.uni(-1.0, 1.0) * M_PI / 180.0, pitch = g.uni(-1.0, 1.0) * M_PI / 180.0, dz = g.uni(-0.1, 0.1);
   const Pose Ps = make_pose(0, 0, 0, 0, 0, h);
   const Pose Pt = make_pose(yaw, pitch, roll, dist * std::cos(dir), dist * std::sin(dir), h + dz);
   const double sensors[2][2] = {{Ps.t[0], Ps.t[1]}, {Pt.t[0], Pt.t[1]}};
-  const Scene s = make_outdoor_scene(g, sensors, 30, 50, 15, 70.0);
-  const int ns = scan(s, Ps, seed * 2 + 1000003ull, rings, azimuths, 25.0, 26.9, 0.02, 2.7, 80.0, src4, cap);
-  const int nt = scan(s, Pt, seed * 2 + 1000004ull, rings, azimuths, 25.0, 26.9, 0.02, 2.7, 80.0, tgt4, cap);
+  const Scene s = make_outdoor_scene(g, sensors, sc->n_build, sc->n_pole, sc->n_car, sc->extent, sc->n_clutter);
+  const int ns = scan(s, Ps, seed * 2 + 1000003ull, rings, azimuths, 25.0, 26.9, sc->sigma, 2.7, 80.0, src4, cap);
+  const int nt = scan(s, Pt, seed * 2 + 1000004ull, rings, azimuths, 25.0, 26.9, sc->sigma, 2.7, 80.0, tgt4, cap);
   *n_src = std::min(ns, cap);
   *n_tgt = std::min(nt, cap);
   // T_gt = Pt^-1 * Ps
@@ -217,6 +237,12 @@ int qb200_synth_outdoor_pair(uint64_t seed, int rings, int azimuths, float* src4
   }
   T_gt[15] = 1;
   return (ns > cap || nt > cap) ? 1 : 0;
+}
+
+int qb200_synth_outdoor_pair(uint64_t seed, int rings, int azimuths, float* src4, int* n_src, float* tgt4, int* n_tgt, int cap,
+                             double* T_gt) {
+  const qb200_synth_scene street = {30, 50, 15, 70.0, 10.0, 0.02, 0};
+  return qb200_synth_outdoor_pair_ex(seed, rings, azimuths, &street, src4, n_src, tgt4, n_tgt, cap, T_gt);
 }
 
 }  // extern "C"

@@ -6,9 +6,12 @@ import pytest
 
 from conftest import adj_to_dense, dense_to_adj
 from quatro_b200 import synth
-from quatro_b200.capi import default_params, PMC_HEU, KCORE_HEU, INLIER_NONE, COTE_WEIGHTED_MEAN, RESULT_DTYPE
+from quatro_b200.capi import Handle, default_params, PMC_HEU, KCORE_HEU, INLIER_NONE, COTE_WEIGHTED_MEAN, RESULT_DTYPE
 
 pytestmark = pytest.mark.gpu
+
+# the production default of the neighbour lattice: (1 + 2^-9) * fpfh_radius (api.cu lattice_cell(), oracle default)
+DEFAULT_CELL = float(np.float32(0.75) * np.float32(1.001953125))
 
 
 def P4(xyz, w=1.0):
@@ -71,10 +74,10 @@ def test_voxelize_edge_cases(handle, oracle):
 
 # ---- K2-K5 normals + FPFH ------------------------------------------------------------------------------
 def test_fpfh_bit_exact(handle, oracle, scan_pair, small_pair):
-    for raw in (scan_pair[0], small_pair[1]):
+    for raw, cell in ((scan_pair[0], 0.3), (small_pair[1], 0.3), (scan_pair[1], DEFAULT_CELL), (small_pair[0], DEFAULT_CELL)):
         vox, _ = oracle.voxelize(raw, 0.3, 1)
-        n_ref, d_ref = oracle.compute_fpfh(vox, 0.5, 0.75, 0.3)
-        n_got, d_got = handle.compute_fpfh(vox, 0.5, 0.75, 0.3)
+        n_ref, d_ref = oracle.compute_fpfh(vox, 0.5, 0.75, cell)
+        n_got, d_got = handle.compute_fpfh(vox, 0.5, 0.75, cell)
         same_n = (n_got.view(np.uint32) == n_ref.view(np.uint32)) | (np.isnan(n_got) & np.isnan(n_ref))
         assert same_n.all(), f"{(~same_n).any(1).sum()} of {len(vox)} normals differ"
         same_d = d_got.view(np.uint32) == d_ref.view(np.uint32)
@@ -89,7 +92,7 @@ def test_fpfh_other_lattice_and_unsorted_input(handle, oracle):
                           np.stack([np.full(xx.size, 5.0), xx.ravel(), yy.ravel()], 1),
                           rng.uniform(-4, 4, (500, 3))])
     pts = pts[rng.permutation(len(pts))] + rng.normal(0, 0.01, (len(pts), 3))
-    for cell in (0.3, 0.5, 0.2):
+    for cell in (0.3, 0.5, 0.2, DEFAULT_CELL):
         n_ref, d_ref = oracle.compute_fpfh(P4(pts), 0.5, 0.75, cell)
         n_got, d_got = handle.compute_fpfh(P4(pts), 0.5, 0.75, cell)
         assert np.array_equal(d_got.view(np.uint32), d_ref.view(np.uint32))
@@ -282,6 +285,118 @@ def test_clique_on_registration_graphs(handle, oracle):
         ref = oracle.max_clique(adj, KCORE_HEU, 0.1)
         got = handle.max_clique(adj, KCORE_HEU, 0.1)
         assert np.array_equal(got[0], ref[0])
+
+
+def _structured_graphs():
+    """graph families that stress the bucket mechanics of the peel: many vertices of equal degree (groups whose members
+    already sit inside the target slots -> serial replay), many levels, many improving start vertices in the clique search"""
+    out = []
+    n = 60; R = np.ones((n, n), bool); np.fill_diagonal(R, False); out.append(("K60", R))
+    n = 200; R = np.zeros((n, n), bool)
+    for i in range(n):
+        for k in (1, 2, 3):
+            R[i, (i + k) % n] = R[(i + k) % n, i] = True
+    out.append(("ring3", R))
+    n = 150; R = np.zeros((n, n), bool); R[0, 1:] = True; R[1:, 0] = True; out.append(("star", R))
+    R = np.ones((150, 150), bool)
+    for P in (range(0, 40), range(40, 90), range(90, 150)):
+        R[np.ix_(list(P), list(P))] = False
+    out.append(("multipartite", R))
+    R = np.zeros((300, 300), bool)
+    for s0 in range(0, 300, 30):
+        R[s0:s0 + 30, s0:s0 + 30] = True
+    np.fill_diagonal(R, False); out.append(("disjoint cliques", R))
+    R = np.zeros((256, 256), bool)
+    for i in range(256):
+        for b in range(8):
+            R[i, i ^ (1 << b)] = True
+    out.append(("hypercube8", R))
+    # nested cliques of growing size joined by sparse noise: the incumbent improves many times
+    rng = np.random.default_rng(5)
+    R = rng.uniform(size=(900, 900)) < 0.01; R = np.triu(R, 1); R = R | R.T
+    o = 0
+    for k in range(3, 40, 3):
+        R[o:o + k, o:o + k] = True; o += k
+    np.fill_diagonal(R, False); out.append(("growing cliques", R))
+    rng = np.random.default_rng(6)
+    for n, p_ in ((600, 0.2), (1200, 0.08), (2500, 0.05)):
+        R = rng.uniform(size=(n, n)) < p_; R = np.triu(R, 1); R = R | R.T
+        out.append((f"G({n},{p_})", R))
+    return out
+
+
+def test_kcore_and_clique_structured_graphs(handle, oracle):
+    for name, R in _structured_graphs():
+        adj = dense_to_adj(R)
+        c_ref, k_ref, o_ref, mc_ref = oracle.max_clique(adj, PMC_HEU)
+        c_got, k_got, o_got, mc_got = handle.max_clique(adj, PMC_HEU)
+        assert mc_got == mc_ref, name
+        assert np.array_equal(k_got, k_ref), f"{name}: core numbers differ"
+        assert np.array_equal(o_got, o_ref), f"{name}: peel order differs"
+        assert np.array_equal(c_got, c_ref), f"{name}: clique membership differs"
+
+
+def test_graph_and_clique_wide_handle(oracle):
+    """max_corr = 8192: 256-word rows (8-warp peel, 64-bit packed group sizes, 8 adjacency words per lane in the descent)."""
+    with Handle(max_batch_slots=2, max_corr=8192) as h:
+        a4, b4, T, inl = synth.matched_pairs(4321, 6000, inlier_ratio=0.1, noise=0.05)
+        adj_r, deg_r, ne_r = oracle.build_graph(a4, b4, 0.3, 1.0)
+        adj_g, deg_g, ne_g = h.build_graph(a4, b4, 0.3, 1.0)
+        assert np.array_equal(adj_g, adj_r) and np.array_equal(deg_g, deg_r) and ne_g == ne_r
+        ref = oracle.max_clique(adj_r, PMC_HEU)
+        got = h.max_clique(adj_r, PMC_HEU)
+        assert got[3] == ref[3] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]) and np.array_equal(got[0], ref[0])
+        p = default_params()
+        r_g, st_g = h.solve_correspondences(a4, b4, p)
+        r_o, st_o = oracle.solve_correspondences(a4, b4, p)
+        assert st_g == st_o and r_g.clique_size == r_o.clique_size and np.allclose(r_g.matrix(), r_o.matrix(), atol=1e-9)
+        R = _random_graph(np.random.default_rng(77), 8192, 0.004, 120)
+        adj = dense_to_adj(R)
+        ref = oracle.max_clique(adj, PMC_HEU)
+        got = h.max_clique(adj, PMC_HEU)
+        assert got[3] == ref[3] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]) and np.array_equal(got[0], ref[0])
+
+
+def test_graph_error_band_adversarial(handle, oracle):
+    """The fp32 Gram-form filter of K8 must hand every pair it cannot decide to the literal fp64 expression: coincident
+    duplicates in both clouds (0/0 in the literal form), tiny triangles (da + db < beta), points far from the origin
+    (large |a|^2: wide error band), points on the threshold to 1 ulp, and everything shifted by a large offset."""
+    rng = np.random.default_rng(11)
+    n = 700
+    a = rng.uniform(-2, 2, (n, 3)); b = a + rng.normal(0, 0.05, (n, 3))
+    a[5] = a[6]; b[5] = b[6]            # coincident in both clouds
+    a[7] = a[8]                         # coincident in one cloud only
+    a[100:140] = a[100] + rng.normal(0, 0.05, (40, 3)); b[100:140] = b[100] + rng.normal(0, 0.05, (40, 3))   # tiny triangles
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    b[200:300] = a[200:300] + d[200:300] * 0.6
+    for shift, scale in ((0.0, 1.0), (75.0, 1.0), (0.0, 40.0), (400.0, 1.0)):
+        a4, b4 = P4(a * scale + shift), P4(b * scale + shift)
+        for nb in (0.3, 0.05):
+            g, dg, ng = handle.build_graph(a4, b4, nb, 1.0)
+            r, dr, nr = oracle.build_graph(a4, b4, nb, 1.0)
+            assert np.array_equal(g, r), (shift, scale, nb, int((g != r).sum()))
+            assert np.array_equal(dg, dr) and ng == nr
+    z = np.zeros((70, 3)); z4 = P4(z)   # every point identical
+    assert np.array_equal(handle.build_graph(z4, z4, 0.3, 1.0)[0], oracle.build_graph(z4, z4, 0.3, 1.0)[0])
+
+
+def test_small_capacity_handles(oracle, small_pair):
+    """Configurations the default tests never touch: one slot, V = 128 / 256, max_raw_points < max_voxel_points."""
+    src, tgt, _ = small_pair
+    p = default_params()
+    sv, _ = oracle.voxelize(src, 0.3, 1); tv, _ = oracle.voxelize(tgt, 0.3, 1)
+    for kw in (dict(max_batch_slots=1, max_voxel_points=16384, max_raw_points=4096), dict(max_batch_slots=1, max_voxel_points=128),
+               dict(max_batch_slots=1, max_voxel_points=256), dict(max_batch_slots=1)):
+        with Handle(**kw) as h:
+            V = h.cfg.max_voxel_points
+            a, b = sv[:min(len(sv), V, h.cfg.max_raw_points)], tv[:min(len(tv), V, h.cfg.max_raw_points)]
+            n_g, d_g = h.compute_fpfh(a, 0.5, 0.75, DEFAULT_CELL)
+            n_r, d_r = oracle.compute_fpfh(a, 0.5, 0.75, DEFAULT_CELL)
+            assert np.array_equal(d_g.view(np.uint32), d_r.view(np.uint32)), kw
+            _, d_b = oracle.compute_fpfh(b, 0.5, 0.75, DEFAULT_CELL)
+            c_g = h.match(a, d_r, b, d_b, p)[0]
+            c_r = oracle.match(a, d_r, b, d_b, p)[0]
+            assert np.array_equal(c_g, c_r), kw
 
 
 # ---- K10/K11 pose --------------------------------------------------------------------------------------
