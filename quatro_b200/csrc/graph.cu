@@ -247,7 +247,7 @@ int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2)
   gc.c3 = (float)(46.0 * u * beta * beta * 1.02);
   gc.two_b2_slack = (float)(2.0 * beta * beta * 1.00001);
   // capacity-sized grid: Lc/256 x Lc/512 work items per pair; few pairs -> more CTAs per pair
-  int gx = 2 * 148 / n_pairs;
+  int gx = 8 * 148 / n_pairs;  // >= 8 CTAs (32 warps) per SM when every pair is large; idle CTAs of small pairs exit at once
   gx = gx < 8 ? 8 : (gx > 128 ? 128 : gx);
   const dim3 g(gx, n_pairs);
   cudaEventRecord(h->kev[2], h->stream);
