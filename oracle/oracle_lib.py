@@ -50,6 +50,11 @@ class Oracle:
         L.qo_test_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
         L.qo_test_kcore.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 
+    def set_literal(self, on: bool) -> bool:
+        """Literal mode: libstdc++ std::sort on tied keys and distance-ordered neighbour accumulation instead of the determinism
+        fixes D3 / D8 (measurement only; the CUDA library is compared with the canonical mode).  Returns the previous mode."""
+        return bool(self.lib.qo_set_literal(1 if on else 0))
+
     def set_num_threads(self, n: int) -> int:
         return self.lib.qo_set_num_threads(n)
 

@@ -59,6 +59,13 @@ struct P4 {
 
 inline bool finite3(const P4& p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); }
 
+// LITERAL mode (qo_set_literal): undo the determinism fixes D3 and D8 where the literal behaviour of the reference's libraries can
+// be reproduced with this toolchain -- libstdc++'s unstable std::sort on tied keys (VoxelGrid's (voxel, point) sort, pmc's sort of
+// P, the COTE event sort of quatro.hpp:641) and PCL's distance-ordered neighbour accumulation (KdTreeFLANN returns sorted radius
+// results).  It exists only to MEASURE how far "bit-exact with the canonical oracle" can be from the literal reference
+// (tests/test_literal_mode.py); the CUDA library is compared with the canonical mode.
+int g_literal = 0;
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11), counter = (ctr_lo, ctr_hi, 0, 0), key = (seed_lo, seed_hi)
 // ---------------------------------------------------------------------------------------------
@@ -122,8 +129,9 @@ int voxelize(const P4* pts, int n, float leaf, int skip_flagged, std::vector<P4>
     const int ijk2 = (int)(std::floor(p.z * inv) - (float)min_b[2]);
     iv.emplace_back(ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2], i);
   }
-  std::stable_sort(iv.begin(), iv.end(),
-                   [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });  // D3
+  const auto by_voxel = [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; };
+  if (g_literal) std::sort(iv.begin(), iv.end(), by_voxel);  // [EXT] PCL: std::sort with operator< on the voxel index only
+  else std::stable_sort(iv.begin(), iv.end(), by_voxel);      // D3
   size_t first = 0;
   while (first < iv.size()) {
     size_t last = first + 1;
@@ -190,10 +198,21 @@ struct Lattice {
 
   static int reach(float radius, float inv) { return (int)std::ceil(radius * inv + 1e-3f); }
 
-  // f(index, dist2) in canonical order
+  // f(index, dist2) in canonical order ((cell, index), D8); literal mode: ascending distance like a sorted FLANN radius search
   template <class F>
   void for_each_neighbor(const P4* pts, int q, float radius, F&& f) const {
     if (!in[q]) return;
+    if (g_literal) {
+      std::vector<std::pair<float, int>> found;
+      walk(pts, q, radius, [&](int p, float d2) { found.emplace_back(d2, p); });
+      std::sort(found.begin(), found.end());
+      for (const auto& e : found) f(e.second, e.first);
+      return;
+    }
+    walk(pts, q, radius, f);
+  }
+  template <class F>
+  void walk(const P4* pts, int q, float radius, F&& f) const {
     const int m = reach(radius, inv);
     const float r2 = (float)((double)radius * (double)radius);
     const P4& pq = pts[q];
@@ -677,8 +696,9 @@ int pmc_heuristic(const Csr& g, const std::vector<int>& K, const std::vector<int
       if (K[u] > mc) P.emplace_back(u, K[u]);
     }
     if ((int)P.size() <= mc) continue;
-    std::stable_sort(P.begin(), P.end(),
-                     [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second < b.second; });
+    const auto by_bound = [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.second < b.second; };
+    if (g_literal) std::sort(P.begin(), P.end(), by_bound);
+    else std::stable_sort(P.begin(), P.end(), by_bound);
     // branch(): a single greedy descent, no backtracking
     std::vector<int> popped;
     int sz = 1;
@@ -838,8 +858,9 @@ double cote_estimate(const double* X, int N, double range, bool median_mode, std
     h.emplace_back(X[i] - range, i + 1);
     h.emplace_back(X[i] + range, -i - 1);
   }
-  std::stable_sort(h.begin(), h.end(),
-                   [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });  // D3
+  const auto by_value = [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; };
+  if (g_literal) std::sort(h.begin(), h.end(), by_value);  // quatro.hpp:641
+  else std::stable_sort(h.begin(), h.end(), by_value);      // D3
   const double weight = 1.0 / (range * range);  // ranges.square().inverse()
   const int nr_centers = 2 * N;
   std::vector<double> x_hat(nr_centers, 0.0), x_cost(nr_centers, 0.0);
@@ -996,6 +1017,13 @@ double now_s() {
 // C interface (loaded by tests/ and bench.py via ctypes)
 // =====================================================================================
 extern "C" {
+
+// 1 = literal mode (see g_literal), 0 = canonical (default).  Returns the previous value.
+int qo_set_literal(int on) {
+  const int prev = g_literal;
+  g_literal = on ? 1 : 0;
+  return prev;
+}
 
 int qo_set_num_threads(int n) {
 #ifdef _OPENMP
