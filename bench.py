@@ -294,16 +294,32 @@ def main():
         return hd
 
     handle = make_handle(args.scene)
+    numa_cores = handle.bind_numa()   # launches and pinned copies from the GPU's own socket
     p = scene_params(args.scene)
     out = np.zeros(P, RESULT_DTYPE)
-    out_t = torch.zeros((P, RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    gathered = [torch.empty_like(out_t) for _ in range(world)] if world > 1 else None
+    out_all = np.zeros(world * P, RESULT_DTYPE) if world > 1 else None
+    host_ms = {"enqueue": 0.0, "collective_wait": 0.0}
+    if world > 1:
+        # the path's only collective lives in the C++ library: one ncclAllGather of the result records per batch on the handle's
+        # communication stream, deferred so that it overlaps the next step (qb200_register_batch_rank / qb200_comm_wait)
+        uid = [Handle.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        handle.comm_init_rank(world, rank, uid[0])
 
     def step(hd, prm, pa, kind):
-        hd.register_batch_raw(pa, P, prm, kind, out)
-        if world > 1:  # the path's only collective: gather the per-pair result records
-            out_t.copy_(torch.from_numpy(out.view(np.uint8).reshape(P, -1)), non_blocking=True)
-            dist.all_gather(gathered, out_t)
+        t0 = time.perf_counter()
+        if world > 1 and hd is handle:
+            hd.register_batch_rank_raw(pa, P, prm, kind, out_all, defer=True)   # waits for the PREVIOUS step's gather first
+        else:
+            hd.register_batch_raw(pa, P, prm, kind, out)
+        host_ms["enqueue"] += 1e3 * (time.perf_counter() - t0)
+
+    def finish_gather():
+        if world > 1:
+            t0 = time.perf_counter()
+            handle.comm_wait()
+            host_ms["collective_wait"] += 1e3 * (time.perf_counter() - t0)
+            out[:] = out_all[rank::world]
 
     def timed(hd, prm, pa, kind, steps, sampler=None):
         if world > 1:
@@ -319,6 +335,8 @@ def main():
             step(hd, prm, pa, kind)
             m, c = hd.kernel_ms()
             kms += m; kcalls += c; sms += hd.stage_ms()
+        if hd is handle:
+            finish_gather()   # the last step's gather; qb200_comm_wait orders the handle's stream after it
         e1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -359,10 +377,18 @@ def main():
 
     for _ in range(args.warmup):
         step(handle, p, pa_dev, MEM_DEVICE)
+    finish_gather()
+    host_ms = {"enqueue": 0.0, "collective_wait": 0.0}
     dev_ms, launches, kms, kcalls, sms, clocks = timed(handle, p, pa_dev, MEM_DEVICE, args.steps, ClockSampler(local_rank) if rank == 0 else None)
     res_dev = out.copy()
+    out_all_dev = out_all.copy() if world > 1 else None
+    host_dev = dict(host_ms)
+    if world > 1:
+        # every rank holds every record: the gathered copy of this rank's slice must be the local result
+        assert out_all.reshape(P, world)[:, rank].tobytes() == out.tobytes()
     for _ in range(max(1, args.warmup // 2)):
         step(handle, p, pa_host, MEM_HOST)
+    finish_gather()
     e2e_ms, _, _, _, _, _ = timed(handle, p, pa_host, MEM_HOST, args.steps)
     assert out.tobytes() == res_dev.tobytes(), "host-buffer and device-buffer runs disagree"
 
@@ -377,10 +403,9 @@ def main():
         _, h2, d2, _, pa2, _ = build_inputs(range(nxt * P, nxt * P + k))
         mine = np.zeros(k, RESULT_DTYPE)
         handle.register_batch_raw(pa2, k, p, MEM_DEVICE, mine)
-        theirs = torch.from_numpy(res_dev[:k].copy().view(np.uint8).reshape(k, -1)).to(dev)
-        allrec = [torch.empty_like(theirs) for _ in range(world)]
-        dist.all_gather(allrec, theirs)
-        same = bool(allrec[nxt].cpu().numpy().tobytes() == mine.tobytes())
+        # rank nxt's own records came with the library's gather: out_all[i * world + r]
+        theirs = out_all_dev.reshape(P, world)[:k, nxt]
+        same = bool(theirs.tobytes() == mine.tobytes())
         flag = torch.tensor([1 if same else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         cross = {"pairs_per_rank": k, "identical_on_all_ranks": bool(flag.item() == 1),
@@ -522,6 +547,10 @@ def main():
             "valid_pairs": int(res_dev["valid"].sum()), "mean_n_vox": float((nA.mean() + nB.mean()) / 2), "mean_L": float(L.mean()),
             "mean_clique": float(res_dev["clique_size"].mean()),
             "single_pair_latency_ms": single_ms,
+            "host_ms_per_step_rank0": {"enqueue": host_dev["enqueue"] / args.steps, "collective_wait": host_dev["collective_wait"] / args.steps,
+                                       "device": step_ms, "numa_cores_bound": numa_cores,
+                                       "what": "host time inside qb200_register_batch(_rank) per step; time blocked in qb200_comm_wait (the deferred "
+                                               "gather of the last step only); device time per step (CUDA events, max over ranks)"},
         }
         print(json.dumps(line))
     handle.close()

@@ -15,6 +15,7 @@
  *   qb200_solve_correspondences <- Quatro::computeTransformation(Eigen::Matrix4d&)  include/quatro.hpp:769-936
  *   qb200_match_and_pack        <- FPFHManager::setFeaturePair          include/fpfh_manager.hpp:98-153
  *   qb200_register_pair/_batch  <- examples/run_global_registration.cpp:206-246 (voxelize .. computeTransformation)
+ *   qb200_register_batch_sharded / _rank  <- the same loop over a list of pairs, sharded over the GPUs of one box
  *
  * Conventions
  *   - extern "C", plain pointers and sizes, no C++/torch types.  All pointers are HOST pointers
@@ -100,7 +101,7 @@ typedef struct qb200_config {
   int32_t max_batch_slots;   /* pairs resident in one wave of the batch pipeline (default 64) */
   int32_t max_raw_points;    /* per cloud (default 131072) */
   int32_t max_voxel_points;  /* per cloud (default 16384; multiple of 128) */
-  int32_t max_corr;          /* per pair  (default 4096)  */
+  int32_t max_corr;          /* per pair  (default 4096; multiple of 32, <= 8192; the pose solver holds cliques of <= 4096) */
   int32_t reserved[3];
 } qb200_config;
 
@@ -208,6 +209,33 @@ int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const
  * or the lane. */
 int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs,
                          const qb200_params* p, qb200_mem_kind kind, qb200_result* results);
+
+/* --- multi-GPU: batches of independent pairs shard across the GPUs of one box; the only communication is ONE all-gather (NCCL over
+ * NVLink) of the fixed-size result records per batch -- north_star / SURVEY.md 8(e).  The reference has no counterpart (it is a
+ * single-process CPU program: examples/run_global_registration.cpp processes one pair); these entry points are what a loop-closure
+ * sweep over the reference's `quatro.computeTransformation` would call instead.  libnccl.so.2 is opened at the first call
+ * (QB200_ERR_UNSUPPORTED when it is absent).
+ *
+ * (A) one process, several devices: handles[i] was created on device i' (any distinct devices); pair g runs on handles[g mod n_dev]
+ *     (QB200_MEM_DEVICE pointers of pair g must live on that device); results come back in the order of `pairs`. */
+#define QB200_UNIQUE_ID_BYTES 128
+int qb200_comm_init_all(qb200_handle** handles, int32_t n_dev);
+int qb200_register_batch_sharded(qb200_handle** handles, int32_t n_dev, const qb200_pair* pairs, int32_t n_pairs,
+                                 const qb200_params* p, qb200_mem_kind kind, qb200_result* results);
+/* (B) one process per device (torchrun / mpirun): rank 0 calls qb200_comm_unique_id and hands the 128 bytes to every rank (any
+ *     out-of-band channel), every rank calls qb200_comm_init_rank.  qb200_register_batch_rank registers this rank's n_local pairs
+ *     (the same n_local on every rank) and gathers all records: all_results[i * world + r] = record of rank r's i-th pair
+ *     (round-robin sharding of a global list).  defer != 0: the call returns as soon as the gather is enqueued on the handle's
+ *     communication stream -- all_results is complete after qb200_comm_wait (or the next qb200_register_batch_rank), so the
+ *     gather overlaps the next batch and no rank waits for the slowest one inside a step. */
+int qb200_comm_unique_id(void* id128);
+int qb200_comm_init_rank(qb200_handle* h, int32_t world, int32_t rank, const void* id128);
+int qb200_register_batch_rank(qb200_handle* h, const qb200_pair* local_pairs, int32_t n_local, const qb200_params* p,
+                              qb200_mem_kind kind, qb200_result* all_results, int32_t defer);
+int qb200_comm_wait(qb200_handle* h);
+/* Bind the calling host thread to the cores of the NUMA node of the handle's GPU (kernel launches and pinned copies from the far
+ * socket of a 2-socket box are slower).  Returns the number of cores bound (0: topology unknown, nothing changed). */
+int qb200_bind_numa(qb200_handle* h);
 
 /* Introspection of the most recent single-pair solve on this handle (getMaxCliques,
  * getFinalInliersIndices, getCorrespondences; quatro.hpp:949-972, fpfh_manager.hpp:234-236). */

@@ -51,7 +51,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
         return CUDA_LIB
     LIB_DIR.mkdir(exist_ok=True)
     cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", HOST_CXX, "-I", str(ROOT / "include"), "-I", str(CSRC),
-           "-o", str(CUDA_LIB), *map(str, srcs), "-lcudart"]
+           "-o", str(CUDA_LIB), *map(str, srcs), "-lcudart", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -130,6 +130,13 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_debug_tc_distances": (i32, [vp, vp, i32, vp, i32, vp]),
         "qb200_debug_match_stats": (i32, [vp, vp, i32]),
         "qb200_solve_batch": (i32, [vp, vp, i32, vp, i32, vp]),
+        "qb200_comm_init_all": (i32, [P(vp), i32]),
+        "qb200_register_batch_sharded": (i32, [P(vp), i32, P(Pair), i32, P(Params), i32, vp]),
+        "qb200_comm_unique_id": (i32, [vp]),
+        "qb200_comm_init_rank": (i32, [vp, i32, i32, vp]),
+        "qb200_register_batch_rank": (i32, [vp, P(Pair), i32, P(Params), i32, vp, i32]),
+        "qb200_comm_wait": (i32, [vp]),
+        "qb200_bind_numa": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
@@ -148,6 +155,8 @@ EXPORTED_SYMBOLS = [
     "qb200_debug_tc_distances",
     "qb200_debug_match_stats",
     "qb200_solve_batch",
+    "qb200_comm_init_all", "qb200_register_batch_sharded", "qb200_comm_unique_id", "qb200_comm_init_rank",
+    "qb200_register_batch_rank", "qb200_comm_wait", "qb200_bind_numa",
 ]
 
 
@@ -165,6 +174,35 @@ def default_params() -> Params:
     for i in range(9):
         p.RyRx[i] = 1.0 if i in (0, 4, 8) else 0.0
     return p
+
+
+def comm_init_all(handles: Sequence["Handle"]):
+    """(A) one process, several devices: ncclCommInitAll over the handles' devices."""
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    st = load_library().qb200_comm_init_all(arr, len(handles))
+    if st != 0:
+        raise QuatroB200Error(st, "qb200_comm_init_all")
+
+
+def register_batch_sharded(handles: Sequence["Handle"], pairs: Sequence, params: "Params", kind: int = 0) -> np.ndarray:
+    """pairs: (src, tgt) numpy arrays (MEM_HOST) or (src_ptr, n_src, tgt_ptr, n_tgt) device tuples whose pair g lives on the device
+    of handles[g % len(handles)].  Returns the records in the order of `pairs`."""
+    n = len(pairs)
+    arr = (Pair * n)()
+    keep = []
+    for i, pr in enumerate(pairs):
+        if kind == MEM_HOST:
+            s, t = _f32(pr[0], 4), _f32(pr[1], 4)
+            keep.append((s, t))
+            arr[i].src, arr[i].n_src, arr[i].tgt, arr[i].n_tgt = s.ctypes.data, len(s), t.ctypes.data, len(t)
+        else:
+            arr[i].src, arr[i].n_src, arr[i].tgt, arr[i].n_tgt = pr[0], pr[1], pr[2], pr[3]
+    out = np.zeros(n, RESULT_DTYPE)
+    hs = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    st = load_library().qb200_register_batch_sharded(hs, len(handles), arr, n, C.byref(params), kind, _ptr(out))
+    if st != 0:
+        raise QuatroB200Error(st, "qb200_register_batch_sharded " + handles[0].last_error())
+    return out
 
 
 def default_config() -> Config:
@@ -338,6 +376,31 @@ class Handle:
         out = np.zeros(n, RESULT_DTYPE)
         self._check(self.lib.qb200_solve_batch(self.h, arr, n, C.byref(params), kind, _ptr(out)), "qb200_solve_batch")
         return out
+
+    # ---- multi-GPU (comm.cu) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        st = load_library().qb200_comm_unique_id(buf)
+        if st != 0:
+            raise QuatroB200Error(st, "qb200_comm_unique_id")
+        return buf.raw
+
+    def comm_init_rank(self, world: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.lib.qb200_comm_init_rank(self.h, world, rank, buf), "qb200_comm_init_rank")
+        self.world, self.rank = world, rank
+
+    def register_batch_rank_raw(self, pair_array, n_local: int, params: Params, kind: int, out_all: np.ndarray, defer: bool = False):
+        """out_all: RESULT_DTYPE array of world * n_local records, filled in round-robin global order (index i * world + r)."""
+        return self._check(self.lib.qb200_register_batch_rank(self.h, pair_array, n_local, C.byref(params), kind, _ptr(out_all), int(defer)),
+                           "qb200_register_batch_rank")
+
+    def bind_numa(self) -> int:
+        return int(self.lib.qb200_bind_numa(self.h))
+
+    def comm_wait(self):
+        return self._check(self.lib.qb200_comm_wait(self.h), "qb200_comm_wait")
 
     def register_batch_raw(self, pair_array, n: int, params: Params, kind: int, out: np.ndarray):
         """Zero-overhead variant for bench.py: pre-built (Pair * n) array and RESULT_DTYPE output."""

@@ -12,15 +12,16 @@
 // The reference runs the start vertices on 12 racy OpenMP threads; like the CPU oracle these kernels
 // reproduce the SEQUENTIAL semantics bit for bit.  One CTA per registration pair:
 //
-//   kcore_cta_kernel   The peel stays a sequence of L steps (the order is the output), but a step is CTA-wide:
-//     thread t owns adjacency word t of the row being peeled; `above` (bitset of vertices whose current degree exceeds
-//     the current level) turns "neighbour with deg[u] > deg[v]" into one AND; the surviving neighbours are expanded
-//     to an ascending list with one block scan and every neighbour's bucket move is done by its own thread.  Moves
-//     into different buckets commute; the members of one bucket (same current degree) must be applied in id order:
-//     their ranks come from __match_any_sync inside a warp and a packed per-warp size word across warps, and with the
-//     ranks known the moves of a group have a closed form (member t lands on slot bin+t, the displaced vertex takes
-//     the member's old slot) unless a member already sits inside the target slots -- then that group is replayed
-//     serially by one thread while the other groups proceed in parallel.  The next row is prefetched while the current one is processed.
+//   kcore_warp_kernel  The peel stays a sequence of L steps (the order is the output) run by ONE WARP per pair without any
+//     block barrier; a step is warp-wide: lane l owns WPL consecutive adjacency words of the row being peeled; `above`
+//     (bitset of vertices whose current degree exceeds the current level) turns "neighbour with deg[u] > deg[v]" into one
+//     AND; the surviving neighbours are expanded to an ascending list with one warp scan and every neighbour's bucket move
+//     is done by its own lane.  Moves into different buckets commute; the members of one bucket (same current degree) must
+//     be applied in id order: their ranks come from __match_any_sync, and with the ranks known the moves of a group have a
+//     closed form (member t lands on slot bin+t, the displaced vertex takes the member's old slot) unless a member already
+//     sits inside the target slots -- then that group is replayed serially by its first lane while the other groups
+//     proceed.  The next row is prefetched while the current one is processed.  (A CTA-wide variant with 4-8 warps and
+//     five block barriers per step measured 3000 cycles per step -- barrier-bound -- and was dropped)
 //   clique_cta_kernel  The start vertices are tried SPECULATIVELY, one per warp, against the current incumbent size
 //     mc; results are committed in sequential order (the first warp that beats mc wins, later warps are discarded and
 //     redone), which is exactly the sequential outcome because a descent only depends on mc at its start.  Vertices
@@ -33,90 +34,71 @@ namespace qb {
 __device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// per-warp group sizes (0..32, 6 bits each) packed into one word: warp k owns bits [6k, 6k+6)
-template <int NW, typename Acc>
-__device__ __forceinline__ void unpack_sizes(Acc a, int warp, int& before, int& total) {
-  before = 0; total = 0;
-#pragma unroll
-  for (int k = 0; k < NW; ++k) {
-    const int f = (int)((a >> (6 * k)) & (Acc)63);
-    if (k < warp) before += f;
-    total += f;
-  }
-}
-
-// Stable counting sort of vertices by key[v] (ids ascending inside a bucket) by the whole CTA.  On exit bin[d] is the
-// START of bucket d (d = 0..maxkey) and bin[maxkey+1] = n.  acc[] must be all zero on entry and is all zero on exit.
-// tmp: n ints of scratch.  Every thread of the block calls it.
-template <int NW, typename Acc>
-__device__ void block_bucket_sort(const unsigned short* __restrict__ key, int n, int maxkey, int* __restrict__ bin, Acc* __restrict__ acc,
-                                  unsigned short* __restrict__ pos, unsigned short* __restrict__ vert, int* __restrict__ tmp, int* scan_smem) {
-  constexpr int NT = NW * 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int d = tid; d <= maxkey + 1; d += NT) bin[d] = 0;
-  __syncthreads();
-  for (int v = tid; v < n; v += NT) atomicAdd(&bin[key[v]], 1);
-  __syncthreads();
+// stable counting sort of vertices by key[v] (ids ascending inside a bucket); bin[d] ends up as the
+// START of bucket d (d = 0..maxkey), bin[maxkey+1] = n.  One warp.
+__device__ void warp_bucket_sort(const unsigned short* __restrict__ key, int n, int maxkey, int* __restrict__ bin,
+                                 unsigned short* __restrict__ pos, unsigned short* __restrict__ vert) {
+  const int lane = lane_id();
+  for (int d = lane; d <= maxkey + 1; d += 32) bin[d] = 0;
+  __syncwarp();
+  for (int v = lane; v < n; v += 32) atomicAdd(&bin[key[v]], 1);
+  __syncwarp();
   int carry = 0;
-  for (int base = 0; base <= maxkey + 1; base += NT) {
-    const int d = base + tid;
+  for (int base = 0; base <= maxkey + 1; base += 32) {  // exclusive scan
+    const int d = base + lane;
     const int c = d <= maxkey + 1 ? bin[d] : 0;
     int tot;
-    const int ex = block_excl_scan(c, scan_smem, &tot);
+    const int ex = warp_excl_scan(c, &tot);
     if (d <= maxkey + 1) bin[d] = carry + ex;
     carry += tot;
   }
-  __syncthreads();
-  for (int base = 0; base < n; base += NT) {
-    const int v = base + tid;
+  __syncwarp();
+  for (int base = 0; base < n; base += 32) {  // placement, ids ascending inside a bucket
+    const int v = base + lane;
     const bool act = v < n;
     const int d = act ? key[v] : -1 - lane;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int rank_w = __popc(peers & ((1u << lane) - 1));
-    if (act && rank_w == 0) atomicAdd(&acc[d], (Acc)__popc(peers) << (6 * warp));
-    __syncthreads();
-    int before = 0, total = 0, b = 0;
+    const int rank = __popc(peers & ((1u << lane) - 1));
+    const int b = act ? bin[d] : 0;
+    __syncwarp();
     if (act) {
-      unpack_sizes<NW, Acc>(acc[d], warp, before, total);
-      b = bin[d];
-      const int p = b + before + rank_w;
-      pos[v] = (unsigned short)p;
-      vert[p] = (unsigned short)v;
+      pos[v] = (unsigned short)(b + rank);
+      vert[b + rank] = (unsigned short)v;
+      if (rank == 0) bin[d] = b + __popc(peers);
     }
-    __syncthreads();
-    if (act && before + rank_w == 0) { bin[d] = b + total; acc[d] = 0; }
-    __syncthreads();
+    __syncwarp();
   }
-  // bin[d] is now the END of bucket d: shift down to starts
-  for (int d = tid; d <= maxkey; d += NT) tmp[d] = bin[d];
-  __syncthreads();
-  for (int d = tid; d <= maxkey; d += NT) bin[d + 1] = tmp[d];
-  if (tid == 0) bin[0] = 0;
-  __syncthreads();
+  // bin[d] is now the END of bucket d: shift down to starts (descending chunks)
+  for (int base = ((maxkey + 1) / 32) * 32; base >= 0; base -= 32) {
+    const int d = base + lane;
+    int prev = 0;
+    if (d >= 1 && d <= maxkey + 1) prev = bin[d - 1];
+    __syncwarp();
+    if (d >= 1 && d <= maxkey + 1) bin[d] = prev;
+    __syncwarp();
+  }
+  if (lane == 0) bin[0] = 0;
+  __syncwarp();
 }
 
-// One CTA (NW warps) per pair.  Requires W <= NW * 32.
-template <int NW, typename Acc>
-__global__ void __launch_bounds__(NW * 32) kcore_cta_kernel(const uint32_t* __restrict__ adj, const int* __restrict__ deg_in,
-                                                            const int* __restrict__ n_corr, int Lc, int W, int* __restrict__ kcore,
-                                                            int* __restrict__ korder, int* __restrict__ rank_of, int* __restrict__ by_rank,
-                                                            int* __restrict__ kbin, int* __restrict__ max_core_out) {
-  constexpr int NT = NW * 32;
+// One warp per pair; lane l owns the WPL consecutive adjacency words [l*WPL, l*WPL + WPL) of the row being peeled
+// (W <= 32 * WPL).  smem: bin (int x (Lc + 2)), above (u32 x 32*WPL), deg / pos / vert / nbl / slot (u16 x Lc each).
+template <int WPL>
+__global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restrict__ adj, const int* __restrict__ deg_in,
+                                                        const int* __restrict__ n_corr, int Lc, int W, int* __restrict__ kcore,
+                                                        int* __restrict__ korder, int* __restrict__ rank_of, int* __restrict__ by_rank,
+                                                        int* __restrict__ kbin, int* __restrict__ max_core_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Acc* acc = reinterpret_cast<Acc*>(smem_raw);                       // [Lc + 2] packed group sizes per degree (zero between uses)
-  int* bin = reinterpret_cast<int*>(acc + Lc + 2);                   // [Lc + 2]
-  uint32_t* above = reinterpret_cast<uint32_t*>(bin + Lc + 2);       // [W] vertices with current degree > current level
-  unsigned short* deg = reinterpret_cast<unsigned short*>(above + W);
+  int* bin = reinterpret_cast<int*>(smem_raw);                       // [Lc + 2] start of every degree bucket
+  uint32_t* above = reinterpret_cast<uint32_t*>(bin + Lc + 2);       // [32 * WPL] vertices with current degree > current level
+  unsigned short* deg = reinterpret_cast<unsigned short*>(above + 32 * WPL);
   unsigned short* pos = deg + Lc;
   unsigned short* vert = pos + Lc;
   unsigned short* nbl = vert + Lc;                                   // ascending list of the current step's live neighbours
   unsigned short* slot = nbl + Lc;                                   // slot[q] = member that lands on position q (serial replay)
-  unsigned char* gflag = reinterpret_cast<unsigned char*>(slot + Lc);  // [2][Lc] group (keyed by its first slot) needs the serial replay
-  __shared__ int s_wtot[2][NW];
-  __shared__ int s_scan[33];
-  __shared__ int s_red[NW];
 
-  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = blockIdx.x, lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
   const int L = n_corr[pair];
   int* __restrict__ kc = kcore + (size_t)pair * (Lc + 2);
   int* __restrict__ ko = korder + (size_t)pair * (Lc + 2);
@@ -124,108 +106,103 @@ __global__ void __launch_bounds__(NW * 32) kcore_cta_kernel(const uint32_t* __re
   int* __restrict__ br = by_rank + (size_t)pair * (Lc + 2);
   int* __restrict__ kb = kbin + (size_t)pair * (Lc + 2);
   if (L <= 0) {
-    if (tid == 0) max_core_out[pair] = 0;
+    if (lane == 0) max_core_out[pair] = 0;
     return;
   }
   const uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
-  const int nbw = (L + 31) >> 5;  // adjacency words per row (<= NT)
+  const int nbw = (L + 31) >> 5;  // adjacency words per row in use
 
   int md = 0;
-  for (int v = tid; v < L; v += NT) {
+  for (int v = lane; v < L; v += 32) {
     const int d = deg_in[(size_t)pair * Lc + v];
     deg[v] = (unsigned short)d;
     md = max(md, d);
   }
-  for (int d = tid; d < Lc + 2; d += NT) acc[d] = 0;
-  for (int d = tid; d < 2 * Lc; d += NT) gflag[d] = 0;
   md = warp_max(md);
-  if (lane == 0) s_red[warp] = md;
-  __syncthreads();
-  md = 0;
-#pragma unroll
-  for (int k = 0; k < NW; ++k) md = max(md, s_red[k]);
-  block_bucket_sort<NW, Acc>(deg, L, md, bin, acc, pos, vert, reinterpret_cast<int*>(nbl), s_scan);
+  __syncwarp();
+  warp_bucket_sort(deg, L, md, bin, pos, vert);
 
   // ---- peel ----
-  for (int w = tid; w < W; w += NT) {
-    const int lo = w * 32;
-    above[w] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) {
+    const int lo = (lane * WPL + k) * 32;
+    above[lane * WPL + k] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
   }
   int cur = -1;  // current level: every vertex with degree <= cur has its bit in `above` cleared
-  int par = 0, pend = -1;  // gflag buffer of the current pass; flag this thread still has to clear in the other buffer
+  uint32_t wn[WPL];
   int guess = vert[0];
-  uint32_t wn = tid < nbw ? G[(size_t)guess * W + tid] : 0u;
-  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) wn[k] = lane * WPL + k < nbw ? G[(size_t)guess * W + lane * WPL + k] : 0u;
+  __syncwarp();
   for (int i = 0; i < L; ++i) {
     const int v = vert[i];
     const int dv = deg[v];
-    uint32_t w = wn;
-    if (v != guess) w = tid < nbw ? G[(size_t)v * W + tid] : 0u;  // the speculation failed (block-uniform)
+    uint32_t w[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) w[k] = wn[k];
+    if (v != guess) {  // the speculation failed (warp-uniform)
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) w[k] = lane * WPL + k < nbw ? G[(size_t)v * W + lane * WPL + k] : 0u;
+    }
     if (i + 1 < L) {  // positions inside the current bucket are final: the vertex at i+1 rarely changes during this step
       guess = vert[i + 1];
-      wn = tid < nbw ? G[(size_t)guess * W + tid] : 0u;
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) wn[k] = lane * WPL + k < nbw ? G[(size_t)guess * W + lane * WPL + k] : 0u;
     }
-    if (dv > cur) {  // level rise (block-uniform): bucket dv = positions [i, bin[dv+1]) leaves `above`
+    if (dv > cur) {  // level rise: bucket dv = positions [i, bin[dv+1]) leaves `above`
       const int end = bin[dv + 1];
-      for (int p = i + tid; p < end; p += NT) {
+      for (int p = i + lane; p < end; p += 32) {
         const int x = vert[p];
         atomicAnd(&above[x >> 5], ~(1u << (x & 31)));
       }
       cur = dv;
-      __syncthreads();
+      __syncwarp();
     }
-    uint32_t aw = tid < nbw ? (w & above[tid]) : 0u;
-    const int c = __popc(aw);
-    int inc = c;
+    int c = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int nb = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += nb;
+    for (int k = 0; k < WPL; ++k) {
+      w[k] &= above[lane * WPL + k];  // neighbours with deg[u] > deg[v]
+      c += __popc(w[k]);
     }
-    if (lane == 31) s_wtot[i & 1][warp] = inc;
-    __syncthreads();  // (A)
-    int base = 0, cnt = 0;
+    int cnt;
+    int off = warp_excl_scan(c, &cnt);
+    if (cnt == 0) continue;
 #pragma unroll
-    for (int k = 0; k < NW; ++k) {
-      const int t = s_wtot[i & 1][k];
-      if (k < warp) base += t;
-      cnt += t;
+    for (int k = 0; k < WPL; ++k) {
+      uint32_t x = w[k];
+      const int basebit = (lane * WPL + k) * 32;
+      while (x) {
+        const int b = __ffs(x) - 1;
+        x &= x - 1;
+        nbl[off++] = (unsigned short)(basebit + b);
+      }
     }
-    if (cnt == 0) continue;  // block-uniform; s_wtot is double-buffered, (A) of the next step orders the reuse
-    int off = base + inc - c;
-    while (aw) {
-      const int b = __ffs(aw) - 1;
-      aw &= aw - 1;
-      nbl[off++] = (unsigned short)(tid * 32 + b);
-    }
-    __syncthreads();  // (B)
-    for (int c0 = 0; c0 < cnt; c0 += NT) {
-      const int e = c0 + tid;
+    __syncwarp();
+    // bucket moves, 32 neighbours at a time.  Moves into different buckets commute; the members of one bucket (same current
+    // degree) must land in id order: member `rank` takes slot bin + rank and the vertex it displaces takes the member's old
+    // slot -- unless a member already sits inside the target slots, then that group is replayed serially by its first lane.
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+      const int e = c0 + lane;
       const bool act = e < cnt;
       const int u = act ? nbl[e] : 0;
-      const int du = act ? deg[u] : -1 - lane;  // every listed neighbour has du > dv
+      const int du = act ? deg[u] : -1 - lane;
       const unsigned grp = __match_any_sync(0xffffffffu, du);
-      const int rank_w = __popc(grp & ((1u << lane) - 1));
-      if (act && rank_w == 0) atomicAdd(&acc[du], (Acc)__popc(grp) << (6 * warp));
-      if (pend >= 0) { gflag[(par ^ 1) * Lc + pend] = 0; pend = -1; }
-      __syncthreads();  // (b)
-      int rank = 0, m = 0, b0 = 0, pu = 0, q = 0, wv = 0;
+      const int rank = __popc(grp & lt), m = __popc(grp);
+      int b0 = 0, pu = 0, q = 0, wv = 0;
+      bool inside = false;
       if (act) {
-        int before;
-        unpack_sizes<NW, Acc>(acc[du], warp, before, m);
-        rank = before + rank_w;
         b0 = bin[du];
         pu = pos[u];
         q = b0 + rank;
         wv = vert[q];
         slot[q] = (unsigned short)u;
-        if (m > 1 && pu < b0 + m) gflag[par * Lc + b0] = 1;  // a member already sits inside the target slots: replay this group serially
+        inside = m > 1 && pu < b0 + m;
       }
-      __syncthreads();  // (d)
+      const bool serial = (__ballot_sync(0xffffffffu, inside) & grp) != 0u;
+      __syncwarp();
       if (act) {
-        const bool serial = gflag[par * Lc + b0] != 0;
         if (!serial) {
-          if (pu != q) {  // member `rank` lands on slot b0+rank, the displaced vertex takes its old slot
+          if (pu != q) {
             vert[q] = (unsigned short)u; pos[u] = (unsigned short)q;
             vert[pu] = (unsigned short)wv; pos[wv] = (unsigned short)pu;
           }
@@ -240,28 +217,27 @@ __global__ void __launch_bounds__(NW * 32) kcore_cta_kernel(const uint32_t* __re
         }
         deg[u] = (unsigned short)(du - 1);
         if (du - 1 == dv) atomicAnd(&above[u >> 5], ~(1u << (u & 31)));
-        if (rank == 0) { bin[du] = b0 + m; acc[du] = 0; pend = b0; }
+        if (rank == 0) bin[du] = b0 + m;
       }
-      __syncthreads();  // (f)
-      par ^= 1;
+      __syncwarp();
     }
   }
-  __syncthreads();
+  __syncwarp();
   // ---- outputs: kcore = core + 1, peel order, max core ----
   const int max_core = deg[vert[L - 1]];
-  for (int v = tid; v < L; v += NT) {
+  for (int v = lane; v < L; v += 32) {
     kc[v] = (int)deg[v] + 1;
     ko[v] = vert[v];
   }
-  if (tid == 0) max_core_out[pair] = max_core;
-  __syncthreads();
+  if (lane == 0) max_core_out[pair] = max_core;
+  __syncwarp();
   // ---- (kcore, id) ranks for the clique search: stable bucket sort by core number ----
-  block_bucket_sort<NW, Acc>(deg, L, max_core, bin, acc, pos, vert, reinterpret_cast<int*>(nbl), s_scan);
-  for (int v = tid; v < L; v += NT) {
+  warp_bucket_sort(deg, L, max_core, bin, pos, vert);
+  for (int v = lane; v < L; v += 32) {
     ro[v] = pos[v];
     br[v] = vert[v];
   }
-  for (int d = tid; d <= max_core + 1; d += NT) kb[d] = bin[d];
+  for (int d = lane; d <= max_core + 1; d += 32) kb[d] = bin[d];
 }
 
 // adjacency rows/columns renumbered by rank: adjp[rank(v)] bit rank(u) = adj[v] bit u.  One warp per row.
@@ -453,10 +429,14 @@ __global__ void __launch_bounds__(kCliqueWarps * 32) clique_cta_kernel(const uin
   if (tid == 0) n_clique[pair] = csize;
 }
 
-template <int NW, typename Acc>
-static size_t kcore_smem_bytes(int Lc, int W) {
-  return (size_t)(Lc + 2) * sizeof(Acc) + (size_t)(Lc + 2) * sizeof(int) + (size_t)W * sizeof(uint32_t) + (size_t)5 * Lc * sizeof(unsigned short) +
-         (size_t)2 * Lc;
+template <int WPL>
+static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
+  const int Lc = h->Lc, W = h->W;
+  const size_t smem = (size_t)(Lc + 2) * sizeof(int) + (size_t)32 * WPL * sizeof(uint32_t) + (size_t)5 * Lc * sizeof(unsigned short);
+  if (set_attr) QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_warp_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kcore_warp_kernel<WPL><<<n_pairs, 32, smem, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of, h->by_rank,
+                                                           h->kbin, h->ctr.max_core);
+  return QB200_OK;
 }
 
 int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
@@ -465,23 +445,18 @@ int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
   const int Lc = h->Lc, W = h->W;
   // shared-memory adjacency cache of the descent: 14336 words (56 KB) hold graphs up to L ~ 660
   const int cache_words = 14336;
-  const bool wide = W > 128;
-  const size_t sm_kcore = wide ? kcore_smem_bytes<8, unsigned long long>(Lc, W) : kcore_smem_bytes<4, uint32_t>(Lc, W);
   const size_t sm_clique = (size_t)kCliqueWarps * Lc * sizeof(unsigned short) + (size_t)W * sizeof(uint32_t) + (size_t)cache_words * 4;
-  if (!(h->func_attr_set & 1u)) {  // per handle: the opt-in is a per-device property of the function
-    if (wide)
-      QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_cta_kernel<8, unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_kcore));
-    else
-      QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_cta_kernel<4, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_kcore));
+  const bool set_attr = !(h->func_attr_set & 1u);  // per handle: the opt-in is a per-device property of the function
+  if (set_attr) {
     QB_CUDA_TRY(h, cudaFuncSetAttribute(clique_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_clique));
     h->func_attr_set |= 1u;
   }
-  if (wide)
-    kcore_cta_kernel<8, unsigned long long><<<n_pairs, 256, sm_kcore, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, h->kcore, h->korder,
-                                                                                   h->rank_of, h->by_rank, h->kbin, h->ctr.max_core);
-  else
-    kcore_cta_kernel<4, uint32_t><<<n_pairs, 128, sm_kcore, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of,
-                                                                         h->by_rank, h->kbin, h->ctr.max_core);
+  int rc;
+  if (W <= 32) rc = launch_kcore<1>(h, n_pairs, set_attr);
+  else if (W <= 64) rc = launch_kcore<2>(h, n_pairs, set_attr);
+  else if (W <= 128) rc = launch_kcore<4>(h, n_pairs, set_attr);
+  else rc = launch_kcore<8>(h, n_pairs, set_attr);
+  if (rc) return rc;
   const dim3 gp((Lc + 7) / 8, n_pairs);
   permute_adj_kernel<<<gp, 256, 8 * W * sizeof(uint32_t), h->stream>>>(h->adj, h->ctr.n_corr, Lc, W, h->rank_of, h->adjp);
   clique_cta_kernel<<<n_pairs, kCliqueWarps * 32, sm_clique, h->stream>>>(h->adjp, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of, h->by_rank,

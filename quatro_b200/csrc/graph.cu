@@ -13,7 +13,9 @@
 // The kernel evaluates this in fp32 with A, B in Gram form (|a_i|^2 + |a_j|^2 - 2 a_i.a_j: 4 instead of 6 operations per
 // distance) -- ~18 instructions per pair test -- together with a RIGOROUS bound of its own rounding error:
 //        |t_c - t| <= 36u M |D_c| + 1500 u^2 M^2 + 46 u beta^2 M =: q,   u = 2^-24,  M >= |a_i|^2+|b_i|^2+|a_j|^2+|b_j|^2 + 2 beta^2
-// (derivation in DESIGN.md 5.2).  Only pairs with |t_c| <= q -- a band of ~1e-4 relative width around the threshold --
+// (derivation in DESIGN.md 5.2).  The arithmetic runs on packed pairs (fma.rn.f32x2 -> FFMA2 / FADD2: the fp32 pipe issues one
+// 3-register FMA per two cycles per scheduler, so two columns per instruction double the rate; results are bit-identical to the
+// scalar forms).  Only pairs with |t_c| <= q -- a band of ~1e-4 relative width around the threshold --
 // or with both distances ~0 (the literal expression is NaN -> false for coincident duplicates) evaluate the literal fp64
 // expression, so the adjacency is bit-identical to the fp64 reference.
 //
@@ -57,6 +59,31 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
   return x;
 }
 
+// packed fp32 pairs (sm_100 FFMA2 / FADD2: one instruction, two IEEE-rn results -- bit-identical to the scalar forms)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7fffffff7fffffffull; }
+
 struct GraphConst {
   float b2, hb2q, twob2, b4;   // beta^2, beta^2/4, 2 beta^2, beta^4 (fp32)
   float c1, c2, c3;            // q = c1 M |D| + (c2 M + c3) M
@@ -67,7 +94,7 @@ struct GraphConst {
 __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __restrict__ ma, const float4* __restrict__ mb,
                                                              const int* __restrict__ n_corr, int Lc, int W, GraphConst gc,
                                                              uint32_t* __restrict__ adj) {
-  __shared__ float4 s_ra[kGRB * 32], s_rb[kGRB * 32];
+  __shared__ float4 s_row[kGRB * 32][4];  // per row: (x,x,y,y) (z,z,n,n) of -2a | the same of -2b: operands of the packed FMAs
   __shared__ float s_rm[kGRB * 32];
   __shared__ float s_mmax[kGRB];
   const int pair = blockIdx.y;
@@ -92,8 +119,12 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
       const float4 pa = v ? A[i] : zero4, pb = v ? B[i] : zero4;
       const float na = fmaf(pa.z, pa.z, fmaf(pa.y, pa.y, pa.x * pa.x));
       const float nbn = fmaf(pb.z, pb.z, fmaf(pb.y, pb.y, pb.x * pb.x));
-      s_ra[idx] = make_float4(-2.0f * pa.x, -2.0f * pa.y, -2.0f * pa.z, na - gc.hb2q);
-      s_rb[idx] = make_float4(-2.0f * pb.x, -2.0f * pb.y, -2.0f * pb.z, nbn - gc.hb2q);
+      const float ax = -2.0f * pa.x, ay = -2.0f * pa.y, az = -2.0f * pa.z, an = na - gc.hb2q;
+      const float bx = -2.0f * pb.x, by = -2.0f * pb.y, bz = -2.0f * pb.z, bn = nbn - gc.hb2q;
+      s_row[idx][0] = make_float4(ax, ax, ay, ay);
+      s_row[idx][1] = make_float4(az, az, an, an);
+      s_row[idx][2] = make_float4(bx, bx, by, by);
+      s_row[idx][3] = make_float4(bz, bz, bn, bn);
       s_rm[idx] = na + nbn;
     }
     __syncthreads();
@@ -134,23 +165,41 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
       }
       uint32_t wt[kGC] = {0u, 0u, 0u, 0u}, ws[kGC] = {0u, 0u, 0u, 0u}, wa[kGC] = {0u, 0u, 0u, 0u};
       float smin[kGC] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
-      const float4* __restrict__ ra_p = s_ra + rbl * 32;
-      const float4* __restrict__ rb_p = s_rb + rbl * 32;
+      // the four columns as two packed pairs
+      f32x2 cax[2], cay[2], caz[2], can[2], cbx[2], cby[2], cbz[2], cbn[2], qa2[2], qk2[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        cax[p] = pk2(ca[2 * p].x, ca[2 * p + 1].x); cay[p] = pk2(ca[2 * p].y, ca[2 * p + 1].y);
+        caz[p] = pk2(ca[2 * p].z, ca[2 * p + 1].z); can[p] = pk2(ca[2 * p].w, ca[2 * p + 1].w);
+        cbx[p] = pk2(cb[2 * p].x, cb[2 * p + 1].x); cby[p] = pk2(cb[2 * p].y, cb[2 * p + 1].y);
+        cbz[p] = pk2(cb[2 * p].z, cb[2 * p + 1].z); cbn[p] = pk2(cb[2 * p].w, cb[2 * p + 1].w);
+        qa2[p] = pk2(qa[2 * p], qa[2 * p + 1]); qk2[p] = pk2(qk[2 * p], qk[2 * p + 1]);
+      }
+      const f32x2 ntwob2 = pk2(-gc.twob2, -gc.twob2), nb4 = pk2(-gc.b4, -gc.b4);
+      const float4(* __restrict__ row_p)[4] = s_row + rbl * 32;
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
-        const float4 ra = ra_p[r], rb = rb_p[r];
+        const float4 r0 = row_p[r][0], r1 = row_p[r][1], r2 = row_p[r][2], r3 = row_p[r][3];
+        const f32x2 rax = pk2(r0.x, r0.y), ray = pk2(r0.z, r0.w), raz = pk2(r1.x, r1.y), ran = pk2(r1.z, r1.w);
+        const f32x2 rbx = pk2(r2.x, r2.y), rby = pk2(r2.z, r2.w), rbz = pk2(r3.x, r3.y), rbn = pk2(r3.z, r3.w);
 #pragma unroll
-        for (int c = 0; c < kGC; ++c) {
-          const float Ap = fmaf(ra.x, ca[c].x, fmaf(ra.y, ca[c].y, fmaf(ra.z, ca[c].z, ra.w + ca[c].w)));
-          const float Bp = fmaf(rb.x, cb[c].x, fmaf(rb.y, cb[c].y, fmaf(rb.z, cb[c].z, rb.w + cb[c].w)));
-          const float D = Ap - Bp, sp = Ap + Bp;
-          const float g = fmaf(gc.twob2, sp, gc.b4);
-          const float t = fmaf(D, D, -g);
-          const float w = fabsf(t) - fmaf(fabsf(D), qa[c], qk[c]);
-          wt[c] = __funnelshift_l(__float_as_uint(t), wt[c], 1);    // sign(t):  t < 0
-          ws[c] = __funnelshift_l(__float_as_uint(sp), ws[c], 1);   // sign(s'): s' < 0
-          wa[c] = __funnelshift_l(__float_as_uint(w), wa[c], 1);    // |t| inside the error band
-          smin[c] = fminf(smin[c], sp);
+        for (int p = 0; p < 2; ++p) {
+          const f32x2 Ap = fma2(rax, cax[p], fma2(ray, cay[p], fma2(raz, caz[p], add2(ran, can[p]))));
+          const f32x2 Bp = fma2(rbx, cbx[p], fma2(rby, cby[p], fma2(rbz, cbz[p], add2(rbn, cbn[p]))));
+          const f32x2 D = sub2(Ap, Bp), sp = add2(Ap, Bp);
+          const f32x2 ng = fma2(ntwob2, sp, nb4);               // -g = -(2 beta^2 s' + beta^4)
+          const f32x2 t = fma2(D, D, ng);
+          const f32x2 w = sub2(abs2(t), fma2(abs2(D), qa2[p], qk2[p]));
+          float t0, t1, s0, s1, w0, w1;
+          upk2(t, t0, t1); upk2(sp, s0, s1); upk2(w, w0, w1);
+          wt[2 * p] = __funnelshift_l(__float_as_uint(t0), wt[2 * p], 1);          // sign(t):  t < 0
+          wt[2 * p + 1] = __funnelshift_l(__float_as_uint(t1), wt[2 * p + 1], 1);
+          ws[2 * p] = __funnelshift_l(__float_as_uint(s0), ws[2 * p], 1);          // sign(s'): s' < 0
+          ws[2 * p + 1] = __funnelshift_l(__float_as_uint(s1), ws[2 * p + 1], 1);
+          wa[2 * p] = __funnelshift_l(__float_as_uint(w0), wa[2 * p], 1);          // |t| inside the error band
+          wa[2 * p + 1] = __funnelshift_l(__float_as_uint(w1), wa[2 * p + 1], 1);
+          smin[2 * p] = fminf(smin[2 * p], s0);
+          smin[2 * p + 1] = fminf(smin[2 * p + 1], s1);
         }
       }
       const int nvalid = L - bi * 32;
@@ -169,9 +218,9 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
           sm = 3.0e38f;
 #pragma unroll 1
           for (int r = 0; r < 32; ++r) {
-            const float4 ra = ra_p[r], rb = rb_p[r];
-            const float Ap = fmaf(ra.x, ca[c].x, fmaf(ra.y, ca[c].y, fmaf(ra.z, ca[c].z, ra.w + ca[c].w)));
-            const float Bp = fmaf(rb.x, cb[c].x, fmaf(rb.y, cb[c].y, fmaf(rb.z, cb[c].z, rb.w + cb[c].w)));
+            const float4 r0 = row_p[r][0], r1 = row_p[r][1], r2 = row_p[r][2], r3 = row_p[r][3];
+            const float Ap = fmaf(r0.x, ca[c].x, fmaf(r0.z, ca[c].y, fmaf(r1.x, ca[c].z, r1.z + ca[c].w)));
+            const float Bp = fmaf(r2.x, cb[c].x, fmaf(r2.z, cb[c].y, fmaf(r3.x, cb[c].z, r3.z + cb[c].w)));
             if (r != lane) sm = fminf(sm, Ap + Bp);
           }
         }

@@ -74,6 +74,15 @@ struct qb200_handle {
   qb::WaveCounters ctr;
   int* ctr_block; size_t ctr_ints;
 
+  // ---- multi-GPU gather of the result records (comm.cu) ----
+  void* comm;                 // ncclComm_t
+  int comm_world, comm_rank, comm_cap;   // cap: records per rank the staging buffers hold
+  cudaStream_t comm_stream;
+  cudaEvent_t comm_done;
+  qb200_result *d_send, *d_recv, *h_send, *h_recv;   // device staging; pinned host staging (h_recv is rank-major)
+  int pend_gather_n;          // > 0: a deferred gather is in flight (records per rank)
+  qb200_result* pend_gather_dst;
+
   // ---- state mirrored from the reference's statics ----
   double rot_noise_bound_latched;  // quatro.hpp:469-470 (0 = not latched yet)
   int last_n_corr, last_n_clique, last_n_final;  // slot 0 of the most recent single-pair call
@@ -108,6 +117,7 @@ int launch_tc_debug_tile(qb200_handle* h, float* d_out);
 int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33);
 int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33);
 size_t sort_temp_bytes(int max_items);
+void comm_release(qb200_handle* h);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);
 int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit);
 

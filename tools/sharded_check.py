@@ -42,7 +42,24 @@ def main():
             out["T"][:, 12] = np.asarray(ids) * 0.5
             return out
 
-    full = register_sharded(register_local, n_pairs, rank, world, device)
+    if backend == "nccl" and len(sys.argv) > 3 and sys.argv[3] == "cabi":
+        # the C-ABI path: qb200_comm_init_rank + qb200_register_batch_rank (ncclAllGather inside the library, deferred gather)
+        from quatro_b200.capi import Pair, MEM_HOST, RESULT_DTYPE as RD
+        uid = [Handle.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        handle.comm_init_rank(world, rank, uid[0])
+        n_local = (n_pairs + world - 1) // world
+        ids = [i * world + rank for i in range(n_local)]            # round-robin: global pair g = i * world + r (ids beyond n_pairs: extra work, ignored)
+        prs = [synth.outdoor_pair(int(i), rings=32, azimuths=900)[:2] for i in ids]
+        arr = (Pair * n_local)()
+        for k, (s_, t_) in enumerate(prs):
+            arr[k].src, arr[k].n_src, arr[k].tgt, arr[k].n_tgt = s_.ctypes.data, len(s_), t_.ctypes.data, len(t_)
+        allrec = np.zeros(world * n_local, RD)
+        handle.register_batch_rank_raw(arr, n_local, p, MEM_HOST, allrec, defer=True)
+        handle.comm_wait()
+        full = allrec[:n_pairs].copy()
+    else:
+        full = register_sharded(register_local, n_pairs, rank, world, device)
     assert len(full) == n_pairs
     ok = True
     if rank == 0:
