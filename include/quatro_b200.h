@@ -210,6 +210,24 @@ int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const
 int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs,
                          const qb200_params* p, qb200_mem_kind kind, qb200_result* results);
 
+/* --- scan cache: one scan against many (loop-closure sweeps) and odometry chains -------------------------------------------------
+ * FPFHManager keeps the previous target's cloud and descriptors and reuses them as the next source (swapTgt2Src / is_odometry_test_,
+ * include/fpfh_manager.hpp:74-77, 111-118) and hands its descriptors out (getObjDescriptor / getSceneDescriptor / getTgtNormals,
+ * :161-177).  The cache keeps voxel points, normals and FPFH-33 of a scan resident on the DEVICE, so the front end runs once per
+ * scan instead of once per pair.  Slots are indexed 0 .. n_slots-1; results never depend on whether a scan came from the cache
+ * (tests/test_gpu_parity.py::test_scan_cache_*). */
+typedef struct qb200_slot_pair { int32_t src_slot, tgt_slot; } qb200_slot_pair;
+int qb200_cache_reserve(qb200_handle* h, int32_t n_slots);   /* (re)allocates; 0 frees.  ~3.1 MB per slot at max_voxel_points = 16384 */
+/* voxelize + normals + FPFH of n_scans raw scans (scans4[i]: n_points[i] x {x,y,z,w}) into slots slot_ids[i] */
+int qb200_cache_scans(qb200_handle* h, const float* const* scans4, const int32_t* n_points, const int32_t* slot_ids, int32_t n_scans,
+                      const qb200_params* p, qb200_mem_kind kind);
+/* match + graph + clique + pose for pairs of cached scans (= qb200_register_batch without its front end); p's front-end parameters
+ * must be the ones the slots were cached with */
+int qb200_register_cached(qb200_handle* h, const qb200_slot_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_result* results);
+int qb200_cache_copy(qb200_handle* h, int32_t from_slot, int32_t to_slot);   /* swapTgt2Src */
+/* read a cached scan back: voxel points (n x 4), normals (n x {nx,ny,nz,curvature}), descriptors (n x 33); any may be NULL */
+int qb200_cache_read(qb200_handle* h, int32_t slot, float* vox4, float* normals4, float* desc33, int32_t cap, int32_t* n);
+
 /* --- multi-GPU: batches of independent pairs shard across the GPUs of one box; the only communication is ONE all-gather (NCCL over
  * NVLink) of the fixed-size result records per batch -- north_star / SURVEY.md 8(e).  The reference has no counterpart (it is a
  * single-process CPU program: examples/run_global_registration.cpp processes one pair); these entry points are what a loop-closure

@@ -137,6 +137,11 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_register_batch_rank": (i32, [vp, P(Pair), i32, P(Params), i32, vp, i32]),
         "qb200_comm_wait": (i32, [vp]),
         "qb200_bind_numa": (i32, [vp]),
+        "qb200_cache_reserve": (i32, [vp, i32]),
+        "qb200_cache_scans": (i32, [vp, P(vp), P(i32), P(i32), i32, P(Params), i32]),
+        "qb200_register_cached": (i32, [vp, vp, i32, P(Params), vp]),
+        "qb200_cache_copy": (i32, [vp, i32, i32]),
+        "qb200_cache_read": (i32, [vp, i32, vp, vp, vp, i32, P(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError = header/library mismatch: fail loudly
@@ -157,6 +162,7 @@ EXPORTED_SYMBOLS = [
     "qb200_solve_batch",
     "qb200_comm_init_all", "qb200_register_batch_sharded", "qb200_comm_unique_id", "qb200_comm_init_rank",
     "qb200_register_batch_rank", "qb200_comm_wait", "qb200_bind_numa",
+    "qb200_cache_reserve", "qb200_cache_scans", "qb200_register_cached", "qb200_cache_copy", "qb200_cache_read",
 ]
 
 
@@ -376,6 +382,37 @@ class Handle:
         out = np.zeros(n, RESULT_DTYPE)
         self._check(self.lib.qb200_solve_batch(self.h, arr, n, C.byref(params), kind, _ptr(out)), "qb200_solve_batch")
         return out
+
+    # ---- scan cache ----
+    def cache_reserve(self, n_slots: int):
+        self._check(self.lib.qb200_cache_reserve(self.h, n_slots), "qb200_cache_reserve")
+
+    def cache_scans(self, scans: Sequence, slot_ids: Sequence[int], params: Params, kind: int = MEM_HOST):
+        """scans: (n,4) float32 arrays (MEM_HOST) or (device_ptr, n) tuples (MEM_DEVICE)."""
+        n = len(scans)
+        keep = [_f32(sc, 4) for sc in scans] if kind == MEM_HOST else None
+        ptrs = (C.c_void_p * n)(*([a.ctypes.data for a in keep] if kind == MEM_HOST else [sc[0] for sc in scans]))
+        cnts = (C.c_int32 * n)(*([len(a) for a in keep] if kind == MEM_HOST else [sc[1] for sc in scans]))
+        ids = (C.c_int32 * n)(*[int(x) for x in slot_ids])
+        self._check(self.lib.qb200_cache_scans(self.h, ptrs, cnts, ids, n, C.byref(params), kind), "qb200_cache_scans")
+
+    def register_cached(self, slot_pairs, params: Params) -> np.ndarray:
+        sp = np.ascontiguousarray(np.asarray(slot_pairs, np.int32).reshape(-1, 2))
+        out = np.zeros(len(sp), RESULT_DTYPE)
+        self._check(self.lib.qb200_register_cached(self.h, _ptr(sp), len(sp), C.byref(params), _ptr(out)), "qb200_register_cached")
+        return out
+
+    def cache_copy(self, from_slot: int, to_slot: int):
+        self._check(self.lib.qb200_cache_copy(self.h, from_slot, to_slot), "qb200_cache_copy")
+
+    def cache_read(self, slot: int, cap: Optional[int] = None):
+        """-> (voxel points (n,4), normals (n,4), descriptors (n,33)) of a cached scan."""
+        cap = cap or self.cfg.max_voxel_points
+        vox, nrm, desc = np.zeros((cap, 4), np.float32), np.zeros((cap, 4), np.float32), np.zeros((cap, 33), np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.qb200_cache_read(self.h, slot, _ptr(vox), _ptr(nrm), _ptr(desc), cap, C.byref(n)), "qb200_cache_read")
+        m = min(n.value, cap)
+        return vox[:m].copy(), nrm[:m].copy(), desc[:m].copy()
 
     # ---- multi-GPU (comm.cu) ----
     @staticmethod

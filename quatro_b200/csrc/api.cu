@@ -25,6 +25,34 @@ __global__ void wave_init_kernel(int* ctr_block, int n_ints, int* bbox, int n_cl
   if (i < n_clouds * 6) bbox[i] = (i % 6) < 3 ? INT_MAX : INT_MIN;
 }
 
+// ---- scan cache (qb200_cache_*): copies between the wave buffers of a lane and the per-scan cache slots ----
+// blockIdx.z = cloud of the wave, blockIdx.y = 0..39 descriptor row | 40 voxel points | 41 normals | 42 counters
+__global__ void cache_copy_kernel(int to_cache, const int* __restrict__ slot_of_cloud, int V, float4* __restrict__ w_vox, float4* __restrict__ w_nrm,
+                                  float* __restrict__ w_desc, int* __restrict__ w_n, int* __restrict__ w_status, float4* __restrict__ c_vox,
+                                  float4* __restrict__ c_nrm, float* __restrict__ c_desc, int* __restrict__ c_n, int* __restrict__ c_status) {
+  const int cloud = blockIdx.z, slot = slot_of_cloud[cloud], row = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < 0) return;
+  const int n = to_cache ? w_n[cloud] : c_n[slot];
+  if (row == 42) {
+    if (q == 0) {
+      if (to_cache) { c_n[slot] = w_n[cloud]; c_status[slot] = w_status[cloud]; }
+      else { w_n[cloud] = c_n[slot]; w_status[cloud] = c_status[slot]; }
+    }
+    return;
+  }
+  if (q >= n || q >= V) return;
+  if (row < kDescK) {
+    float* w = w_desc + ((size_t)cloud * kDescK + row) * V + q;
+    float* c = c_desc + ((size_t)slot * kDescK + row) * V + q;
+    if (to_cache) *c = *w; else *w = *c;
+  } else if (row == 40) {
+    if (to_cache) c_vox[(size_t)slot * V + q] = w_vox[(size_t)cloud * V + q]; else w_vox[(size_t)cloud * V + q] = c_vox[(size_t)slot * V + q];
+  } else {
+    if (to_cache) c_nrm[(size_t)slot * V + q] = w_nrm[(size_t)cloud * V + q]; else w_nrm[(size_t)cloud * V + q] = c_nrm[(size_t)slot * V + q];
+  }
+}
+
 template <class T>
 cudaError_t dalloc(T** p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
@@ -217,6 +245,11 @@ int fetch_result(qb200_handle* h, qb200_result* res) {
 }  // namespace
 
 extern "C" {
+static void cache_free(qb200_handle* h);
+}
+static void cache_free_public(qb200_handle* h) { cache_free(h); }
+
+extern "C" {
 
 int qb200_version(void) { return QB200_VERSION; }
 
@@ -280,6 +313,7 @@ void qb200_destroy(qb200_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   comm_release(h);
+  cache_free_public(h);
   void* dev_ptrs[] = {(void*)h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, h->raw_stage, h->key_a, h->key_b, h->val_a, h->val_b, h->cub_temp,
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t, h->rowbest, h->colpart, h->colbest,
                       h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats, h->aos_scratch,
@@ -848,6 +882,188 @@ int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, cons
   QB_CUDA_TRY(h, cudaMemcpyAsync(out, d_out, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return QB200_OK;
+}
+
+// ---- scan cache ---------------------------------------------------------------------------------------------------------
+// FPFHManager keeps the last target's descriptors and reuses them as the next source (odometry mode, fpfh_manager.hpp:74-77,
+// 111-118); a loop-closure sweep matches one scan against many.  The cache keeps voxel points, normals and FPFH-33 of a scan
+// resident on the device so that the front end (voxel + normals + FPFH, ~45 % of a wave) runs once per SCAN, not once per pair.
+static void cache_free(qb200_handle* h) {
+  if (h->c_vox) cudaFree(h->c_vox);
+  if (h->c_nrm) cudaFree(h->c_nrm);
+  if (h->c_desc) cudaFree(h->c_desc);
+  if (h->c_n) cudaFree(h->c_n);
+  if (h->c_status) cudaFree(h->c_status);
+  if (h->d_slot_of_cloud) cudaFree(h->d_slot_of_cloud);
+  if (h->h_slot_of_cloud) cudaFreeHost(h->h_slot_of_cloud);
+  delete[] h->c_sig;
+  h->c_vox = h->c_nrm = nullptr; h->c_desc = nullptr; h->c_n = h->c_status = h->d_slot_of_cloud = h->h_slot_of_cloud = nullptr;
+  h->c_sig = nullptr;
+  h->c_slots = 0;
+}
+
+int qb200_cache_reserve(qb200_handle* h, int32_t n_slots) {
+  if (!h || n_slots < 0 || n_slots > (1 << 20)) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cache_free(h);
+  if (n_slots == 0) return QB200_OK;
+  const size_t V = h->V, N = (size_t)n_slots;
+  QB_ALLOC(h, h->c_vox, N * V);
+  QB_ALLOC(h, h->c_nrm, N * V);
+  QB_ALLOC(h, h->c_desc, N * kDescK * V);
+  QB_ALLOC(h, h->c_n, N);
+  QB_ALLOC(h, h->c_status, N);
+  QB_ALLOC(h, h->d_slot_of_cloud, 2 * (size_t)h->S);
+  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_slot_of_cloud, 2 * (size_t)h->S * sizeof(int)));
+  QB_CUDA_TRY(h, cudaMemset(h->c_n, 0, N * sizeof(int)));
+  QB_CUDA_TRY(h, cudaMemset(h->c_status, 0, N * sizeof(int)));
+  QB_CUDA_TRY(h, cudaMemset(h->c_desc, 0, N * kDescK * V * sizeof(float)));
+  h->c_sig = new (std::nothrow) float[4 * N]();
+  if (!h->c_sig) return QB200_ERR_CUDA;
+  h->c_slots = n_slots;
+  return QB200_OK;
+}
+
+static int cache_copy(qb200_handle* h, int to_cache, int n_clouds) {
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_slot_of_cloud, h->h_slot_of_cloud, (size_t)n_clouds * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  const dim3 g((h->V + 255) / 256, 43, n_clouds);
+  cache_copy_kernel<<<g, 256, 0, h->stream>>>(to_cache, h->d_slot_of_cloud, h->V, h->vox_pts, h->normals, h->desc_t, h->ctr.n_vox, h->ctr.cloud_status,
+                                              h->c_vox, h->c_nrm, h->c_desc, h->c_n, h->c_status);
+  h->launches++;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_cache_scans(qb200_handle* h, const float* const* scans4, const int32_t* n_points, const int32_t* slot_ids, int32_t n_scans,
+                      const qb200_params* p, qb200_mem_kind kind) {
+  if (!h || n_scans < 0 || (n_scans > 0 && (!scans4 || !n_points || !slot_ids)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
+  for (int i = 0; i < n_scans; ++i)
+    if (slot_ids[i] < 0 || slot_ids[i] >= h->c_slots || n_points[i] < 0 || n_points[i] > h->R || (n_points[i] > 0 && !scans4[i])) {
+      h->fail(__FILE__, __LINE__, "scan is null, exceeds max_raw_points or names a slot outside qb200_cache_reserve()");
+      return QB200_ERR_BAD_ARG;
+    }
+  cudaSetDevice(h->device);
+  const float cell = lattice_cell(*p);
+  const int C = 2 * h->S;
+  for (int c0 = 0; c0 < n_scans; c0 += C) {
+    const int nc = n_scans - c0 < C ? n_scans - c0 : C;
+    int total = 0, rc;
+    for (int c = 0; c < nc; ++c) {
+      const int n = n_points[c0 + c];
+      h->h_raw_off[c] = total;
+      h->h_cloud_n[c] = n;
+      h->h_slot_of_cloud[c] = slot_ids[c0 + c];
+      if (kind == QB200_MEM_HOST) {
+        h->h_cloud_ptr[c] = h->raw_stage + total;
+        if (n > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(h->raw_stage + total, scans4[c0 + c], (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+      } else {
+        h->h_cloud_ptr[c] = reinterpret_cast<const float4*>(scans4[c0 + c]);
+      }
+      total += n;
+      float* sig = h->c_sig + 4 * (size_t)slot_ids[c0 + c];
+      sig[0] = p->voxel_size; sig[1] = p->normal_radius; sig[2] = p->fpfh_radius; sig[3] = cell;
+    }
+    h->h_raw_off[nc] = total;
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_ptr, h->h_cloud_ptr, (size_t)nc * sizeof(float4*), cudaMemcpyHostToDevice, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_cloud_n, h->h_cloud_n, (size_t)nc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_raw_off, h->h_raw_off, (size_t)(nc + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = wave_reset(h, nc))) return rc;
+    if ((rc = launch_voxel(h, nc, total, p->voxel_size, p->skip_flagged))) return rc;
+    if ((rc = launch_fpfh(h, nc, p->normal_radius, p->fpfh_radius, cell))) return rc;
+    if ((rc = cache_copy(h, 1, nc))) return rc;
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // the pinned tables are reused by the next wave
+  }
+  return QB200_OK;
+}
+
+int qb200_register_cached(qb200_handle* h, const qb200_slot_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_result* results) {
+  if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
+  if (p->inlier_selection_mode == QB200_PMC_EXACT || !p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
+  const float cell = lattice_cell(*p);
+  for (int i = 0; i < n_pairs; ++i) {
+    const int sl[2] = {pairs[i].src_slot, pairs[i].tgt_slot};
+    for (int k = 0; k < 2; ++k) {
+      if (sl[k] < 0 || sl[k] >= h->c_slots) { h->fail(__FILE__, __LINE__, "slot outside qb200_cache_reserve()"); return QB200_ERR_BAD_ARG; }
+      const float* sig = h->c_sig + 4 * (size_t)sl[k];
+      if (sig[0] != p->voxel_size || sig[1] != p->normal_radius || sig[2] != p->fpfh_radius || sig[3] != cell) {
+        h->fail(__FILE__, __LINE__, "cached scan was computed with other front-end parameters (or the slot is empty)");
+        return QB200_ERR_BAD_ARG;
+      }
+    }
+  }
+  cudaSetDevice(h->device);
+  qb200_params pr = *p;
+  if (!(pr.rot_noise_bound > 0)) {
+    if (h->rot_noise_bound_latched <= 0) h->rot_noise_bound_latched = 2.0 * p->noise_bound;
+    pr.rot_noise_bound = h->rot_noise_bound_latched;
+  }
+  for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
+  for (int w0 = 0; w0 < n_pairs; w0 += h->S) {
+    const int np = n_pairs - w0 < h->S ? n_pairs - w0 : h->S;
+    int rc;
+    for (int s = 0; s < np; ++s) {
+      h->h_slot_of_cloud[2 * s] = pairs[w0 + s].src_slot;
+      h->h_slot_of_cloud[2 * s + 1] = pairs[w0 + s].tgt_slot;
+    }
+    if ((rc = wave_reset(h, 2 * np))) return rc;
+    cudaEventRecord(h->ev[2], h->stream);
+    if ((rc = cache_copy(h, 0, 2 * np))) return rc;
+    cudaEventRecord(h->ev[3], h->stream);
+    if ((rc = launch_match(h, np, pr))) return rc;
+    cudaEventRecord(h->ev[4], h->stream);
+    cudaEventRecord(h->ev[5], h->stream);
+    if ((rc = run_solver(h, np, pr, 1))) return rc;
+    cudaEventRecord(h->ev[7], h->stream);
+    QB_CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results, (size_t)np * sizeof(qb200_result), cudaMemcpyDeviceToHost, h->stream));
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(results + w0, h->h_results, (size_t)np * sizeof(qb200_result));
+    for (int i = 2; i < 7; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
+    }
+  }
+  if (n_pairs == 1) {
+    h->last_n_corr = results[0].n_corr;
+    h->last_n_clique = results[0].clique_size;
+    h->last_n_final = results[0].n_final_inliers;
+  }
+  return QB200_OK;
+}
+
+int qb200_cache_copy(qb200_handle* h, int32_t from_slot, int32_t to_slot) {
+  if (!h || from_slot < 0 || to_slot < 0 || from_slot >= h->c_slots || to_slot >= h->c_slots) return QB200_ERR_BAD_ARG;
+  if (from_slot == to_slot) return QB200_OK;
+  cudaSetDevice(h->device);
+  const size_t V = h->V;
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->c_vox + to_slot * V, h->c_vox + from_slot * V, V * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->c_nrm + to_slot * V, h->c_nrm + from_slot * V, V * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->c_desc + to_slot * kDescK * V, h->c_desc + from_slot * kDescK * V, kDescK * V * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->c_n + to_slot, h->c_n + from_slot, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->c_status + to_slot, h->c_status + from_slot, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+  memcpy(h->c_sig + 4 * (size_t)to_slot, h->c_sig + 4 * (size_t)from_slot, 4 * sizeof(float));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return QB200_OK;
+}
+
+int qb200_cache_read(qb200_handle* h, int32_t slot, float* vox4, float* normals4, float* desc33, int32_t cap, int32_t* n_out) {
+  if (!h || !n_out || slot < 0 || slot >= h->c_slots || cap < 0) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  int n = 0, rc;
+  if ((rc = get_counter(h, h->c_n + slot, &n))) return rc;
+  *n_out = n;
+  const int m = n < cap ? n : cap;
+  const size_t V = h->V;
+  if (m > 0) {
+    if (vox4) QB_CUDA_TRY(h, cudaMemcpyAsync(vox4, h->c_vox + slot * V, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (normals4) QB_CUDA_TRY(h, cudaMemcpyAsync(normals4, h->c_nrm + slot * V, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (desc33) {
+      desc_to_aos_rows(h, h->c_desc + slot * kDescK * V, m, h->aos_scratch);
+      QB_CUDA_TRY(h, cudaMemcpyAsync(desc33, h->aos_scratch, (size_t)m * kDescDim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return n > cap ? QB200_CAPACITY_EXCEEDED : QB200_OK;
 }
 
 int qb200_get_kernel_ms(qb200_handle* h, float* ms, int32_t* launches, int32_t n) {

@@ -18,9 +18,9 @@
 //     AND; the surviving neighbours are expanded to an ascending list with one warp scan and every neighbour's bucket move
 //     is done by its own lane.  Moves into different buckets commute; the members of one bucket (same current degree) must
 //     be applied in id order: their ranks come from __match_any_sync, and with the ranks known the moves of a group have a
-//     closed form (member t lands on slot bin+t, the displaced vertex takes the member's old slot) unless a member already
-//     sits inside the target slots -- then that group is replayed serially by its first lane while the other groups
-//     proceed.  The next row is prefetched while the current one is processed.  (A CTA-wide variant with 4-8 warps and
+//     closed form (member t lands on slot bin+t; the non-members displaced from the target slots take the old slots of the
+//     members that sat outside, found by a short chain walk) -- no serial replay.  Rows come from shared memory: the whole
+//     adjacency when it fits (L up to ~1000), otherwise a ring of 8 rows prefetched with cp.async along the peel order.  (A CTA-wide variant with 4-8 warps and
 //     five block barriers per step measured 3000 cycles per step -- barrier-bound -- and was dropped)
 //   clique_cta_kernel  The start vertices are tried SPECULATIVELY, one per warp, against the current incumbent size
 //     mc; results are committed in sequential order (the first warp that beats mc wins, later warps are discarded and
@@ -81,21 +81,34 @@ __device__ void warp_bucket_sort(const unsigned short* __restrict__ key, int n, 
   __syncwarp();
 }
 
-// One warp per pair; lane l owns the WPL consecutive adjacency words [l*WPL, l*WPL + WPL) of the row being peeled
-// (W <= 32 * WPL).  smem: bin (int x (Lc + 2)), above (u32 x 32*WPL), deg / pos / vert / nbl / slot (u16 x Lc each).
+constexpr int kRing = 8;  // rows in flight when the adjacency does not fit in shared memory (covers DRAM latency at ~8 steps)
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One warp per pair; lane l owns adjacency words l, l + 32, ... (WPL of them, W <= 32 * WPL) of the row being peeled.
+// smem: bin (int x (Lc + 2)), above (u32 x 32*WPL), deg / pos / vert / nbl / mrk (u16 x Lc each), rows (u32 x row_words):
+// the whole adjacency when L * ceil(L/32) <= row_words, otherwise a ring of kRing prefetched rows.
 template <int WPL>
 __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restrict__ adj, const int* __restrict__ deg_in,
-                                                        const int* __restrict__ n_corr, int Lc, int W, int* __restrict__ kcore,
+                                                        const int* __restrict__ n_corr, int Lc, int W, int row_words, int* __restrict__ kcore,
                                                         int* __restrict__ korder, int* __restrict__ rank_of, int* __restrict__ by_rank,
                                                         int* __restrict__ kbin, int* __restrict__ max_core_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* bin = reinterpret_cast<int*>(smem_raw);                       // [Lc + 2] start of every degree bucket
   uint32_t* above = reinterpret_cast<uint32_t*>(bin + Lc + 2);       // [32 * WPL] vertices with current degree > current level
-  unsigned short* deg = reinterpret_cast<unsigned short*>(above + 32 * WPL);
+  uint32_t* rows = above + 32 * WPL;                                 // [row_words] adjacency cache or prefetch ring
+  unsigned short* deg = reinterpret_cast<unsigned short*>(rows + row_words);
   unsigned short* pos = deg + Lc;
   unsigned short* vert = pos + Lc;
   unsigned short* nbl = vert + Lc;                                   // ascending list of the current step's live neighbours
-  unsigned short* slot = nbl + Lc;                                   // slot[q] = member that lands on position q (serial replay)
+  unsigned short* mrk = nbl + Lc;                                    // mrk[u] = 1 + rank of u inside its group during a pass, else 0
+  __shared__ int ring_tag[kRing];
 
   const int pair = blockIdx.x, lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
@@ -110,14 +123,19 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
     return;
   }
   const uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
-  const int nbw = (L + 31) >> 5;  // adjacency words per row in use
+  const int nbw = (L + 31) >> 5;   // adjacency words per row in use
+  const int nwl = (nbw + 31) >> 5; // words per lane in use (<= WPL)
+  const bool cached = (long long)L * nbw <= (long long)row_words;
 
   int md = 0;
   for (int v = lane; v < L; v += 32) {
     const int d = deg_in[(size_t)pair * Lc + v];
     deg[v] = (unsigned short)d;
+    mrk[v] = 0;
     md = max(md, d);
   }
+  if (cached)  // the peel is a chain of dependent row reads: stage the whole graph once
+    for (int idx = lane; idx < L * nbw; idx += 32) rows[idx] = G[(size_t)(idx / nbw) * W + (idx % nbw)];
   md = warp_max(md);
   __syncwarp();
   warp_bucket_sort(deg, L, md, bin, pos, vert);
@@ -125,29 +143,43 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
   // ---- peel ----
 #pragma unroll
   for (int k = 0; k < WPL; ++k) {
-    const int lo = (lane * WPL + k) * 32;
-    above[lane * WPL + k] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
+    const int lo = (lane + 32 * k) * 32;
+    above[lane + 32 * k] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
   }
-  int cur = -1;  // current level: every vertex with degree <= cur has its bit in `above` cleared
-  uint32_t wn[WPL];
-  int guess = vert[0];
+  auto fetch = [&](int p) {  // prefetch the row of the vertex that sits at position p right now into its ring slot
+    if (p < L) {
+      const int x = vert[p], sl = p % kRing;
+      if (lane == 0) ring_tag[sl] = x;
 #pragma unroll
-  for (int k = 0; k < WPL; ++k) wn[k] = lane * WPL + k < nbw ? G[(size_t)guess * W + lane * WPL + k] : 0u;
+      for (int k = 0; k < WPL; ++k)
+        if (lane + 32 * k < nbw) cp_async4(rows + sl * W + lane + 32 * k, G + (size_t)x * W + lane + 32 * k);
+    }
+    cp_async_commit();
+  };
+  if (!cached)
+    for (int p = 0; p < kRing; ++p) fetch(p);
+  int cur = -1;  // current level: every vertex with degree <= cur has its bit in `above` cleared
   __syncwarp();
   for (int i = 0; i < L; ++i) {
     const int v = vert[i];
     const int dv = deg[v];
     uint32_t w[WPL];
+    if (cached) {
 #pragma unroll
-    for (int k = 0; k < WPL; ++k) w[k] = wn[k];
-    if (v != guess) {  // the speculation failed (warp-uniform)
+      for (int k = 0; k < WPL; ++k) w[k] = lane + 32 * k < nbw ? rows[v * nbw + lane + 32 * k] : 0u;
+    } else {
+      cp_async_wait<kRing - 1>();  // the group of position i has landed
+      __syncwarp();
+      const int sl = i % kRing;
+      if (ring_tag[sl] == v) {  // positions inside the current bucket are final: the prefetch usually holds the right row
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) w[k] = lane * WPL + k < nbw ? G[(size_t)v * W + lane * WPL + k] : 0u;
-    }
-    if (i + 1 < L) {  // positions inside the current bucket are final: the vertex at i+1 rarely changes during this step
-      guess = vert[i + 1];
+        for (int k = 0; k < WPL; ++k) w[k] = lane + 32 * k < nbw ? rows[sl * W + lane + 32 * k] : 0u;
+      } else {
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) wn[k] = lane * WPL + k < nbw ? G[(size_t)guess * W + lane * WPL + k] : 0u;
+        for (int k = 0; k < WPL; ++k) w[k] = lane + 32 * k < nbw ? G[(size_t)v * W + lane + 32 * k] : 0u;
+      }
+      __syncwarp();
+      fetch(i + kRing);
     }
     if (dv > cur) {  // level rise: bucket dv = positions [i, bin[dv+1]) leaves `above`
       const int end = bin[dv + 1];
@@ -158,29 +190,31 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
       cur = dv;
       __syncwarp();
     }
-    int c = 0;
+    // live neighbours (deg[u] > deg[v]) -> ascending list; word order = (k, lane)
+    int cnt = 0;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
-      w[k] &= above[lane * WPL + k];  // neighbours with deg[u] > deg[v]
-      c += __popc(w[k]);
-    }
-    int cnt;
-    int off = warp_excl_scan(c, &cnt);
-    if (cnt == 0) continue;
-#pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      uint32_t x = w[k];
-      const int basebit = (lane * WPL + k) * 32;
-      while (x) {
-        const int b = __ffs(x) - 1;
-        x &= x - 1;
-        nbl[off++] = (unsigned short)(basebit + b);
+      if (k < nwl) {
+        uint32_t x = w[k] & above[lane + 32 * k];
+        int tot;
+        int off = cnt + warp_excl_scan(__popc(x), &tot);
+        const int basebit = (lane + 32 * k) * 32;
+        while (x) {
+          const int b = __ffs(x) - 1;
+          x &= x - 1;
+          nbl[off++] = (unsigned short)(basebit + b);
+        }
+        cnt += tot;
       }
     }
+    if (cnt == 0) continue;
     __syncwarp();
-    // bucket moves, 32 neighbours at a time.  Moves into different buckets commute; the members of one bucket (same current
-    // degree) must land in id order: member `rank` takes slot bin + rank and the vertex it displaces takes the member's old
-    // slot -- unless a member already sits inside the target slots, then that group is replayed serially by its first lane.
+    // Bucket moves, 32 neighbours at a time.  Moves into different buckets commute; the members u_0 < u_1 < ... of one bucket
+    // (same current degree, ranks from __match_any_sync) are applied in id order by pmc: "swap u_t with the vertex on slot
+    // bin + t".  That sequence has a closed form: u_t ends on slot bin + t, and the vertex y that is not a member but sat
+    // on one of the target slots ends on the old slot of the member found by walking  slot s -> member that sat there -> its
+    // target slot -> ... ; each member that sat OUTSIDE the target slots walks that chain backwards from its own rank and
+    // hands its old slot to the non-member it reaches (verified against the sequential mechanic, tests + DESIGN.md 5.3).
     for (int c0 = 0; c0 < cnt; c0 += 32) {
       const int e = c0 + lane;
       const bool act = e < cnt;
@@ -188,33 +222,28 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
       const int du = act ? deg[u] : -1 - lane;
       const unsigned grp = __match_any_sync(0xffffffffu, du);
       const int rank = __popc(grp & lt), m = __popc(grp);
-      int b0 = 0, pu = 0, q = 0, wv = 0;
-      bool inside = false;
+      int b0 = 0, pu = 0;
       if (act) {
         b0 = bin[du];
         pu = pos[u];
-        q = b0 + rank;
-        wv = vert[q];
-        slot[q] = (unsigned short)u;
-        inside = m > 1 && pu < b0 + m;
+        mrk[u] = (unsigned short)(rank + 1);
       }
-      const bool serial = (__ballot_sync(0xffffffffu, inside) & grp) != 0u;
+      __syncwarp();
+      int y = -1;  // the non-member that moves to this member's old slot
+      if (act && pu >= b0 + m) {
+        int curk = rank;
+        for (;;) {
+          y = vert[b0 + curk];
+          const int r = mrk[y];
+          if (r == 0) break;
+          curk = r - 1;
+        }
+      }
       __syncwarp();
       if (act) {
-        if (!serial) {
-          if (pu != q) {
-            vert[q] = (unsigned short)u; pos[u] = (unsigned short)q;
-            vert[pu] = (unsigned short)wv; pos[wv] = (unsigned short)pu;
-          }
-        } else if (rank == 0) {
-          for (int t = 0; t < m; ++t) {
-            const int uu = slot[b0 + t], pw = b0 + t, p2 = pos[uu], w2 = vert[pw];
-            if (uu != w2) {
-              pos[uu] = (unsigned short)pw; vert[p2] = (unsigned short)w2;
-              pos[w2] = (unsigned short)p2; vert[pw] = (unsigned short)uu;
-            }
-          }
-        }
+        vert[b0 + rank] = (unsigned short)u; pos[u] = (unsigned short)(b0 + rank);
+        if (y >= 0) { vert[pu] = (unsigned short)y; pos[y] = (unsigned short)pu; }
+        mrk[u] = 0;
         deg[u] = (unsigned short)(du - 1);
         if (du - 1 == dv) atomicAnd(&above[u >> 5], ~(1u << (u & 31)));
         if (rank == 0) bin[du] = b0 + m;
@@ -222,6 +251,7 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
       __syncwarp();
     }
   }
+  if (!cached) cp_async_wait<0>();
   __syncwarp();
   // ---- outputs: kcore = core + 1, peel order, max core ----
   const int max_core = deg[vert[L - 1]];
@@ -432,10 +462,15 @@ __global__ void __launch_bounds__(kCliqueWarps * 32) clique_cta_kernel(const uin
 template <int WPL>
 static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
   const int Lc = h->Lc, W = h->W;
-  const size_t smem = (size_t)(Lc + 2) * sizeof(int) + (size_t)32 * WPL * sizeof(uint32_t) + (size_t)5 * Lc * sizeof(unsigned short);
+  const size_t fixed = (size_t)(Lc + 2) * sizeof(int) + (size_t)32 * WPL * sizeof(uint32_t) + (size_t)5 * Lc * sizeof(unsigned short);
+  // rows: as much of the 200 KB budget as is left (whole graphs up to L ~ 1000 at max_corr 4096), at least the prefetch ring
+  size_t row_words = (200 * 1024 - fixed) / 4;
+  if (row_words < (size_t)kRing * W) row_words = (size_t)kRing * W;
+  if (row_words > (size_t)Lc * W) row_words = (size_t)Lc * W;
+  const size_t smem = fixed + row_words * 4;
   if (set_attr) QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_warp_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kcore_warp_kernel<WPL><<<n_pairs, 32, smem, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of, h->by_rank,
-                                                           h->kbin, h->ctr.max_core);
+  kcore_warp_kernel<WPL><<<n_pairs, 32, smem, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, (int)row_words, h->kcore, h->korder, h->rank_of,
+                                                           h->by_rank, h->kbin, h->ctr.max_core);
   return QB200_OK;
 }
 

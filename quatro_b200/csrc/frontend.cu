@@ -625,6 +625,14 @@ int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33) {
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
 }
+// any dimension-major descriptor block [40][V] (e.g. a cache slot) -> AoS n x 33
+int desc_to_aos_rows(qb200_handle* h, const float* desc_rows, int n, float* d_out33) {
+  if (n <= 0) return QB200_OK;
+  desc_to_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(desc_rows, h->V, n, d_out33);
+  h->launches++;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  return QB200_OK;
+}
 int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33) {
   if (n <= 0) return QB200_OK;
   desc_from_aos_kernel<<<(n * kDescDim + 255) / 256, 256, 0, h->stream>>>(d_in33, h->V, n, h->desc_t + (size_t)cloud * kDescK * h->V);

@@ -74,6 +74,14 @@ struct qb200_handle {
   qb::WaveCounters ctr;
   int* ctr_block; size_t ctr_ints;
 
+  // ---- scan cache (qb200_cache_*): front-end results of whole scans, resident on the device ----
+  int c_slots;
+  float4 *c_vox, *c_nrm;      // [slots*V]
+  float* c_desc;              // [slots*40*V] dimension-major like desc_t
+  int *c_n, *c_status;        // [slots]
+  int *d_slot_of_cloud, *h_slot_of_cloud;   // [2S] cache slot of every cloud of the current wave (device / pinned)
+  float* c_sig;               // host [slots*4]: (voxel, normal_r, fpfh_r, cell) a slot was computed with
+
   // ---- multi-GPU gather of the result records (comm.cu) ----
   void* comm;                 // ncclComm_t
   int comm_world, comm_rank, comm_cap;   // cap: records per rank the staging buffers hold
@@ -116,6 +124,7 @@ int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);
 int launch_tc_debug_tile(qb200_handle* h, float* d_out);
 int launch_desc_to_aos(qb200_handle* h, int cloud, int n, float* d_out33);
 int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33);
+int desc_to_aos_rows(qb200_handle* h, const float* desc_rows, int n, float* d_out33);
 size_t sort_temp_bytes(int max_items);
 void comm_release(qb200_handle* h);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);

@@ -562,3 +562,39 @@ def test_launch_counter_and_stage_times(handle):
     assert handle.launch_count() - before >= 25
     ms = handle.stage_ms()
     assert (ms >= 0).all() and ms[1:7].sum() > 0
+
+
+# ---- scan cache (descriptor reuse: odometry chains, loop-closure sweeps) ----------------------------------------------------
+def test_scan_cache_matches_uncached_pipeline(oracle):
+    """qb200_cache_scans + qb200_register_cached must give the records of qb200_register_batch byte for byte, whichever slots the
+    scans sit in and however often a scan is reused; the cached descriptors are the ones of the stage entry points."""
+    p = default_params()
+    scans = []
+    for seed in (21, 22, 23):
+        s, t, _ = synth.outdoor_pair(seed, rings=32, azimuths=900)
+        scans += [s, t]
+    pairs_idx = [(0, 1), (2, 3), (4, 5), (0, 3), (1, 0), (5, 5)]     # three ordinary pairs, a cross pair, a reversed pair, a scan with itself
+    with Handle(max_batch_slots=4) as h:
+        ref = h.register_batch([(scans[a], scans[b]) for a, b in pairs_idx], p)
+        h.cache_reserve(9)
+        slots = [7, 0, 3, 8, 1, 5]                                    # arbitrary slot placement
+        h.cache_scans(scans, slots, p)
+        got = h.register_cached([(slots[a], slots[b]) for a, b in pairs_idx], p)
+        assert got.tobytes() == ref.tobytes()
+        # odometry chain: swapTgt2Src = copy the target's slot over the source's
+        h.cache_copy(slots[1], 2)
+        again = h.register_cached([(2, slots[3])], p)
+        direct = h.register_batch([(scans[1], scans[3])], p)
+        assert again.tobytes() == direct.tobytes()
+        # getSceneDescriptor / getTgtNormals: what the cache holds is what the stage entry points compute
+        vox, nrm, desc = h.cache_read(slots[2])
+        v_ref, _ = oracle.voxelize(scans[2], p.voxel_size, 1)
+        n_ref, d_ref = oracle.compute_fpfh(v_ref, p.normal_radius, p.fpfh_radius, DEFAULT_CELL)
+        assert np.array_equal(vox.view(np.uint32), v_ref.view(np.uint32))
+        assert np.array_equal(desc.view(np.uint32), d_ref.view(np.uint32))
+        assert ((nrm.view(np.uint32) == n_ref.view(np.uint32)) | (np.isnan(nrm) & np.isnan(n_ref))).all()
+        # parameters other than the cached ones are refused
+        q = default_params(); q.voxel_size = 0.25
+        from quatro_b200.capi import QuatroB200Error
+        with pytest.raises(QuatroB200Error):
+            h.register_cached([(slots[0], slots[1])], q)
