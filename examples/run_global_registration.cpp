@@ -7,45 +7,49 @@
 //   ./run_example src.bin tgt.bin        (KITTI .bin: float32 x,y,z,intensity records)
 #include <chrono>
 #include <cstdio>
+#include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 
 #include "quatro_b200/fpfh_manager.hpp"
 #include "quatro_b200/quatro.hpp"
 
 using namespace std;
 
-void setParams(double noise_bound_of_each_measurement, double square_of_the_ratio_btw_noise_and_noise_bound, double estimating_scale,
-               int num_max_iter, double control_parameter_for_gnc, double rot_cost_thr, const string& reg_type_name,
-               Quatro<PointType, PointType>::Params& params) {
-  params.noise_bound = noise_bound_of_each_measurement;
-  params.cbar2 = square_of_the_ratio_btw_noise_and_noise_bound;
-  params.estimate_scaling = estimating_scale;
-  params.rotation_max_iterations = num_max_iter;
-  params.rotation_gnc_factor = control_parameter_for_gnc;
-  params.rotation_estimation_algorithm = Quatro<PointType, PointType>::ROTATION_ESTIMATION_ALGORITHM::GNC_TLS;
-  params.rotation_cost_threshold = rot_cost_thr;
-  params.reg_name = reg_type_name;
-  params.inlier_selection_mode = Quatro<PointType, PointType>::INLIER_SELECTION_MODE::PMC_HEU;
+using QuatroReg = Quatro<PointType, PointType>;
+
+// Solver parameters of the "Quatro" configuration of the reference's caller (run_global_registration.cpp:357-375 selects GNC-TLS
+// rotation + PMC_HEU inlier selection; the numbers come from config/params.yaml).
+static QuatroReg::Params quatro_params(double noise_bound, double noise_bound_coeff, bool estimating_scale, int num_max_iter,
+                                       double gnc_factor, double rot_cost_diff_thr) {
+  QuatroReg::Params prm;
+  prm.reg_name = "Quatro";
+  prm.noise_bound = noise_bound;
+  prm.cbar2 = noise_bound_coeff;
+  prm.estimate_scaling = estimating_scale;
+  prm.rotation_estimation_algorithm = QuatroReg::ROTATION_ESTIMATION_ALGORITHM::GNC_TLS;
+  prm.rotation_max_iterations = (size_t)num_max_iter;
+  prm.rotation_gnc_factor = gnc_factor;
+  prm.rotation_cost_threshold = rot_cost_diff_thr;
+  prm.inlier_selection_mode = QuatroReg::INLIER_SELECTION_MODE::PMC_HEU;
+  return prm;
 }
 
-pcl::PointCloud<PointType>::ConstPtr getCloud(std::string filename) {  // run_global_registration.cpp:377-402
-  FILE* file = fopen(filename.c_str(), "rb");
-  if (!file) {
-    std::cerr << "error: failed to load " << filename << std::endl;
+// KITTI velodyne .bin: float32 records (x, y, z, intensity).  Like the reference's loader (:377-402) at most 250 000 records are read.
+static pcl::PointCloud<PointType>::ConstPtr read_kitti_bin(const std::string& path) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) {
+    std::cerr << "error: failed to load " << path << std::endl;
     return nullptr;
   }
-  std::vector<float> buffer(1000000);
-  size_t num_points = fread(reinterpret_cast<char*>(buffer.data()), sizeof(float), buffer.size(), file) / 4;
-  fclose(file);
-  pcl::PointCloud<PointType>::Ptr cloud(new pcl::PointCloud<PointType>());
-  cloud->resize(num_points);
-  for (size_t i = 0; i < num_points; i++) {
-    auto& pt = cloud->at(i);
-    pt.x = buffer[i * 4];
-    pt.y = buffer[i * 4 + 1];
-    pt.z = buffer[i * 4 + 2];
-  }
+  constexpr size_t kMaxRecords = 250000;
+  std::vector<float> rec(4 * kMaxRecords);
+  in.read(reinterpret_cast<char*>(rec.data()), (std::streamsize)(rec.size() * sizeof(float)));
+  const size_t n = (size_t)in.gcount() / (4 * sizeof(float));
+  auto cloud = std::make_shared<pcl::PointCloud<PointType>>();
+  cloud->reserve(n);
+  for (size_t i = 0; i < n; ++i) cloud->push_back(PointType(rec[4 * i], rec[4 * i + 1], rec[4 * i + 2]));
   return cloud;
 }
 
@@ -60,14 +64,13 @@ int main(int argc, char** argv) {
   bool estimating_scale = false;
   int num_max_iter = 50;
 
-  pcl::PointCloud<PointType>::ConstPtr srcRaw = getCloud(argv[1]);
-  pcl::PointCloud<PointType>::ConstPtr tgtRaw = getCloud(argv[2]);
+  pcl::PointCloud<PointType>::ConstPtr srcRaw = read_kitti_bin(argv[1]);
+  pcl::PointCloud<PointType>::ConstPtr tgtRaw = read_kitti_bin(argv[2]);
   if (!srcRaw || !tgtRaw) return 1;
 
   // ===================================================================================================
   Quatro<PointType, PointType> quatro;
-  Quatro<PointType, PointType>::Params params;
-  setParams(noise_bound, noise_bound_coeff, estimating_scale, num_max_iter, gnc_factor, rot_cost_diff_thr, "Quatro", params);
+  Quatro<PointType, PointType>::Params params = quatro_params(noise_bound, noise_bound_coeff, estimating_scale, num_max_iter, gnc_factor, rot_cost_diff_thr);
   quatro.reset(params);
 
   std::chrono::system_clock::time_point start = std::chrono::system_clock::now();

@@ -262,6 +262,11 @@ int qb200_get_last_final_inliers(qb200_handle* h, int32_t* idx, int32_t cap, int
 int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_matched4,
                                    float* tgt_matched4, int32_t cap, int32_t* n);
 
+/* Normals (n x {nx,ny,nz,curvature}) and FPFH-33 descriptors (n x 33) the most recent qb200_match_and_pack (which = 0 source,
+ * 1 target) or qb200_compute_fpfh (which = 0) left on the device: FPFHManager::getObjDescriptor / getSceneDescriptor /
+ * getTgtNormals (include/fpfh_manager.hpp:161-177).  Either pointer may be NULL. */
+int qb200_get_last_features(qb200_handle* h, int32_t which, float* normals4, float* desc33, int32_t cap, int32_t* n);
+
 /* Per-stage device time of the last qb200_register_batch call in milliseconds (CUDA events):
  * [0]=h2d [1]=voxel [2]=fpfh [3]=match [4]=graph [5]=clique [6]=pose [7]=d2h; n<=8. */
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n);

@@ -75,6 +75,7 @@ struct FPFHSignature33 {
   float histogram[33];
   static int descriptorSize() { return 33; }
 };
+static_assert(sizeof(FPFHSignature33) == 132, "pcl::FPFHSignature33 is 33 packed floats");
 
 struct Normal {
   float normal_x, normal_y, normal_z, curvature;
@@ -150,6 +151,36 @@ inline void transformPointCloud(const PointCloud<PointXYZ>& in, PointCloud<Point
   }
   out.width = (unsigned)out.points.size();
 }
+
+namespace io {
+// pcl::io::savePCDFile / loadPCDFile for xyz clouds (ASCII, PCD v0.7): what FPFHManager::save/loadFeaturePair need
+inline int savePCDFile(const std::string& name, const PointCloud<PointXYZ>& c) {
+  FILE* f = std::fopen(name.c_str(), "w");
+  if (!f) return -1;
+  std::fprintf(f, "# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\n"
+                  "WIDTH %zu\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %zu\nDATA ascii\n", c.points.size(), c.points.size());
+  for (const PointXYZ& p : c.points) std::fprintf(f, "%.9g %.9g %.9g\n", p.x, p.y, p.z);
+  std::fclose(f);
+  return 0;
+}
+inline int loadPCDFile(const std::string& name, PointCloud<PointXYZ>& c) {
+  FILE* f = std::fopen(name.c_str(), "r");
+  if (!f) return -1;
+  char line[256];
+  size_t n = 0;
+  bool data = false;
+  while (std::fgets(line, sizeof(line), f)) {
+    if (std::sscanf(line, "POINTS %zu", &n) == 1) continue;
+    if (std::string(line).rfind("DATA ascii", 0) == 0) { data = true; break; }
+  }
+  c.clear();
+  if (!data) { std::fclose(f); return -1; }
+  float x, y, z;
+  for (size_t i = 0; i < n && std::fscanf(f, "%f %f %f", &x, &y, &z) == 3; ++i) c.push_back(PointXYZ(x, y, z));
+  std::fclose(f);
+  return c.points.size() == n ? 0 : -1;
+}
+}  // namespace io
 
 }  // namespace pcl
 

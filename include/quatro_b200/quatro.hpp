@@ -24,11 +24,12 @@ struct HandleDeleter {
 };
 using HandlePtr = std::unique_ptr<qb200_handle, HandleDeleter>;
 
-inline HandlePtr make_handle(int device = 0, int slots = 1) {
+inline HandlePtr make_handle(int device = 0, int slots = 1, int max_voxel_points = 16384) {
   qb200_config cfg;
   qb200_default_config(&cfg);
   cfg.device = device;
   cfg.max_batch_slots = slots;
+  cfg.max_voxel_points = max_voxel_points;
   cfg.max_raw_points = 262144;  // the example's loader reads at most 250 k points (run_global_registration.cpp:384-388)
   qb200_handle* h = nullptr;
   const int st = qb200_create(&cfg, &h);
@@ -38,9 +39,16 @@ inline HandlePtr make_handle(int device = 0, int slots = 1) {
 
 // One handle shared by the free functions / FPFHManager of a process, like the reference's
 // function-local static filter and FPFH objects (quatro.hpp:53, fpfh_manager.hpp:110): not thread-safe.
-inline qb200_handle* shared_handle() {
+inline HandlePtr& shared_handle_slot() {
   static HandlePtr h = make_handle();
-  return h.get();
+  return h;
+}
+inline qb200_handle* shared_handle() { return shared_handle_slot().get(); }
+// pcl::VoxelGrid / FLANN have no capacity: when a scan or a match overflows the handle's per-cloud capacity, the shared handle is
+// rebuilt once with the largest voxel capacity (65536 per cloud) instead of handing truncated data to the next stage
+inline qb200_handle* grow_shared_handle() {
+  shared_handle_slot() = make_handle(0, 1, 65536);
+  return shared_handle();
 }
 
 template <class PointT>
@@ -59,8 +67,14 @@ void voxelize_impl(const pcl::PointCloud<T>& src, pcl::PointCloud<T>& dst, doubl
   std::vector<T> out(src.points.size());
   int32_t n_out = 0;
   // PCL's VoxelGrid keeps every finite point: flagged-point dropping (skip_flagged) is a batch-pipeline option only
-  const int st = qb200_voxelize(h, qb200::as_float4(src), (int32_t)src.points.size(), (float)voxelSize, 0,
-                                out.empty() ? nullptr : reinterpret_cast<float*>(out.data()), (int32_t)out.size(), &n_out);
+  int st = qb200_voxelize(h, qb200::as_float4(src), (int32_t)src.points.size(), (float)voxelSize, 0,
+                          out.empty() ? nullptr : reinterpret_cast<float*>(out.data()), (int32_t)out.size(), &n_out);
+  if (st == QB200_CAPACITY_EXCEEDED) {  // more occupied voxels than the handle holds: never return the truncated (lowest-z) subset
+    h = qb200::grow_shared_handle();
+    st = qb200_voxelize(h, qb200::as_float4(src), (int32_t)src.points.size(), (float)voxelSize, 0,
+                        out.empty() ? nullptr : reinterpret_cast<float*>(out.data()), (int32_t)out.size(), &n_out);
+    if (st == QB200_CAPACITY_EXCEEDED) throw std::runtime_error("voxelize: more than 65536 occupied voxels in one cloud exceed the device capacity");
+  }
   if (st < 0 && st != QB200_ERR_VOXEL_OVERFLOW) throw std::runtime_error(std::string("qb200_voxelize: ") + qb200_last_error(h));
   out.resize((size_t)n_out);
   dst.points.assign(out.begin(), out.end());

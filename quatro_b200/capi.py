@@ -137,6 +137,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_register_batch_rank": (i32, [vp, P(Pair), i32, P(Params), i32, vp, i32]),
         "qb200_comm_wait": (i32, [vp]),
         "qb200_bind_numa": (i32, [vp]),
+        "qb200_get_last_features": (i32, [vp, i32, vp, vp, i32, P(i32)]),
         "qb200_cache_reserve": (i32, [vp, i32]),
         "qb200_cache_scans": (i32, [vp, P(vp), P(i32), P(i32), i32, P(Params), i32]),
         "qb200_register_cached": (i32, [vp, vp, i32, P(Params), vp]),
@@ -162,7 +163,7 @@ EXPORTED_SYMBOLS = [
     "qb200_solve_batch",
     "qb200_comm_init_all", "qb200_register_batch_sharded", "qb200_comm_unique_id", "qb200_comm_init_rank",
     "qb200_register_batch_rank", "qb200_comm_wait", "qb200_bind_numa",
-    "qb200_cache_reserve", "qb200_cache_scans", "qb200_register_cached", "qb200_cache_copy", "qb200_cache_read",
+    "qb200_get_last_features", "qb200_cache_reserve", "qb200_cache_scans", "qb200_register_cached", "qb200_cache_copy", "qb200_cache_read",
 ]
 
 
@@ -382,6 +383,15 @@ class Handle:
         out = np.zeros(n, RESULT_DTYPE)
         self._check(self.lib.qb200_solve_batch(self.h, arr, n, C.byref(params), kind, _ptr(out)), "qb200_solve_batch")
         return out
+
+    def last_features(self, which: int, cap: Optional[int] = None):
+        """(normals (n,4), descriptors (n,33)) of the source (0) / target (1) cloud of the last match_and_pack."""
+        cap = cap or self.cfg.max_voxel_points
+        nrm, desc = np.zeros((cap, 4), np.float32), np.zeros((cap, 33), np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.qb200_get_last_features(self.h, which, _ptr(nrm), _ptr(desc), cap, C.byref(n)), "qb200_get_last_features")
+        m = min(n.value, cap)
+        return nrm[:m].copy(), desc[:m].copy()
 
     # ---- scan cache ----
     def cache_reserve(self, n_slots: int):

@@ -839,6 +839,24 @@ int qb200_get_last_correspondences(qb200_handle* h, int32_t* corr, float* src_ma
   return nc > cap ? QB200_CAPACITY_EXCEEDED : QB200_OK;
 }
 
+int qb200_get_last_features(qb200_handle* h, int32_t which, float* normals4, float* desc33, int32_t cap, int32_t* n_out) {
+  if (!h || !n_out || which < 0 || which > 1 || cap < 0) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  int n = 0, rc;
+  if ((rc = get_counter(h, h->ctr.n_vox + which, &n))) return rc;
+  *n_out = n;
+  const int m = n < cap ? n : cap;
+  if (m > 0) {
+    if (normals4) QB_CUDA_TRY(h, cudaMemcpyAsync(normals4, h->normals + (size_t)which * h->V, (size_t)m * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (desc33) {
+      if ((rc = launch_desc_to_aos(h, which, m, h->aos_scratch))) return rc;
+      QB_CUDA_TRY(h, cudaMemcpyAsync(desc33, h->aos_scratch, (size_t)m * kDescDim * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return n > cap ? QB200_CAPACITY_EXCEEDED : QB200_OK;
+}
+
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n) {
   if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->stage_ms[i];

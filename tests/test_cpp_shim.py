@@ -36,7 +36,9 @@ def test_shim_keeps_the_reference_surface():
                  "getNumRotaionInliers", "getNumMaxCliqueInliers", "setPreEstaimatedRyRx", "INLIER_SELECTION_MODE", "PMC_HEU",
                  "rotation_gnc_factor", "rotation_cost_threshold", "noise_bound_", "void voxelize("]:
         assert name in q, name
-    for name in ["class FPFHManager", "flushAllFeatures", "setFeaturePair", "getSrcKps", "getTgtKps", "getSrcMatched", "getCorrespondences"]:
+    for name in ["class FPFHManager", "flushAllFeatures", "setFeaturePair", "getSrcKps", "getTgtKps", "getSrcMatched", "getCorrespondences",
+                 "getObjDescriptor", "getSceneDescriptor", "getTgtNormals", "swapTgt2Src", "saveFeaturePair", "loadFeaturePair", "setLoadDir",
+                 "setSaveDir", "clearInputs", "setParams"]:
         assert name in f, name
 
 
@@ -63,3 +65,35 @@ def test_example_reproduces_the_oracle(tmp_path, oracle):
     assert np.allclose(T_cpp, ref.matrix(), atol=1e-6)
     rot, tr = synth.pose_error(T_cpp, T)
     assert rot < 2.0 and tr < 0.5
+
+
+def build_fixture(tmp_path, name):
+    from quatro_b200 import _build
+    lib = _build.build_cuda()
+    exe = tmp_path / name
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "fixtures" / f"{name}.cpp"),
+           f"-L{lib.parent}", "-lquatro_b200", f"-Wl,-rpath,{lib.parent}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_shim_extras_compile(tmp_path):
+    build_fixture(tmp_path, "shim_extras")
+
+
+@pytest.mark.gpu
+def test_fpfh_manager_getters_odometry_and_pcd_cache(tmp_path):
+    from quatro_b200 import synth
+    exe = build_fixture(tmp_path, "shim_extras")
+    a, b, _ = synth.outdoor_pair(11, rings=32, azimuths=900)
+    c, _, _ = synth.outdoor_pair(12, rings=32, azimuths=900)
+    names = []
+    for i, sc in enumerate((a, b, c)):
+        sc = sc[sc[:, 3] > 0]
+        f = tmp_path / f"s{i}.bin"
+        f.write_bytes(sc.astype(np.float32).tobytes())
+        names.append(str(f))
+    r = subprocess.run([str(exe), *names, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHIM_EXTRAS_OK" in r.stdout, r.stdout + r.stderr
+    assert (tmp_path / "000540_to_001319.pcd").exists()
