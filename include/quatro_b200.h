@@ -287,6 +287,11 @@ int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, cons
  * [2] = warm-up passes, [3] = stripes handed to the exact kernel.  Synchronises the handle's stream. */
 int qb200_debug_match_stats(qb200_handle* h, uint64_t* out4, int32_t reset);
 
+/* Diagnostics: with QB200_TC_VERIFY=1 in the environment every batch is matched by the tensor-core path AND by the exact CUDA-core
+ * kernel; out2[0] = nearest-neighbour table entries compared so far, out2[1] = entries whose packed (distance, index) differ
+ * (0 unless the filter's error bound is violated).  Synchronises the handle's stream. */
+int qb200_debug_match_verify(qb200_handle* h, uint64_t* out2, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

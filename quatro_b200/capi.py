@@ -137,6 +137,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_register_batch_rank": (i32, [vp, P(Pair), i32, P(Params), i32, vp, i32]),
         "qb200_comm_wait": (i32, [vp]),
         "qb200_bind_numa": (i32, [vp]),
+        "qb200_debug_match_verify": (i32, [vp, vp, i32]),
         "qb200_get_last_features": (i32, [vp, i32, vp, vp, i32, P(i32)]),
         "qb200_cache_reserve": (i32, [vp, i32]),
         "qb200_cache_scans": (i32, [vp, P(vp), P(i32), P(i32), i32, P(Params), i32]),
@@ -163,7 +164,7 @@ EXPORTED_SYMBOLS = [
     "qb200_solve_batch",
     "qb200_comm_init_all", "qb200_register_batch_sharded", "qb200_comm_unique_id", "qb200_comm_init_rank",
     "qb200_register_batch_rank", "qb200_comm_wait", "qb200_bind_numa",
-    "qb200_get_last_features", "qb200_cache_reserve", "qb200_cache_scans", "qb200_register_cached", "qb200_cache_copy", "qb200_cache_read",
+    "qb200_debug_match_verify", "qb200_get_last_features", "qb200_cache_reserve", "qb200_cache_scans", "qb200_register_cached", "qb200_cache_copy", "qb200_cache_read",
 ]
 
 
@@ -478,6 +479,11 @@ class Handle:
         out = np.zeros(4, np.uint64)
         self._check(self.lib.qb200_debug_match_stats(self.h, _ptr(out), int(reset)), "qb200_debug_match_stats")
         return {"exact_evals": int(out[0]), "tiles": int(out[1]), "warmups": int(out[2]), "aborted_stripes": int(out[3])}
+
+    def debug_match_verify(self, reset: bool = True) -> dict:
+        out = np.zeros(2, np.uint64)
+        self._check(self.lib.qb200_debug_match_verify(self.h, _ptr(out), int(reset)), "qb200_debug_match_verify")
+        return {"compared": int(out[0]), "mismatches": int(out[1])}
 
     def debug_tc_distances(self, a33, b33) -> np.ndarray:
         a33, b33 = _f32(a33, 33), _f32(b33, 33)

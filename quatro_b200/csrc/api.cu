@@ -101,8 +101,8 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMemset(h->desc_tiles, 0, C * kDescK * V * 3 * sizeof(float)));
   QB_ALLOC(h, h->desc_norm, C * V);
   QB_ALLOC(h, h->tc_fallback, S);
-  QB_ALLOC(h, h->tc_stats, 4);
-  QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 4 * sizeof(unsigned long long)));
+  QB_ALLOC(h, h->tc_stats, 8);
+  QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 8 * sizeof(unsigned long long)));
   QB_ALLOC(h, h->rowbest, S * V);
   {  // two layouts share colpart: [S][NS][V] stripe partials (exact kernel) and [2][S][V] class results + tile cache (tc_match.cu)
     const size_t a = S * h->NS * V, b = 2 * S * V + S * (V >> 7) / 2 + 1;
@@ -860,6 +860,24 @@ int qb200_get_last_features(qb200_handle* h, int32_t which, float* normals4, flo
 int qb200_get_stage_ms(qb200_handle* h, float* ms, int32_t n) {
   if (!h || !ms || n < 0) return QB200_ERR_BAD_ARG;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->stage_ms[i];
+  return QB200_OK;
+}
+
+// QB200_TC_VERIFY=1: every batch is matched by BOTH K6 implementations and the packed (distance, index) results are compared;
+// out2[0] = nearest-neighbour entries compared, out2[1] = entries that differ (must stay 0: the tensor-core filter is exact).
+int qb200_debug_match_verify(qb200_handle* h, uint64_t* out2, int32_t reset) {
+  if (!h || !out2) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  QB_CUDA_TRY(h, cudaMemcpy(out2, h->tc_stats + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) QB_CUDA_TRY(h, cudaMemset(h->tc_stats + 4, 0, 2 * sizeof(unsigned long long)));
+  for (int l = 0; l < 7; ++l) {
+    if (!h->lane[l]) continue;
+    uint64_t o2[2];
+    const int rc = qb200_debug_match_verify(h->lane[l], o2, reset);
+    if (rc) return rc;
+    out2[0] += o2[0]; out2[1] += o2[1];
+  }
   return QB200_OK;
 }
 

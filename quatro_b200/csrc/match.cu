@@ -13,6 +13,8 @@
 // folds.  Distances are the fused-multiply-add chain over d = 0..32 of (a_d - b_d)^2 and minima
 // carry the candidate index in the low word, so ties resolve to the lowest index -- exactly the
 // CPU oracle's arithmetic, hence bit-identical argmins.
+#include <stdlib.h>
+
 #include "handle.cuh"
 
 namespace qb {
@@ -389,11 +391,42 @@ int launch_match_exact(qb200_handle* h, int n_pairs, const int* only) {
   return QB200_OK;
 }
 
+// QB200_TC_VERIFY: count nearest-neighbour entries whose packed (distance bits, index) differ between the two K6 implementations
+__global__ void match_verify_kernel(const unsigned long long* __restrict__ rb_tc, const unsigned long long* __restrict__ cb_tc,
+                                    const unsigned long long* __restrict__ rb_ex, const unsigned long long* __restrict__ cb_ex,
+                                    const int* __restrict__ n_vox, int V, unsigned long long* __restrict__ stats) {
+  const int pair = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ns = n_vox[2 * pair], nt = n_vox[2 * pair + 1];
+  if (ns <= 0 || nt <= 0) return;
+  const int nr = ns, ncol = nt;  // rowbest: best target of every source point; colbest: best source of every target point
+  unsigned bad = 0, cnt = 0;
+  if (i < nr) { ++cnt; bad += rb_tc[(size_t)pair * V + i] != rb_ex[(size_t)pair * V + i]; }
+  if (i < ncol) { ++cnt; bad += cb_tc[(size_t)pair * V + i] != cb_ex[(size_t)pair * V + i]; }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    atomicAdd(stats + 4, (unsigned long long)cnt);
+    if (bad) atomicAdd(stats + 5, (unsigned long long)bad);
+  }
+}
+
 int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p) {
   if (n_pairs <= 0) return QB200_OK;
   const int V = h->V;
   int rc = h->force_exact_match ? launch_match_exact(h, n_pairs, nullptr) : launch_match_nn(h, n_pairs);
   if (rc) return rc;
+  static const int verify = (getenv("QB200_TC_VERIFY") && getenv("QB200_TC_VERIFY")[0] == '1') ? 1 : 0;
+  if (verify && !h->force_exact_match) {
+    // whole-batch self-check: keep the tensor-core results, redo every pair with the exact CUDA-core kernel, compare
+    unsigned long long* rb_tc = reinterpret_cast<unsigned long long*>(h->key_b);                   // the sort workspace is idle here
+    unsigned long long* cb_tc = rb_tc + (size_t)h->S * V;
+    QB_CUDA_TRY(h, cudaMemcpyAsync(rb_tc, h->rowbest, (size_t)n_pairs * V * 8, cudaMemcpyDeviceToDevice, h->stream));
+    QB_CUDA_TRY(h, cudaMemcpyAsync(cb_tc, h->colbest, (size_t)n_pairs * V * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = launch_match_exact(h, n_pairs, nullptr))) return rc;
+    const dim3 gv((V + 255) / 256, n_pairs);
+    match_verify_kernel<<<gv, 256, 0, h->stream>>>(rb_tc, cb_tc, h->rowbest, h->colbest, h->ctr.n_vox, V, h->tc_stats);
+    h->launches += 1;
+  }
   match_mutual_kernel<<<n_pairs, 1024, 0, h->stream>>>(h->rowbest, h->colbest, h->ctr.n_vox, V, h->mut_i, h->mut_j, h->ctr.n_mutual,
                                                        h->ctr.swapped, h->mark, h->partner);
   h->launches += 1;
