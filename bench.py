@@ -53,6 +53,13 @@ SCENES = {
     "dense": {"params": {"voxel_size": 0.22, "use_tuple_test": 0}, "cfg": {"max_corr": 8192},
               "what": "voxel 0.22 m, tuple test off (every mutual nearest neighbour is a correspondence): L ~ 3 k per pair; "
                       "other parameters = config/params.yaml"},
+    # BASELINE configs[4]: dense indoor pair, ~500 k points, 0.05 m voxel -- the configuration where K6 (N_src x N_tgt x 33 on the
+    # tensor cores) is the dominant work (~50 k voxel points per cloud: 66 * 50k^2 = 0.17 TFLOP per pair)
+    "indoor": {"params": {"voxel_size": 0.05, "normal_radius": 0.10, "fpfh_radius": 0.15, "noise_bound": 0.05, "cote_noise_bound": 0.05,
+                          "skip_flagged": 0},
+               "cfg": {"max_raw_points": 524288, "max_voxel_points": 65536},
+               "what": "voxel 0.05 m, normal_r 0.10, fpfh_r 0.15, noise_bound 0.05 (the reference's ratios of config/params.yaml:17-25 scaled to "
+                       "the voxel), floor kept (no ground removal indoors)"},
 }
 
 
@@ -106,11 +113,12 @@ def load_ncu_facts():
     return json.loads(f.read_text()) if f.exists() else None
 
 
-def gen_pairs(seeds):
+def gen_pairs(seeds, scene="street"):
     from quatro_b200 import synth
     synth._lib()  # build/load once before the threads start
+    make = (lambda s: synth.indoor_pair(int(s))[:2]) if scene == "indoor" else (lambda s: synth.outdoor_pair(int(s))[:2])
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
-        return list(ex.map(lambda s: synth.outdoor_pair(int(s))[:2], seeds))
+        return list(ex.map(make, seeds))
 
 
 class ClockSampler:
@@ -188,7 +196,7 @@ def run_reference(args, rank, world):
     cores = o.set_num_threads(_host_threads())   # torchrun exports OMP_NUM_THREADS=1: ask for every usable host core explicitly
     p = scene_params(args.scene)
     per_step = args.ref_pairs_per_step
-    pairs = gen_pairs(range(per_step))
+    pairs = gen_pairs(range(per_step), args.scene)
     for _ in range(max(args.warmup, 1)):
         o.register_pair(pairs[0][0], pairs[0][1], p)
     t0 = time.perf_counter()
@@ -218,11 +226,16 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     what = {"street": f"batch of {args.pairs} synthetic 64-ring pairs per GPU (BASELINE configs[2]; {world}x{args.pairs} global, 8 GPUs = configs[3])",
             "dense": f"batch of {args.pairs} synthetic 64-ring pairs per GPU, dense preset (L ~ 3 k correspondences per pair: the back end at "
-                     f"BASELINE's stated size; {world}x{args.pairs} global)"}[args.scene]
+                     f"BASELINE's stated size; {world}x{args.pairs} global)",
+            "indoor": f"{args.pairs} dense indoor pairs per GPU per step (BASELINE configs[4]: ~500 k points per scan, 0.05 m voxel, ~50 k voxel "
+                      f"points per cloud; {world}x{args.pairs} global)"}[args.scene]
+    scan = "500 k uniformly distributed rays in a furnished 18 x 18 x 3 m hall, 5 mm range noise" if args.scene == "indoor" else \
+        "64 rings x 1800 azimuths, ~111k returns, ground flagged"
     return {"workload": what, "scene": args.scene,
-            "pairs_per_gpu": args.pairs, "global_pairs": args.pairs * world, "scan": "64 rings x 1800 azimuths, ~111k returns, ground flagged",
+            "pairs_per_gpu": args.pairs, "global_pairs": args.pairs * world, "scan": scan,
             "params": SCENES[args.scene]["what"],
-            "l2": "inputs larger than L2 (~0.9 GB of raw scans per GPU per step vs 126 MB)",
+            "l2": "inputs larger than L2 (~0.9 GB of raw scans per GPU per step vs 126 MB)" if args.scene != "indoor" else
+                  f"inputs of {args.pairs} x 16 MB per step; L2 (126 MB) is flushed by the first pair's 0.8 GB of K6 operand traffic",
             "parallelism": f"dp{world}: independent pairs sharded across ranks, one NCCL all_gather of result records per step"}
 
 
@@ -267,7 +280,7 @@ def main():
 
     # ---- synthetic inputs: pinned host copy (e2e) and device-resident copy (value) ----
     def build_inputs(seeds):
-        prs = gen_pairs(seeds)
+        prs = gen_pairs(seeds, args.scene)
         total = sum(len(s) + len(t) for s, t in prs)
         host = torch.empty((total, 4), dtype=torch.float32).pin_memory()
         hv = host.numpy()
@@ -289,7 +302,8 @@ def main():
     d2h_bytes = P * RESULT_DTYPE.itemsize
 
     def make_handle(scene):
-        hd = Handle(device=local_rank, max_batch_slots=min(args.slots, P), **SCENES[scene]["cfg"])
+        slots = min(args.slots, P, 2) if scene == "indoor" else min(args.slots, P)   # indoor: 64 MB of operand images per cloud
+        hd = Handle(device=local_rank, max_batch_slots=slots, **SCENES[scene]["cfg"])
         hd.set_stream(stream.cuda_stream)
         return hd
 

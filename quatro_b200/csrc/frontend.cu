@@ -173,24 +173,40 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
     return;
   }
   int carry = 0, valid_total = 0;
-  for (int base = 0; base < n; base += blockDim.x) {
-    const int p = base + threadIdx.x;
-    uint64_t k = 0, kprev = 0;
-    bool valid = false;
-    if (p < n) {
-      k = keys[off + p] >> key_shift;  // mode 0: the low bits carry the point index
-      valid = mode == 0 ? (k & kVoxMask) != kVoxInvalid : (k & kCellMask) != kCellInvalid;
-      if (p > 0) kprev = keys[off + p - 1] >> key_shift;
+  // four consecutive keys per thread and round: a quarter of the block scans (three barriers each) of a key-per-thread loop
+  constexpr int kPer = 4;
+  for (int base = 0; base < n; base += kPer * blockDim.x) {
+    const int p0 = base + kPer * threadIdx.x;
+    uint64_t k[kPer];
+    bool valid[kPer];
+    int head[kPer], nh = 0, nv = 0;
+    uint64_t kprev = (p0 > 0 && p0 < n) ? keys[off + p0 - 1] >> key_shift : 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int p = p0 + j;
+      k[j] = 0; valid[j] = false; head[j] = 0;
+      if (p < n) {
+        k[j] = keys[off + p] >> key_shift;  // mode 0: the low bits carry the point index
+        valid[j] = mode == 0 ? (k[j] & kVoxMask) != kVoxInvalid : (k[j] & kCellMask) != kCellInvalid;
+        head[j] = (valid[j] && (p == 0 || k[j] != kprev)) ? 1 : 0;
+        kprev = k[j];
+      }
+      nh += head[j]; nv += valid[j] ? 1 : 0;
     }
-    const int head = (valid && (p == 0 || k != kprev)) ? 1 : 0;
-    // one scan for both counts: heads in the low half, valid points in the high half (<= 1024 each per chunk)
+    // one scan for both counts: heads in the low half, valid points in the high half (<= 4096 each per round)
     int both;
-    const int exb = block_excl_scan(head | ((valid ? 1 : 0) << 16), sm, &both);
-    const int ex = exb & 0xFFFF, tot = both & 0xFFFF, vtot = both >> 16;
-    const int rank = carry + ex;
-    if (head && rank <= V) {
-      starts[(size_t)cloud * (V + 1) + rank] = p;
-      if (mode == 1 && rank < V) cell_keys[(size_t)cloud * V + rank] = k & kCellMask;
+    const int exb = block_excl_scan(nh | (nv << 16), sm, &both);
+    int rank = carry + (exb & 0xFFFF);
+    const int tot = both & 0xFFFF, vtot = both >> 16;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (head[j]) {
+        if (rank <= V) {
+          starts[(size_t)cloud * (V + 1) + rank] = p0 + j;
+          if (mode == 1 && rank < V) cell_keys[(size_t)cloud * V + rank] = k[j] & kCellMask;
+        }
+        ++rank;
+      }
     }
     carry += tot;
     valid_total += vtot;

@@ -19,9 +19,10 @@
 // or with both distances ~0 (the literal expression is NaN -> false for coincident duplicates) evaluate the literal fp64
 // expression, so the adjacency is bit-identical to the fp64 reference.
 //
-// Work decomposition.  A CTA work item is 256 rows x 512 columns of the upper triangle; the 256 row points are staged in
-// shared memory as (-2a, |a|^2 - beta^2/4 | -2b, |b|^2 - beta^2/4), each lane keeps FOUR columns in registers (one
-// broadcast row load feeds 4 tests).  Result bits are shifted in from the SIGN BITS of t, s' and |t| - q with funnel
+// Work decomposition.  A CTA work item is 256 rows x 256 columns of the upper triangle; the 256 row points are staged in
+// shared memory as (-2a, |a|^2 - beta^2/4 | -2b, |b|^2 - beta^2/4), each lane keeps TWO columns in registers as one
+// packed pair (64 registers per thread: 8 CTAs = 32 warps per SM hide the dependent-FMA latency; four columns per lane ran at
+// 12 warps per SM and 67 % issue utilisation).  Result bits are shifted in from the SIGN BITS of t, s' and |t| - q with funnel
 // shifts (no compare / select per test); a warp shuffle transpose turns the per-column words into the row-major half,
 // so both halves of the symmetric matrix come out of one evaluation of the M pair tests.
 #include "handle.cuh"
@@ -29,7 +30,8 @@
 namespace qb {
 
 constexpr int kGW = 4;    // warps per CTA
-constexpr int kGC = 4;    // columns per lane: a warp covers 4 x 32 columns
+constexpr int kGC = 4;    // columns per lane (two packed pairs): a warp covers 4 x 32 columns
+constexpr int kGP = kGC / 2;
 constexpr int kGRB = 8;   // 32-row blocks per work item
 
 // the literal reference expression (fp64, no FMA contraction: library is built with -fmad=false)
@@ -91,27 +93,62 @@ struct GraphConst {
   double beta;
 };
 
+// work items (256 rows x 512 columns) of the upper triangle of one pair: row group rg meets column groups cg >= rg / 2
+__device__ __forceinline__ int graph_items(int L) {
+  if (L <= 0) return 0;
+  const int nb = (L + 31) >> 5, ncg = (nb + kGW * kGC - 1) / (kGW * kGC), nrg = (nb + kGRB - 1) / kGRB;
+  int t = 0;
+  for (int rg = 0; rg < nrg; ++rg) t += max(0, ncg - rg * kGRB / (kGW * kGC));
+  return t;
+}
+
+constexpr int kGraphMaxPairs = 2048;  // = the largest max_batch_slots qb200_create accepts
+
 __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __restrict__ ma, const float4* __restrict__ mb,
-                                                             const int* __restrict__ n_corr, int Lc, int W, GraphConst gc,
+                                                             const int* __restrict__ n_corr, int n_pairs, int Lc, int W, GraphConst gc,
                                                              uint32_t* __restrict__ adj) {
-  __shared__ float4 s_row[kGRB * 32][4];  // per row: (x,x,y,y) (z,z,n,n) of -2a | the same of -2b: operands of the packed FMAs
+  __shared__ float4 s_row[kGRB * 32][2];  // per row: (-2a, |a|^2 - beta^2/4) | (-2b, |b|^2 - beta^2/4); broadcast into both halves of the packed FMAs
   __shared__ float s_rm[kGRB * 32];
   __shared__ float s_mmax[kGRB];
-  const int pair = blockIdx.y;
-  const int L = n_corr[pair];
-  if (L <= 0) return;
-  const int nb = (L + 31) >> 5;                                 // 32-wide blocks per side
-  const int ncg = (nb + kGW * kGC - 1) / (kGW * kGC);           // column groups of 16 blocks
-  const int nrg = (nb + kGRB - 1) / kGRB;                       // row groups of 8 blocks
-  const float4* __restrict__ A = ma + (size_t)pair * Lc;
-  const float4* __restrict__ B = mb + (size_t)pair * Lc;
-  uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
+  __shared__ int s_pref[kGraphMaxPairs + 1];  // exclusive prefix of the pairs' item counts: the CTAs stride over ALL pairs' items,
+  __shared__ int s_scan[33];                  // so a pair with many correspondences is spread over the whole grid
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    int carry = 0;
+    for (int base = 0; base < n_pairs; base += kGW * 32) {
+      const int p = base + tid;
+      const int c = p < n_pairs ? graph_items(n_corr[p]) : 0;
+      int tot;
+      const int ex = block_excl_scan(c, s_scan, &tot);
+      if (p < n_pairs) s_pref[p] = carry + ex;
+      carry += tot;
+    }
+    if (tid == 0) s_pref[n_pairs] = carry;
+    __syncthreads();
+  }
+  const int total_items = s_pref[n_pairs];
 
-  for (int item = blockIdx.x; item < nrg * ncg; item += gridDim.x) {
-    const int rg = item / ncg, cg = item % ncg;
-    if (cg * (kGW * kGC) + kGW * kGC - 1 < rg * kGRB) continue;  // entirely below the diagonal (uniform per CTA)
+  for (int g = blockIdx.x; g < total_items; g += gridDim.x) {
+    int lo = 0, hi = n_pairs - 1;  // the pair that owns item g (CTA-uniform binary search)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_pref[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int pair = lo;
+    const int L = n_corr[pair];
+    const int nb = (L + 31) >> 5;                                 // 32-wide blocks per side
+    const int ncg = (nb + kGW * kGC - 1) / (kGW * kGC);           // column groups of 16 blocks
+    int item = g - s_pref[pair], rg = 0;
+    for (;; ++rg) {
+      const int cnt = max(0, ncg - rg * kGRB / (kGW * kGC));
+      if (item < cnt) break;
+      item -= cnt;
+    }
+    const int cg = rg * kGRB / (kGW * kGC) + item;
+    const float4* __restrict__ A = ma + (size_t)pair * Lc;
+    const float4* __restrict__ B = mb + (size_t)pair * Lc;
+    uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
     __syncthreads();
     for (int idx = tid; idx < kGRB * 32; idx += kGW * 32) {
       const int i = rg * (kGRB * 32) + idx;
@@ -121,10 +158,8 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
       const float nbn = fmaf(pb.z, pb.z, fmaf(pb.y, pb.y, pb.x * pb.x));
       const float ax = -2.0f * pa.x, ay = -2.0f * pa.y, az = -2.0f * pa.z, an = na - gc.hb2q;
       const float bx = -2.0f * pb.x, by = -2.0f * pb.y, bz = -2.0f * pb.z, bn = nbn - gc.hb2q;
-      s_row[idx][0] = make_float4(ax, ax, ay, ay);
-      s_row[idx][1] = make_float4(az, az, an, an);
-      s_row[idx][2] = make_float4(bx, bx, by, by);
-      s_row[idx][3] = make_float4(bz, bz, bn, bn);
+      s_row[idx][0] = make_float4(ax, ay, az, an);
+      s_row[idx][1] = make_float4(bx, by, bz, bn);
       s_rm[idx] = na + nbn;
     }
     __syncthreads();
@@ -163,12 +198,14 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
         qa[c] = gc.c1 * Mj[c];
         qk[c] = (gc.c2 * Mj[c] + gc.c3) * Mj[c];
       }
-      uint32_t wt[kGC] = {0u, 0u, 0u, 0u}, ws[kGC] = {0u, 0u, 0u, 0u}, wa[kGC] = {0u, 0u, 0u, 0u};
-      float smin[kGC] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
-      // the four columns as two packed pairs
-      f32x2 cax[2], cay[2], caz[2], can[2], cbx[2], cby[2], cbz[2], cbn[2], qa2[2], qk2[2];
+      uint32_t wt[kGC], ws[kGC], wa[kGC];
+      float smin[kGC];
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int c = 0; c < kGC; ++c) { wt[c] = ws[c] = wa[c] = 0u; smin[c] = 3.0e38f; }
+      // the columns as packed pairs
+      f32x2 cax[kGP], cay[kGP], caz[kGP], can[kGP], cbx[kGP], cby[kGP], cbz[kGP], cbn[kGP], qa2[kGP], qk2[kGP];
+#pragma unroll
+      for (int p = 0; p < kGP; ++p) {
         cax[p] = pk2(ca[2 * p].x, ca[2 * p + 1].x); cay[p] = pk2(ca[2 * p].y, ca[2 * p + 1].y);
         caz[p] = pk2(ca[2 * p].z, ca[2 * p + 1].z); can[p] = pk2(ca[2 * p].w, ca[2 * p + 1].w);
         cbx[p] = pk2(cb[2 * p].x, cb[2 * p + 1].x); cby[p] = pk2(cb[2 * p].y, cb[2 * p + 1].y);
@@ -176,14 +213,14 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
         qa2[p] = pk2(qa[2 * p], qa[2 * p + 1]); qk2[p] = pk2(qk[2 * p], qk[2 * p + 1]);
       }
       const f32x2 ntwob2 = pk2(-gc.twob2, -gc.twob2), nb4 = pk2(-gc.b4, -gc.b4);
-      const float4(* __restrict__ row_p)[4] = s_row + rbl * 32;
+      const float4(* __restrict__ row_p)[2] = s_row + rbl * 32;
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
-        const float4 r0 = row_p[r][0], r1 = row_p[r][1], r2 = row_p[r][2], r3 = row_p[r][3];
-        const f32x2 rax = pk2(r0.x, r0.y), ray = pk2(r0.z, r0.w), raz = pk2(r1.x, r1.y), ran = pk2(r1.z, r1.w);
-        const f32x2 rbx = pk2(r2.x, r2.y), rby = pk2(r2.z, r2.w), rbz = pk2(r3.x, r3.y), rbn = pk2(r3.z, r3.w);
+        const float4 r0 = row_p[r][0], r1 = row_p[r][1];
+        const f32x2 rax = pk2(r0.x, r0.x), ray = pk2(r0.y, r0.y), raz = pk2(r0.z, r0.z), ran = pk2(r0.w, r0.w);
+        const f32x2 rbx = pk2(r1.x, r1.x), rby = pk2(r1.y, r1.y), rbz = pk2(r1.z, r1.z), rbn = pk2(r1.w, r1.w);
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < kGP; ++p) {
           const f32x2 Ap = fma2(rax, cax[p], fma2(ray, cay[p], fma2(raz, caz[p], add2(ran, can[p]))));
           const f32x2 Bp = fma2(rbx, cbx[p], fma2(rby, cby[p], fma2(rbz, cbz[p], add2(rbn, cbn[p]))));
           const f32x2 D = sub2(Ap, Bp), sp = add2(Ap, Bp);
@@ -218,9 +255,9 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
           sm = 3.0e38f;
 #pragma unroll 1
           for (int r = 0; r < 32; ++r) {
-            const float4 r0 = row_p[r][0], r1 = row_p[r][1], r2 = row_p[r][2], r3 = row_p[r][3];
-            const float Ap = fmaf(r0.x, ca[c].x, fmaf(r0.z, ca[c].y, fmaf(r1.x, ca[c].z, r1.z + ca[c].w)));
-            const float Bp = fmaf(r2.x, cb[c].x, fmaf(r2.z, cb[c].y, fmaf(r3.x, cb[c].z, r3.z + cb[c].w)));
+            const float4 r0 = row_p[r][0], r1 = row_p[r][1];
+            const float Ap = fmaf(r0.x, ca[c].x, fmaf(r0.y, ca[c].y, fmaf(r0.z, ca[c].z, r0.w + ca[c].w)));
+            const float Bp = fmaf(r1.x, cb[c].x, fmaf(r1.y, cb[c].y, fmaf(r1.z, cb[c].z, r1.w + cb[c].w)));
             if (r != lane) sm = fminf(sm, Ap + Bp);
           }
         }
@@ -296,11 +333,9 @@ int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2)
   gc.c3 = (float)(46.0 * u * beta * beta * 1.02);
   gc.two_b2_slack = (float)(2.0 * beta * beta * 1.00001);
   // capacity-sized grid: Lc/256 x Lc/512 work items per pair; few pairs -> more CTAs per pair
-  int gx = 8 * 148 / n_pairs;  // >= 8 CTAs (32 warps) per SM when every pair is large; idle CTAs of small pairs exit at once
-  gx = gx < 8 ? 8 : (gx > 128 ? 128 : gx);
-  const dim3 g(gx, n_pairs);
+  const dim3 g(148 * 4);  // one wave of resident CTAs (128 registers x 128 threads: 4 per SM) striding over every pair's work items
   cudaEventRecord(h->kev[2], h->stream);
-  tim_graph_kernel<<<g, kGW * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, h->Lc, h->W, gc, h->adj);
+  tim_graph_kernel<<<g, kGW * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, n_pairs, h->Lc, h->W, gc, h->adj);
   cudaEventRecord(h->kev[3], h->stream);
   h->kev_armed[1] = 1;
   const dim3 gd((h->Lc + 7) / 8, n_pairs);

@@ -214,24 +214,31 @@ __global__ void __launch_bounds__(1024) match_mutual_kernel(const unsigned long 
 // shared memory with coalesced loads (two chunks ahead); lanes 0..2 each own one coordinate and run its serial addition
 // chain from shared memory (a 4-cycle dependent add per point instead of a shuffle round trip).
 __global__ void __launch_bounds__(32) cloud_mean_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V, float* __restrict__ mean) {
-  __shared__ float buf[2][3][32];
+  constexpr int kChunk = 4;                 // 32-point rows per round: 4 loads per lane in flight cover the L2 / DRAM latency
+  __shared__ float buf[2][3][32 * kChunk];
   const int cloud = blockIdx.x, lane = (int)lane_id();
   const int n = n_pts[cloud];
   const float4* __restrict__ p = pts + (size_t)cloud * V;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   float acc = 0.f;
-  float4 nxt = lane < n ? p[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = 0, it = 0; base < n; base += 32, ++it) {
+  float4 nxt[kChunk];
+#pragma unroll
+  for (int c = 0; c < kChunk; ++c) nxt[c] = 32 * c + lane < n ? p[32 * c + lane] : zero;
+  for (int base = 0, it = 0; base < n; base += 32 * kChunk, ++it) {
     const int b = it & 1;
-    buf[b][0][lane] = nxt.x; buf[b][1][lane] = nxt.y; buf[b][2][lane] = nxt.z;
-    const int i = base + 32 + lane;
-    nxt = i < n ? p[i] : make_float4(0.f, 0.f, 0.f, 0.f);  // in flight while this chunk is summed
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c) {
+      buf[b][0][32 * c + lane] = nxt[c].x; buf[b][1][32 * c + lane] = nxt[c].y; buf[b][2][32 * c + lane] = nxt[c].z;
+      const int i = base + 32 * kChunk + 32 * c + lane;
+      nxt[c] = i < n ? p[i] : zero;          // in flight while this round is summed
+    }
     __syncwarp();
-    const int lim = min(32, n - base);
+    const int lim = min(32 * kChunk, n - base);
     if (lane < 3) {
       const float* __restrict__ src = buf[b][lane];
-      if (lim == 32) {
+      if (lim == 32 * kChunk) {
 #pragma unroll
-        for (int l = 0; l < 32; ++l) acc = acc + src[l];
+        for (int l = 0; l < 32 * kChunk; ++l) acc = acc + src[l];
       } else {
         for (int l = 0; l < lim; ++l) acc = acc + src[l];
       }

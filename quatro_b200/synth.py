@@ -25,6 +25,9 @@ def _lib():
         lib.qb200_synth_outdoor_pair_ex.restype = C.c_int
         lib.qb200_synth_outdoor_pair_ex.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(Scene), C.c_void_p, C.POINTER(C.c_int),
                                                     C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+        lib.qb200_synth_indoor_pair.restype = C.c_int
+        lib.qb200_synth_indoor_pair.argtypes = [C.c_uint64, C.c_int, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
+                                                C.POINTER(C.c_int), C.c_int, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -49,6 +52,18 @@ def outdoor_pair(seed: int, rings: int = 64, azimuths: int = 1800, scene=STREET)
     sc = Scene(*scene)
     _lib().qb200_synth_outdoor_pair_ex(seed, rings, azimuths, C.byref(sc), src.ctypes.data, C.byref(ns), tgt.ctypes.data, C.byref(nt), cap,
                                        T.ctypes.data)
+    return src[: ns.value].copy(), tgt[: nt.value].copy(), T.reshape(4, 4).T.copy()
+
+
+def indoor_pair(seed: int, n_rays: int = 500000, extent: float = 9.0, n_furniture: int = 60):
+    """Dense indoor pair (BASELINE configs[4]): a furnished hall scanned with n_rays uniformly distributed rays from two poses,
+    5 mm range noise, nothing flagged (the floor stays in).  Returns (src (n,4), tgt (m,4), T_gt 4x4) with p_tgt = T_gt @ p_src."""
+    src = np.zeros((n_rays, 4), np.float32)
+    tgt = np.zeros((n_rays, 4), np.float32)
+    ns, nt = C.c_int(0), C.c_int(0)
+    T = np.zeros(16, np.float64)
+    _lib().qb200_synth_indoor_pair(seed, n_rays, extent, n_furniture, src.ctypes.data, C.byref(ns), tgt.ctypes.data, C.byref(nt), n_rays,
+                                   T.ctypes.data)
     return src[: ns.value].copy(), tgt[: nt.value].copy(), T.reshape(4, 4).T.copy()
 
 

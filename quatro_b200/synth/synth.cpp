@@ -189,9 +189,117 @@ int scan(const Scene& s, const Pose& P, uint64_t noise_seed, int rings, int azim
   return n;
 }
 
+// nearest hit from INSIDE the hull box (the ray leaves it through a wall, the floor or the ceiling) or on an interior object
+double cast_indoor(const Scene& s, const Box& hull, const double o[3], const double d[3]) {
+  double best = 1e30;
+  for (int a = 0; a < 3; ++a) {
+    if (std::fabs(d[a]) < 1e-12) continue;
+    const double t = ((d[a] > 0 ? hull.hi[a] : hull.lo[a]) - o[a]) / d[a];
+    if (t > 1e-9 && t < best) best = t;
+  }
+  int kind;
+  const double t_obj = cast(s, o, d, kind);   // boxes + cylinders (the ground-plane test of cast() never wins: it lies below the floor)
+  if (kind == 1 && t_obj < best) best = t_obj;
+  return best;
+}
+
+int scan_indoor(const Scene& s, const Box& hull, const Pose& P, uint64_t noise_seed, int n_rays, double sigma, double rmin, float* out4, int cap) {
+  int n = 0;
+  const double o[3] = {P.t[0], P.t[1], P.t[2]};
+  const double golden = M_PI * (3.0 - std::sqrt(5.0));
+  for (int r = 0; r < n_rays; ++r) {
+    // Fibonacci sphere: uniform directions in the SENSOR frame
+    const double z = 1.0 - 2.0 * (r + 0.5) / n_rays, rad = std::sqrt(std::max(0.0, 1.0 - z * z)), th = golden * r;
+    const double dl[3] = {rad * std::cos(th), rad * std::sin(th), z};
+    const double dw[3] = {P.R[0] * dl[0] + P.R[1] * dl[1] + P.R[2] * dl[2], P.R[3] * dl[0] + P.R[4] * dl[1] + P.R[5] * dl[2],
+                          P.R[6] * dl[0] + P.R[7] * dl[1] + P.R[8] * dl[2]};
+    double t = cast_indoor(s, hull, o, dw);
+    if (t > 1e29) continue;
+    uint32_t rb[4];
+    Rng::philox(noise_seed, (uint64_t)r, rb);
+    const double u1 = (rb[0] + 0.5) / 4294967296.0, u2 = (rb[1] + 0.5) / 4294967296.0;
+    t += sigma * std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
+    if (t < rmin) continue;
+    if (n < cap) {
+      out4[4 * n + 0] = (float)(t * dl[0]);
+      out4[4 * n + 1] = (float)(t * dl[1]);
+      out4[4 * n + 2] = (float)(t * dl[2]);
+      out4[4 * n + 3] = 1.0f;   // indoors the floor stays in (no Patchwork): nothing is flagged
+    }
+    ++n;
+  }
+  return n;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Dense indoor pair (BASELINE configs[4] / SURVEY.md 8d config 5): a hall of `extent` x `extent` x 3 m with interior wall slabs
+// (doorways left open), furniture boxes and columns, scanned from two poses with n_rays uniformly distributed rays each
+// (sigma = 5 mm).  T_gt: column-major 4x4 with p_tgt = T_gt * p_src.  Returns 0, or 1 if cap was too small.
+int qb200_synth_indoor_pair(uint64_t seed, int n_rays, double extent, int n_furniture, float* src4, int* n_src, float* tgt4, int* n_tgt, int cap,
+                            double* T_gt) {
+  Rng g(seed * 0x9E3779B97F4A7C15ull + 0x7654321ull);
+  const double h = 1.2;
+  const double yaw = g.uni(-M_PI, M_PI), dist = g.uni(0.0, 1.5), dir = g.uni(-M_PI, M_PI);
+  const double roll = g.uni(-1.0, 1.0) * M_PI / 180.0, pitch = g.uni(-1.0, 1.0) * M_PI / 180.0, dz = g.uni(-0.05, 0.05);
+  const Pose Ps = make_pose(0, 0, 0, 0, 0, h);
+  const Pose Pt = make_pose(yaw, pitch, roll, dist * std::cos(dir), dist * std::sin(dir), h + dz);
+  const double sensors[2][2] = {{Ps.t[0], Ps.t[1]}, {Pt.t[0], Pt.t[1]}};
+  const Box hull{{-extent, -extent, 0.0}, {extent, extent, 3.0}};
+  Scene s;
+  auto clear_of_sensors = [&](const Box& b, double margin) {
+    for (int k = 0; k < 2; ++k)
+      if (footprint_dist(b, sensors[k][0], sensors[k][1]) < margin) return false;
+    return true;
+  };
+  // interior walls: slabs 0.15 m thick along x or y, floor to ceiling, each with a doorway gap
+  int guard = 0;
+  const int n_walls = 4 + (int)(g.uni() * 4.0);
+  while ((int)s.boxes.size() < 2 * n_walls && guard++ < 10000) {
+    const bool along_x = g.uni() < 0.5;
+    const double c = g.uni(-0.8 * extent, 0.8 * extent), a0 = g.uni(-extent, 0.0), a1 = g.uni(0.0, extent), door = g.uni(a0 + 0.5, a1 - 1.5);
+    Box b1, b2;
+    if (along_x) { b1 = Box{{a0, c - 0.075, 0.0}, {door, c + 0.075, 3.0}}; b2 = Box{{door + 1.0, c - 0.075, 0.0}, {a1, c + 0.075, 3.0}}; }
+    else { b1 = Box{{c - 0.075, a0, 0.0}, {c + 0.075, door, 3.0}}; b2 = Box{{c - 0.075, door + 1.0, 0.0}, {c + 0.075, a1, 3.0}}; }
+    if (!clear_of_sensors(b1, 0.8) || !clear_of_sensors(b2, 0.8)) continue;
+    s.boxes.push_back(b1); s.boxes.push_back(b2);
+  }
+  const int n_wall_boxes = (int)s.boxes.size();
+  guard = 0;
+  while ((int)s.boxes.size() < n_wall_boxes + n_furniture && guard++ < 100000) {
+    const double cx = g.uni(-extent, extent), cy = g.uni(-extent, extent);
+    const double hx = g.uni(0.15, 0.9), hy = g.uni(0.15, 0.9), z0 = g.uni() < 0.8 ? 0.0 : g.uni(0.5, 1.5), hh = g.uni(0.3, 1.8);
+    Box b{{cx - hx, cy - hy, z0}, {cx + hx, cy + hy, std::min(3.0, z0 + hh)}};
+    if (!clear_of_sensors(b, 0.6)) continue;
+    s.boxes.push_back(b);
+  }
+  guard = 0;
+  const int n_col = n_furniture / 4;
+  while ((int)s.cyls.size() < n_col && guard++ < 100000) {
+    Cyl c{g.uni(-extent, extent), g.uni(-extent, extent), g.uni(0.05, 0.3), 0.0, g.uni(0.8, 3.0)};
+    bool ok = true;
+    for (int k = 0; k < 2; ++k)
+      if (std::hypot(c.cx - sensors[k][0], c.cy - sensors[k][1]) < 0.8) ok = false;
+    if (ok) s.cyls.push_back(c);
+  }
+  const int ns = scan_indoor(s, hull, Ps, seed * 2 + 2000003ull, n_rays, 0.005, 0.3, src4, cap);
+  const int nt = scan_indoor(s, hull, Pt, seed * 2 + 2000004ull, n_rays, 0.005, 0.3, tgt4, cap);
+  *n_src = std::min(ns, cap);
+  *n_tgt = std::min(nt, cap);
+  double Rt[9], tt[3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rt[3 * r + c] = Pt.R[3 * c + r];
+  for (int r = 0; r < 3; ++r) tt[r] = -(Rt[3 * r] * Pt.t[0] + Rt[3 * r + 1] * Pt.t[1] + Rt[3 * r + 2] * Pt.t[2]);
+  for (int i = 0; i < 16; ++i) T_gt[i] = 0;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T_gt[4 * c + r] = Rt[3 * r] * Ps.R[c] + Rt[3 * r + 1] * Ps.R[3 + c] + Rt[3 * r + 2] * Ps.R[6 + c];
+    T_gt[12 + r] = Rt[3 * r] * Ps.t[0] + Rt[3 * r + 1] * Ps.t[1] + Rt[3 * r + 2] * Ps.t[2] + tt[r];
+  }
+  T_gt[15] = 1;
+  return (ns > cap || nt > cap) ? 1 : 0;
+}
 
 // Scene / motion knobs of the outdoor generator.  {30, 50, 15, 70, 10, 0.02} is the street scene of BASELINE configs[1..3];
 // the "dense" preset (more clutter, a revisit within ~1 m, see synth.py) yields the ~3 k correspondences per pair that
