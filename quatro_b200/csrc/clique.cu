@@ -91,7 +91,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One warp per pair; lane l owns adjacency words l, l + 32, ... (WPL of them, W <= 32 * WPL) of the row being peeled.
+// One warp per pair; lane l owns the nwl = ceil(nbw / 32) CONSECUTIVE adjacency words l * nwl .. l * nwl + nwl - 1 of the row being
+// peeled (nwl <= WPL, W <= 32 * WPL), so the ascending neighbour list needs one warp scan per step whatever L is.
 // smem: bin (int x (Lc + 2)), above (u32 x 32*WPL), deg / pos / vert / nbl / mrk (u16 x Lc each), rows (u32 x row_words):
 // the whole adjacency when L * ceil(L/32) <= row_words, otherwise a ring of kRing prefetched rows.
 template <int WPL>
@@ -141,18 +142,18 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
   warp_bucket_sort(deg, L, md, bin, pos, vert);
 
   // ---- peel ----
-#pragma unroll
-  for (int k = 0; k < WPL; ++k) {
-    const int lo = (lane + 32 * k) * 32;
-    above[lane + 32 * k] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
+  for (int wd = lane; wd < 32 * WPL; wd += 32) {
+    const int lo = wd * 32;
+    above[wd] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
   }
+  const int w0 = lane * nwl;  // first adjacency word of this lane
   auto fetch = [&](int p) {  // prefetch the row of the vertex that sits at position p right now into its ring slot
     if (p < L) {
       const int x = vert[p], sl = p % kRing;
       if (lane == 0) ring_tag[sl] = x;
 #pragma unroll
       for (int k = 0; k < WPL; ++k)
-        if (lane + 32 * k < nbw) cp_async4(rows + sl * W + lane + 32 * k, G + (size_t)x * W + lane + 32 * k);
+        if (k < nwl && w0 + k < nbw) cp_async4(rows + sl * W + w0 + k, G + (size_t)x * W + w0 + k);
     }
     cp_async_commit();
   };
@@ -166,17 +167,17 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
     uint32_t w[WPL];
     if (cached) {
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) w[k] = lane + 32 * k < nbw ? rows[v * nbw + lane + 32 * k] : 0u;
+      for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? rows[v * nbw + w0 + k] : 0u;
     } else {
       cp_async_wait<kRing - 1>();  // the group of position i has landed
       __syncwarp();
       const int sl = i % kRing;
       if (ring_tag[sl] == v) {  // positions inside the current bucket are final: the prefetch usually holds the right row
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) w[k] = lane + 32 * k < nbw ? rows[sl * W + lane + 32 * k] : 0u;
+        for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? rows[sl * W + w0 + k] : 0u;
       } else {
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) w[k] = lane + 32 * k < nbw ? G[(size_t)v * W + lane + 32 * k] : 0u;
+        for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? G[(size_t)v * W + w0 + k] : 0u;
       }
       __syncwarp();
       fetch(i + kRing);
@@ -190,21 +191,25 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
       cur = dv;
       __syncwarp();
     }
-    // live neighbours (deg[u] > deg[v]) -> ascending list; word order = (k, lane)
-    int cnt = 0;
+    // live neighbours (deg[u] > deg[v]) -> ascending list; word order = (lane, k)
+    int c = 0;
 #pragma unroll
     for (int k = 0; k < WPL; ++k) {
-      if (k < nwl) {
-        uint32_t x = w[k] & above[lane + 32 * k];
-        int tot;
-        int off = cnt + warp_excl_scan(__popc(x), &tot);
-        const int basebit = (lane + 32 * k) * 32;
+      w[k] = (k < nwl && w0 + k < nbw) ? (w[k] & above[w0 + k]) : 0u;
+      c += __popc(w[k]);
+    }
+    int cnt;
+    int off = warp_excl_scan(c, &cnt);
+    if (cnt != 0) {
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        uint32_t x = w[k];
+        const int basebit = (w0 + k) * 32;
         while (x) {
           const int b = __ffs(x) - 1;
           x &= x - 1;
           nbl[off++] = (unsigned short)(basebit + b);
         }
-        cnt += tot;
       }
     }
     if (cnt == 0) continue;
