@@ -468,8 +468,9 @@ template <int WPL>
 static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
   const int Lc = h->Lc, W = h->W;
   const size_t fixed = (size_t)(Lc + 2) * sizeof(int) + (size_t)32 * WPL * sizeof(uint32_t) + (size_t)5 * Lc * sizeof(unsigned short);
-  // rows: as much of the 200 KB budget as is left (whole graphs up to L ~ 1000 at max_corr 4096), at least the prefetch ring
-  size_t row_words = (200 * 1024 - fixed) / 4;
+  // rows: what is left of a 128 KB budget (whole graphs up to L ~ 740 at max_corr 4096; the other ~100 KB of the SM stay free for the
+  // dense kernels of the other lanes), at least the prefetch ring
+  size_t row_words = fixed < 120 * 1024 ? (128 * 1024 - fixed) / 4 : 0;
   if (row_words < (size_t)kRing * W) row_words = (size_t)kRing * W;
   if (row_words > (size_t)Lc * W) row_words = (size_t)Lc * W;
   const size_t smem = fixed + row_words * 4;
