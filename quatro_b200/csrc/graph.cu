@@ -25,13 +25,14 @@
 // 12 warps per SM and 67 % issue utilisation).  Result bits are shifted in from the SIGN BITS of t, s' and |t| - q with funnel
 // shifts (no compare / select per test); a warp shuffle transpose turns the per-column words into the row-major half,
 // so both halves of the symmetric matrix come out of one evaluation of the M pair tests.
+#include <stdlib.h>
+
 #include "handle.cuh"
 
 namespace qb {
 
 constexpr int kGW = 4;    // warps per CTA
-constexpr int kGC = 4;    // columns per lane (two packed pairs): a warp covers 4 x 32 columns
-constexpr int kGP = kGC / 2;
+// columns per lane = template parameter GC (2 or 4: one or two packed pairs; a warp covers GC x 32 columns)
 constexpr int kGRB = 8;   // 32-row blocks per work item
 
 // the literal reference expression (fp64, no FMA contraction: library is built with -fmad=false)
@@ -94,6 +95,7 @@ struct GraphConst {
 };
 
 // work items (256 rows x 512 columns) of the upper triangle of one pair: row group rg meets column groups cg >= rg / 2
+template <int kGC>
 __device__ __forceinline__ int graph_items(int L) {
   if (L <= 0) return 0;
   const int nb = (L + 31) >> 5, ncg = (nb + kGW * kGC - 1) / (kGW * kGC), nrg = (nb + kGRB - 1) / kGRB;
@@ -104,9 +106,11 @@ __device__ __forceinline__ int graph_items(int L) {
 
 constexpr int kGraphMaxPairs = 2048;  // = the largest max_batch_slots qb200_create accepts
 
-__global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __restrict__ ma, const float4* __restrict__ mb,
+template <int kGC>
+__global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(const float4* __restrict__ ma, const float4* __restrict__ mb,
                                                              const int* __restrict__ n_corr, int n_pairs, int Lc, int W, GraphConst gc,
                                                              uint32_t* __restrict__ adj) {
+  constexpr int kGP = kGC / 2;
   __shared__ float4 s_row[kGRB * 32][2];  // per row: (-2a, |a|^2 - beta^2/4) | (-2b, |b|^2 - beta^2/4); broadcast into both halves of the packed FMAs
   __shared__ float s_rm[kGRB * 32];
   __shared__ float s_mmax[kGRB];
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(kGW * 32) tim_graph_kernel(const float4* __res
     int carry = 0;
     for (int base = 0; base < n_pairs; base += kGW * 32) {
       const int p = base + tid;
-      const int c = p < n_pairs ? graph_items(n_corr[p]) : 0;
+      const int c = p < n_pairs ? graph_items<kGC>(n_corr[p]) : 0;
       int tot;
       const int ex = block_excl_scan(c, s_scan, &tot);
       if (p < n_pairs) s_pref[p] = carry + ex;
@@ -333,9 +337,12 @@ int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2)
   gc.c3 = (float)(46.0 * u * beta * beta * 1.02);
   gc.two_b2_slack = (float)(2.0 * beta * beta * 1.00001);
   // capacity-sized grid: Lc/256 x Lc/512 work items per pair; few pairs -> more CTAs per pair
-  const dim3 g(148 * 4);  // one wave of resident CTAs (128 registers x 128 threads: 4 per SM) striding over every pair's work items
+  // one wave of resident CTAs striding over every pair's work items.  QB200_GRAPH_COLS=2 selects the 2-columns-per-lane variant
+  // (64 registers, 8 CTAs per SM) for A/B runs; results are identical
+  static const int cols = (getenv("QB200_GRAPH_COLS") && getenv("QB200_GRAPH_COLS")[0] == '2') ? 2 : 4;
   cudaEventRecord(h->kev[2], h->stream);
-  tim_graph_kernel<<<g, kGW * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, n_pairs, h->Lc, h->W, gc, h->adj);
+  if (cols == 2) tim_graph_kernel<2><<<dim3(148 * 8), kGW * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, n_pairs, h->Lc, h->W, gc, h->adj);
+  else tim_graph_kernel<4><<<dim3(148 * 4), kGW * 32, 0, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, n_pairs, h->Lc, h->W, gc, h->adj);
   cudaEventRecord(h->kev[3], h->stream);
   h->kev_armed[1] = 1;
   const dim3 gd((h->Lc + 7) / 8, n_pairs);

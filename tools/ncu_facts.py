@@ -57,7 +57,7 @@ def main():
                     pass
         if key not in best or rec.get("gpu__time_duration.sum", 0) > best[key].get("gpu__time_duration.sum", 0):
             best[key] = rec
-    line = json.loads(Path(bench_json).read_text().strip().splitlines()[-1])
+    line = json.loads([ln for ln in Path(bench_json).read_text().splitlines() if ln.startswith("{")][-1])   # ncu prints its own lines around it
     facts = {"source": {"report": Path(rep).name, "bench_line": Path(bench_json).name, "bench_config": line["config"]["workload"]}}
     for key, rec in best.items():
         f = {"launch": rec["launch"], "duration_ms": rec.get("gpu__time_duration.sum"),
