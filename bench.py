@@ -297,10 +297,6 @@ def main():
             pa_d[i].src, pa_d[i].n_src, pa_d[i].tgt, pa_d[i].n_tgt = dvc.data_ptr() + so * 16, sn, dvc.data_ptr() + to * 16, tn
         return prs, host, dvc, pa_h, pa_d, total
 
-    pairs, host, dvc, pa_host, pa_dev, total_pts = build_inputs(range(rank * P, rank * P + P))
-    h2d_bytes = total_pts * 16
-    d2h_bytes = P * RESULT_DTYPE.itemsize
-
     def make_handle(scene):
         slots = min(args.slots, P, 2) if scene == "indoor" else min(args.slots, P)   # indoor: 64 MB of operand images per cloud
         hd = Handle(device=local_rank, max_batch_slots=slots, **SCENES[scene]["cfg"])
@@ -308,7 +304,12 @@ def main():
         return hd
 
     handle = make_handle(args.scene)
-    numa_cores = handle.bind_numa()   # launches and pinned copies from the GPU's own socket
+    # bind this rank's host thread to the GPU's NUMA node BEFORE the pinned input buffers are allocated and filled (first touch puts
+    # the pages on the local socket): launches and host->device copies then never cross the inter-socket link
+    numa_cores = handle.bind_numa()
+    pairs, host, dvc, pa_host, pa_dev, total_pts = build_inputs(range(rank * P, rank * P + P))
+    h2d_bytes = total_pts * 16
+    d2h_bytes = P * RESULT_DTYPE.itemsize
     p = scene_params(args.scene)
     out = np.zeros(P, RESULT_DTYPE)
     out_all = np.zeros(world * P, RESULT_DTYPE) if world > 1 else None

@@ -12,16 +12,16 @@
 // The reference runs the start vertices on 12 racy OpenMP threads; like the CPU oracle these kernels
 // reproduce the SEQUENTIAL semantics bit for bit.  One CTA per registration pair:
 //
-//   kcore_warp_kernel  The peel stays a sequence of L steps (the order is the output) run by ONE WARP per pair without any
-//     block barrier; a step is warp-wide: lane l owns WPL consecutive adjacency words of the row being peeled; `above`
-//     (bitset of vertices whose current degree exceeds the current level) turns "neighbour with deg[u] > deg[v]" into one
-//     AND; the surviving neighbours are expanded to an ascending list with one warp scan and every neighbour's bucket move
-//     is done by its own lane.  Moves into different buckets commute; the members of one bucket (same current degree) must
-//     be applied in id order: their ranks come from __match_any_sync, and with the ranks known the moves of a group have a
-//     closed form (member t lands on slot bin+t; the non-members displaced from the target slots take the old slots of the
-//     members that sat outside, found by a short chain walk) -- no serial replay.  Rows come from shared memory: the whole
-//     adjacency when it fits (L up to ~1000), otherwise a ring of 8 rows prefetched with cp.async along the peel order.  (A CTA-wide variant with 4-8 warps and
-//     five block barriers per step measured 3000 cycles per step -- barrier-bound -- and was dropped)
+//   kcore_kernel  The peel stays a sequence of L steps (the order is the output); a step is parallel inside: `above` (bitset of
+//     vertices whose current degree exceeds the current level) turns "neighbour with deg[u] > deg[v]" into one AND; the surviving
+//     neighbours are expanded to an ascending list with one warp scan and every neighbour's bucket move is done by its own lane.
+//     Moves into different buckets commute; the members of one bucket (same current degree) must be applied in id order: their
+//     ranks come from __match_any_sync, and with the ranks known the moves of a group have a closed form (member t lands on slot
+//     bin+t; the non-members displaced from the target slots take the old slots of the members that sat outside, found by a short
+//     chain walk) -- no serial replay.  Small graphs (L up to ~700) run on ONE warp with the whole adjacency in shared memory and
+//     no block barrier; large graphs split the degree buckets over four warps by residue class (one block barrier per step) and
+//     stream rows through a cp.async ring.  (A variant with thread-per-word ownership and five block barriers per step measured
+//     3000 cycles per step -- barrier-bound -- and was dropped)
 //   clique_cta_kernel  The start vertices are tried SPECULATIVELY, one per warp, against the current incumbent size
 //     mc; results are committed in sequential order (the first warp that beats mc wins, later warps are discarded and
 //     redone), which is exactly the sequential outcome because a descent only depends on mc at its start.  Vertices
@@ -81,7 +81,7 @@ __device__ void warp_bucket_sort(const unsigned short* __restrict__ key, int n, 
   __syncwarp();
 }
 
-constexpr int kRing = 8;  // rows in flight when the adjacency does not fit in shared memory (covers DRAM latency at ~8 steps)
+constexpr int kRing = 16;  // rows in flight when the adjacency does not fit in shared memory (covers the DRAM latency at ~15 steps)
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -91,28 +91,115 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One warp per pair; lane l owns the nwl = ceil(nbw / 32) CONSECUTIVE adjacency words l * nwl .. l * nwl + nwl - 1 of the row being
-// peeled (nwl <= WPL, W <= 32 * WPL), so the ascending neighbour list needs one warp scan per step whatever L is.
-// smem: bin (int x (Lc + 2)), above (u32 x 32*WPL), deg / pos / vert / nbl / mrk (u16 x Lc each), rows (u32 x row_words):
-// the whole adjacency when L * ceil(L/32) <= row_words, otherwise a ring of kRing prefetched rows.
+constexpr int kKcWarps = 4;  // warps of the k-core CTA (large graphs: one degree class per warp; small graphs: warp 0 alone)
+
+// Bucket moves of one warp's neighbour list nbl[0..cnt), 32 neighbours at a time.  Moves into different buckets commute; the members
+// u_0 < u_1 < ... of one bucket (same current degree, ranks from __match_any_sync) are applied in id order by pmc: "swap u_t with
+// the vertex on slot bin + t".  That sequence has a closed form: u_t ends on slot bin + t, and the vertex y that is not a member
+// but sat on one of the target slots ends on the old slot of the member found by walking  slot s -> member that sat there -> its
+// target slot -> ... ; each member that sat OUTSIDE the target slots walks that chain backwards from its own rank and hands its
+// old slot to the non-member it reaches (verified against the sequential mechanic, tests + DESIGN.md 5.3).
+// above_own: the calling warp's bitset (neighbours leave it); add_next: bitset that receives neighbours whose new degree is still
+// above the level (the same bitset in the single-warp path, the next lower degree class otherwise).
+__device__ __forceinline__ void kcore_apply_moves(const unsigned short* __restrict__ nbl, int cnt, int dv, int* __restrict__ bin,
+                                                  unsigned short* __restrict__ deg, unsigned short* __restrict__ pos,
+                                                  unsigned short* __restrict__ vert, unsigned short* __restrict__ mrk,
+                                                  uint32_t* __restrict__ above_own, uint32_t* __restrict__ add_next, bool classes) {
+  const int lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int c0 = 0; c0 < cnt; c0 += 32) {
+    const int e = c0 + lane;
+    const bool act = e < cnt;
+    const int u = act ? nbl[e] : 0;
+    const int du = act ? deg[u] : -1 - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, du);
+    const int rank = __popc(grp & lt), m = __popc(grp);
+    int b0 = 0, pu = 0;
+    if (act) {
+      b0 = bin[du];
+      pu = pos[u];
+      mrk[u] = (unsigned short)(rank + 1);
+    }
+    __syncwarp();
+    int y = -1;  // the non-member that moves to this member's old slot
+    if (act && pu >= b0 + m) {
+      int curk = rank;
+      for (;;) {
+        y = vert[b0 + curk];
+        const int r = mrk[y];
+        if (r == 0) break;
+        curk = r - 1;
+      }
+    }
+    __syncwarp();
+    if (act) {
+      vert[b0 + rank] = (unsigned short)u; pos[u] = (unsigned short)(b0 + rank);
+      if (y >= 0) { vert[pu] = (unsigned short)y; pos[y] = (unsigned short)pu; }
+      mrk[u] = 0;
+      deg[u] = (unsigned short)(du - 1);
+      const uint32_t bit = 1u << (u & 31);
+      if (classes) {
+        atomicAnd(&above_own[u >> 5], ~bit);                       // u leaves this degree class ...
+        if (du - 1 > dv) atomicOr(&add_next[u >> 5], bit);         // ... and joins the next lower one unless it reached the level
+      } else if (du - 1 == dv) {
+        atomicAnd(&above_own[u >> 5], ~bit);
+      }
+      if (rank == 0) bin[du] = b0 + m;
+    }
+    __syncwarp();
+  }
+}
+
+// live words of this lane -> ascending list (word order = (lane, k)); returns the list length
 template <int WPL>
-__global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restrict__ adj, const int* __restrict__ deg_in,
-                                                        const int* __restrict__ n_corr, int Lc, int W, int row_words, int* __restrict__ kcore,
-                                                        int* __restrict__ korder, int* __restrict__ rank_of, int* __restrict__ by_rank,
-                                                        int* __restrict__ kbin, int* __restrict__ max_core_out) {
+__device__ __forceinline__ int kcore_expand(const uint32_t (&w)[WPL], int w0, unsigned short* __restrict__ nbl) {
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) c += __popc(w[k]);
+  int cnt;
+  int off = warp_excl_scan(c, &cnt);
+  if (cnt != 0) {
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      uint32_t x = w[k];
+      const int basebit = (w0 + k) * 32;
+      while (x) {
+        const int b = __ffs(x) - 1;
+        x &= x - 1;
+        nbl[off++] = (unsigned short)(basebit + b);
+      }
+    }
+  }
+  return cnt;
+}
+
+// One CTA of kKcWarps warps per pair.  Lane l owns the nwl = ceil(nbw / 32) CONSECUTIVE adjacency words l * nwl .. l * nwl + nwl - 1 of the
+// row being peeled (nwl <= WPL, W <= 32 * WPL), so the ascending neighbour list needs one warp scan per step whatever L is.
+//   small graphs (the whole adjacency fits into the shared-memory row area): warp 0 alone, no block barrier at all;
+//   large graphs: every warp owns the degree buckets of one residue class (bucket e belongs to warp e mod 4).  A step's events on
+//     different buckets commute, so the four warps apply their classes' events concurrently from their own `above` bitsets; a
+//     neighbour whose degree drops moves to the next lower class through a double-buffered `add` bitset that the receiving warp
+//     merges at the start of the next step -- ONE block barrier per step.  Rows arrive through a cp.async ring of kRing rows (warp 0 prefetches kRing - 1 steps ahead).
+// smem: bin (int x (Lc + 2)) | above [4][32 WPL] | add [2][4][32 WPL] | rows [row_words] | deg, pos, vert, mrk (u16 x Lc) | nbl [4][Lc] u16
+template <int WPL>
+__global__ void __launch_bounds__(kKcWarps * 32) kcore_kernel(const uint32_t* __restrict__ adj, const int* __restrict__ deg_in,
+                                                              const int* __restrict__ n_corr, int Lc, int W, int row_words, int* __restrict__ kcore,
+                                                              int* __restrict__ korder, int* __restrict__ rank_of, int* __restrict__ by_rank,
+                                                              int* __restrict__ kbin, int* __restrict__ max_core_out) {
+  constexpr int NW = kKcWarps, AW = 32 * WPL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* bin = reinterpret_cast<int*>(smem_raw);                       // [Lc + 2] start of every degree bucket
-  uint32_t* above = reinterpret_cast<uint32_t*>(bin + Lc + 2);       // [32 * WPL] vertices with current degree > current level
-  uint32_t* rows = above + 32 * WPL;                                 // [row_words] adjacency cache or prefetch ring
+  uint32_t* above = reinterpret_cast<uint32_t*>(bin + Lc + 2);       // [NW][AW] vertices with current degree > current level (per class)
+  uint32_t* add = above + NW * AW;                                   // [2][NW][AW] arrivals of the next step, by parity
+  uint32_t* rows = add + 2 * NW * AW;                                // [row_words] adjacency cache or prefetch ring
   unsigned short* deg = reinterpret_cast<unsigned short*>(rows + row_words);
   unsigned short* pos = deg + Lc;
   unsigned short* vert = pos + Lc;
-  unsigned short* nbl = vert + Lc;                                   // ascending list of the current step's live neighbours
-  unsigned short* mrk = nbl + Lc;                                    // mrk[u] = 1 + rank of u inside its group during a pass, else 0
+  unsigned short* mrk = vert + Lc;                                   // mrk[u] = 1 + rank of u inside its group during a pass, else 0
+  unsigned short* nbl_all = mrk + Lc;                                // [NW][Lc] ascending list of a warp's live neighbours of the step
   __shared__ int ring_tag[kRing];
 
-  const int pair = blockIdx.x, lane = lane_id();
-  const unsigned lt = (1u << lane) - 1u;
+  const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = n_corr[pair];
   int* __restrict__ kc = kcore + (size_t)pair * (Lc + 2);
   int* __restrict__ ko = korder + (size_t)pair * (Lc + 2);
@@ -120,145 +207,130 @@ __global__ void __launch_bounds__(32) kcore_warp_kernel(const uint32_t* __restri
   int* __restrict__ br = by_rank + (size_t)pair * (Lc + 2);
   int* __restrict__ kb = kbin + (size_t)pair * (Lc + 2);
   if (L <= 0) {
-    if (lane == 0) max_core_out[pair] = 0;
+    if (tid == 0) max_core_out[pair] = 0;
     return;
   }
   const uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
   const int nbw = (L + 31) >> 5;   // adjacency words per row in use
   const int nwl = (nbw + 31) >> 5; // words per lane in use (<= WPL)
   const bool cached = (long long)L * nbw <= (long long)row_words;
+  const int w0 = lane * nwl;       // first adjacency word of this lane
+  unsigned short* nbl = nbl_all + (size_t)warp * Lc;
 
+  // ---- set-up: degrees, row cache, bucket sort by degree (warp 0 sorts; everybody helps loading) ----
   int md = 0;
-  for (int v = lane; v < L; v += 32) {
+  for (int v = tid; v < L; v += NW * 32) {
     const int d = deg_in[(size_t)pair * Lc + v];
     deg[v] = (unsigned short)d;
     mrk[v] = 0;
     md = max(md, d);
   }
   if (cached)  // the peel is a chain of dependent row reads: stage the whole graph once
-    for (int idx = lane; idx < L * nbw; idx += 32) rows[idx] = G[(size_t)(idx / nbw) * W + (idx % nbw)];
+    for (int idx = tid; idx < L * nbw; idx += NW * 32) rows[idx] = G[(size_t)(idx / nbw) * W + (idx % nbw)];
+  for (int wd = tid; wd < 3 * NW * AW; wd += NW * 32) above[wd] = 0u;  // above + add
+  __shared__ int s_md[NW];
   md = warp_max(md);
-  __syncwarp();
-  warp_bucket_sort(deg, L, md, bin, pos, vert);
-
-  // ---- peel ----
-  for (int wd = lane; wd < 32 * WPL; wd += 32) {
-    const int lo = wd * 32;
-    above[wd] = lo + 32 <= L ? ~0u : (lo < L ? (1u << (L - lo)) - 1u : 0u);
+  if (lane == 0) s_md[warp] = md;
+  __syncthreads();
+  md = max(max(s_md[0], s_md[1]), max(s_md[2], s_md[3]));
+  if (warp == 0) warp_bucket_sort(deg, L, md, bin, pos, vert);
+  __syncthreads();
+  // membership of `above`: everything (single-warp path) / by degree class
+  for (int v = tid; v < L; v += NW * 32) {
+    const int c = cached ? 0 : (int)deg[v] % NW;
+    atomicOr(&above[c * AW + (v >> 5)], 1u << (v & 31));
   }
-  const int w0 = lane * nwl;  // first adjacency word of this lane
-  auto fetch = [&](int p) {  // prefetch the row of the vertex that sits at position p right now into its ring slot
-    if (p < L) {
-      const int x = vert[p], sl = p % kRing;
-      if (lane == 0) ring_tag[sl] = x;
-#pragma unroll
-      for (int k = 0; k < WPL; ++k)
-        if (k < nwl && w0 + k < nbw) cp_async4(rows + sl * W + w0 + k, G + (size_t)x * W + w0 + k);
-    }
-    cp_async_commit();
-  };
-  if (!cached)
-    for (int p = 0; p < kRing; ++p) fetch(p);
+  __syncthreads();
+
   int cur = -1;  // current level: every vertex with degree <= cur has its bit in `above` cleared
-  __syncwarp();
-  for (int i = 0; i < L; ++i) {
-    const int v = vert[i];
-    const int dv = deg[v];
-    uint32_t w[WPL];
-    if (cached) {
+  if (cached) {
+    // ================= small graph: warp 0 alone, rows from the cache, no block barrier =================
+    if (warp != 0) return;
+    for (int i = 0; i < L; ++i) {
+      const int v = vert[i];
+      const int dv = deg[v];
+      if (dv > cur) {  // level rise: bucket dv = positions [i, bin[dv+1]) leaves `above`
+        const int end = bin[dv + 1];
+        for (int p = i + lane; p < end; p += 32) {
+          const int x = vert[p];
+          atomicAnd(&above[x >> 5], ~(1u << (x & 31)));
+        }
+        cur = dv;
+        __syncwarp();
+      }
+      uint32_t w[WPL];
 #pragma unroll
-      for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? rows[v * nbw + w0 + k] : 0u;
-    } else {
-      cp_async_wait<kRing - 1>();  // the group of position i has landed
+      for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? (rows[v * nbw + w0 + k] & above[w0 + k]) : 0u;
+      const int cnt = kcore_expand<WPL>(w, w0, nbl);
+      if (cnt == 0) continue;
       __syncwarp();
+      kcore_apply_moves(nbl, cnt, dv, bin, deg, pos, vert, mrk, above, above, false);
+    }
+  } else {
+    // ================= large graph: one degree class per warp, rows through the cp.async ring =================
+    uint32_t* above_w = above + warp * AW;                                  // buckets e with e % NW == warp
+    const int lower = (warp + NW - 1) % NW;                                 // class that receives my neighbours after a decrement
+    auto fetch = [&](int p) {  // warp 0: prefetch the row of the vertex that sits at position p right now into its ring slot
+      if (p < L) {
+        const int x = vert[p], sl = p % kRing;
+        if (lane == 0) ring_tag[sl] = x;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k)
+          if (k < nwl && w0 + k < nbw) cp_async4(rows + sl * W + w0 + k, G + (size_t)x * W + w0 + k);
+      }
+      cp_async_commit();
+    };
+    if (warp == 0) {
+      for (int p = 0; p < kRing - 1; ++p) fetch(p);
+      cp_async_wait<kRing - 2>();  // position 0 has landed
+    }
+    __syncthreads();
+    for (int i = 0; i < L; ++i) {
+      const int v = vert[i];
+      const int dv = deg[v];
+      const int par = i & 1;
+      if (warp == 0) fetch(i + kRing - 1);  // into the slot of step i - 1, which every warp left before the last barrier
+      // arrivals of the previous step (written by the next higher class) join my bitset
+      uint32_t* add_in = add + ((par ^ 1) * NW + warp) * AW;
+      uint32_t w[WPL];
       const int sl = i % kRing;
-      if (ring_tag[sl] == v) {  // positions inside the current bucket are final: the prefetch usually holds the right row
-#pragma unroll
-        for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? rows[sl * W + w0 + k] : 0u;
-      } else {
-#pragma unroll
-        for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? G[(size_t)v * W + w0 + k] : 0u;
-      }
-      __syncwarp();
-      fetch(i + kRing);
-    }
-    if (dv > cur) {  // level rise: bucket dv = positions [i, bin[dv+1]) leaves `above`
-      const int end = bin[dv + 1];
-      for (int p = i + lane; p < end; p += 32) {
-        const int x = vert[p];
-        atomicAnd(&above[x >> 5], ~(1u << (x & 31)));
-      }
-      cur = dv;
-      __syncwarp();
-    }
-    // live neighbours (deg[u] > deg[v]) -> ascending list; word order = (lane, k)
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < WPL; ++k) {
-      w[k] = (k < nwl && w0 + k < nbw) ? (w[k] & above[w0 + k]) : 0u;
-      c += __popc(w[k]);
-    }
-    int cnt;
-    int off = warp_excl_scan(c, &cnt);
-    if (cnt != 0) {
+      const bool hit = ring_tag[sl] == v;  // positions inside the current bucket are final: the prefetch usually holds the right row
 #pragma unroll
       for (int k = 0; k < WPL; ++k) {
-        uint32_t x = w[k];
-        const int basebit = (w0 + k) * 32;
-        while (x) {
-          const int b = __ffs(x) - 1;
-          x &= x - 1;
-          nbl[off++] = (unsigned short)(basebit + b);
-        }
-      }
-    }
-    if (cnt == 0) continue;
-    __syncwarp();
-    // Bucket moves, 32 neighbours at a time.  Moves into different buckets commute; the members u_0 < u_1 < ... of one bucket
-    // (same current degree, ranks from __match_any_sync) are applied in id order by pmc: "swap u_t with the vertex on slot
-    // bin + t".  That sequence has a closed form: u_t ends on slot bin + t, and the vertex y that is not a member but sat
-    // on one of the target slots ends on the old slot of the member found by walking  slot s -> member that sat there -> its
-    // target slot -> ... ; each member that sat OUTSIDE the target slots walks that chain backwards from its own rank and
-    // hands its old slot to the non-member it reaches (verified against the sequential mechanic, tests + DESIGN.md 5.3).
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-      const int e = c0 + lane;
-      const bool act = e < cnt;
-      const int u = act ? nbl[e] : 0;
-      const int du = act ? deg[u] : -1 - lane;
-      const unsigned grp = __match_any_sync(0xffffffffu, du);
-      const int rank = __popc(grp & lt), m = __popc(grp);
-      int b0 = 0, pu = 0;
-      if (act) {
-        b0 = bin[du];
-        pu = pos[u];
-        mrk[u] = (unsigned short)(rank + 1);
-      }
-      __syncwarp();
-      int y = -1;  // the non-member that moves to this member's old slot
-      if (act && pu >= b0 + m) {
-        int curk = rank;
-        for (;;) {
-          y = vert[b0 + curk];
-          const int r = mrk[y];
-          if (r == 0) break;
-          curk = r - 1;
+        w[k] = 0u;
+        if (k < nwl && w0 + k < nbw) {
+          const uint32_t a = add_in[w0 + k];
+          if (a) { above_w[w0 + k] |= a; add_in[w0 + k] = 0u; }
+          w[k] = hit ? rows[sl * W + w0 + k] : G[(size_t)v * W + w0 + k];
         }
       }
       __syncwarp();
-      if (act) {
-        vert[b0 + rank] = (unsigned short)u; pos[u] = (unsigned short)(b0 + rank);
-        if (y >= 0) { vert[pu] = (unsigned short)y; pos[y] = (unsigned short)pu; }
-        mrk[u] = 0;
-        deg[u] = (unsigned short)(du - 1);
-        if (du - 1 == dv) atomicAnd(&above[u >> 5], ~(1u << (u & 31)));
-        if (rank == 0) bin[du] = b0 + m;
+      if (dv > cur) {  // level rise: bucket dv leaves `above` -- it lives in class dv % NW only
+        if (dv % NW == warp) {
+          const int end = bin[dv + 1];
+          for (int p = i + lane; p < end; p += 32) {
+            const int x = vert[p];
+            atomicAnd(&above_w[x >> 5], ~(1u << (x & 31)));
+          }
+          __syncwarp();
+        }
+        cur = dv;
       }
-      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) w[k] = (k < nwl && w0 + k < nbw) ? (w[k] & above_w[w0 + k]) : 0u;
+      const int cnt = kcore_expand<WPL>(w, w0, nbl);
+      if (cnt != 0) {
+        __syncwarp();
+        kcore_apply_moves(nbl, cnt, dv, bin, deg, pos, vert, mrk, above_w, add + (par * NW + lower) * AW, true);
+      }
+      if (warp == 0) cp_async_wait<kRing - 2>();  // the row of position i + 1 has landed
+      __syncthreads();  // every class is done with step i: vert / deg / add are consistent, the next row is visible
     }
+    if (warp == 0) cp_async_wait<0>();
+    if (warp != 0) return;
   }
-  if (!cached) cp_async_wait<0>();
   __syncwarp();
-  // ---- outputs: kcore = core + 1, peel order, max core ----
+  // ---- outputs (warp 0): kcore = core + 1, peel order, max core ----
   const int max_core = deg[vert[L - 1]];
   for (int v = lane; v < L; v += 32) {
     kc[v] = (int)deg[v] + 1;
@@ -286,7 +358,7 @@ __global__ void __launch_bounds__(256) permute_adj_kernel(const uint32_t* __rest
   if (v >= L) return;
   uint32_t* row = rows + wib * W;
   const int nb = (L + 31) >> 5;
-  for (int w = lane; w < W; w += 32) row[w] = 0;
+  for (int w = lane; w < nb; w += 32) row[w] = 0;
   __syncwarp();
   const int* __restrict__ ro = rank_of + (size_t)pair * (Lc + 2);
   const uint32_t* __restrict__ src = adj + ((size_t)pair * Lc + v) * W;
@@ -301,7 +373,7 @@ __global__ void __launch_bounds__(256) permute_adj_kernel(const uint32_t* __rest
   }
   __syncwarp();
   uint32_t* __restrict__ dst = adjp + ((size_t)pair * Lc + ro[v]) * W;
-  for (int w = lane; w < W; w += 32) dst[w] = row[w];
+  for (int w = lane; w < nb; w += 32) dst[w] = row[w];  // the descent never reads beyond ceil(L/32) words
 }
 
 constexpr int kCliqueWarps = 8;
@@ -467,16 +539,17 @@ __global__ void __launch_bounds__(kCliqueWarps * 32) clique_cta_kernel(const uin
 template <int WPL>
 static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
   const int Lc = h->Lc, W = h->W;
-  const size_t fixed = (size_t)(Lc + 2) * sizeof(int) + (size_t)32 * WPL * sizeof(uint32_t) + (size_t)5 * Lc * sizeof(unsigned short);
-  // rows: what is left of a 128 KB budget (whole graphs up to L ~ 740 at max_corr 4096; the other ~100 KB of the SM stay free for the
+  const size_t fixed = (size_t)(Lc + 2) * sizeof(int) + (size_t)3 * kKcWarps * 32 * WPL * sizeof(uint32_t) +
+                       (size_t)(4 + kKcWarps) * Lc * sizeof(unsigned short);
+  // rows: what is left of a 144 KB budget (whole graphs up to L ~ 680 at max_corr 4096; the rest of the SM stays free for the
   // dense kernels of the other lanes), at least the prefetch ring
-  size_t row_words = fixed < 120 * 1024 ? (128 * 1024 - fixed) / 4 : 0;
+  size_t row_words = fixed < 136 * 1024 ? (144 * 1024 - fixed) / 4 : 0;
   if (row_words < (size_t)kRing * W) row_words = (size_t)kRing * W;
   if (row_words > (size_t)Lc * W) row_words = (size_t)Lc * W;
   const size_t smem = fixed + row_words * 4;
-  if (set_attr) QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_warp_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kcore_warp_kernel<WPL><<<n_pairs, 32, smem, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, (int)row_words, h->kcore, h->korder, h->rank_of,
-                                                           h->by_rank, h->kbin, h->ctr.max_core);
+  if (set_attr) QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kcore_kernel<WPL><<<n_pairs, kKcWarps * 32, smem, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, (int)row_words, h->kcore, h->korder,
+                                                                 h->rank_of, h->by_rank, h->kbin, h->ctr.max_core);
   return QB200_OK;
 }
 

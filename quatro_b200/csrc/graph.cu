@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(c
   }
 }
 
-// degrees + edge count + clearing of the words beyond ceil(L/32) (one warp per row)
+// degrees + edge count (one warp per row)
 __global__ void __launch_bounds__(256) degree_kernel(uint32_t* __restrict__ adj, const int* __restrict__ n_corr, int Lc, int W,
                                                      int* __restrict__ deg, long long* __restrict__ n_edges) {
   const int pair = blockIdx.y;
@@ -301,10 +301,8 @@ __global__ void __launch_bounds__(256) degree_kernel(uint32_t* __restrict__ adj,
   const int nb = (L + 31) >> 5;
   uint32_t* __restrict__ G = adj + ((size_t)pair * Lc + row) * W;
   int d = 0;
-  for (int w = lane_id(); w < W; w += 32) {
-    if (w < nb) d += __popc(G[w]);
-    else G[w] = 0;
-  }
+  for (int w = lane_id(); w < nb; w += 32) d += __popc(G[w]);  // words beyond ceil(L/32) are never read by any consumer: leaving them
+                                                               // untouched keeps the wave's adjacency footprint (L * nb words per pair) inside the L2
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
   if (lane_id() == 0) {
