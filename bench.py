@@ -54,7 +54,7 @@ SCENES = {
               "what": "voxel 0.22 m, tuple test off (every mutual nearest neighbour is a correspondence): L ~ 3 k per pair; "
                       "other parameters = config/params.yaml"},
     # BASELINE configs[4]: dense indoor pair, ~500 k points, 0.05 m voxel -- the configuration where K6 (N_src x N_tgt x 33 on the
-    # tensor cores) is the dominant work (~50 k voxel points per cloud: 66 * 50k^2 = 0.17 TFLOP per pair)
+    # tensor cores) is the dominant work (34-53 k voxel points per cloud: 66 * 45k^2 = 0.13 TFLOP per pair)
     "indoor": {"params": {"voxel_size": 0.05, "normal_radius": 0.10, "fpfh_radius": 0.15, "noise_bound": 0.05, "cote_noise_bound": 0.05,
                           "skip_flagged": 0},
                "cfg": {"max_raw_points": 524288, "max_voxel_points": 65536},
@@ -229,7 +229,7 @@ def workload_config(args, world):
                      f"BASELINE's stated size; {world}x{args.pairs} global)",
             "indoor": f"{args.pairs} dense indoor pairs per GPU per step (BASELINE configs[4]: ~500 k points per scan, 0.05 m voxel, ~50 k voxel "
                       f"points per cloud; {world}x{args.pairs} global)"}[args.scene]
-    scan = "500 k uniformly distributed rays in a furnished 18 x 18 x 3 m hall, 5 mm range noise" if args.scene == "indoor" else \
+    scan = "500 k uniformly distributed rays in a furnished 6 x 6 x 3 m room, 5 mm range noise" if args.scene == "indoor" else \
         "64 rings x 1800 azimuths, ~111k returns, ground flagged"
     return {"workload": what, "scene": args.scene,
             "pairs_per_gpu": args.pairs, "global_pairs": args.pairs * world, "scan": scan,

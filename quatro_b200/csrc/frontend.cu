@@ -72,17 +72,25 @@ __global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __
   const int n = cloud_n[cloud];
   const float4* __restrict__ pts = cloud_ptr[cloud];
   int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN, cnt = 0, bad = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float4 p = __ldg(pts + i);
-    if (!raw_point_kept(p, skip_flagged)) continue;
-    const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
-    if (cell_ok(ci, cj, ck)) {
-      const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
-      mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
-      mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
-      ++cnt;
-    } else {
-      bad = 1;  // outside the representable lattice: PCL's index would overflow as well
+  // four independent 16-byte loads in flight per thread: this pass streams the raw scans (230 MB per 64-pair wave) from HBM
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    float4 pp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pp[j] = i0 + j * stride < n ? __ldg(pts + i0 + j * stride) : make_float4(NAN, NAN, NAN, 0.f);  // NaN = not kept
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 p = pp[j];
+      if (i0 + j * stride >= n || !raw_point_kept(p, skip_flagged)) continue;
+      const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
+      if (cell_ok(ci, cj, ck)) {
+        const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
+        mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+        mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+        ++cnt;
+      } else {
+        bad = 1;  // outside the representable lattice: PCL's index would overflow as well
+      }
     }
   }
 #pragma unroll
@@ -612,7 +620,9 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
   const dim3 gl((V + 255) / 256, n_clouds);
   lattice_keys_kernel<<<gl, 256, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, inv, h->key_a, h->val_a);
   h->launches++;
-  const int rc = sort_pairs(h, n_clouds * V, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
+  // per-cloud shared-memory sort (sort.cu); clouds too large for it go through the device-wide radix sort
+  int rc = launch_cloud_sort(h, n_clouds, h->ctr.n_vox);
+  if (rc == QB200_ERR_UNSUPPORTED) rc = sort_pairs(h, n_clouds * V, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
   if (rc) return rc;
   run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, V, 0, inv, nullptr, nullptr, h->cell_start, h->cell_key,
                                                      h->ctr.n_cells, h->ctr.n_lat, h->ctr.cloud_status);

@@ -129,5 +129,6 @@ size_t sort_temp_bytes(int max_items);
 void comm_release(qb200_handle* h);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);
 int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit);
+int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items);
 
 }  // namespace qb
