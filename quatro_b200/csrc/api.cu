@@ -7,6 +7,9 @@
 #include <new>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "handle.cuh"
@@ -15,6 +18,18 @@ using namespace qb;
 
 namespace qb {
 int launch_degree(qb200_handle* h, int n_pairs);
+
+int ensure_dyn_smem(qb200_handle* h, const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> current;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = current[std::make_pair(kernel, h->device)];
+  if (bytes > cur) {
+    QB_CUDA_TRY(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  return QB200_OK;
+}
 }
 
 namespace {

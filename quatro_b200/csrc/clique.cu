@@ -547,7 +547,8 @@ static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
   if (row_words < (size_t)kRing * W) row_words = (size_t)kRing * W;
   if (row_words > (size_t)Lc * W) row_words = (size_t)Lc * W;
   const size_t smem = fixed + row_words * 4;
-  if (set_attr) QB_CUDA_TRY(h, cudaFuncSetAttribute(kcore_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  (void)set_attr;
+  if (int rc = ensure_dyn_smem(h, (const void*)kcore_kernel<WPL>, smem)) return rc;
   kcore_kernel<WPL><<<n_pairs, kKcWarps * 32, smem, h->stream>>>(h->adj, h->deg, h->ctr.n_corr, Lc, W, (int)row_words, h->kcore, h->korder,
                                                                  h->rank_of, h->by_rank, h->kbin, h->ctr.max_core);
   return QB200_OK;
@@ -560,12 +561,9 @@ int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
   // shared-memory adjacency cache of the descent: 14336 words (56 KB) hold graphs up to L ~ 660
   const int cache_words = 14336;
   const size_t sm_clique = (size_t)kCliqueWarps * Lc * sizeof(unsigned short) + (size_t)W * sizeof(uint32_t) + (size_t)cache_words * 4;
-  const bool set_attr = !(h->func_attr_set & 1u);  // per handle: the opt-in is a per-device property of the function
-  if (set_attr) {
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(clique_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_clique));
-    h->func_attr_set |= 1u;
-  }
+  const bool set_attr = true;
   int rc;
+  if ((rc = ensure_dyn_smem(h, (const void*)clique_cta_kernel, sm_clique))) return rc;
   if (W <= 32) rc = launch_kcore<1>(h, n_pairs, set_attr);
   else if (W <= 64) rc = launch_kcore<2>(h, n_pairs, set_attr);
   else if (W <= 128) rc = launch_kcore<4>(h, n_pairs, set_attr);

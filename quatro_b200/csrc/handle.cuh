@@ -127,6 +127,9 @@ int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33)
 int desc_to_aos_rows(qb200_handle* h, const float* desc_rows, int n, float* d_out33);
 size_t sort_temp_bytes(int max_items);
 void comm_release(qb200_handle* h);
+// Raise a kernel's dynamic shared-memory opt-in to at least `bytes` on the handle's device.  The attribute is a property of the
+// (function, device), not of a handle: handles of different capacities share it, so it is only ever raised (process-wide maximum).
+int ensure_dyn_smem(qb200_handle* h, const void* kernel, size_t bytes);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);
 int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit);
 int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items);

@@ -380,10 +380,7 @@ size_t match_smem_bytes() { return 3 * sizeof(float) * kDescDim * kMT + 8 * kMT 
 int launch_match_exact(qb200_handle* h, int n_pairs, const int* only) {
   const int V = h->V;
   const size_t smem = match_smem_bytes();
-  if (!(h->func_attr_set & 2u)) {  // per handle: the opt-in is a per-device property of the function
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(match_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->func_attr_set |= 2u;
-  }
+  if (int rc = ensure_dyn_smem(h, (const void*)match_stripe_kernel, smem)) return rc;
   const dim3 gs(h->NS, n_pairs);
   if (only == nullptr) cudaEventRecord(h->kev[0], h->stream);
   match_stripe_kernel<<<gs, kMatchThreads, smem, h->stream>>>(h->desc_t, h->ctr.n_vox, V, h->NS, only, h->rowbest, h->colpart);

@@ -379,10 +379,7 @@ int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p) {
   for (int i = 0; i < 9; ++i) pp.RyRx[i] = p.RyRx[i];
   const int Lp = next_pow2(h->Lc < 4096 ? h->Lc : 4096);
   const size_t smem = pose_smem_bytes(Lp);
-  if (!(h->func_attr_set & 4u)) {  // per handle: the opt-in is a per-device property of the function
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->func_attr_set |= 4u;
-  }
+  if (int rc = ensure_dyn_smem(h, (const void*)pose_kernel, smem)) return rc;
   pose_kernel<<<n_pairs, kPoseThreads, smem, h->stream>>>(h->ma, h->mb, h->ctr.n_corr, h->Lc, Lp, h->clique, h->ctr.n_clique, pp, h->d_results,
                                                           h->rot_mask, h->trans_mask, h->final_inl, h->ctr.n_final);
   h->launches++;

@@ -112,10 +112,7 @@ int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items) {
   if (n_clouds <= 0) return QB200_OK;
   const size_t smem = cloud_sort_smem_bytes(h->V);
   if (smem > 227 * 1024 || h->V > 65535) return QB200_ERR_UNSUPPORTED;
-  if (!(h->func_attr_set & 16u)) {  // per handle: the opt-in is a per-device property of the function
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(cloud_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->func_attr_set |= 16u;
-  }
+  if (int rc = ensure_dyn_smem(h, (const void*)cloud_sort_kernel, smem)) return rc;
   cloud_sort_kernel<<<n_clouds, kSortThreads, smem, h->stream>>>(h->key_a, n_items, h->V, h->key_b, h->val_b);
   h->launches += 1;
   QB_CUDA_TRY(h, cudaGetLastError());

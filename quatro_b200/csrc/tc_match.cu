@@ -704,10 +704,7 @@ static int sort_and_dedup(qb200_handle* h, int n_clouds, int dedup) {
 int launch_match_nn(qb200_handle* h, int n_pairs) {
   const int V = h->V;
   const size_t smem = tc_smem_bytes();
-  if (!(h->func_attr_set & 8u)) {  // per handle: the opt-in is a per-device property of the function
-    QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->func_attr_set |= 8u;
-  }
+  if (int rc = ensure_dyn_smem(h, (const void*)tc_nn_kernel<false>, smem)) return rc;
   // triage switches (results are identical either way): QB200_TC_NODEDUP=1 keeps duplicate descriptors, QB200_TC_NOPRUNE=1
   // visits every column tile
   static const int no_dedup = (getenv("QB200_TC_NODEDUP") && getenv("QB200_TC_NODEDUP")[0] == '1') ? 1 : 0;
@@ -743,7 +740,7 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
 // duplicates are kept so that every (row, column) of the dump is filled)
 int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
   const size_t smem = tc_smem_bytes();
-  QB_CUDA_TRY(h, cudaFuncSetAttribute(tc_nn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc0 = ensure_dyn_smem(h, (const void*)tc_nn_kernel<true>, smem)) return rc0;
   int rc = sort_and_dedup(h, 2, 0);
   if (rc) return rc;
   const uint32_t* uperm = h->val_a;
