@@ -132,6 +132,6 @@ void comm_release(qb200_handle* h);
 int ensure_dyn_smem(qb200_handle* h, const void* kernel, size_t bytes);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);
 int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit);
-int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items);
+int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items, int f1, int f2);
 
 }  // namespace qb

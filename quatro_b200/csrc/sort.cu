@@ -15,8 +15,12 @@ constexpr int kSortThreads = 512;
 
 size_t cloud_sort_smem_bytes(int V) { return (size_t)V * 8 + (size_t)2 * V * 2 + (size_t)16 * kSortThreads * 2; }
 
+// f1, f2: bit offsets that split the low 52 key bits into up to three fields [0,f1) [f1,f2) [f2,52) (lattice keys: i | j | k at 0 / 18 /
+// 36; norm keys: one field).  Every field is sorted relative to its minimum inside the cloud: the cell coordinates carry offsets of
+// 2^17 / 2^15, so neighbouring cells on either side of an axis differ in ALL bits of a field (0x1FFFF vs 0x20000) although their
+// difference is 1; relative fields vary in 2-3 digits instead of 4-5.  The order is unchanged (no borrow crosses a field).
 __global__ void __launch_bounds__(kSortThreads) cloud_sort_kernel(const uint64_t* __restrict__ key_in, const int* __restrict__ n_items, int V,
-                                                                  uint64_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
+                                                                  int f1, int f2, uint64_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
   constexpr int NT = kSortThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);                 // [V] never moved
@@ -25,15 +29,28 @@ __global__ void __launch_bounds__(kSortThreads) cloud_sort_kernel(const uint64_t
   unsigned short* counts = idx_b + V;                                     // [16][NT] per-(digit value, thread) counts -> start offsets
   __shared__ int s_scan[33];
   __shared__ unsigned long long s_vary;
+  __shared__ unsigned int s_min[3];
   const int cloud = blockIdx.x, tid = threadIdx.x;
   const size_t base = (size_t)cloud * V;
   int n = n_items[cloud];
   n = n < 0 ? 0 : (n > V ? V : n);
-  if (tid == 0) s_vary = 0ull;
-  for (int q = tid; q < n; q += NT) {
-    keys[q] = key_in[base + q];
-    idx_a[q] = (unsigned short)q;
+  if (tid == 0) { s_vary = 0ull; s_min[0] = s_min[1] = s_min[2] = 0xFFFFFFFFu; }
+  __syncthreads();
+  const unsigned long long m0 = (1ull << f1) - 1ull, m1 = (1ull << (f2 - f1)) - 1ull, m2 = (1ull << (52 - f2)) - 1ull;
+  {
+    unsigned int a0 = 0xFFFFFFFFu, a1 = 0xFFFFFFFFu, a2 = 0xFFFFFFFFu;
+    for (int q = tid; q < n; q += NT) {
+      const unsigned long long k = key_in[base + q];
+      keys[q] = k;
+      idx_a[q] = (unsigned short)q;
+      a0 = min(a0, (unsigned int)(k & m0)); a1 = min(a1, (unsigned int)((k >> f1) & m1)); a2 = min(a2, (unsigned int)((k >> f2) & m2));
+    }
+    a0 = __reduce_min_sync(0xffffffffu, a0); a1 = __reduce_min_sync(0xffffffffu, a1); a2 = __reduce_min_sync(0xffffffffu, a2);
+    if ((tid & 31) == 0) { atomicMin(&s_min[0], a0); atomicMin(&s_min[1], a1); atomicMin(&s_min[2], a2); }
   }
+  __syncthreads();
+  const unsigned long long kmin = (unsigned long long)s_min[0] | ((unsigned long long)s_min[1] << f1) | ((unsigned long long)s_min[2] << f2);
+  for (int q = tid; q < n; q += NT) keys[q] -= kmin;   // field-wise: every field is >= its minimum, no borrow
   __syncthreads();
   {  // which key bits differ inside this cloud?
     unsigned long long v = 0ull;
@@ -97,7 +114,7 @@ __global__ void __launch_bounds__(kSortThreads) cloud_sort_kernel(const uint64_t
   for (int r = tid; r < V; r += NT) {
     if (r < n) {
       const unsigned short i = cur[r];
-      key_out[base + r] = keys[i];
+      key_out[base + r] = keys[i] + kmin;
       val_out[base + r] = (uint32_t)i;
     } else {  // dead items keep their place behind the live ones (their keys compare above every live key)
       key_out[base + r] = key_in[base + r];
@@ -108,12 +125,12 @@ __global__ void __launch_bounds__(kSortThreads) cloud_sort_kernel(const uint64_t
 
 // Sort the first n_items[c] keys of every cloud c (key_a -> key_b, val_b = source index).  Returns QB200_ERR_UNSUPPORTED when
 // max_voxel_points is too large for the shared-memory layout (the caller then uses the device-wide sort).
-int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items) {
+int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items, int f1, int f2) {
   if (n_clouds <= 0) return QB200_OK;
   const size_t smem = cloud_sort_smem_bytes(h->V);
   if (smem > 227 * 1024 || h->V > 65535) return QB200_ERR_UNSUPPORTED;
   if (int rc = ensure_dyn_smem(h, (const void*)cloud_sort_kernel, smem)) return rc;
-  cloud_sort_kernel<<<n_clouds, kSortThreads, smem, h->stream>>>(h->key_a, n_items, h->V, h->key_b, h->val_b);
+  cloud_sort_kernel<<<n_clouds, kSortThreads, smem, h->stream>>>(h->key_a, n_items, h->V, f1, f2, h->key_b, h->val_b);
   h->launches += 1;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;

@@ -690,7 +690,7 @@ static int sort_and_dedup(qb200_handle* h, int n_clouds, int dedup) {
   h->launches += 1;
   int bits = 0;
   while ((1 << bits) < n_clouds) ++bits;
-  int rc = launch_cloud_sort(h, n_clouds, h->ctr.n_vox);  // per-cloud shared-memory sort; device-wide radix sort for very large clouds
+  int rc = launch_cloud_sort(h, n_clouds, h->ctr.n_vox, 32, 32);  // per-cloud shared-memory sort; device-wide radix sort for very large clouds
   if (rc == QB200_ERR_UNSUPPORTED) rc = sort_pairs(h, n_clouds * V, 32 + bits);
   if (rc) return rc;
   uint32_t* class_of = reinterpret_cast<uint32_t*>(h->key_a);
