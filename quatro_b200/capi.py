@@ -129,6 +129,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_get_kernel_ms": (i32, [vp, vp, vp, i32]),
         "qb200_debug_tc_distances": (i32, [vp, vp, i32, vp, i32, vp]),
         "qb200_debug_match_stats": (i32, [vp, vp, i32]),
+        "qb200_debug_tc_profile": (i32, [vp, vp, i32]),
         "qb200_solve_batch": (i32, [vp, vp, i32, vp, i32, vp]),
         "qb200_comm_init_all": (i32, [P(vp), i32]),
         "qb200_register_batch_sharded": (i32, [P(vp), i32, P(Pair), i32, P(Params), i32, vp]),
@@ -161,6 +162,7 @@ EXPORTED_SYMBOLS = [
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
     "qb200_debug_match_stats",
+    "qb200_debug_tc_profile",
     "qb200_solve_batch",
     "qb200_comm_init_all", "qb200_register_batch_sharded", "qb200_comm_unique_id", "qb200_comm_init_rank",
     "qb200_register_batch_rank", "qb200_comm_wait", "qb200_bind_numa",
@@ -479,6 +481,11 @@ class Handle:
         out = np.zeros(4, np.uint64)
         self._check(self.lib.qb200_debug_match_stats(self.h, _ptr(out), int(reset)), "qb200_debug_match_stats")
         return {"exact_evals": int(out[0]), "tiles": int(out[1]), "warmups": int(out[2]), "aborted_stripes": int(out[3])}
+
+    def debug_tc_profile(self, reset: bool = True) -> np.ndarray:
+        out = np.zeros(24, np.uint64)
+        self._check(self.lib.qb200_debug_tc_profile(self.h, _ptr(out), int(reset)), "qb200_debug_tc_profile")
+        return out
 
     def debug_match_verify(self, reset: bool = True) -> dict:
         out = np.zeros(2, np.uint64)

@@ -116,11 +116,11 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMemset(h->desc_tiles, 0, C * kDescK * V * 3 * sizeof(float)));
   QB_ALLOC(h, h->desc_norm, C * V);
   QB_ALLOC(h, h->tc_fallback, S);
-  QB_ALLOC(h, h->tc_stats, 8);
-  QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 8 * sizeof(unsigned long long)));
+  QB_ALLOC(h, h->tc_stats, 32);
+  QB_CUDA_TRY(h, cudaMemset(h->tc_stats, 0, 32 * sizeof(unsigned long long)));
   QB_ALLOC(h, h->rowbest, S * V);
   {  // two layouts share colpart: [S][NS][V] stripe partials (exact kernel) and [2][S][V] class results + tile cache (tc_match.cu)
-    const size_t a = S * h->NS * V, b = 2 * S * V + S * (V >> 7) / 2 + 1;
+    const size_t a = S * h->NS * V, b = 2 * S * V + S * (V >> 7) * 2 + 2;
     QB_ALLOC(h, h->colpart, a > b ? a : b);
   }
   QB_ALLOC(h, h->colbest, S * V);
@@ -892,6 +892,23 @@ int qb200_debug_match_verify(qb200_handle* h, uint64_t* out2, int32_t reset) {
     const int rc = qb200_debug_match_verify(h->lane[l], o2, reset);
     if (rc) return rc;
     out2[0] += o2[0]; out2[1] += o2[1];
+  }
+  return QB200_OK;
+}
+
+// QB200_TC_PROF=1: clock64 accounting of tc_nn_kernel's roles (cycles summed over CTAs / warps), stats[8..31] -> out24
+int qb200_debug_tc_profile(qb200_handle* h, uint64_t* out24, int32_t reset) {
+  if (!h || !out24) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  QB_CUDA_TRY(h, cudaMemcpy(out24, h->tc_stats + 8, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) QB_CUDA_TRY(h, cudaMemset(h->tc_stats + 8, 0, 24 * sizeof(unsigned long long)));
+  for (int l = 0; l < 7; ++l) {
+    if (!h->lane[l]) continue;
+    uint64_t o[24];
+    const int rc = qb200_debug_tc_profile(h->lane[l], o, reset);
+    if (rc) return rc;
+    for (int i = 0; i < 24; ++i) out24[i] += o[i];
   }
   return QB200_OK;
 }

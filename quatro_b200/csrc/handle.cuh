@@ -49,7 +49,7 @@ struct qb200_handle {
                               // shared-memory operand layout (one bulk copy per tile)
   float* desc_norm;           // [2S*V] squared norms (fp32 fma chain)
   int* tc_fallback;           // [S] 1 = too many exact ties for the filter to pay off: pair re-done by the exact fp32 kernel
-  unsigned long long* tc_stats; // [4] diagnostics, cumulative: exact evaluations, tiles drained, warm-up passes, aborted stripes
+  unsigned long long* tc_stats; // [32] diagnostics, cumulative: [0..3] exact evaluations, tiles drained, warm-up passes, aborted stripes; [4..5] QB200_TC_VERIFY; [8..31] QB200_TC_PROF
   int force_exact_match;      // 0 (default): tcgen05 filter + exact evaluation; 1 (QB200_MATCH_EXACT=1): exact CUDA-core K6 only
   // ---- matching ----
   unsigned long long* rowbest;// [S*V] packed (dist bits << 32 | tgt idx) per source point

@@ -25,8 +25,8 @@
 //                       exact CUDA-core kernel, so results never depend on the filter.
 //   broadcast_best_kernel : class results -> every member, in point order for the mutual-NN stage
 //
-// tc_nn_kernel, one CTA per SM, 18 warps, mbarrier hand-offs only: warp 17 chooses tiles and issues the bulk copies
-// (2 operand stages, 4 exact-image stages), warp 16 issues the 15 MMAs per tile into one of 4 TMEM accumulator stages,
+// tc_nn_kernel, one CTA per SM, 19 warps, mbarrier hand-offs only: warp 18 chooses tiles and issues the exact-image copies
+// (4 stages), warp 17 the operand copies (2 stages), warp 16 issues the 15 MMAs per tile into one of 4 TMEM accumulator stages,
 // warps 0..15 drain them with tcgen05.ld.32x32b.x32 (lane = row) and run the filter / exact evaluation.
 #include "handle.cuh"
 #include <cstdlib>
@@ -39,7 +39,7 @@ constexpr int kTcTileBytes = kDescK * 128 * 4;    // one operand image (128 poin
 constexpr int kTileFloats = kDescK * 128;         // 5120
 constexpr int kTcImages = 3;                      // hi | lo | exact
 constexpr int kTcEpiWarps = 16;                   // filter / evaluation warps: TMEM lane quadrant = warp & 3, column quarter = warp >> 2
-constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;  // + MMA warp + copy warp
+constexpr int kTcThreads = (kTcEpiWarps + 3) * 32;  // + MMA warp + operand-copy warp + scheduler warp
 constexpr int kTcAcc = 4;                          // TMEM accumulator stages (4 x 128 columns = all of TMEM)
 constexpr int kTcStages = 4;                      // ring of exact B images (prefetch distance 3); operand images: 2 stages
 constexpr float kTcC = 1.2e-4f;                   // |d~ - d| <= kTcC/2 * (|a'|^2 + |b'|^2): 3x the worst error measured (test_tc_filter_error_bound)
@@ -118,6 +118,11 @@ __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict
   const size_t base = (size_t)cloud * kDescK * V + (q < n ? perm[(size_t)cloud * V + q] : 0u);
   const int blk = q >> 7, p = q & 127;
   float4* __restrict__ img = reinterpret_cast<float4*>(tiles + (size_t)(cloud * NB + blk) * kTcImages * kTileFloats) + p;
+  // The tensor core delivers the filter's LOWER BOUND itself: rows (source clouds, even) carry x' in dims 0..32, kLow |x'|^2 in
+  // dim 33 and 1 in dim 34; columns (target clouds, odd) carry -2 x', 1 and kLow |x'|^2 -- the contraction over the 35 dims is
+  // kLow (|a'|^2 + |b'|^2) - 2 a'.b'.  (Scaling by -2 is exact; the norm term is split hi | lo like every other value.)
+  const bool is_col = (cloud & 1) != 0;
+  const float kLow = 1.0f - 0.5f * kTcC;
   float acc = 0.0f;
 #pragma unroll
   for (int kc = 0; kc < kDescK / 4; ++kc) {
@@ -129,16 +134,19 @@ __global__ void __launch_bounds__(256) split_desc_kernel(const float* __restrict
       const float x = live ? desc_t[base + (size_t)d * V] : 0.0f;
       const float xc = live ? x - tc_mu(d) : 0.0f;
       xv[e] = x;
-      hv[e] = __uint_as_float(__float_as_uint(xc) & 0xFFFFE000u);
-      lv[e] = __uint_as_float(__float_as_uint(xc - hv[e]) & 0xFFFFE000u);
       acc = __fmaf_rn(xc, xc, acc);
+      float xs = is_col ? -2.0f * xc : xc;
+      if (q < n && d == kDescDim) xs = is_col ? 1.0f : kLow * acc;       // acc is complete here: d runs upwards
+      if (q < n && d == kDescDim + 1) xs = is_col ? kLow * acc : 1.0f;
+      hv[e] = __uint_as_float(__float_as_uint(xs) & 0xFFFFE000u);
+      lv[e] = __uint_as_float(__float_as_uint(xs - hv[e]) & 0xFFFFE000u);
     }
     img[0 * (kTileFloats / 4) + kc * 128] = make_float4(hv[0], hv[1], hv[2], hv[3]);
     img[1 * (kTileFloats / 4) + kc * 128] = make_float4(lv[0], lv[1], lv[2], lv[3]);
     if (kc < kDescK / 4 - 1) img[2 * (kTileFloats / 4) + kc * 128] = make_float4(xv[0], xv[1], xv[2], xv[3]);
   }
   // the exact image has no data in dims 36..39: slot 36 carries the column's filter term kLow |x'|^2 (+inf = padding)
-  img[2 * (kTileFloats / 4) + (kDescK / 4 - 1) * 128] = make_float4(q < n ? (1.0f - 0.5f * kTcC) * acc : INFINITY, 0.0f, 0.0f, 0.0f);
+  img[2 * (kTileFloats / 4) + (kDescK / 4 - 1) * 128] = make_float4(q < n ? kLow * acc : INFINITY, 0.0f, 0.0f, 0.0f);
   if (q < n) norm[(size_t)cloud * V + q] = acc;  // rank order
 }
 
@@ -249,7 +257,8 @@ __device__ __forceinline__ float tc_fkey_inv(unsigned key) { return __uint_as_fl
 //   warps 0..15  : warp w owns TMEM lanes 32 (w & 3) .. +31 (rows) and columns 32 (w >> 2) .. +31 of every tile:
 //                  tcgen05.ld -> release the TMEM stage -> branch-free filter -> the warp's survivors are compacted
 //                  into batches of 32 and evaluated exactly, ONE CANDIDATE PER LANE -> release the exact-image stage.
-template <bool kDbg>
+// kProf: clock64 accounting of every role's waits into stats[8..31] (tools/tc_profile.py; QB200_TC_PROF=1)
+template <bool kDbg, bool kProf = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, const int* __restrict__ n_vox, int V,
              const uint32_t* __restrict__ perm, unsigned long long* __restrict__ rowbest, unsigned long long* __restrict__ colbest_r,
@@ -265,6 +274,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   __shared__ int s_seq[8];                                     // column tile of sequence position n (ring), -1 = end of the stripe
   __shared__ float s_tlb[128];                                 // lower bound of every distance between the stripe and column tile t
   __shared__ int s_dead, s_abort, s_evals, s_warm, s_npos;
+  __shared__ int s_ndec;                                       // sequence positions 0 .. s_ndec-1 have been decided (s_seq ring)
 
   const int pair = blockIdx.y, stripe = blockIdx.x;
   const int cloudA = 2 * pair, cloudB = 2 * pair + 1;
@@ -274,6 +284,9 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NB = V >> 7;
+  auto tick = [&]() -> long long { return kProf ? clock64() : 0ll; };
+  auto prof = [&](int slot, long long cyc) { if (kProf && lane == 0) atomicAdd(stats + slot, (unsigned long long)cyc); };
+  const long long t_begin = tick();
   // shared-memory map: A block (hi | lo | exact) | 2 stages of B (hi | lo) | 4 stages of B exact images.  The operand images
   // are dead as soon as the MMAs of their tile completed, the exact image only when every warp evaluated the tile.
   constexpr uint32_t kABytes = kTcImages * kTcTileBytes;
@@ -300,7 +313,7 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     for (int i = 0; i < 2; ++i) mbar_init(bar_fullhl0 + 8 * i, 1);
     for (int i = 0; i < kTcAcc; ++i) { mbar_init(bar_mma0 + 8 * i, 1); mbar_init(bar_tfree0 + 8 * i, kTcEpiWarps); }
     mbar_init(bar_a, 1);
-    s_dead = 0; s_abort = 0; s_evals = 0; s_warm = 0; s_npos = 0;
+    s_dead = 0; s_abort = 0; s_evals = 0; s_warm = 0; s_npos = 0; s_ndec = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (threadIdx.x < kTcM) s_rbest[threadIdx.x] = ~0ull;
@@ -308,9 +321,20 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = s_tmem;
+  const long long t_setup = tick();
+  if (kProf && threadIdx.x == 0) { atomicAdd(stats + 8, 1ull); atomicAdd(stats + 10, (unsigned long long)(t_setup - t_begin)); }
   volatile int* v_dead = &s_dead;
   volatile int* v_abort = &s_abort;
   volatile int* v_seq = s_seq;
+  volatile int* v_ndec = &s_ndec;
+  // bounded wait until sequence position n has been decided by the scheduler warp
+  auto wait_decided = [&](int n) -> bool {
+    for (int spin = 0; spin < kSpinLimit; ++spin) {
+      if (*v_ndec > n) { __threadfence_block(); return true; }
+      __nanosleep(32);
+    }
+    return false;
+  };
   volatile unsigned long long* v_rbest = s_rbest;
 
   if (warp == kTcEpiWarps) {
@@ -318,11 +342,18 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     // instruction descriptor: D=F32 (bits 4-5), A=B=TF32 (bits 7-9, 10-12), both K-major (bits 15,16 = 0), N>>3 (17-22), M>>4 (24-28)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
     bool ok = mbar_wait(bar_a, 0);
+    long long p_hl = 0, p_tf = 0, p_is = 0;
+    prof(15, tick() - t_setup);
     for (int k = 0; ok; ++k) {
       const int ts = k & (kTcAcc - 1), hs = k & 1;
+      const long long t0 = tick();
       ok = mbar_wait(bar_fullhl0 + 8 * hs, (uint32_t)((k >> 1) & 1));
+      const long long t1 = tick();
+      p_hl += t1 - t0;
       if (!ok || v_seq[k & 7] < 0) break;
       if (k >= kTcAcc) ok = mbar_wait(bar_tfree0 + 8 * ts, (uint32_t)(((k >> 2) - 1) & 1));  // accumulator stage drained (position k-4)
+      const long long t2 = tick();
+      p_tf += t2 - t1;
       if (!ok) break;
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       if (lane == 0) {
@@ -339,10 +370,45 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_mma0 + 8 * ts) : "memory");
       }
       __syncwarp();
+      p_is += tick() - t2;
     }
+    prof(16, p_hl); prof(17, p_tf); prof(18, p_is);
     if (!ok) *v_dead = 1;
   } else if (warp == kTcEpiWarps + 1) {
-    // ================= copy + schedule warp =================
+    // ================= operand-copy warp: A images once, then the hi | lo images of every decided position =================
+    auto issue_hl = [&](int n) {  // operand images (hi | lo, 40 KB) of position n -> stage n & 1; end marker: plain arrive
+      const int t = v_seq[n & 7];
+      if (lane != 0) return;
+      const uint32_t bar = bar_fullhl0 + 8 * (n & 1);
+      if (t < 0) { mbar_arrive(bar); return; }
+      mbar_expect_tx(bar, kHLBytes);
+      bulk_g2s(sHL0 + (n & 1) * kHLBytes, tB + (size_t)t * kTcImages * kTileFloats, kHLBytes, bar);
+    };
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, kABytes);
+      bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
+    }
+    bool ok = wait_decided(0);
+    if (ok) { issue_hl(0); ok = wait_decided(1); }
+    if (ok) issue_hl(1);
+    long long p_wm = 0, p_wd = 0;
+    bool ended = !ok || v_seq[0] < 0 || v_seq[1] < 0;  // (an end marker has gone out already)
+    for (int k = 0; ok && !ended; ++k) {
+      // operand stage k & 1 is free once the MMAs of position k completed
+      const long long t0 = tick();
+      ok = mbar_wait(bar_mma0 + 8 * (k & (kTcAcc - 1)), (uint32_t)((k >> 2) & 1));
+      const long long t1 = tick();
+      p_wm += t1 - t0;
+      if (ok) ok = wait_decided(k + 2);
+      p_wd += tick() - t1;
+      if (!ok) break;
+      issue_hl(k + 2);
+      ended = v_seq[(k + 2) & 7] < 0;  // that was the end marker
+    }
+    prof(12, p_wm); prof(28, p_wd);
+    if (!ok) *v_dead = 1;
+  } else if (warp == kTcEpiWarps + 2) {
+    // ================= scheduler warp: chooses the tiles and issues the exact-image copies =================
     // norm range of the stripe's rows and of a column tile (ranks are sorted by norm: first / last valid entry)
     const float amin = sqrtf(nrmA[r0]), amax = sqrtf(nrmA[(r0 + kTcM < nA ? r0 + kTcM : nA) - 1]);
     auto tile_lb = [&](int t) -> float {  // lower bound of every exact distance between the stripe and column tile t
@@ -351,6 +417,22 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       if (!(amin <= amax && bmin <= bmax)) return 0.0f;               // NaN norms: never skip
       return gap > 0.0f ? gap * gap * 0.9999f : 0.0f;
     };
+    // Shared per-tile column maxima: tcm4[t][g] = an upper bound of the best exact distances of columns 32 g .. 32 g + 31 of tile t
+    // (float bits; every filter warp refreshes its group after evaluating the tile, bests only shrink).  The values of the first
+    // 128 tiles (4 tiles per lane) are fetched at the END of a choice for the NEXT one, so no choice waits for L2.
+    const uint4* __restrict__ tcm4 = reinterpret_cast<const uint4*>(tile_cmax) + (size_t)pair * (V >> 7);
+    uint4 pq0, pq1, pq2, pq3;
+    auto fetch_tcm = [&]() {
+      pq0 = pq1 = pq2 = pq3 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (!no_prune) {
+        if (lane < n_tiles) pq0 = __ldcg(tcm4 + lane);
+        if (lane + 32 < n_tiles) pq1 = __ldcg(tcm4 + lane + 32);
+        if (lane + 64 < n_tiles) pq2 = __ldcg(tcm4 + lane + 64);
+        if (lane + 96 < n_tiles) pq3 = __ldcg(tcm4 + lane + 96);
+      }
+    };
+    auto max4 = [](const uint4& q) -> unsigned { return max(max(q.x, q.y), max(q.z, q.w)); };
+    fetch_tcm();
     // lower bounds of all column tiles (at most 128: V <= 16384 ... 65536 / 128 = 512 tiles are covered by the loop stride),
     // kept in shared memory; start at the tile whose norm range is closest to the stripe's, then walk outwards on both sides
     int t0 = 0;
@@ -367,14 +449,12 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       __syncwarp();
     }
     auto tlb = [&](int t) -> float { return t < 128 ? s_tlb[t] : tile_lb(t); };
-    unsigned* __restrict__ tcm = tile_cmax + (size_t)pair * (V >> 7);  // per column tile: a recent max of its column bests
     int lo = t0 - 1, hi = t0 + 1;
     bool first = true, done = false;
     auto next_tile = [&]() -> int {  // warp-uniform
       if (first) { first = false; return t0; }
-      // One choice walks over several skipped tiles; its inputs are fetched once: the current worst row best of the stripe
-      // (+inf while any row is unknown) and the shared per-tile column maxima of the first 128 tiles (4 per lane, one L2
-      // round trip for the whole walk instead of one per candidate).
+      // Inputs of a choice: the current worst row best of the stripe (+inf while any row is unknown) and the prefetched per-tile
+      // column maxima.  A tile whose lower bound exceeds both is skipped for good (bests only shrink).
       unsigned rmax = 0;
 #pragma unroll
       for (int i = 0; i < kTcM / 32; ++i) {
@@ -385,46 +465,37 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         }
       }
       const float rmaxf = __uint_as_float(__reduce_max_sync(0xffffffffu, rmax));  // distances are >= 0: the bit patterns order them
-      unsigned tc0 = 0xFFFFFFFFu, tc1 = 0xFFFFFFFFu, tc2 = 0xFFFFFFFFu, tc3 = 0xFFFFFFFFu;
-      if (!no_prune) {
-        if (lane < n_tiles) tc0 = __ldcg(tcm + lane);
-        if (lane + 32 < n_tiles) tc1 = __ldcg(tcm + lane + 32);
-        if (lane + 64 < n_tiles) tc2 = __ldcg(tcm + lane + 64);
-        if (lane + 96 < n_tiles) tc3 = __ldcg(tcm + lane + 96);
-      }
+      const unsigned tc0 = max4(pq0), tc1 = max4(pq1), tc2 = max4(pq2), tc3 = max4(pq3);
+      if (*v_abort || *v_dead) return -1;
+      // The walk, 32 candidates per round: lanes 0..15 look at the next 16 tiles on the left (lo, lo-1, ...), lanes 16..31 at the
+      // next 16 on the right.  Lower bounds grow outwards on either side, so the next tile in nearest-first order is the first
+      // one that cannot be skipped on the left or on the right, whichever has the smaller bound (left on ties); the tiles in
+      // front of them are skipped for good.
+      const bool is_left = lane < 16;
       while (true) {
-        if ((lo < 0 && hi >= n_tiles) || *v_abort || *v_dead) return -1;
-        const float gl = lo >= 0 ? tlb(lo) : INFINITY, gh = hi < n_tiles ? tlb(hi) : INFINITY;
-        const bool left = gl <= gh;
-        const int t = left ? lo : hi;
-        const float lb = left ? gl : gh;
-        if (left) --lo; else ++hi;
-        if (lb <= 0.0f || no_prune) return t;
-        if (!(lb > rmaxf)) return t;
-        // worst column best of the tile: first the shared per-tile value (an upper bound: bests only shrink), and only if
-        // that does not settle it the 128 current column bests themselves, whose max refreshes the shared value
-        unsigned cmax;
-        if (t < 128) {
-          const int sl = t >> 5;
-          const unsigned mine = sl == 0 ? tc0 : sl == 1 ? tc1 : sl == 2 ? tc2 : tc3;
-          cmax = __shfl_sync(0xffffffffu, mine, t & 31);
-        } else {
-          cmax = __ldcg(tcm + t);
+        if (lo < 0 && hi >= n_tiles) return -1;
+        const int t = is_left ? lo - lane : hi + (lane - 16);
+        const bool valid = is_left ? t >= 0 : t < n_tiles;
+        const float lb = valid ? tlb(t) : INFINITY;
+        unsigned cm = 0xFFFFFFFFu;
+        {
+          const int src = t & 31, sl = (t >> 5) & 3;
+          const unsigned a0 = __shfl_sync(0xffffffffu, tc0, src), a1 = __shfl_sync(0xffffffffu, tc1, src);
+          const unsigned a2 = __shfl_sync(0xffffffffu, tc2, src), a3 = __shfl_sync(0xffffffffu, tc3, src);
+          if (valid && t < 128) cm = sl == 0 ? a0 : sl == 1 ? a1 : sl == 2 ? a2 : a3;
+          else if (valid && !no_prune) cm = max4(__ldcg(tcm4 + t));
         }
-        if (lb > __uint_as_float(cmax)) continue;
-        cmax = 0;
-#pragma unroll
-        for (int i = 0; i < kTcN / 32; ++i) {
-          const int j = t * kTcN + lane + 32 * i;
-          if (j < nB) {
-            const unsigned long long cb = __ldcg(cbg + j);
-            cmax = max(cmax, cb == ~0ull ? 0x7F800000u : (unsigned)(cb >> 32));
-          }
-        }
-        cmax = __reduce_max_sync(0xffffffffu, cmax);
-        if (lane == 0) atomicMin(tcm + t, cmax);
-        if (!(lb > __uint_as_float(cmax))) return t;
-        // every entry of the tile is farther than all current bests (strictly: ties go to the lower index): skipped for good
+        const bool visit = valid && (no_prune || lb <= 0.0f || !(lb > rmaxf) || !(lb > __uint_as_float(cm)));
+        const unsigned vb = __ballot_sync(0xffffffffu, visit);
+        const int fl = (vb & 0xFFFFu) ? __ffs(vb & 0xFFFFu) - 1 : 16;   // first tile to visit on either side (16 = none in this window)
+        const int fr = (vb >> 16) ? __ffs(vb >> 16) - 1 : 16;
+        if (fl == 16 && fr == 16) { lo -= 16; hi += 16; continue; }
+        const float gl = __shfl_sync(0xffffffffu, lb, fl & 15), gh = __shfl_sync(0xffffffffu, lb, 16 + (fr & 15));
+        const bool left = fr == 16 || (fl < 16 && gl <= gh);
+        const int tv = left ? lo - fl : hi + fr;
+        lo -= left ? fl + 1 : fl;
+        hi += left ? fr : fr + 1;
+        return tv;
       }
     };
     int n_issued = 0;
@@ -434,17 +505,14 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         t = next_tile();
         if (t < 0) done = true; else ++n_issued;
       }
-      if (lane == 0) v_seq[n & 7] = t;
+      if (lane == 0) {  // (no loads are in flight here: the fence is cheap)
+        v_seq[n & 7] = t;
+        __threadfence_block();
+        *v_ndec = n + 1;
+      }
       __syncwarp();
+      if (!done) fetch_tcm();  // for the next choice: lands while this warp waits for the MMAs / the free exact-image stage
       return t;
-    };
-    auto issue_hl = [&](int n) {  // operand images (hi | lo, 40 KB) of position n -> stage n & 1; end marker: plain arrive
-      const int t = v_seq[n & 7];
-      if (lane != 0) return;
-      const uint32_t bar = bar_fullhl0 + 8 * (n & 1);
-      if (t < 0) { mbar_arrive(bar); return; }
-      mbar_expect_tx(bar, kHLBytes);
-      bulk_g2s(sHL0 + (n & 1) * kHLBytes, tB + (size_t)t * kTcImages * kTileFloats, kHLBytes, bar);
     };
     auto issue_x = [&](int n) {  // exact image (20 KB) of position n -> stage n & 3
       const int t = v_seq[n & 7];
@@ -454,27 +522,54 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       mbar_expect_tx(bar, kXBytes);
       bulk_g2s(sX0 + (n & (kTcStages - 1)) * kXBytes, tB + ((size_t)t * kTcImages + 2) * kTileFloats, kXBytes, bar);
     };
-    if (lane == 0) {
-      mbar_expect_tx(bar_a, kABytes);
-      bulk_g2s(sA, tA + (size_t)stripe * kTcImages * kTileFloats, kABytes, bar_a);
+    for (int n = 0; n < 3; ++n) { decide(n); issue_x(n); }
+    prof(11, tick() - t_setup);
+    long long p_wm = 0, p_dec = 0, p_sf = 0;
+    auto mbar_test = [&](uint32_t bar, uint32_t parity) -> bool {
+      uint32_t ready;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(ready)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      return __all_sync(0xffffffffu, ready != 0);
+    };
+    // Two duties, neither blocks the other: the exact image of position nx goes out as soon as every warp evaluated position nx-4
+    // (its stage), and positions are chosen ahead (at most 3 beyond nx: the s_seq ring, and not before the MMAs of position nd-3
+    // completed, so that a choice sees the bests of the tiles before it) while that stage is still busy.
+    int nd = 3, nx = 3;
+    bool ok = true, end_decided = v_seq[0] < 0 || v_seq[1] < 0 || v_seq[2] < 0;
+    if (end_decided) nx = nd;  // (all three end-marker arrivals were issued above; nothing else to do)
+    int idle = 0;
+    long long t_idle = 0;
+    while (ok && !(end_decided && nx == nd)) {
+      const uint32_t bar_s = bar_sfree0 + 8 * (nx & (kTcStages - 1)), par_s = (uint32_t)(((nx - 4) >> 2) & 1);
+      const uint32_t bar_m = bar_mma0 + 8 * ((nd - 3) & (kTcAcc - 1)), par_m = (uint32_t)(((nd - 3) >> 2) & 1);
+      const bool can_x = nx < nd, can_d = !end_decided && nd < nx + 4;
+      if (can_x && (nx < 4 || mbar_test(bar_s, par_s))) {
+        if (kProf && idle) { (can_d ? p_wm : p_sf) += tick() - t_idle; }
+        idle = 0;
+        issue_x(nx);
+        ++nx;
+        continue;
+      }
+      if (can_d && mbar_test(bar_m, par_m)) {
+        const long long t1 = tick();
+        if (kProf && idle) { (can_x ? p_wm : p_sf) += t1 - t_idle; }
+        idle = 0;
+        if (decide(nd) < 0) end_decided = true;
+        ++nd;
+        p_dec += tick() - t1;
+        continue;
+      }
+      // nothing is ready: poll both events (bounded)
+      if (idle == 0) t_idle = tick();
+      if (++idle > kSpinLimit) { ok = false; break; }
+      __nanosleep(32);
     }
-    for (int n = 0; n < 3; ++n) decide(n);
-    issue_hl(0); issue_hl(1);
-    issue_x(0); issue_x(1); issue_x(2);
-    bool ok = true;
-    for (int k = 0; ok; ++k) {
-      if (v_seq[k & 7] < 0) break;
-      // operand stage k & 1 is free once the MMAs of position k completed
-      ok = mbar_wait(bar_mma0 + 8 * (k & (kTcAcc - 1)), (uint32_t)((k >> 2) & 1));
-      if (!ok) break;
-      issue_hl(k + 2);
-      // the exact image of position k+3 replaces that of position k-1: every warp must have evaluated it.  The tile is
-      // chosen BEFORE the wait (the choice needs no free stage; its L2 round trips hide behind the evaluation of tile k-1)
-      decide(k + 3);
-      if (k >= 1) ok = mbar_wait(bar_sfree0 + 8 * ((k + 3) & (kTcStages - 1)), (uint32_t)(((k - 1) >> 2) & 1));
-      if (!ok) break;
-      issue_x(k + 3);
-    }
+    prof(29, p_wm); prof(13, p_dec); prof(14, p_sf);
     if (!ok) *v_dead = 1;
     if (lane == 0) s_npos = n_issued;
   } else {
@@ -483,25 +578,44 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
     const int row = quad * 32 + lane, gi = r0 + row;
     const bool row_ok = gi < nA;
     const float4* __restrict__ aex = reinterpret_cast<const float4*>(smem + 2 * kTcTileBytes) + quad * 32;  // exact image of the A block
-    const float kLow = 1.0f - 0.5f * kTcC;                   // d~ - e_ij = kLow (na' + nb') - 2 dot
-    const float kHighOverLow = (1.0f + 0.5f * kTcC) / kLow;  // (1 + c/2) x from the stored kLow x
-    const float nam = row_ok ? kLow * nrmA[gi] : 0.0f;
-    const float negna = row_ok ? -nam : -INFINITY;           // column test:  kLow nb' - 2 dot - cbest_j <= -kLow na'
+    // TMEM holds LB_ij = d~_ij - e_ij = kLow (na' + nb') - 2 dot (split_desc_kernel); an entry is a candidate iff LB_ij <= the best
+    // exact distance known for row i or for column j
+    const float kLow = 1.0f - 0.5f * kTcC;
+    const float kW = kTcC / kLow;                            // d~ + e = LB + kW (kLow na' + kLow nb')
+    const float nam = row_ok ? kLow * nrmA[gi] : INFINITY;   // +inf: a padded row yields no upper bounds
     const unsigned oa = row_ok ? permA[gi] : 0u;             // point index of this lane's row
-    float Ri_ub = row_ok ? INFINITY : -INFINITY;             // row test:     kLow nb' - 2 dot <= best_i - kLow na'
+    float Ri_ub = row_ok ? INFINITY : -INFINITY;             // row threshold from the tile-local upper bounds (padded rows: never)
     float* wnbm = s_wnbm[warp];
     float* wcj = s_wcj[warp];
     unsigned short* wq = s_queue[warp];
     int evals_w = 0;
     bool alive = mbar_wait(bar_a, 0);
+    const long long t_loop = tick();
+    prof(19, t_loop - t_setup);
+    long long p_wx = 0, p_wmm = 0, p_ld = 0, p_prep = 0, p_fil = 0, p_ev = 0;
+    int p_tiles = 0;
     // column snapshot (best | point index) of the NEXT tile, fetched while the current one is processed when the scheduler
     // has already published it (pf_tile = tile the prefetch belongs to, -1 = none)
     int pf_tile = -1;
     unsigned long long pf_cb = ~0ull;
     unsigned pf_ob = 0;
+    // shared per-tile column maxima (scheduler warp): after a tile is evaluated its 32 column bests are read again, and one tile
+    // later (the load has landed) their max refreshes tcm4[tile][cq]
+    unsigned* __restrict__ tcmw = tile_cmax + ((size_t)pair * (V >> 7)) * 4 + cq;
+    int rr_tile = -1;
+    unsigned rr_val = 0;
+    auto rr_flush = [&]() {
+      if (rr_tile < 0) return;
+      const unsigned m = __reduce_max_sync(0xffffffffu, rr_val);
+      if (lane == 0) atomicMin(tcmw + (size_t)rr_tile * 4, m);
+      rr_tile = -1;
+    };
     for (int k = 0;; ++k) {
       const int ts = k & (kTcAcc - 1), st = k & (kTcStages - 1);
+      const long long q0 = tick();
       if (alive) alive = mbar_wait(bar_fullx0 + 8 * st, (uint32_t)((k >> 2) & 1));  // the exact image is read below
+      const long long q1 = tick();
+      p_wx += q1 - q0;
       alive = __all_sync(0xffffffffu, alive);
       if (!alive) { *v_dead = 1; break; }
       const int jt = v_seq[k & 7];
@@ -517,17 +631,9 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         ob = permB[c0 + cb + lane];
       }
       pf_tile = -1;
-      {  // one non-blocking look at the next position: if its exact image is already announced, start its snapshot loads
-        uint32_t ready;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ready)
-            : "r"(bar_fullx0 + 8 * ((k + 1) & (kTcStages - 1))), "r"((uint32_t)(((k + 1) >> 2) & 1))
-            : "memory");
-        if (__all_sync(0xffffffffu, ready != 0)) {
-          const int jn = v_seq[(k + 1) & 7];
+      {  // the next position is normally decided already (the scheduler runs 3 ahead): start its snapshot loads now
+        if (__all_sync(0xffffffffu, *v_ndec > k + 1)) {  // (volatile shared loads of one warp are performed in order: no fence,
+          const int jn = v_seq[(k + 1) & 7];               //  which would wait for this warp's global loads in flight)
           if (jn >= 0) {
             pf_tile = jn; pf_cb = ~0ull; pf_ob = 0;
             if (jn * kTcN + cb + lane < nB) {
@@ -537,7 +643,12 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
           }
         }
       }
+      const long long q2 = tick();
       alive = mbar_wait(bar_mma0 + 8 * ts, (uint32_t)((k >> 2) & 1));
+      const long long q3 = tick();
+      p_wmm += q3 - q2;
+      p_prep += q2 - q1;
+      ++p_tiles;
       alive = __all_sync(0xffffffffu, alive);
       if (!alive) { *v_dead = 1; break; }
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -547,14 +658,16 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tfree0 + 8 * ts);  // accumulators are in registers: the stage may be overwritten
+      const long long q4 = tick();
+      p_ld += q4 - q3;
       if (!skip) {
         const float4* __restrict__ bex = reinterpret_cast<const float4*>(smem + kABytes + 2 * kHLBytes + st * kXBytes);  // exact image
         // ---- per-column filter data of this warp's 32 columns (lane = column)
         const float nbm = bex[9 * 128 + cb + lane].x;  // kLow |b'_j|^2, +inf for padded columns (split_desc_kernel)
         const float dbest = cb_cur == ~0ull ? INFINITY : __uint_as_float((unsigned)(cb_cur >> 32));
-        float cj = nbm == INFINITY ? INFINITY : nbm - dbest;  // -inf while the column has no exact distance yet
+        float cj = nbm == INFINITY ? -INFINITY : dbest;  // column threshold: +inf while the column has no exact distance yet
         const unsigned long long rb = v_rbest[row];
-        float Ri = fminf(Ri_ub, rb == ~0ull ? INFINITY : __uint_as_float((unsigned)(rb >> 32)) - nam);
+        float Ri = fminf(Ri_ub, rb == ~0ull ? INFINITY : __uint_as_float((unsigned)(rb >> 32)));
         wnbm[lane] = nbm;
         __syncwarp();
         const float4* __restrict__ wn4 = reinterpret_cast<const float4*>(wnbm);
@@ -563,7 +676,6 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         // exact minima come from the tile itself: UB_ij = d~_ij + e_ij = (1+c/2)(na'+nb') - 2 dot >= d_ij.
         if (__any_sync(0xffffffffu, (row_ok && Ri == INFINITY) || (cb_cur == ~0ull && nbm != INFINITY))) {
           if (lane == 0) atomicAdd(&s_warm, 1);
-          const float nah = row_ok ? nam * kHighOverLow : INFINITY;
           float rowub = INFINITY;
           unsigned mine = 0xFFFFFFFFu;
 #pragma unroll
@@ -573,38 +685,40 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = 4 * c4 + e;
-              const float ub = fmaf(-2.0f, __uint_as_float(v[c]), wv[e] * kHighOverLow) + nah;
+              const float ub = fmaf(kW, nam + wv[e], __uint_as_float(v[c]));
               rowub = fminf(rowub, ub);
-              const unsigned mn = __reduce_min_sync(0xffffffffu, tc_fkey(ub));  // min over the warp's 32 rows
+              // min over the warp's 32 rows; an upper bound of a distance is >= 0 (bit patterns order them), anything else is dropped
+              const unsigned mn = __reduce_min_sync(0xffffffffu, ub >= 0.0f ? __float_as_uint(ub) : 0xFFFFFFFFu);
               if (lane == c) mine = mn;
             }
           }
-          if (mine != 0xFFFFFFFFu && nbm != INFINITY) cj = fmaxf(cj, nbm - tc_fkey_inv(mine));
-          if (row_ok) { Ri_ub = fminf(Ri_ub, rowub - nam); Ri = fminf(Ri, Ri_ub); }
+          if (mine != 0xFFFFFFFFu && nbm != INFINITY) cj = fminf(cj, __uint_as_float(mine));
+          if (row_ok) { Ri_ub = fminf(Ri_ub, rowub); Ri = fminf(Ri, Ri_ub); }
         }
         wcj[lane] = cj;
         __syncwarp();
-        // ---- branch-free filter of this lane's row over the 32 columns
+        const long long q5 = tick();
+        p_prep += q5 - q4;
+        // ---- branch-free filter of this lane's row over the 32 columns: two compares and a predicated OR per entry
         uint32_t mask = 0;
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 w = wn4[c4], x = wc4[c4];
-          const float wv[4] = {w.x, w.y, w.z, w.w}, xv[4] = {x.x, x.y, x.z, x.w};
+          const float4 x = wc4[c4];
+          const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = 4 * c4 + e;
-            const float dot = __uint_as_float(v[c]);
-            const float t = fmaf(-2.0f, dot, wv[e]);
-            const float u = fmaf(-2.0f, dot, xv[e]);
+            const float lbv = __uint_as_float(v[c]);
             asm("{\n\t.reg .pred p, q;\n\t"
                 "setp.le.f32 p, %1, %2;\n\t"
-                "setp.le.or.f32 q, %3, %4, p;\n\t"
-                "@q or.b32 %0, %0, %5;\n\t}\n"
+                "setp.le.or.f32 q, %1, %3, p;\n\t"
+                "@q or.b32 %0, %0, %4;\n\t}\n"
                 : "+r"(mask)
-                : "f"(u), "f"(negna), "f"(t), "f"(Ri), "r"(1u << c));
+                : "f"(lbv), "f"(xv[e]), "f"(Ri), "r"(1u << c));
             if (kDbg) {
               const unsigned oc = __shfl_sync(0xffffffffu, ob, c);
-              if (stripe == 0 && k == 0 && row_ok && c0 + cb + c < nB) dbg_tile[(size_t)oa * kTcN + oc] = (nam + wv[e]) / kLow - 2.0f * dot;
+              const float nbc = wnbm[c];
+              if (stripe == 0 && k == 0 && row_ok && c0 + cb + c < nB) dbg_tile[(size_t)oa * kTcN + oc] = fmaf(0.5f * kW, nam + nbc, lbv);
             }
           }
         }
@@ -615,6 +729,8 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
         if (!row_ok) mask = 0;
         // ---- exact evaluation, one candidate per lane, 32 per round
         int remaining = __reduce_add_sync(0xffffffffu, __popc(mask));
+        const long long q6 = tick();
+        p_fil += q6 - q5;
         evals_w += remaining;
         while (remaining > 0) {  // warp-uniform
           int tot;
@@ -657,14 +773,28 @@ tc_nn_kernel(const float* __restrict__ tiles, const float* __restrict__ norm, co
           if (k >= 7 && seen > (k + 1) * (kTcM * kTcN / 2)) *v_abort = 1;
         }
         evals_w = 0;
+        p_ev += tick() - q6;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sfree0 + 8 * st);  // the exact-image stage may be refilled
+      rr_flush();
+      if (!skip) {
+        rr_tile = jt;
+        rr_val = 0;  // padding columns do not count
+        if (c0 + cb + lane < nB) {
+          const unsigned long long cbn = __ldcg(cbg + c0 + cb + lane);
+          rr_val = cbn == ~0ull ? 0x7F800000u : (unsigned)(cbn >> 32);
+        }
+      }
     }
+    rr_flush();
+    prof(20, p_wx); prof(21, p_wmm); prof(22, p_ld); prof(23, p_prep); prof(24, p_fil); prof(25, p_ev);
+    prof(26, tick() - t_loop); prof(27, p_tiles);
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   const bool aborted = (s_abort | s_dead) != 0;
+  if (kProf && threadIdx.x == 0) atomicAdd(stats + 9, (unsigned long long)(tick() - t_begin));
   if (threadIdx.x == 0) {
     atomicAdd(stats + 0, (unsigned long long)s_evals);
     atomicAdd(stats + 1, (unsigned long long)s_npos);
@@ -717,17 +847,24 @@ int launch_match_nn(qb200_handle* h, int n_pairs) {
   // class results, indexed by unique rank (colpart is scratch of the exact kernel, which runs later)
   unsigned long long* colbest_u = h->colpart;
   unsigned long long* rowbest_u = h->colpart + (size_t)h->S * V;
-  unsigned* tile_cmax = reinterpret_cast<unsigned*>(h->colpart + (size_t)2 * h->S * V);  // [S][V/128] float bits, starts at "+inf"
+  unsigned* tile_cmax = reinterpret_cast<unsigned*>(h->colpart + (size_t)2 * h->S * V);  // [S][V/128][4] float bits, start above "+inf"
   QB_CUDA_TRY(h, cudaMemsetAsync(h->rowbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->colbest, 0xFF, (size_t)n_pairs * V * 8, h->stream));
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, ((size_t)2 * h->S * V + (size_t)h->S * (V >> 7) / 2 + 1) * 8, h->stream));  // 0xFFFFFFFF > +inf bits
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, ((size_t)2 * h->S * V + (size_t)h->S * (V >> 7) * 2 + 2) * 8, h->stream));  // 0xFFFFFFFF > +inf bits
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, (size_t)n_pairs * sizeof(int), h->stream));
   const dim3 gsplit((V + 255) / 256, 2 * n_pairs);
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, n_unique, V, uperm, h->desc_tiles, h->desc_norm);
   const dim3 g(h->NS, n_pairs);
   cudaEventRecord(h->kev[0], h->stream);
-  tc_nn_kernel<false><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, V, uperm, rowbest_u, colbest_u,
-                                                          tile_cmax, h->tc_fallback, h->tc_stats, nullptr, no_prune);
+  static const int tc_prof = (getenv("QB200_TC_PROF") && getenv("QB200_TC_PROF")[0] == '1') ? 1 : 0;
+  if (tc_prof) {
+    if (int rc2 = ensure_dyn_smem(h, (const void*)tc_nn_kernel<false, true>, smem)) return rc2;
+    tc_nn_kernel<false, true><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, V, uperm, rowbest_u, colbest_u,
+                                                                  tile_cmax, h->tc_fallback, h->tc_stats, nullptr, no_prune);
+  } else {
+    tc_nn_kernel<false><<<g, kTcThreads, smem, h->stream>>>(h->desc_tiles, h->desc_norm, n_unique, V, uperm, rowbest_u, colbest_u,
+                                                            tile_cmax, h->tc_fallback, h->tc_stats, nullptr, no_prune);
+  }
   cudaEventRecord(h->kev[1], h->stream);
   h->kev_armed[0] = 1;
   broadcast_best_kernel<<<gsplit, 256, 0, h->stream>>>(rowbest_u, colbest_u, h->ctr.n_vox, V, h->val_b, class_of, h->rowbest, h->colbest);
@@ -745,7 +882,7 @@ int launch_tc_debug_tile(qb200_handle* h, float* d_out) {
   if (rc) return rc;
   const uint32_t* uperm = h->val_a;
   const int* n_unique = reinterpret_cast<const int*>(reinterpret_cast<const uint32_t*>(h->key_a) + (size_t)2 * h->S * h->V);
-  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, ((size_t)2 * h->S * h->V + (size_t)h->S * (h->V >> 7) / 2 + 1) * 8, h->stream));
+  QB_CUDA_TRY(h, cudaMemsetAsync(h->colpart, 0xFF, ((size_t)2 * h->S * h->V + (size_t)h->S * (h->V >> 7) * 2 + 2) * 8, h->stream));
   QB_CUDA_TRY(h, cudaMemsetAsync(h->tc_fallback, 0, sizeof(int), h->stream));
   const dim3 gsplit((h->V + 255) / 256, 2);
   split_desc_kernel<<<gsplit, 256, 0, h->stream>>>(h->desc_t, n_unique, h->V, uperm, h->desc_tiles, h->desc_norm);
