@@ -252,6 +252,7 @@ def main():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--ref-pairs-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-steps", action="store_true", help="time the blocking qb200_register_batch per step (no batch k+1 under the tail of batch k)")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense sub-measurement of the default (street) run")
     ap.add_argument("--cross-rank-pairs", type=int, default=8, help="pairs of the next rank every rank re-registers and compares (N > 1)")
     args = ap.parse_args()
@@ -321,10 +322,18 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         handle.comm_init_rank(world, rank, uid[0])
 
+    # Throughput mode (BASELINE configs[2]): the timed steps are a stream of batches.  On one GPU batch k+1 is queued
+    # (qb200_register_batch_enqueue) before batch k has been collected, so the latency-bound tail of a batch runs under the copies
+    # and front-end kernels of the next; qb200_register_batch_flush closes the timed region.  --sync-steps times the blocking call
+    # (qb200_register_batch) per step instead; N > 1 uses the blocking call with the deferred gather.
+    mode = {"pipelined": world == 1 and not args.sync_steps}
+
     def step(hd, prm, pa, kind):
         t0 = time.perf_counter()
         if world > 1 and hd is handle:
             hd.register_batch_rank_raw(pa, P, prm, kind, out_all, defer=True)   # waits for the PREVIOUS step's gather first
+        elif mode["pipelined"]:
+            hd.register_batch_enqueue_raw(pa, P, prm, kind, out)
         else:
             hd.register_batch_raw(pa, P, prm, kind, out)
         host_ms["enqueue"] += 1e3 * (time.perf_counter() - t0)
@@ -337,6 +346,7 @@ def main():
             out[:] = out_all[rank::world]
 
     def timed(hd, prm, pa, kind, steps, sampler=None):
+        hd.register_batch_flush()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -348,6 +358,13 @@ def main():
         e0.record(stream)
         for _ in range(steps):
             step(hd, prm, pa, kind)
+            if not mode["pipelined"]:
+                m, c = hd.kernel_ms()
+                kms += m; kcalls += c; sms += hd.stage_ms()
+        if mode["pipelined"]:
+            t0 = time.perf_counter()
+            hd.register_batch_flush()   # every record of every step is in place
+            host_ms["enqueue"] += 1e3 * (time.perf_counter() - t0)
             m, c = hd.kernel_ms()
             kms += m; kcalls += c; sms += hd.stage_ms()
         if hd is handle:
@@ -409,6 +426,15 @@ def main():
 
     value = world * P * args.steps / (dev_ms * 1e-3)
     e2e_value = world * P * args.steps / (e2e_ms * 1e-3)
+    # the blocking call per step next to the pipelined stream of batches (same steps, same buffers)
+    sync_steps = None
+    if mode["pipelined"]:
+        mode["pipelined"] = False
+        sd_ms = timed(handle, p, pa_dev, MEM_DEVICE, args.steps)[0]
+        se_ms = timed(handle, p, pa_host, MEM_HOST, args.steps)[0]
+        mode["pipelined"] = True
+        sync_steps = {"value": P * args.steps / (sd_ms * 1e-3), "e2e": P * args.steps / (se_ms * 1e-3), "unit": UNIT,
+                      "what": "qb200_register_batch (blocking) per step instead of qb200_register_batch_enqueue per step + one flush"}
 
     # ---- N > 1: every rank re-registers the first k pairs of the NEXT rank and compares the bytes of the records ----
     cross = None
@@ -562,6 +588,10 @@ def main():
             "valid_pairs": int(res_dev["valid"].sum()), "mean_n_vox": float((nA.mean() + nB.mean()) / 2), "mean_L": float(L.mean()),
             "mean_clique": float(res_dev["clique_size"].mean()),
             "single_pair_latency_ms": single_ms,
+            "steps_mode": ("pipelined: every step is one qb200_register_batch_enqueue of the whole batch, one qb200_register_batch_flush before the "
+                           "closing event (throughput mode: the tail of batch k overlaps the copies and front end of batch k+1)"
+                           if mode["pipelined"] else "blocking call per step"),
+            "sync_steps": sync_steps,
             "host_ms_per_step_rank0": {"enqueue": host_dev["enqueue"] / args.steps, "collective_wait": host_dev["collective_wait"] / args.steps,
                                        "device": step_ms, "numa_cores_bound": numa_cores,
                                        "what": "host time inside qb200_register_batch(_rank) per step; time blocked in qb200_comm_wait (the deferred "

@@ -197,6 +197,15 @@ typedef struct qb200_corr_set {
 int qb200_solve_batch(qb200_handle* h, const qb200_corr_set* sets, int32_t n_sets, const qb200_params* p,
                       qb200_mem_kind kind, qb200_result* results);
 
+/* Pipelined form of qb200_register_batch for a stream of batches: _enqueue queues the batch and returns (it collects a lane's
+ * earlier wave only when it needs that lane again), so the single-warp tail of one batch runs under the PCIe copies and front-end
+ * kernels of the next; _flush waits for everything queued and completes the record arrays.  The scans (host kind) and `results` of
+ * every queued batch must stay valid until a flush (or qb200_register_batch, = enqueue + flush) returns.  Other entry points flush
+ * implicitly. */
+int qb200_register_batch_enqueue(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_mem_kind kind,
+                                 qb200_result* results);
+int qb200_register_batch_flush(qb200_handle* h);
+
 /* raw scans in -> pose out. */
 int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4,
                         int32_t n_tgt, const qb200_params* p, qb200_result* res);

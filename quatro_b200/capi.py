@@ -129,6 +129,8 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_get_kernel_ms": (i32, [vp, vp, vp, i32]),
         "qb200_debug_tc_distances": (i32, [vp, vp, i32, vp, i32, vp]),
         "qb200_debug_match_stats": (i32, [vp, vp, i32]),
+        "qb200_register_batch_enqueue": (i32, [vp, vp, i32, vp, i32, vp]),
+        "qb200_register_batch_flush": (i32, [vp]),
         "qb200_debug_tc_profile": (i32, [vp, vp, i32]),
         "qb200_solve_batch": (i32, [vp, vp, i32, vp, i32, vp]),
         "qb200_comm_init_all": (i32, [P(vp), i32]),
@@ -162,6 +164,8 @@ EXPORTED_SYMBOLS = [
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
     "qb200_debug_match_stats",
+    "qb200_register_batch_enqueue",
+    "qb200_register_batch_flush",
     "qb200_debug_tc_profile",
     "qb200_solve_batch",
     "qb200_comm_init_all", "qb200_register_batch_sharded", "qb200_comm_unique_id", "qb200_comm_init_rank",
@@ -455,6 +459,13 @@ class Handle:
     def register_batch_raw(self, pair_array, n: int, params: Params, kind: int, out: np.ndarray):
         """Zero-overhead variant for bench.py: pre-built (Pair * n) array and RESULT_DTYPE output."""
         return self._check(self.lib.qb200_register_batch(self.h, pair_array, n, C.byref(params), kind, _ptr(out)), "qb200_register_batch")
+
+    def register_batch_enqueue_raw(self, pair_array, n: int, params: Params, kind: int, out: np.ndarray):
+        """Pipelined form: queue the batch (pair_array, its scans and `out` must stay alive until register_batch_flush)."""
+        return self._check(self.lib.qb200_register_batch_enqueue(self.h, pair_array, n, C.byref(params), kind, _ptr(out)), "qb200_register_batch_enqueue")
+
+    def register_batch_flush(self):
+        return self._check(self.lib.qb200_register_batch_flush(self.h), "qb200_register_batch_flush")
 
     def last_clique(self, cap: int = 1 << 16):
         idx = np.zeros(cap, np.int32)

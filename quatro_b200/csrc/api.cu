@@ -5,6 +5,7 @@
 // implementation of any stage in this library.
 #include <math.h>
 #include <new>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <map>
@@ -91,7 +92,9 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_cloud_n, C * sizeof(int)));
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_raw_off, (C + 1) * sizeof(int)));
   QB_ALLOC(h, h->raw_stage, C * R);
-  QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  QB_CUDA_TRY(h, cudaEventCreate(&h->ev_fork));  // (timing enabled: QB200_TIMELINE measures the waves against it)
+  QB_CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  QB_CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
   // the sort workspace serves the voxel sort (C*R items), the lattice / norm sorts (C*V items) and, afterwards, the duplicate-class
   // tables of K6 (2S*V + 2S words in key_a): size it for the largest user
   const size_t n_sort = C * (R > V ? R : V) + 64;
@@ -259,7 +262,17 @@ int fetch_result(qb200_handle* h, qb200_result* res) {
 
 }  // namespace
 
+// entry points that use the handle's wave buffers first collect whatever qb200_register_batch_enqueue left in flight
+#define QB_IDLE(h)                                        \
+  do {                                                    \
+    if ((h) && (h)->lanes_active) {                       \
+      const int rc_idle_ = batch_flush(h);                \
+      if (rc_idle_) return rc_idle_;                      \
+    }                                                     \
+  } while (0)
+
 extern "C" {
+static int batch_flush(qb200_handle* h);
 static void cache_free(qb200_handle* h);
 }
 static void cache_free_public(qb200_handle* h) { cache_free(h); }
@@ -346,6 +359,8 @@ void qb200_destroy(qb200_handle* h) {
   for (int i = 0; i < 4; ++i)
     if (h->kev[i]) cudaEventDestroy(h->kev[i]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 7; ++i)
     if (h->lane[i]) qb200_destroy(h->lane[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -370,6 +385,7 @@ int64_t qb200_launch_count(const qb200_handle* h) {
 // ---- stage: voxelize ----------------------------------------------------------------------------
 int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, int32_t skip_flagged, float* out4, int32_t cap,
                    int32_t* n_out) {
+  QB_IDLE(h);
   if (!h || !n_out || n < 0 || (n > 0 && !pts4) || !(leaf > 0) || cap < 0 || (cap > 0 && !out4)) return QB200_ERR_BAD_ARG;
   *n_out = 0;
   if (n > h->R) { h->fail(__FILE__, __LINE__, "n exceeds max_raw_points"); return QB200_ERR_BAD_ARG; }
@@ -411,6 +427,7 @@ int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, in
 // ---- stage: normals + FPFH ------------------------------------------------------------------------
 int qb200_compute_fpfh(qb200_handle* h, const float* pts4, int32_t n, float normal_radius, float fpfh_radius, float grid_cell,
                        float* normals4, float* desc33) {
+  QB_IDLE(h);
   if (!h || n < 0 || (n > 0 && !pts4) || !(normal_radius > 0) || !(fpfh_radius > 0) || !(grid_cell > 0)) return QB200_ERR_BAD_ARG;
   if (normal_radius > fpfh_radius) return QB200_ERR_BAD_ARG;  // fpfh_manager.hpp:99-102
   cudaSetDevice(h->device);
@@ -455,6 +472,7 @@ static int download_corr(qb200_handle* h, int32_t* corr, float* sm4, float* tm4,
 
 int qb200_match(qb200_handle* h, const float* src4, int32_t n_src, const float* src_desc33, const float* tgt4, int32_t n_tgt,
                 const float* tgt_desc33, const qb200_params* p, int32_t* corr, int32_t cap, int32_t* n_corr, int32_t* n_mutual) {
+  QB_IDLE(h);
   if (!h || !p || !n_corr || n_src < 0 || n_tgt < 0 || cap < 0) return QB200_ERR_BAD_ARG;
   if ((n_src > 0 && (!src4 || !src_desc33)) || (n_tgt > 0 && (!tgt4 || !tgt_desc33))) return QB200_ERR_BAD_ARG;
   if (!p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
@@ -479,6 +497,7 @@ int qb200_match(qb200_handle* h, const float* src4, int32_t n_src, const float* 
 
 int qb200_match_and_pack(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4, int32_t n_tgt, const qb200_params* p,
                          int32_t* corr, float* src_matched4, float* tgt_matched4, int32_t cap, int32_t* n_corr) {
+  QB_IDLE(h);
   if (!h || !n_corr || !params_ok(p) || n_src < 0 || n_tgt < 0 || cap < 0) return QB200_ERR_BAD_ARG;
   if (!p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
   *n_corr = 0;
@@ -497,6 +516,7 @@ int qb200_match_and_pack(qb200_handle* h, const float* src4, int32_t n_src, cons
 // ---- stage: graph ---------------------------------------------------------------------------------
 int qb200_build_graph(qb200_handle* h, const float* a4, const float* b4, int32_t L, double noise_bound, double cbar2, uint32_t* adj,
                       int32_t words_per_row, int32_t* degree, int64_t* n_edges) {
+  QB_IDLE(h);
   if (!h || L < 0 || (L > 0 && (!a4 || !b4 || !adj)) || words_per_row < (L + 31) / 32 || !(noise_bound > 0) || !(cbar2 > 0))
     return QB200_ERR_BAD_ARG;
   cudaSetDevice(h->device);
@@ -519,6 +539,7 @@ int qb200_build_graph(qb200_handle* h, const float* a4, const float* b4, int32_t
 // ---- stage: max clique ------------------------------------------------------------------------------
 int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row, int32_t mode, double kcore_thr,
                      int32_t* clique, int32_t* n_clique, int32_t* kcore, int32_t* kcore_order, int32_t* max_core) {
+  QB_IDLE(h);
   if (!h || !n_clique || L < 0 || (L > 0 && (!adj || !clique)) || words_per_row < (L + 31) / 32) return QB200_ERR_BAD_ARG;
   if (mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
   if (mode != QB200_PMC_HEU && mode != QB200_KCORE_HEU) return QB200_ERR_BAD_ARG;
@@ -551,6 +572,7 @@ int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t wo
 // ---- stage: pose given the clique -------------------------------------------------------------------
 int qb200_solve_pose(qb200_handle* h, const float* a4, const float* b4, int32_t L, const int32_t* clique, int32_t n_clique,
                      const qb200_params* p, qb200_result* res, uint8_t* rot_inlier_mask, uint8_t* trans_inlier_mask) {
+  QB_IDLE(h);
   if (!h || !res || !params_ok(p) || L < 0 || (L > 0 && (!a4 || !b4)) || n_clique < 0 || n_clique > L || (n_clique > 0 && !clique))
     return QB200_ERR_BAD_ARG;
   cudaSetDevice(h->device);
@@ -585,6 +607,7 @@ int qb200_solve_correspondences(qb200_handle* h, const float* a4, const float* b
 // ---- batches of precomputed correspondences -> poses ------------------------------------------------------
 int qb200_solve_batch(qb200_handle* h, const qb200_corr_set* sets, int32_t n_sets, const qb200_params* p, qb200_mem_kind kind,
                       qb200_result* results) {
+  QB_IDLE(h);
   if (!h || n_sets < 0 || (n_sets > 0 && (!sets || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
   if (p->inlier_selection_mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
   for (int i = 0; i < n_sets; ++i)
@@ -636,10 +659,16 @@ int qb200_solve_batch(qb200_handle* h, const qb200_corr_set* sets, int32_t n_set
 
 // ---- raw scans -> pose ------------------------------------------------------------------------------
 // enqueue one wave (np <= S pairs) on lane L: H2D of the scans (host kind), K1..K11, D2H of the result records.  No sync.
-static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np, qb200_mem_kind kind, const qb200_params* p, float cell) {
+// cs: the batch's copy stream (host scans of a multi-wave batch), or nullptr = copy on the lane's own stream.  Copies queued on
+// several streams share the PCIe link, so every wave's scans would arrive late; on one stream they arrive wave after wave and the
+// first waves compute while the later ones are still crossing.
+static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np, qb200_mem_kind kind, const qb200_params* p, float cell,
+                       cudaStream_t cs) {
   const int ncl = 2 * np;
   int rc;
   cudaEventRecord(L->ev[0], L->stream);
+  const cudaStream_t cps = cs ? cs : L->stream;
+  // (the lane's previous wave has been collected: raw_stage and the pinned tables are free)
   int total = 0;
   // host scans that lie back to back in the caller's memory (one big pinned buffer is the usual case) go over PCIe as one
   // copy: far fewer DMA descriptors than one per scan
@@ -647,7 +676,7 @@ static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np,
   int run_dst = 0, run_n = 0;
   auto flush_run = [&]() -> int {
     if (run_n > 0)
-      QB_CUDA_TRY(L, cudaMemcpyAsync(L->raw_stage + run_dst, run_src, (size_t)run_n * sizeof(float4), cudaMemcpyHostToDevice, L->stream));
+      QB_CUDA_TRY(L, cudaMemcpyAsync(L->raw_stage + run_dst, run_src, (size_t)run_n * sizeof(float4), cudaMemcpyHostToDevice, cps));
     run_n = 0;
     return QB200_OK;
   };
@@ -677,10 +706,14 @@ static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np,
   }
   if ((rc = flush_run())) return rc;
   L->h_raw_off[ncl] = total;
-  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_ptr, L->h_cloud_ptr, (size_t)ncl * sizeof(float4*), cudaMemcpyHostToDevice, L->stream));
-  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_n, L->h_cloud_n, (size_t)ncl * sizeof(int), cudaMemcpyHostToDevice, L->stream));
-  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_raw_off, L->h_raw_off, (size_t)(ncl + 1) * sizeof(int), cudaMemcpyHostToDevice, L->stream));
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_ptr, L->h_cloud_ptr, (size_t)ncl * sizeof(float4*), cudaMemcpyHostToDevice, cps));
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_cloud_n, L->h_cloud_n, (size_t)ncl * sizeof(int), cudaMemcpyHostToDevice, cps));
+  QB_CUDA_TRY(L, cudaMemcpyAsync(L->d_raw_off, L->h_raw_off, (size_t)(ncl + 1) * sizeof(int), cudaMemcpyHostToDevice, cps));
   if ((rc = wave_reset(L, ncl))) return rc;
+  if (cs) {
+    QB_CUDA_TRY(L, cudaEventRecord(L->ev_copied, cs));
+    QB_CUDA_TRY(L, cudaStreamWaitEvent(L->stream, L->ev_copied, 0));
+  }
   cudaEventRecord(L->ev[1], L->stream);
   if ((rc = launch_voxel(L, ncl, total, p->voxel_size, p->skip_flagged))) return rc;
   cudaEventRecord(L->ev[2], L->stream);
@@ -699,7 +732,7 @@ static int wave_submit(qb200_handle* L, const qb200_pair* pairs, int w0, int np,
 }
 
 // wait for the wave in flight on lane L, hand out its records and add its stage / kernel times to the public handle h
-static int wave_collect(qb200_handle* h, qb200_handle* L, qb200_result* results) {
+static int wave_collect(qb200_handle* h, qb200_handle* L) {
   if (L->pend_np == 0) return QB200_OK;
   const int np = L->pend_np;
   L->pend_np = 0;
@@ -707,7 +740,17 @@ static int wave_collect(qb200_handle* h, qb200_handle* L, qb200_result* results)
     h->fail(__FILE__, __LINE__, cudaGetErrorString(cudaGetLastError()));
     return QB200_ERR_CUDA;
   }
-  memcpy(results + L->pend_w0, L->h_results, (size_t)np * sizeof(qb200_result));
+  memcpy(L->pend_dst + L->pend_w0, L->h_results, (size_t)np * sizeof(qb200_result));
+  static const int timeline = (getenv("QB200_TIMELINE") && getenv("QB200_TIMELINE")[0] == '1') ? 1 : 0;
+  if (timeline) {  // stage boundaries of this wave relative to the start of the batch (ms): start, h2d, voxel, fpfh, match, graph, clique, pose, d2h
+    fprintf(stderr, "[qb200 timeline] wave w0=%d np=%d:", L->pend_w0, np);
+    for (int i = 0; i < 9; ++i) {
+      float ms = -1.f;
+      cudaEventElapsedTime(&ms, h->ev_fork, L->ev[i]);
+      fprintf(stderr, " %.2f", ms);
+    }
+    fprintf(stderr, "\n");
+  }
   for (int i = 0; i < 8; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, L->ev[i], L->ev[i + 1]) == cudaSuccess) h->stage_ms[i] += ms;
@@ -723,8 +766,47 @@ static int wave_collect(qb200_handle* h, qb200_handle* L, qb200_result* results)
   return QB200_OK;
 }
 
+// wait for every wave in flight (oldest first) and hand out its records
+static int batch_flush(qb200_handle* h) {
+  int rc = QB200_OK;
+  const int n = h->lanes_active > 0 ? h->lanes_active : 1;
+  for (int i = 0; i < n; ++i) {
+    const int l = (h->lane_cursor + i) % n;
+    qb200_handle* L = l == 0 ? h : h->lane[l - 1];
+    if (!L) continue;
+    const int rc2 = wave_collect(h, L);
+    if (rc == QB200_OK) rc = rc2;
+  }
+  h->lanes_active = 0;
+  h->lane_cursor = 0;
+  return rc;
+}
+
+int qb200_register_batch_flush(qb200_handle* h) {
+  if (!h) return QB200_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  return batch_flush(h);
+}
+
 int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_mem_kind kind,
                          qb200_result* results) {
+  int rc = qb200_register_batch_enqueue(h, pairs, n_pairs, p, kind, results);
+  const int rc2 = h ? batch_flush(h) : QB200_OK;  // on an error still wait for everything in flight (the copies read caller memory)
+  if (rc == QB200_OK) rc = rc2;
+  if (rc != QB200_OK) return rc;
+  if (n_pairs == 1) {
+    h->last_n_corr = results[0].n_corr;
+    h->last_n_clique = results[0].clique_size;
+    h->last_n_final = results[0].n_final_inliers;
+  }
+  return QB200_OK;
+}
+
+// Queue a batch and return: waves rotate over the lanes, a lane is collected (its records copied out) only when it is needed
+// again, so the tail of one batch runs under the copies and front-end kernels of the next.  pairs' scans (host kind) and
+// `results` must stay valid until qb200_register_batch_flush (or a later enqueue / qb200_register_batch) has returned them.
+int qb200_register_batch_enqueue(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_mem_kind kind,
+                                 qb200_result* results) {
   if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
   if (p->inlier_selection_mode == QB200_PMC_EXACT || !p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
   for (int i = 0; i < n_pairs; ++i) {
@@ -735,8 +817,11 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
     }
   }
   cudaSetDevice(h->device);
-  for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
-  for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
+  const bool pipelined = h->lanes_active > 0;  // waves of an earlier enqueue are still in flight
+  if (!pipelined) {
+    for (int i = 0; i < 8; ++i) h->stage_ms[i] = 0.f;
+    for (int i = 0; i < 2; ++i) { h->kernel_ms[i] = 0.f; h->kernel_calls[i] = 0; h->kev_armed[i] = 0; }
+  }
   // the rotation noise bound latches on the PUBLIC handle (quatro.hpp:469-470) and every lane gets the resolved value, so a pair's
   // GNC bound never depends on the wave / lane it lands on
   qb200_params p_resolved = *p;
@@ -764,10 +849,28 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
       left -= wave_n[n_waves++];
     }
     if (left > 0) n_waves = 0;  // more than ~60 waves: no special opening, walk uniformly below
+    // experiments: QB200_WAVE_PLAN="16,48,64,..." replaces the plan when it covers exactly n_pairs with waves of at most S pairs
+    if (const char* wp = getenv("QB200_WAVE_PLAN")) {
+      int plan[64], k = 0, sum = 0;
+      bool good = true;
+      for (const char* c = wp; *c && k < 63;) {
+        const int v = atoi(c);
+        if (v <= 0 || v > h->S) { good = false; break; }
+        plan[k++] = v; sum += v;
+        while (*c && *c != ',') ++c;
+        if (*c == ',') ++c;
+      }
+      if (good && sum == n_pairs) { n_waves = k; for (int i = 0; i < k; ++i) wave_n[i] = plan[i]; }
+    }
   }
   const bool planned = n_waves > 0;
   if (!planned) n_waves = (n_pairs + h->S - 1) / h->S;
-  const int n_lanes = n_waves < h->max_lanes ? (n_waves < 1 ? 1 : n_waves) : h->max_lanes;
+  int n_lanes = n_waves < h->max_lanes ? (n_waves < 1 ? 1 : n_waves) : h->max_lanes;
+  if (pipelined && h->lanes_active != n_lanes) {  // a different lane count: start a fresh rotation
+    const int rc0 = batch_flush(h);
+    if (rc0) return rc0;
+  }
+  const bool fresh = h->lanes_active == 0;
   qb200_handle* lanes[8] = {h, h, h, h, h, h, h, h};
   for (int l = 1; l < n_lanes; ++l) {
     if (!h->lane[l - 1]) {
@@ -779,32 +882,33 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
       h->lane[l - 1]->max_lanes = 1;
     }
     lanes[l] = h->lane[l - 1];
-    // the lane starts after whatever the caller queued on this handle's stream
-    if (l == 1) QB_CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
-    QB_CUDA_TRY(h, cudaStreamWaitEvent(lanes[l]->stream, h->ev_fork, 0));
+    // the lanes start after whatever the caller queued on this handle's stream (first batch of a pipelined sequence only: later
+    // on this handle's stream carries a wave of its own)
+    if (fresh) {
+      if (l == 1) QB_CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+      QB_CUDA_TRY(h, cudaStreamWaitEvent(lanes[l]->stream, h->ev_fork, 0));
+    }
   }
+  // host scans of a multi-wave batch: one copy stream, ordered after whatever the caller queued on this handle's stream
+  cudaStream_t copy_stream = nullptr;
+  if (kind == QB200_MEM_HOST && n_lanes > 1) {
+    copy_stream = h->copy_stream;
+    if (fresh) QB_CUDA_TRY(h, cudaStreamWaitEvent(copy_stream, h->ev_fork, 0));
+  }
+  h->lanes_active = n_lanes;
   int rc = QB200_OK, wave = 0;
   for (int w0 = 0; w0 < n_pairs && rc == QB200_OK; ++wave) {
-    qb200_handle* L = lanes[wave % n_lanes];
+    qb200_handle* L = lanes[h->lane_cursor];
     int np = planned ? wave_n[wave] : h->S;
     if (np > n_pairs - w0) np = n_pairs - w0;
-    if ((rc = wave_collect(h, L, results))) break;  // the lane's previous wave (its pinned tables are reused)
-    rc = wave_submit(L, pairs, w0, np, kind, p, cell);
+    if ((rc = wave_collect(h, L))) break;  // the lane's previous wave (its pinned tables are reused)
+    L->pend_dst = results;
+    rc = wave_submit(L, pairs, w0, np, kind, p, cell, copy_stream);
     if (rc != QB200_OK && L != h) h->fail(__FILE__, __LINE__, L->err);
+    h->lane_cursor = (h->lane_cursor + 1) % n_lanes;  // always the lane that has been busy longest
     w0 += np;
   }
-  // drain in submission order; on an error still wait for everything in flight (the copies read caller memory)
-  for (int i = 0; i < n_lanes; ++i) {
-    const int rc2 = wave_collect(h, lanes[(wave + i) % n_lanes], results);
-    if (rc == QB200_OK) rc = rc2;
-  }
-  if (rc != QB200_OK) return rc;
-  if (n_pairs == 1) {
-    h->last_n_corr = results[0].n_corr;
-    h->last_n_clique = results[0].clique_size;
-    h->last_n_final = results[0].n_final_inliers;
-  }
-  return QB200_OK;
+  return rc;
 }
 
 int qb200_register_pair(qb200_handle* h, const float* src4, int32_t n_src, const float* tgt4, int32_t n_tgt, const qb200_params* p,
@@ -932,6 +1036,7 @@ int qb200_debug_match_stats(qb200_handle* h, uint64_t* out4, int32_t reset) {
 // Validation hook: tensor-core (3xTF32) approximate squared distances between up to 128 source and 128 target
 // descriptors -> out[128*128] (row = source).  Lets tests measure the filter's error against the exact chain.
 int qb200_debug_tc_distances(qb200_handle* h, const float* a33, int32_t na, const float* b33, int32_t nb, float* out) {
+  QB_IDLE(h);
   if (!h || !a33 || !b33 || !out || na < 1 || nb < 1 || na > 128 || nb > 128) return QB200_ERR_BAD_ARG;
   cudaSetDevice(h->device);
   int rc = wave_reset(h, 2);
@@ -1005,6 +1110,7 @@ static int cache_copy(qb200_handle* h, int to_cache, int n_clouds) {
 
 int qb200_cache_scans(qb200_handle* h, const float* const* scans4, const int32_t* n_points, const int32_t* slot_ids, int32_t n_scans,
                       const qb200_params* p, qb200_mem_kind kind) {
+  QB_IDLE(h);
   if (!h || n_scans < 0 || (n_scans > 0 && (!scans4 || !n_points || !slot_ids)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
   for (int i = 0; i < n_scans; ++i)
     if (slot_ids[i] < 0 || slot_ids[i] >= h->c_slots || n_points[i] < 0 || n_points[i] > h->R || (n_points[i] > 0 && !scans4[i])) {
@@ -1046,6 +1152,7 @@ int qb200_cache_scans(qb200_handle* h, const float* const* scans4, const int32_t
 }
 
 int qb200_register_cached(qb200_handle* h, const qb200_slot_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_result* results) {
+  QB_IDLE(h);
   if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
   if (p->inlier_selection_mode == QB200_PMC_EXACT || !p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
   const float cell = lattice_cell(*p);

@@ -27,7 +27,11 @@ struct qb200_handle {
   int max_lanes;              // 1..8 (QB200_LANES, default 4)
   unsigned func_attr_set;     // which kernels already got their dynamic shared-memory opt-in on this handle's device
   int pend_w0, pend_np;       // wave in flight on this lane (pend_np == 0: none)
+  qb200_result* pend_dst;     // ... and the caller's record array of its batch
+  int lanes_active, lane_cursor;  // public handle: lanes of the rotation in use (0 = nothing in flight), next lane = busy longest
   cudaEvent_t ev_fork;
+  cudaStream_t copy_stream;   // host scans of a multi-wave batch cross PCIe on ONE stream, wave after wave (api.cu: wave_submit)
+  cudaEvent_t ev_copied;      // this lane's scans have arrived (recorded on the copy stream)
 
   // ---- sort workspace (voxel sort, then lattice sort) ----
   uint64_t *key_a, *key_b;    // [2S*R]

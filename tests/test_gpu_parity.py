@@ -552,6 +552,39 @@ def test_register_batch_matches_single_and_oracle(handle, oracle):
         del os.environ["QB200_LANES"]
 
 
+def test_register_batch_enqueue_flush_pipelined(oracle):
+    """qb200_register_batch_enqueue / _flush: three batches in flight over reused lanes give the records of the blocking call,
+    and an entry point called in between flushes implicitly."""
+    import ctypes as C
+    from quatro_b200.capi import Handle, Pair, MEM_HOST
+    p = default_params()
+    batches = [[synth.outdoor_pair(s, rings=32, azimuths=900)[:2] for s in range(b, b + n)] for b, n in ((200, 11), (220, 5), (240, 9))]
+    with Handle(max_batch_slots=4) as h:
+        ref = [h.register_batch(b, p) for b in batches]
+        arrs, outs, keep = [], [], []
+        for b in batches:
+            arr = (Pair * len(b))()
+            for i, (s, t) in enumerate(b):
+                s, t = np.ascontiguousarray(s, np.float32), np.ascontiguousarray(t, np.float32)
+                keep.append((s, t))
+                arr[i].src, arr[i].n_src, arr[i].tgt, arr[i].n_tgt = s.ctypes.data, len(s), t.ctypes.data, len(t)
+            arrs.append(arr)
+            outs.append(np.zeros(len(b), RESULT_DTYPE))
+        for arr, out in zip(arrs, outs):
+            h.register_batch_enqueue_raw(arr, len(out), p, MEM_HOST, out)
+        h.register_batch_flush()
+        for out, r in zip(outs, ref):
+            assert out.tobytes() == r.tobytes()
+        # implicit flush: a blocking call right after an enqueue completes the queued batch first
+        outs[0][:] = 0
+        h.register_batch_enqueue_raw(arrs[0], len(outs[0]), p, MEM_HOST, outs[0])
+        again = h.register_batch(batches[1], p)
+        assert outs[0].tobytes() == ref[0].tobytes() and again.tobytes() == ref[1].tobytes()
+        h.register_batch_flush()   # nothing in flight: a no-op
+    r_ref, _ = oracle.register_pair(batches[0][0][0], batches[0][0][1], p)
+    _same_record(ref[0][0], r_ref)
+
+
 def test_register_batch_device_resident_inputs(handle, oracle):
     import torch
     p = default_params()
