@@ -324,14 +324,15 @@ def main():
 
     # Throughput mode (BASELINE configs[2]): the timed steps are a stream of batches.  On one GPU batch k+1 is queued
     # (qb200_register_batch_enqueue) before batch k has been collected, so the latency-bound tail of a batch runs under the copies
-    # and front-end kernels of the next; qb200_register_batch_flush closes the timed region.  --sync-steps times the blocking call
-    # (qb200_register_batch) per step instead; N > 1 uses the blocking call with the deferred gather.
-    mode = {"pipelined": world == 1 and not args.sync_steps}
+    # and front-end kernels of the next; qb200_register_batch_flush closes the timed region.  N > 1: the same through
+    # qb200_register_batch_rank(defer = 2), which also starts batch k's all-gather while batch k+1 computes; qb200_comm_wait closes.
+    # --sync-steps times the blocking call per step instead (N > 1: blocking local batch, deferred gather).
+    mode = {"pipelined": not args.sync_steps}
 
     def step(hd, prm, pa, kind):
         t0 = time.perf_counter()
         if world > 1 and hd is handle:
-            hd.register_batch_rank_raw(pa, P, prm, kind, out_all, defer=True)   # waits for the PREVIOUS step's gather first
+            hd.register_batch_rank_raw(pa, P, prm, kind, out_all, defer=2 if mode["pipelined"] else 1)   # collects the PREVIOUS step's gather first
         elif mode["pipelined"]:
             hd.register_batch_enqueue_raw(pa, P, prm, kind, out)
         else:
@@ -365,10 +366,11 @@ def main():
             t0 = time.perf_counter()
             hd.register_batch_flush()   # every record of every step is in place
             host_ms["enqueue"] += 1e3 * (time.perf_counter() - t0)
-            m, c = hd.kernel_ms()
-            kms += m; kcalls += c; sms += hd.stage_ms()
         if hd is handle:
             finish_gather()   # the last step's gather; qb200_comm_wait orders the handle's stream after it
+        if mode["pipelined"]:
+            m, c = hd.kernel_ms()
+            kms += m; kcalls += c; sms += hd.stage_ms()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -433,7 +435,7 @@ def main():
         sd_ms = timed(handle, p, pa_dev, MEM_DEVICE, args.steps)[0]
         se_ms = timed(handle, p, pa_host, MEM_HOST, args.steps)[0]
         mode["pipelined"] = True
-        sync_steps = {"value": P * args.steps / (sd_ms * 1e-3), "e2e": P * args.steps / (se_ms * 1e-3), "unit": UNIT,
+        sync_steps = {"value": world * P * args.steps / (sd_ms * 1e-3), "e2e": world * P * args.steps / (se_ms * 1e-3), "unit": UNIT,
                       "what": "qb200_register_batch (blocking) per step instead of qb200_register_batch_enqueue per step + one flush"}
 
     # ---- N > 1: every rank re-registers the first k pairs of the NEXT rank and compares the bytes of the records ----

@@ -254,7 +254,10 @@ int qb200_register_batch_sharded(qb200_handle** handles, int32_t n_dev, const qb
  *     (the same n_local on every rank) and gathers all records: all_results[i * world + r] = record of rank r's i-th pair
  *     (round-robin sharding of a global list).  defer != 0: the call returns as soon as the gather is enqueued on the handle's
  *     communication stream -- all_results is complete after qb200_comm_wait (or the next qb200_register_batch_rank), so the
- *     gather overlaps the next batch and no rank waits for the slowest one inside a step. */
+ *     gather overlaps the next batch and no rank waits for the slowest one inside a step.  defer == 2 (a stream of batches): the
+ *     local batch is only queued (qb200_register_batch_enqueue), the call then completes the PREVIOUS batch's records and starts
+ *     their gather; local_pairs' scans and all_results of a batch must stay valid until its records were delivered (two calls
+ *     later, or qb200_comm_wait, which ends the stream). */
 int qb200_comm_unique_id(void* id128);
 int qb200_comm_init_rank(qb200_handle* h, int32_t world, int32_t rank, const void* id128);
 int qb200_register_batch_rank(qb200_handle* h, const qb200_pair* local_pairs, int32_t n_local, const qb200_params* p,

@@ -782,6 +782,20 @@ static int batch_flush(qb200_handle* h) {
   return rc;
 }
 
+// wait for the waves in flight whose records go to dst (a batch queued by qb200_register_batch_enqueue), oldest first
+static int collect_batch_impl(qb200_handle* h, const qb200_result* dst) {
+  int rc = QB200_OK;
+  const int n = h->lanes_active > 0 ? h->lanes_active : 1;
+  for (int i = 0; i < n; ++i) {
+    const int l = (h->lane_cursor + i) % n;
+    qb200_handle* L = l == 0 ? h : h->lane[l - 1];
+    if (!L || L->pend_np == 0 || L->pend_dst != dst) continue;
+    const int rc2 = wave_collect(h, L);
+    if (rc == QB200_OK) rc = rc2;
+  }
+  return rc;
+}
+
 int qb200_register_batch_flush(qb200_handle* h) {
   if (!h) return QB200_ERR_BAD_ARG;
   cudaSetDevice(h->device);
@@ -1251,3 +1265,10 @@ int qb200_get_kernel_ms(qb200_handle* h, float* ms, int32_t* launches, int32_t n
 }
 
 }  // extern "C"
+
+namespace qb {
+int collect_batch(qb200_handle* h, const qb200_result* dst) {
+  cudaSetDevice(h->device);
+  return collect_batch_impl(h, dst);
+}
+}  // namespace qb

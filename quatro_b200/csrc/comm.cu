@@ -80,7 +80,7 @@ int ensure_staging(qb200_handle* h, int n_local) {
   const size_t one = (size_t)n_local * sizeof(qb200_result), all = one * (size_t)h->comm_world;
   QB_CUDA_TRY(h, cudaMalloc((void**)&h->d_send, one));
   QB_CUDA_TRY(h, cudaMalloc((void**)&h->d_recv, all));
-  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_send, one));
+  QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_send, 2 * one));  // two halves: the pipelined mode fills one while the other is gathered
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_recv, all));
   h->comm_cap = n_local;
   return QB200_OK;
@@ -96,9 +96,9 @@ int comm_common_init(qb200_handle* h, int world, int rank) {
 }
 
 // enqueue H2D of this rank's records + the all-gather + D2H of everything on the comm stream (no host wait)
-int enqueue_gather(qb200_handle* h, int n_local, bool group_managed) {
+int enqueue_gather(qb200_handle* h, int n_local, bool group_managed, const qb200_result* src = nullptr) {
   const size_t one = (size_t)n_local * sizeof(qb200_result);
-  QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_send, h->h_send, one, cudaMemcpyHostToDevice, h->comm_stream));
+  QB_CUDA_TRY(h, cudaMemcpyAsync(h->d_send, src ? src : h->h_send, one, cudaMemcpyHostToDevice, h->comm_stream));
   (void)group_managed;
   QB_NCCL_TRY(h, nccl().AllGather(h->d_send, h->d_recv, one, ncclChar, (ncclComm_t)h->comm, h->comm_stream));
   return QB200_OK;
@@ -224,8 +224,8 @@ int qb200_bind_numa(qb200_handle* h) {
   return n;
 }
 
-int qb200_comm_wait(qb200_handle* h) {
-  if (!h) return QB200_ERR_BAD_ARG;
+// wait for the gather in flight and hand out its records
+static int gather_wait(qb200_handle* h) {
   if (h->pend_gather_n <= 0) return QB200_OK;
   cudaSetDevice(h->device);
   QB_CUDA_TRY(h, cudaEventSynchronize(h->comm_done));
@@ -237,14 +237,55 @@ int qb200_comm_wait(qb200_handle* h) {
   return QB200_OK;
 }
 
+// pipelined mode: the local batch that has been queued but not gathered yet -> complete its records, start its gather
+static int pipe_finish(qb200_handle* h) {
+  if (h->pipe_n <= 0) return QB200_OK;
+  const qb200_result* src = h->h_send + (size_t)h->pipe_buf * h->comm_cap;
+  int rc = qb::collect_batch(h, src);          // every wave that writes into this half
+  if (rc == QB200_OK) rc = gather_wait(h);     // the gather before it owns d_send / h_recv
+  if (rc == QB200_OK) rc = enqueue_gather(h, h->pipe_n, false, src);
+  if (rc == QB200_OK) rc = enqueue_readback(h, h->pipe_n);
+  if (rc == QB200_OK) { h->pend_gather_n = h->pipe_n; h->pend_gather_dst = h->pipe_dst; }
+  h->pipe_n = 0;
+  h->pipe_dst = nullptr;
+  return rc;
+}
+
+int qb200_comm_wait(qb200_handle* h) {
+  if (!h) return QB200_ERR_BAD_ARG;
+  const int rc = pipe_finish(h);
+  const int rc2 = gather_wait(h);
+  return rc ? rc : rc2;
+}
+
 int qb200_register_batch_rank(qb200_handle* h, const qb200_pair* local_pairs, int32_t n_local, const qb200_params* p, qb200_mem_kind kind,
                               qb200_result* all_results, int32_t defer) {
   if (!h || n_local < 0 || (n_local > 0 && (!local_pairs || !all_results))) return QB200_ERR_BAD_ARG;
   if (!h->comm) { h->fail(__FILE__, __LINE__, "qb200_comm_init_rank / _init_all has not been called on this handle"); return QB200_ERR_BAD_ARG; }
-  int rc = qb200_comm_wait(h);  // a deferred gather of the previous batch still owns the staging buffers
+  int rc;
+  if (defer == 2 && n_local > 0 && n_local <= h->comm_cap) {
+    // Pipelined (a stream of batches): queue this rank's batch k+1 first, then complete batch k's records (its waves are the
+    // oldest in flight) and start ITS gather; the gather of batch k-1 is collected on the way.  qb200_comm_wait ends the stream.
+    if ((rc = gather_wait(h))) return rc;
+    const int buf = h->pipe_n > 0 ? 1 - h->pipe_buf : 0;
+    if ((rc = qb200_register_batch_enqueue(h, local_pairs, n_local, p, kind, h->h_send + (size_t)buf * h->comm_cap))) return rc;
+    if ((rc = pipe_finish(h))) return rc;
+    h->pipe_n = n_local;
+    h->pipe_dst = all_results;
+    h->pipe_buf = buf;
+    return QB200_OK;
+  }
+  rc = qb200_comm_wait(h);  // a deferred gather of the previous batch still owns the staging buffers
   if (rc) return rc;
   if (n_local == 0) return QB200_OK;
   if ((rc = ensure_staging(h, n_local))) return rc;
+  if (defer == 2) {  // first batch of a pipelined stream (the staging buffers have just been sized)
+    if ((rc = qb200_register_batch_enqueue(h, local_pairs, n_local, p, kind, h->h_send))) return rc;
+    h->pipe_n = n_local;
+    h->pipe_dst = all_results;
+    h->pipe_buf = 0;
+    return QB200_OK;
+  }
   if ((rc = qb200_register_batch(h, local_pairs, n_local, p, kind, h->h_send))) return rc;
   if ((rc = enqueue_gather(h, n_local, false))) return rc;
   if ((rc = enqueue_readback(h, n_local))) return rc;

@@ -94,6 +94,8 @@ struct qb200_handle {
   qb200_result *d_send, *d_recv, *h_send, *h_recv;   // device staging; pinned host staging (h_recv is rank-major)
   int pend_gather_n;          // > 0: a deferred gather is in flight (records per rank)
   qb200_result* pend_gather_dst;
+  int pipe_n, pipe_buf;       // pipelined rank mode: local batch queued, gather not started yet (records per rank, half of h_send)
+  qb200_result* pipe_dst;
 
   // ---- state mirrored from the reference's statics ----
   double rot_noise_bound_latched;  // quatro.hpp:469-470 (0 = not latched yet)
@@ -131,6 +133,7 @@ int launch_desc_from_aos(qb200_handle* h, int cloud, int n, const float* d_in33)
 int desc_to_aos_rows(qb200_handle* h, const float* desc_rows, int n, float* d_out33);
 size_t sort_temp_bytes(int max_items);
 void comm_release(qb200_handle* h);
+int collect_batch(qb200_handle* h, const qb200_result* dst);  // api.cu: wait for every wave in flight that writes into dst[...]
 // Raise a kernel's dynamic shared-memory opt-in to at least `bytes` on the handle's device.  The attribute is a property of the
 // (function, device), not of a handle: handles of different capacities share it, so it is only ever raised (process-wide maximum).
 int ensure_dyn_smem(qb200_handle* h, const void* kernel, size_t bytes);

@@ -74,6 +74,18 @@ def test_c_abi_comm_on_every_visible_gpu():
         h0.register_batch_rank_raw(arr, len(pairs), p, MEM_HOST, out, defer=True)
         h0.comm_wait()
         assert out.tobytes() == ref.tobytes()
+        # pipelined stream of batches (defer = 2): three batches in flight, separate record arrays, one comm_wait at the end
+        outs = [np.zeros(len(pairs), RESULT_DTYPE) for _ in range(3)]
+        for o in outs:
+            h0.register_batch_rank_raw(arr, len(pairs), p, MEM_HOST, o, defer=2)
+        h0.comm_wait()
+        for o in outs:
+            assert o.tobytes() == ref.tobytes()
+        out[:] = 0
+        h0.register_batch_rank_raw(arr, len(pairs), p, MEM_HOST, out, defer=2)   # a single queued batch, then the blocking form
+        out2 = np.zeros(len(pairs), RESULT_DTYPE)
+        h0.register_batch_rank_raw(arr, len(pairs), p, MEM_HOST, out2, defer=0)
+        assert out.tobytes() == ref.tobytes() and out2.tobytes() == ref.tobytes()
     hs = [Handle(device=d, max_batch_slots=4) for d in range(n_dev)]
     try:
         comm_init_all(hs)
