@@ -72,14 +72,16 @@ __global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __
   const int n = cloud_n[cloud];
   const float4* __restrict__ pts = cloud_ptr[cloud];
   int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN, cnt = 0, bad = 0;
-  // four independent 16-byte loads in flight per thread: this pass streams the raw scans (230 MB per 64-pair wave) from HBM
+  // eight independent 16-byte loads in flight per thread and ~30 points per thread: this pass streams the raw scans (230 MB per
+  // 64-pair wave) from HBM, and the reduction tail (shuffles, atomics) is paid once per 30 points instead of once per 7
+  constexpr int kInFlight = 8;
   const int stride = gridDim.x * blockDim.x;
-  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
-    float4 pp[4];
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kInFlight * stride) {
+    float4 pp[kInFlight];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pp[j] = i0 + j * stride < n ? __ldg(pts + i0 + j * stride) : make_float4(NAN, NAN, NAN, 0.f);  // NaN = not kept
+    for (int j = 0; j < kInFlight; ++j) pp[j] = i0 + j * stride < n ? __ldg(pts + i0 + j * stride) : make_float4(NAN, NAN, NAN, 0.f);  // NaN = not kept
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kInFlight; ++j) {
       const float4 p = pp[j];
       if (i0 + j * stride >= n || !raw_point_kept(p, skip_flagged)) continue;
       const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
@@ -100,14 +102,27 @@ __global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __
     mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = max(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o); bad |= __shfl_xor_sync(0xffffffffu, bad, o);
   }
+  // one set of global atomics per CTA
+  __shared__ int s_red[8];
+  if (threadIdx.x == 0) { s_red[0] = s_red[1] = s_red[2] = INT_MAX; s_red[3] = s_red[4] = s_red[5] = INT_MIN; s_red[6] = 0; s_red[7] = 0; }
+  __syncthreads();
   if (lane_id() == 0) {
     if (cnt) {
-      int* b = bbox + cloud * 6;
-      atomicMin(b + 0, mn0); atomicMin(b + 1, mn1); atomicMin(b + 2, mn2);
-      atomicMax(b + 3, mx0); atomicMax(b + 4, mx1); atomicMax(b + 5, mx2);
-      atomicAdd(n_valid + cloud, cnt);
+      atomicMin(&s_red[0], mn0); atomicMin(&s_red[1], mn1); atomicMin(&s_red[2], mn2);
+      atomicMax(&s_red[3], mx0); atomicMax(&s_red[4], mx1); atomicMax(&s_red[5], mx2);
+      atomicAdd(&s_red[6], cnt);
     }
-    if (bad) cloud_status[cloud] = QB200_ERR_VOXEL_OVERFLOW;
+    if (bad) s_red[7] = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_red[6]) {
+      int* b = bbox + cloud * 6;
+      atomicMin(b + 0, s_red[0]); atomicMin(b + 1, s_red[1]); atomicMin(b + 2, s_red[2]);
+      atomicMax(b + 3, s_red[3]); atomicMax(b + 4, s_red[4]); atomicMax(b + 5, s_red[5]);
+      atomicAdd(n_valid + cloud, s_red[6]);
+    }
+    if (s_red[7]) cloud_status[cloud] = QB200_ERR_VOXEL_OVERFLOW;
   }
 }
 
@@ -245,7 +260,17 @@ __global__ void __launch_bounds__(128) voxel_centroid_kernel(const float4* const
   const int off = raw_off[cloud];
   const int a = starts[(size_t)cloud * (V + 1) + r], b = starts[(size_t)cloud * (V + 1) + r + 1];
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  for (int t = a; t < b; ++t) {
+  int t = a;
+  for (; t + 4 <= b; t += 4) {  // four gathers in flight, summed in order
+    const uint64_t k0 = sorted_keys[off + t], k1 = sorted_keys[off + t + 1], k2 = sorted_keys[off + t + 2], k3 = sorted_keys[off + t + 3];
+    const float4 p0 = __ldg(pts + (k0 & idx_mask)), p1 = __ldg(pts + (k1 & idx_mask)), p2 = __ldg(pts + (k2 & idx_mask)),
+                 p3 = __ldg(pts + (k3 & idx_mask));
+    sx += p0.x; sy += p0.y; sz += p0.z;
+    sx += p1.x; sy += p1.y; sz += p1.z;
+    sx += p2.x; sy += p2.y; sz += p2.z;
+    sx += p3.x; sy += p3.y; sz += p3.z;
+  }
+  for (; t < b; ++t) {
     const float4 p = __ldg(pts + (sorted_keys[off + t] & idx_mask));
     sx += p.x; sy += p.y; sz += p.z;
   }
@@ -594,7 +619,8 @@ int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int s
   if (n_clouds <= 0) return QB200_OK;
   const float inv = 1.0f / leaf;
   const dim3 gk(64, n_clouds);
-  voxel_bbox_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid, h->ctr.cloud_status);
+  const dim3 gb(n_clouds >= 16 ? 16 : 64, n_clouds);  // ~30 points per thread when the batch fills the device on its own
+  voxel_bbox_kernel<<<gb, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid, h->ctr.cloud_status);
   const int idx_bits = clog2(h->R > 2 ? h->R : 2);  // point index inside its scan
   voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid,
                                                idx_bits, h->key_a);
