@@ -490,7 +490,12 @@ __global__ void __launch_bounds__(128) normals_kernel(const float4* __restrict__
 
 // K4: SPFH.  Bin COUNTS are order-free; the float histogram value is rebuilt by repeated addition
 // of the same increment, which is what the sequential reference loop produces.
+// kRare = false: the points whose neighbourhood is in the K2c list (all but a handful): no lattice walk compiled in, no list
+// buffer in shared memory.  kRare = true: only the points with more than kNbrGlobalCap neighbours, which walk the lattice.
+// SPFH rows are stored as three padded thirds [11 bins, 0][11 bins, 0][11 bins, 0] (36 floats): a third is three 16-byte loads.
 constexpr int kSpfhThreads = kNbrThreads;
+__device__ __forceinline__ int spfh_slot(int b) { return b + b / 11; }
+template <bool kRare>
 __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __restrict__ pts, const float4* __restrict__ normals,
                                                             const int* __restrict__ n_pts, int V, const uint64_t* __restrict__ cell_key,
                                                             const int* __restrict__ cell_start, const uint32_t* __restrict__ order,
@@ -498,10 +503,12 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
                                                             float* __restrict__ spfh, const unsigned short* __restrict__ nbr_list,
                                                             const int* __restrict__ nbr_cnt) {
   __shared__ unsigned short cnts[kDescDim][kSpfhThreads];
-  __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
+  __shared__ unsigned short nbr[kRare ? kNbrCap : 1][kNbrThreads];
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_pts[cloud]) return;
+  int k = nbr_cnt[(size_t)cloud * V + q];
+  if ((k > kNbrGlobalCap) != kRare) return;
   const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
   const float4* __restrict__ nrm = normals + (size_t)cloud * V;
   const float4 pq = L.pts[q];
@@ -520,36 +527,78 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
     cnts[11 + b2][threadIdx.x]++;
     cnts[22 + b3][threadIdx.x]++;
   };
-  int k = nbr_cnt[(size_t)cloud * V + q];
-  if (k <= kNbrGlobalCap) {
+  if (!kRare) {
     const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
     for (int t = 0; t < k; ++t) feature((int)gl[(size_t)t * V]);
   } else {
     k = for_each_neighbor_listed(L, pq, m, r2, nbr, feature);
   }
-  float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescPad;  // rows padded to 36 floats: 16-byte gathers in K5
+  float* __restrict__ out = spfh + ((size_t)cloud * V + q) * kDescPad;  // three padded thirds: 16-byte gathers in K5
   const float incr = k >= 2 ? 100.0f / (float)(k - 1) : 0.0f;
   for (int b = 0; b < kDescDim; ++b) {
     const int c = cnts[b][threadIdx.x];
     float v = 0.0f;
     for (int t = 0; t < c; ++t) v += incr;
-    out[b] = v;
+    out[spfh_slot(b)] = v;
   }
-  out[33] = 0.0f; out[34] = 0.0f; out[35] = 0.0f;
+  out[11] = 0.0f; out[23] = 0.0f; out[35] = 0.0f;
 }
 
 // K5: FPFH = per-third renormalised sum of neighbour SPFHs weighted by 1/d^2, neighbours in lattice
 // order.  Output is written dimension-major (desc_t[d][q]) for the matching kernel's tile loads.
-__global__ void __launch_bounds__(kNbrThreads) fpfh_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
-                                                           const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
-                                                           const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv,
-                                                           int m, float r2, const float* __restrict__ spfh,
-                                                           const unsigned short* __restrict__ nbr_list, const int* __restrict__ nbr_cnt,
-                                                           float* __restrict__ desc_t) {
+//
+// fpfh_list_kernel (the points whose neighbourhood is in the K2c list): the three thirds of the signature are independent
+// (own 11 accumulators, own fp64 normaliser), so a point is served by three threads in three different warps -- 11 accumulators
+// and three 16-byte gathers per neighbour each instead of 33 and nine: 3x the warps at well under half the registers.
+// Per-bin accumulation order (lattice order of the neighbours) is unchanged.
+__global__ void __launch_bounds__(3 * kNbrThreads) fpfh_list_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                                    const float* __restrict__ spfh, const unsigned short* __restrict__ nbr_list,
+                                                                    const int* __restrict__ nbr_cnt, float* __restrict__ desc_t) {
+  const int cloud = blockIdx.y;
+  const int third = threadIdx.x / kNbrThreads;  // warp-uniform
+  const int q = blockIdx.x * kNbrThreads + (threadIdx.x - third * kNbrThreads);
+  if (q >= n_pts[cloud]) return;
+  const int kq = nbr_cnt[(size_t)cloud * V + q];
+  if (kq > kNbrGlobalCap) return;  // fpfh_rare_kernel
+  const float4* __restrict__ P = pts + (size_t)cloud * V;
+  const float4* __restrict__ sp = reinterpret_cast<const float4*>(spfh + (size_t)cloud * V * kDescPad) + 3 * third;
+  const float4 pq = P[q];
+  float o[11];
+#pragma unroll
+  for (int b = 0; b < 11; ++b) o[b] = 0.0f;
+  double sum = 0.0;
+  const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
+  for (int t = 0; t < kq; ++t) {
+    const int p = (int)gl[(size_t)t * V];
+    const float4 pp = P[p];
+    const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
+    const float d2 = (dx * dx + dy * dy) + dz * dz;  // the same expression as the neighbour test: bit-identical
+    if (d2 == 0.0f) continue;
+    const float weight = 1.0f / d2;
+    const float4 t0 = __ldg(sp + (size_t)p * (kDescPad / 4)), t1 = __ldg(sp + (size_t)p * (kDescPad / 4) + 1),
+                 t2 = __ldg(sp + (size_t)p * (kDescPad / 4) + 2);
+    const float sv[11] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z};
+#pragma unroll
+    for (int b = 0; b < 11; ++b) { const float v = sv[b] * weight; sum += v; o[b] += v; }
+  }
+  if (sum != 0.0) sum = 100.0 / sum;
+  const float g = (float)sum;
+  float* __restrict__ out = desc_t + (size_t)cloud * kDescK * V + (size_t)(11 * third) * V + q;
+#pragma unroll
+  for (int b = 0; b < 11; ++b) out[(size_t)b * V] = o[b] * g;
+}
+
+// the rare point with more than kNbrGlobalCap neighbours walks the lattice itself (one thread, all 33 bins)
+__global__ void __launch_bounds__(kNbrThreads) fpfh_rare_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+                                                                const uint64_t* __restrict__ cell_key, const int* __restrict__ cell_start,
+                                                                const uint32_t* __restrict__ order, const int* __restrict__ n_cells, float inv,
+                                                                int m, float r2, const float* __restrict__ spfh,
+                                                                const int* __restrict__ nbr_cnt, float* __restrict__ desc_t) {
   __shared__ unsigned short nbr[kNbrCap][kNbrThreads];
   const int cloud = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_pts[cloud]) return;
+  if (nbr_cnt[(size_t)cloud * V + q] <= kNbrGlobalCap) return;  // fpfh_list_kernel
   const LatticeView L = make_view(cloud, V, pts, cell_key, cell_start, order, n_cells, inv);
   const float4* __restrict__ sp = reinterpret_cast<const float4*>(spfh + (size_t)cloud * V * kDescPad);
   const float4 pq = L.pts[q];
@@ -572,19 +621,11 @@ __global__ void __launch_bounds__(kNbrThreads) fpfh_kernel(const float4* __restr
 #pragma unroll
     for (int b = 0; b < 11; ++b) { const float v = s[b] * weight; s0 += v; o[b] += v; }
 #pragma unroll
-    for (int b = 11; b < 22; ++b) { const float v = s[b] * weight; s1 += v; o[b] += v; }
+    for (int b = 0; b < 11; ++b) { const float v = s[12 + b] * weight; s1 += v; o[11 + b] += v; }
 #pragma unroll
-    for (int b = 22; b < 33; ++b) { const float v = s[b] * weight; s2 += v; o[b] += v; }
+    for (int b = 0; b < 11; ++b) { const float v = s[24 + b] * weight; s2 += v; o[22 + b] += v; }
   };
-  // K4 walked the same neighbourhood (same radius, same lattice): reuse its list, in the same (cell, index) order.
-  // The lattice walk is repeated only for the rare point with more than kNbrGlobalCap neighbours (uniform per thread).
-  const int kq = nbr_cnt[(size_t)cloud * V + q];
-  if (kq <= kNbrGlobalCap) {
-    const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
-    for (int t = 0; t < kq; ++t) accumulate((int)gl[(size_t)t * V]);
-  } else {
-    for_each_neighbor_listed(L, pq, m, r2, nbr, accumulate);
-  }
+  for_each_neighbor_listed(L, pq, m, r2, nbr, accumulate);
   if (s0 != 0.0) s0 = 100.0 / s0;
   if (s1 != 0.0) s1 = 100.0 / s1;
   if (s2 != 0.0) s2 = 100.0 / s2;
@@ -660,11 +701,16 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
   const int list_usable = (mn <= mf && rn2 <= rf2) ? 1 : 0;
   normals_kernel<<<gp, 128, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mn, rn2,
                                             h->nbr_list, h->nbr_cnt, list_usable, h->normals);
-  spfh_kernel<<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
-                                                  h->ctr.n_cells, inv, mf, rf2, h->spfh, h->nbr_list, h->nbr_cnt);
-  fpfh_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf, rf2,
-                                         h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t);
-  h->launches += 1;
+  // listed neighbourhoods (all but a handful of points) and the lattice-walking rest are separate launches: the common kernels
+  // carry neither the walk's registers nor its list buffer
+  spfh_kernel<false><<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
+                                                         h->ctr.n_cells, inv, mf, rf2, h->spfh, h->nbr_list, h->nbr_cnt);
+  spfh_kernel<true><<<gp, kSpfhThreads, 0, h->stream>>>(h->vox_pts, h->normals, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b,
+                                                        h->ctr.n_cells, inv, mf, rf2, h->spfh, h->nbr_list, h->nbr_cnt);
+  fpfh_list_kernel<<<gp, 3 * kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t);
+  fpfh_rare_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf,
+                                                      rf2, h->spfh, h->nbr_cnt, h->desc_t);
+  h->launches += 3;
   h->launches += 4;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
