@@ -543,7 +543,8 @@ static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
                        (size_t)(4 + kKcWarps) * Lc * sizeof(unsigned short);
   // rows: what is left of a 144 KB budget (whole graphs up to L ~ 680 at max_corr 4096; the rest of the SM stays free for the
   // dense kernels of the other lanes), at least the prefetch ring
-  size_t row_words = fixed < 136 * 1024 ? (144 * 1024 - fixed) / 4 : 0;
+  static const size_t budget_kb = [] { const char* e = getenv("QB200_KCORE_SMEM_KB"); const int v = e ? atoi(e) : 0; return (size_t)(v >= 64 && v <= 220 ? v : 144); }();
+  size_t row_words = fixed + 8 * 1024 < budget_kb * 1024 ? (budget_kb * 1024 - fixed) / 4 : 0;
   if (row_words < (size_t)kRing * W) row_words = (size_t)kRing * W;
   if (row_words > (size_t)Lc * W) row_words = (size_t)Lc * W;
   const size_t smem = fixed + row_words * 4;

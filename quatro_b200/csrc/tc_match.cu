@@ -172,8 +172,18 @@ __global__ void __launch_bounds__(1024) dedup_kernel(const float* __restrict__ d
       flag = 1;
       if (enable && r > 0 && sk[r] == sk[r - 1]) {  // same norm bits: compare the descriptors bit by bit
         const uint32_t a = pm[r], b = pm[r - 1];
-        bool same = true;
-        for (int d = 0; d < kDescDim && same; ++d) same = __float_as_uint(D[(size_t)d * V + a]) == __float_as_uint(D[(size_t)d * V + b]);
+        bool same = true;  // 11 dimensions per round trip (true duplicates need all 33: one dependent load pair each was 33 L2 latencies)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          if (!same) break;
+          unsigned diff = 0;
+#pragma unroll
+          for (int j = 0; j < 11; ++j) {
+            const int d = 11 * g + j;
+            diff |= __float_as_uint(D[(size_t)d * V + a]) ^ __float_as_uint(D[(size_t)d * V + b]);
+          }
+          same = diff == 0;
+        }
         flag = same ? 0 : 1;
       }
     }
