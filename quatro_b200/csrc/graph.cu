@@ -19,12 +19,13 @@
 // or with both distances ~0 (the literal expression is NaN -> false for coincident duplicates) evaluate the literal fp64
 // expression, so the adjacency is bit-identical to the fp64 reference.
 //
-// Work decomposition.  A CTA work item is 256 rows x 256 columns of the upper triangle; the 256 row points are staged in
-// shared memory as (-2a, |a|^2 - beta^2/4 | -2b, |b|^2 - beta^2/4), each lane keeps TWO columns in registers as one
-// packed pair (64 registers per thread: 8 CTAs = 32 warps per SM hide the dependent-FMA latency; four columns per lane ran at
-// 12 warps per SM and 67 % issue utilisation).  Result bits are shifted in from the SIGN BITS of t, s' and |t| - q with funnel
-// shifts (no compare / select per test); a warp shuffle transpose turns the per-column words into the row-major half,
-// so both halves of the symmetric matrix come out of one evaluation of the M pair tests.
+// Work decomposition.  A WARP work item is 64 rows x 128 columns of the upper triangle (any pair of the launch: one global item
+// list); the warp stages its 64 row points in shared memory as (-2a, |a|^2 - beta^2/4 | -2b, |b|^2 - beta^2/4) -- read back as
+// broadcast operands of the packed FMAs -- and each lane keeps FOUR columns in registers as two packed pairs.  No CTA barrier in
+// the item loop.  Result bits are shifted in from the SIGN BITS of t, s' and |t| - q with funnel shifts (no compare / select per
+// test); a warp shuffle transpose turns the per-column words into the row-major half, so both halves of the symmetric matrix come
+// out of one evaluation of the M pair tests.  (Timing experiment, round 2: without the two 4-byte row-strided stores and the
+// transpose per 32 x 32 block the kernel runs 0.144 instead of 0.174 ms at 32 x L = 3000.)
 #include <stdlib.h>
 
 #include "handle.cuh"
@@ -33,7 +34,7 @@ namespace qb {
 
 constexpr int kGW = 4;    // warps per CTA
 // columns per lane = template parameter GC (2 or 4: one or two packed pairs; a warp covers GC x 32 columns)
-constexpr int kGRB = 8;   // 32-row blocks per work item
+constexpr int kGRB = 2;   // 32-row blocks per work item (a WARP's work item: 64 rows x GC x 32 columns)
 
 // the literal reference expression (fp64, no FMA contraction: library is built with -fmad=false)
 __device__ __noinline__ bool tim_consistent_fp64(const float4 ai, const float4 aj, const float4 bi, const float4 bj, double beta) {
@@ -94,13 +95,17 @@ struct GraphConst {
   double beta;
 };
 
-// work items (256 rows x 512 columns) of the upper triangle of one pair: row group rg meets column groups cg >= rg / 2
+// WARP work items (64 rows x kGC*32 columns) of the upper triangle of one pair: row group rg meets the column groups q >= rg*kGRB/kGC
+// (the first group that is not entirely below the diagonal).  Round 2, first version: a CTA item of 256 rows x 512 columns with the
+// rows staged once per CTA -- 29 % of the items of an L = 3000 pair touch the diagonal, where one of the four warps has half the work,
+// and the barrier around the staging was the top stall reason (1.5 warps per issue).  Every warp now stages its own 64 rows
+// (~1 % of the item's instructions) and no barrier is left in the item loop.
 template <int kGC>
 __device__ __forceinline__ int graph_items(int L) {
   if (L <= 0) return 0;
-  const int nb = (L + 31) >> 5, ncg = (nb + kGW * kGC - 1) / (kGW * kGC), nrg = (nb + kGRB - 1) / kGRB;
+  const int nb = (L + 31) >> 5, ncq = (nb + kGC - 1) / kGC, nrg = (nb + kGRB - 1) / kGRB;
   int t = 0;
-  for (int rg = 0; rg < nrg; ++rg) t += max(0, ncg - rg * kGRB / (kGW * kGC));
+  for (int rg = 0; rg < nrg; ++rg) t += max(0, ncq - rg * kGRB / kGC);
   return t;
 }
 
@@ -111,11 +116,9 @@ __global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(c
                                                              const int* __restrict__ n_corr, int n_pairs, int Lc, int W, GraphConst gc,
                                                              uint32_t* __restrict__ adj) {
   constexpr int kGP = kGC / 2;
-  __shared__ float4 s_row[kGRB * 32][2];  // per row: (-2a, |a|^2 - beta^2/4) | (-2b, |b|^2 - beta^2/4); broadcast into both halves of the packed FMAs
-  __shared__ float s_rm[kGRB * 32];
-  __shared__ float s_mmax[kGRB];
-  __shared__ int s_pref[kGraphMaxPairs + 1];  // exclusive prefix of the pairs' item counts: the CTAs stride over ALL pairs' items,
-  __shared__ int s_scan[33];                  // so a pair with many correspondences is spread over the whole grid
+  __shared__ float4 s_row[kGW][kGRB * 32][2];  // per warp and row: (-2a, |a|^2 - beta^2/4) | (-2b, |b|^2 - beta^2/4)
+  __shared__ int s_pref[kGraphMaxPairs + 1];   // exclusive prefix of the pairs' item counts: the warps stride over ALL pairs' items,
+  __shared__ int s_scan[33];                   // so a pair with many correspondences is spread over the whole grid
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   {
@@ -132,50 +135,47 @@ __global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(c
     __syncthreads();
   }
   const int total_items = s_pref[n_pairs];
+  float4(* __restrict__ row_w)[2] = s_row[warp];
 
-  for (int g = blockIdx.x; g < total_items; g += gridDim.x) {
-    int lo = 0, hi = n_pairs - 1;  // the pair that owns item g (CTA-uniform binary search)
+  for (int g = blockIdx.x * kGW + warp; g < total_items; g += gridDim.x * kGW) {
+    int lo = 0, hi = n_pairs - 1;  // the pair that owns item g (warp-uniform binary search)
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_pref[mid] <= g) lo = mid; else hi = mid - 1;
     }
     const int pair = lo;
     const int L = n_corr[pair];
-    const int nb = (L + 31) >> 5;                                 // 32-wide blocks per side
-    const int ncg = (nb + kGW * kGC - 1) / (kGW * kGC);           // column groups of 16 blocks
+    const int nb = (L + 31) >> 5;                  // 32-wide blocks per side
+    const int ncq = (nb + kGC - 1) / kGC;          // column groups of kGC blocks
     int item = g - s_pref[pair], rg = 0;
     for (;; ++rg) {
-      const int cnt = max(0, ncg - rg * kGRB / (kGW * kGC));
+      const int cnt = max(0, ncq - rg * kGRB / kGC);
       if (item < cnt) break;
       item -= cnt;
     }
-    const int cg = rg * kGRB / (kGW * kGC) + item;
+    const int cb0 = (rg * kGRB / kGC + item) * kGC;  // first column block of this item
     const float4* __restrict__ A = ma + (size_t)pair * Lc;
     const float4* __restrict__ B = mb + (size_t)pair * Lc;
     uint32_t* __restrict__ G = adj + (size_t)pair * Lc * W;
-    __syncthreads();
-    for (int idx = tid; idx < kGRB * 32; idx += kGW * 32) {
-      const int i = rg * (kGRB * 32) + idx;
+    // ---- this warp's rows
+    float mmr[kGRB];
+    __syncwarp();
+#pragma unroll
+    for (int rb = 0; rb < kGRB; ++rb) {
+      const int i = (rg * kGRB + rb) * 32 + lane;
       const bool v = i < L;
       const float4 pa = v ? A[i] : zero4, pb = v ? B[i] : zero4;
       const float na = fmaf(pa.z, pa.z, fmaf(pa.y, pa.y, pa.x * pa.x));
       const float nbn = fmaf(pb.z, pb.z, fmaf(pb.y, pb.y, pb.x * pb.x));
-      const float ax = -2.0f * pa.x, ay = -2.0f * pa.y, az = -2.0f * pa.z, an = na - gc.hb2q;
-      const float bx = -2.0f * pb.x, by = -2.0f * pb.y, bz = -2.0f * pb.z, bn = nbn - gc.hb2q;
-      s_row[idx][0] = make_float4(ax, ay, az, an);
-      s_row[idx][1] = make_float4(bx, by, bz, bn);
-      s_rm[idx] = na + nbn;
-    }
-    __syncthreads();
-    for (int rb = warp; rb < kGRB; rb += kGW) {
-      float m = s_rm[rb * 32 + lane];
+      row_w[rb * 32 + lane][0] = make_float4(-2.0f * pa.x, -2.0f * pa.y, -2.0f * pa.z, na - gc.hb2q);
+      row_w[rb * 32 + lane][1] = make_float4(-2.0f * pb.x, -2.0f * pb.y, -2.0f * pb.z, nbn - gc.hb2q);
+      float m = na + nbn;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) s_mmax[rb] = m;
+      mmr[rb] = m;
     }
-    __syncthreads();
-    const int cb0 = cg * (kGW * kGC) + warp * kGC;
-    if (cb0 >= nb) continue;  // warp-uniform; the barriers above are at the top of the item loop
+    __syncwarp();
+    // ---- this lane's columns
     float4 ca[kGC], cb[kGC];
     float cm[kGC];
     bool cv[kGC];
@@ -190,11 +190,22 @@ __global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(c
       cb[c] = make_float4(pb.x, pb.y, pb.z, nbn - gc.hb2q);
       cm[c] = na + nbn;
     }
+    // the columns as packed pairs
+    f32x2 cax[kGP], cay[kGP], caz[kGP], can[kGP], cbx[kGP], cby[kGP], cbz[kGP], cbn[kGP];
+#pragma unroll
+    for (int p = 0; p < kGP; ++p) {
+      cax[p] = pk2(ca[2 * p].x, ca[2 * p + 1].x); cay[p] = pk2(ca[2 * p].y, ca[2 * p + 1].y);
+      caz[p] = pk2(ca[2 * p].z, ca[2 * p + 1].z); can[p] = pk2(ca[2 * p].w, ca[2 * p + 1].w);
+      cbx[p] = pk2(cb[2 * p].x, cb[2 * p + 1].x); cby[p] = pk2(cb[2 * p].y, cb[2 * p + 1].y);
+      cbz[p] = pk2(cb[2 * p].z, cb[2 * p + 1].z); cbn[p] = pk2(cb[2 * p].w, cb[2 * p + 1].w);
+    }
+    const f32x2 ntwob2 = pk2(-gc.twob2, -gc.twob2), nb4 = pk2(-gc.b4, -gc.b4);
+#pragma unroll
     for (int rbl = 0; rbl < kGRB; ++rbl) {
       const int bi = rg * kGRB + rbl;
       if (bi >= nb) break;
-      if (cb0 + kGC - 1 < bi) continue;  // all four column blocks below the diagonal (warp-uniform)
-      const float mm = s_mmax[rbl];
+      if (cb0 + kGC - 1 < bi) continue;  // all column blocks below the diagonal (warp-uniform)
+      const float mm = mmr[rbl];
       float qa[kGC], qk[kGC], Mj[kGC];
 #pragma unroll
       for (int c = 0; c < kGC; ++c) {
@@ -206,18 +217,7 @@ __global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(c
       float smin[kGC];
 #pragma unroll
       for (int c = 0; c < kGC; ++c) { wt[c] = ws[c] = wa[c] = 0u; smin[c] = 3.0e38f; }
-      // the columns as packed pairs
-      f32x2 cax[kGP], cay[kGP], caz[kGP], can[kGP], cbx[kGP], cby[kGP], cbz[kGP], cbn[kGP], qa2[kGP], qk2[kGP];
-#pragma unroll
-      for (int p = 0; p < kGP; ++p) {
-        cax[p] = pk2(ca[2 * p].x, ca[2 * p + 1].x); cay[p] = pk2(ca[2 * p].y, ca[2 * p + 1].y);
-        caz[p] = pk2(ca[2 * p].z, ca[2 * p + 1].z); can[p] = pk2(ca[2 * p].w, ca[2 * p + 1].w);
-        cbx[p] = pk2(cb[2 * p].x, cb[2 * p + 1].x); cby[p] = pk2(cb[2 * p].y, cb[2 * p + 1].y);
-        cbz[p] = pk2(cb[2 * p].z, cb[2 * p + 1].z); cbn[p] = pk2(cb[2 * p].w, cb[2 * p + 1].w);
-        qa2[p] = pk2(qa[2 * p], qa[2 * p + 1]); qk2[p] = pk2(qk[2 * p], qk[2 * p + 1]);
-      }
-      const f32x2 ntwob2 = pk2(-gc.twob2, -gc.twob2), nb4 = pk2(-gc.b4, -gc.b4);
-      const float4(* __restrict__ row_p)[2] = s_row + rbl * 32;
+      const float4(* __restrict__ row_p)[2] = row_w + rbl * 32;
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
         const float4 r0 = row_p[r][0], r1 = row_p[r][1];
@@ -230,9 +230,11 @@ __global__ void __launch_bounds__(kGW * 32, kGC == 2 ? 8 : 4) tim_graph_kernel(c
           const f32x2 D = sub2(Ap, Bp), sp = add2(Ap, Bp);
           const f32x2 ng = fma2(ntwob2, sp, nb4);               // -g = -(2 beta^2 s' + beta^4)
           const f32x2 t = fma2(D, D, ng);
-          const f32x2 w = sub2(abs2(t), fma2(abs2(D), qa2[p], qk2[p]));
-          float t0, t1, s0, s1, w0, w1;
-          upk2(t, t0, t1); upk2(sp, s0, s1); upk2(w, w0, w1);
+          float t0, t1, s0, s1, D0, D1;
+          upk2(t, t0, t1); upk2(sp, s0, s1); upk2(D, D0, D1);
+          // |t| - q, q = |D| c1 M + K: scalar forms, where |.| is an operand modifier (the packed forms need two LOPs per |.|)
+          const float w0 = fabsf(t0) - fmaf(fabsf(D0), qa[2 * p], qk[2 * p]);
+          const float w1 = fabsf(t1) - fmaf(fabsf(D1), qa[2 * p + 1], qk[2 * p + 1]);
           wt[2 * p] = __funnelshift_l(__float_as_uint(t0), wt[2 * p], 1);          // sign(t):  t < 0
           wt[2 * p + 1] = __funnelshift_l(__float_as_uint(t1), wt[2 * p + 1], 1);
           ws[2 * p] = __funnelshift_l(__float_as_uint(s0), ws[2 * p], 1);          // sign(s'): s' < 0
@@ -334,8 +336,7 @@ int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2)
   gc.c2 = (float)(1500.0 * u * u * 1.02);
   gc.c3 = (float)(46.0 * u * beta * beta * 1.02);
   gc.two_b2_slack = (float)(2.0 * beta * beta * 1.00001);
-  // capacity-sized grid: Lc/256 x Lc/512 work items per pair; few pairs -> more CTAs per pair
-  // one wave of resident CTAs striding over every pair's work items.  QB200_GRAPH_COLS=2 selects the 2-columns-per-lane variant
+  // one wave of resident CTAs whose warps stride over every pair's work items (64 rows x 128 columns each).  QB200_GRAPH_COLS=2 selects the 2-columns-per-lane variant
   // (64 registers, 8 CTAs per SM) for A/B runs; results are identical
   static const int cols = (getenv("QB200_GRAPH_COLS") && getenv("QB200_GRAPH_COLS")[0] == '2') ? 2 : 4;
   cudaEventRecord(h->kev[2], h->stream);
