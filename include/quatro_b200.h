@@ -49,9 +49,13 @@ typedef enum qb200_status {
   QB200_ERR_BAD_ARG = -1,
   QB200_ERR_NO_DEVICE = -2,
   QB200_ERR_CUDA = -3,
-  QB200_ERR_UNSUPPORTED = -4,    /* e.g. PMC_EXACT is not implemented on the device */
+  QB200_ERR_UNSUPPORTED = -4,    /* e.g. use_crosscheck = 0, libnccl absent */
   QB200_ERR_VOXEL_OVERFLOW = -5  /* dx*dy*dz > INT_MAX: PCL warns and returns the input unfiltered */
 } qb200_status;
+
+/* qb200_result.flags */
+enum { QB200_FLAG_CLIQUE_TRUNCATED = 1 /* PMC_EXACT stopped at max_clique_node_limit: the clique is the best found, not proven maximum */ };
+#define QB200_DEFAULT_CLIQUE_NODE_LIMIT 262144
 
 /* Quatro::INLIER_SELECTION_MODE, include/quatro.hpp:184-189 */
 enum { QB200_PMC_EXACT = 0, QB200_PMC_HEU = 1, QB200_KCORE_HEU = 2, QB200_INLIER_NONE = 3 };
@@ -91,7 +95,8 @@ typedef struct qb200_params {
   int32_t cote_mode;                /* QB200_COTE_MEDIAN */
   int32_t using_rot_inliers_when_estimating_cote; /* 0 */
   int32_t use_pre_estimated_RyRx;   /* 0 */
-  int32_t reserved1;
+  int32_t max_clique_node_limit;    /* PMC_EXACT: branch-and-bound nodes per pair before the search returns its best clique so far
+                                       (deterministic stand-in for pmc's wall-clock time_limit, src/graph.cc:44); 0 -> QB200_DEFAULT_CLIQUE_NODE_LIMIT */
   double RyRx[9];                   /* row-major 3x3, setPreEstaimatedRyRx, quatro.hpp:276-279 */
 } qb200_params;
 
@@ -117,7 +122,7 @@ typedef struct qb200_result {
   int32_t gnc_iters;
   int32_t n_rot_inliers;     /* getNumRotaionInliers */
   int32_t n_final_inliers;
-  int32_t reserved;
+  int32_t flags;             /* QB200_FLAG_* bits */
   int64_t n_edges;
   double cost;               /* Quatro::cost_ */
   double T[16];              /* column-major 4x4 (Eigen::Matrix4d memory order); identity when !valid */
@@ -169,6 +174,13 @@ int qb200_build_graph(qb200_handle* h, const float* a4, const float* b4, int32_t
 int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row,
                      int32_t mode, double kcore_heuristic_threshold, int32_t* clique, int32_t* n_clique,
                      int32_t* kcore, int32_t* kcore_order, int32_t* max_core);
+/* The same with the PMC_EXACT knobs: node_limit (0 = default) and the QB200_FLAG_* bits of the search (flags may be NULL).
+ * PMC_EXACT = the heuristic clique as the incumbent, then a bit-parallel branch and bound with greedy-colouring bounds
+ * (src/graph.cc:106-127 -> [EXT] pmc::pmcx_maxclique::search_dense); the clique SIZE is the maximum, membership follows the
+ * canonical sequential order of DESIGN.md 5.3 (pmc's own choice among equal maximum cliques depends on thread timing). */
+int qb200_max_clique_ex(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row,
+                        int32_t mode, double kcore_heuristic_threshold, int64_t node_limit, int32_t* clique, int32_t* n_clique,
+                        int32_t* kcore, int32_t* kcore_order, int32_t* max_core, int32_t* flags);
 
 /* rotation + translation given the (sorted) clique. inlier_mask (n_clique bytes) may be NULL. */
 int qb200_solve_pose(qb200_handle* h, const float* a4, const float* b4, int32_t L,

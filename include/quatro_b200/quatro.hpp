@@ -192,7 +192,6 @@ class Quatro : public pcl::Registration<PointSource, PointTarget, Scalar> {
     tgt_matched_ = target_->points;
     qb200_result res;
     const int st = qb200_solve_correspondences(handle_.get(), qb200::as_float4(*input_), qb200::as_float4(*target_), L, &p, &res);
-    if (st == QB200_ERR_UNSUPPORTED) throw std::invalid_argument("[Quatro] PMC_EXACT is not available on the device path; use PMC_HEU");
     if (st < 0) throw std::runtime_error(std::string("qb200_solve_correspondences: ") + qb200_last_error(handle_.get()));
     fetch_ints(&qb200_get_last_clique, max_clique_);
     num_maxclique_ = res.clique_size;

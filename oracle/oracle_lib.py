@@ -40,6 +40,8 @@ class Oracle:
                                      C.POINTER(C.c_int64)]
         L.qo_max_clique.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_int), C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_int)]
+        L.qo_max_clique_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int64, C.c_void_p, C.POINTER(C.c_int),
+                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.qo_solve_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(Result),
                                     C.c_void_p, C.c_void_p]
         L.qo_solve_correspondences.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Params), C.POINTER(Result), C.c_void_p,
@@ -170,6 +172,16 @@ class Oracle:
         st = self.lib.qo_max_clique(_ptr(adj), L, wpr, mode, kcore_thr, _ptr(clique), C.byref(n), _ptr(kcore), _ptr(order), C.byref(mc))
         assert st >= 0, st
         return clique[: n.value].copy(), kcore[:L].copy(), order[:L].copy(), mc.value
+
+    def max_clique_ex(self, adj, mode: int = 0, kcore_thr: float = 0.5, node_limit: int = 0):
+        adj = np.ascontiguousarray(adj, np.uint32)
+        L, wpr = adj.shape
+        clique, kcore, order = (np.zeros(max(L, 1), np.int32) for _ in range(3))
+        n, mc, fl = C.c_int(0), C.c_int(0), C.c_int(0)
+        st = self.lib.qo_max_clique_ex(_ptr(adj), L, wpr, mode, kcore_thr, node_limit, _ptr(clique), C.byref(n), _ptr(kcore), _ptr(order),
+                                       C.byref(mc), C.byref(fl))
+        assert st >= 0, st
+        return clique[: n.value].copy(), kcore[:L].copy(), order[:L].copy(), mc.value, fl.value
 
     def solve_pose(self, a4, b4, clique, params: Params):
         a4, b4 = _f32(a4, 4), _f32(b4, 4)

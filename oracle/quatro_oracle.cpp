@@ -723,10 +723,121 @@ int pmc_heuristic(const Csr& g, const std::vector<int>& K, const std::vector<int
   return mc;
 }
 
+// [EXT] pmc::pmcx_maxclique::search_dense (src/graph.cc:106-127, PMC_EXACT), restated as its RESULT CONTRACT.  pmc's exact
+// finder is a branch and bound over k-core-pruned, greedily coloured candidate sets run by 12 OpenMP threads (graph.cc:40); which
+// of several maximum cliques it returns depends on thread timing, so the reference itself is only deterministic in the clique
+// SIZE (and in returning the heuristic clique unchanged when that one already reaches the bound).  The canonical form here is one
+// sequential bit-parallel branch and bound (greedy sequential colouring bound, Tomita & Seki / San Segundo) in RANK space:
+// vertices renumbered by (core number, id) ascending -- the order the device path keeps its adjacency in.  Rules that make the
+// returned clique unique:
+//   * the incumbent is the heuristic clique; only a STRICTLY larger clique replaces it (pmc: `if (C.size() > mc)`);
+//   * root candidates: every vertex with core number >= |incumbent| (pmc's k-core pruning, K[v] > mc);
+//   * colouring: colour classes are built one after the other, each takes the lowest-ranked uncoloured candidate that has no
+//     neighbour in the class; only entries whose colour can still beat the incumbent are listed;
+//   * branching: from the END of the (colour, rank)-ascending list; a level is abandoned when |C| + colour <= |incumbent|;
+//   * the search stops after `node_limit` expanded nodes (the deterministic stand-in for pmc's wall-clock time_limit,
+//     graph.cc:44) and then returns the best clique found so far with QB200_FLAG_CLIQUE_TRUNCATED.
+// Returns the new clique size; `clique` (ids, any order) is replaced only when a larger clique was found.
+int pmc_exact(const uint32_t* adj, int L, int wpr, const std::vector<int>& K, int max_core, long long node_limit,
+              std::vector<int>& clique, int& flags) {
+  int best = (int)clique.size();
+  const int ub = max_core + 1;
+  if (L <= 0 || best >= ub) return best;
+  // ranks: stable bucket sort by core number (K = core + 1)
+  std::vector<int> rank_of(L), by_rank(L), kb(max_core + 3, 0);
+  for (int v = 0; v < L; ++v) kb[K[v] - 1 + 1]++;
+  for (int d = 1; d <= max_core + 2; ++d) kb[d] += kb[d - 1];   // kb[d] = first rank with core d
+  {
+    std::vector<int> cur(kb.begin(), kb.end());
+    for (int v = 0; v < L; ++v) { rank_of[v] = cur[K[v] - 1]++; by_rank[rank_of[v]] = v; }
+  }
+  const int nbw = (L + 31) / 32;
+  std::vector<uint32_t> rows((size_t)L * nbw, 0u);
+  for (int v = 0; v < L; ++v)
+    for (int w = 0; w < wpr; ++w) {
+      uint32_t x = adj[(size_t)v * wpr + w];
+      while (x) {
+        const int b = __builtin_ctz(x);
+        x &= x - 1;
+        const int u = w * 32 + b;
+        if (u < L) rows[(size_t)rank_of[v] * nbw + (rank_of[u] >> 5)] |= 1u << (rank_of[u] & 31);
+      }
+    }
+  struct Level { std::vector<uint32_t> P; std::vector<uint32_t> list; };  // list entry: rank | colour << 16
+  std::vector<Level> st(1);
+  std::vector<int> C, bestC;
+  // greedy sequential colouring of P; entries with colour > kmin only
+  auto colour_sort = [&](const std::vector<uint32_t>& P, int kmin, std::vector<uint32_t>& list) {
+    list.clear();
+    std::vector<uint32_t> Q(P), Qk(nbw);
+    int col = 0;
+    for (;;) {
+      bool any = false;
+      for (int w = 0; w < nbw; ++w) any |= Q[w] != 0;
+      if (!any) break;
+      ++col;
+      Qk = Q;
+      for (;;) {
+        int v = -1;
+        for (int w = 0; w < nbw; ++w)
+          if (Qk[w]) { v = w * 32 + __builtin_ctz(Qk[w]); break; }
+        if (v < 0) break;
+        const uint32_t* N = &rows[(size_t)v * nbw];
+        for (int w = 0; w < nbw; ++w) Qk[w] &= ~N[w];
+        Qk[v >> 5] &= ~(1u << (v & 31));
+        Q[v >> 5] &= ~(1u << (v & 31));
+        if (col > kmin) list.push_back((uint32_t)v | ((uint32_t)col << 16));
+      }
+    }
+  };
+  const int thr = kb[std::min(best, max_core + 1)];
+  st[0].P.assign(nbw, 0u);
+  for (int r = thr; r < L; ++r) st[0].P[r >> 5] |= 1u << (r & 31);
+  colour_sort(st[0].P, best, st[0].list);
+  long long nodes = 0;
+  int depth = 0;
+  C.assign(1, 0);
+  bool done = false;
+  while (depth >= 0 && !done) {
+    Level& lv = st[depth];
+    if (lv.list.empty()) { --depth; continue; }
+    const uint32_t e = lv.list.back();
+    lv.list.pop_back();
+    const int v = (int)(e & 0xFFFFu), col = (int)(e >> 16);
+    if (depth + col <= best) { lv.list.clear(); continue; }
+    if ((int)C.size() <= depth) C.resize(depth + 1);
+    C[depth] = v;
+    std::vector<uint32_t> NP(nbw);
+    int cnt = 0;
+    const uint32_t* N = &rows[(size_t)v * nbw];
+    for (int w = 0; w < nbw; ++w) { NP[w] = lv.P[w] & N[w]; cnt += __builtin_popcount(NP[w]); }
+    lv.P[v >> 5] &= ~(1u << (v & 31));
+    if (cnt == 0) {
+      if (depth + 1 > best) {
+        best = depth + 1;
+        bestC.assign(C.begin(), C.begin() + depth + 1);
+        if (best >= ub) done = true;
+      }
+      continue;
+    }
+    if (depth + 1 + cnt <= best) continue;
+    if (++nodes > node_limit) { flags |= QB200_FLAG_CLIQUE_TRUNCATED; break; }
+    if ((int)st.size() <= depth + 1) st.resize(depth + 2);
+    st[depth + 1].P.swap(NP);
+    colour_sort(st[depth + 1].P, best - (depth + 1), st[depth + 1].list);
+    ++depth;
+  }
+  if (!bestC.empty()) {
+    clique.clear();
+    for (int r : bestC) clique.push_back(by_rank[r]);
+  }
+  return best;
+}
+
 int max_clique(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, std::vector<int>& clique,
-               std::vector<int>& kcore, std::vector<int>& order, int& max_core) {
+               std::vector<int>& kcore, std::vector<int>& order, int& max_core, long long node_limit = 0, int* flags_out = nullptr) {
   clique.clear();
-  if (mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
+  if (flags_out) *flags_out = 0;
   const Csr g = to_csr(adj, L, wpr);
   compute_cores(g, kcore, order, max_core);
   if (mode == QB200_KCORE_HEU && kcore_thr != 1 && max_core > (int)(kcore_thr * (double)L)) {  // graph.cc:67-82
@@ -736,6 +847,11 @@ int max_clique(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, 
   }
   const int ub = max_core + 1;  // graph.cc:84-86
   pmc_heuristic(g, kcore, order, ub, clique);
+  if (mode == QB200_PMC_EXACT && (int)clique.size() != ub && !clique.empty()) {  // graph.cc:96-127 (lb == ub returns the heuristic clique)
+    int flags = 0;
+    pmc_exact(adj, L, wpr, kcore, max_core, node_limit > 0 ? node_limit : QB200_DEFAULT_CLIQUE_NODE_LIMIT, clique, flags);
+    if (flags_out) *flags_out = flags;
+  }
   std::sort(clique.begin(), clique.end());  // quatro.hpp:806
   return QB200_OK;
 }
@@ -989,7 +1105,7 @@ struct SolveOut {
 
 int solve_correspondences(const P4* a, const P4* b, int L, const qb200_params& prm, qb200_result& res, SolveOut& so) {
   set_identity(res.T);
-  res.valid = 0; res.n_corr = L; res.n_edges = 0; res.max_core = 0; res.clique_size = 0;
+  res.valid = 0; res.n_corr = L; res.n_edges = 0; res.max_core = 0; res.clique_size = 0; res.flags = 0;
   res.gnc_iters = 0; res.n_rot_inliers = 0; res.n_final_inliers = 0; res.cost = 0;
   if (L < 2) { res.status = QB200_DEGENERATE_INPUT; return QB200_DEGENERATE_INPUT; }
   if (prm.inlier_selection_mode == QB200_INLIER_NONE) {
@@ -1000,8 +1116,10 @@ int solve_correspondences(const P4* a, const P4* b, int L, const qb200_params& p
     const int wpr = (L + 31) / 32;
     std::vector<uint32_t> adj((size_t)L * wpr);
     build_graph(a, b, L, prm.noise_bound, prm.cbar2, adj.data(), wpr, nullptr, &res.n_edges);
+    int fl = 0;
     const int st = max_clique(adj.data(), L, wpr, prm.inlier_selection_mode, prm.kcore_heuristic_threshold, so.clique,
-                              so.kcore, so.order, res.max_core);
+                              so.kcore, so.order, res.max_core, prm.max_clique_node_limit, &fl);
+    res.flags = fl;
     if (st < 0) { res.status = st; return st; }
   }
   return solve_pose(a, b, L, so.clique.data(), (int)so.clique.size(), prm, res, so.rot_mask, so.trans_mask, so.final_inliers);
@@ -1096,18 +1214,24 @@ int qo_build_graph(const float* a4, const float* b4, int L, double noise_bound, 
   return QB200_OK;
 }
 
-int qo_max_clique(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, int* clique, int* n_clique, int* kcore,
-                  int* kcore_order, int* max_core) {
+int qo_max_clique_ex(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, int64_t node_limit, int* clique, int* n_clique,
+                     int* kcore, int* kcore_order, int* max_core, int* flags) {
   std::vector<int> c, k, o;
-  int mcore = 0;
-  const int st = max_clique(adj, L, wpr, mode, kcore_thr, c, k, o, mcore);
+  int mcore = 0, fl = 0;
+  const int st = max_clique(adj, L, wpr, mode, kcore_thr, c, k, o, mcore, node_limit, &fl);
   if (st < 0) return st;
+  if (flags) *flags = fl;
   *n_clique = (int)c.size();
   std::copy(c.begin(), c.end(), clique);
   if (kcore) std::copy(k.begin(), k.end(), kcore);
   if (kcore_order) std::copy(o.begin(), o.end(), kcore_order);
   if (max_core) *max_core = mcore;
   return QB200_OK;
+}
+
+int qo_max_clique(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, int* clique, int* n_clique, int* kcore,
+                  int* kcore_order, int* max_core) {
+  return qo_max_clique_ex(adj, L, wpr, mode, kcore_thr, 0, clique, n_clique, kcore, kcore_order, max_core, nullptr);
 }
 
 int qo_solve_pose(const float* a4, const float* b4, int L, const int* clique, int n_clique, const qb200_params* prm,

@@ -13,6 +13,7 @@ import numpy as np
 from . import _build
 
 PMC_EXACT, PMC_HEU, KCORE_HEU, INLIER_NONE = 0, 1, 2, 3
+FLAG_CLIQUE_TRUNCATED = 1
 COTE_MEDIAN, COTE_WEIGHTED_MEAN = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 
@@ -31,7 +32,7 @@ class Params(C.Structure):
         ("rotation_cost_threshold", C.c_double), ("kcore_heuristic_threshold", C.c_double),
         ("rotation_max_iterations", C.c_int32), ("inlier_selection_mode", C.c_int32), ("cote_mode", C.c_int32),
         ("using_rot_inliers_when_estimating_cote", C.c_int32), ("use_pre_estimated_RyRx", C.c_int32),
-        ("reserved1", C.c_int32), ("RyRx", C.c_double * 9),
+        ("max_clique_node_limit", C.c_int32), ("RyRx", C.c_double * 9),
     ]
 
 
@@ -45,7 +46,7 @@ class Result(C.Structure):
         ("valid", C.c_int32), ("status", C.c_int32), ("n_src_vox", C.c_int32), ("n_tgt_vox", C.c_int32),
         ("n_mutual", C.c_int32), ("n_corr", C.c_int32), ("max_core", C.c_int32), ("clique_size", C.c_int32),
         ("gnc_iters", C.c_int32), ("n_rot_inliers", C.c_int32), ("n_final_inliers", C.c_int32),
-        ("reserved", C.c_int32), ("n_edges", C.c_int64), ("cost", C.c_double), ("T", C.c_double * 16),
+        ("flags", C.c_int32), ("n_edges", C.c_int64), ("cost", C.c_double), ("T", C.c_double * 16),
     ]
 
     def matrix(self) -> np.ndarray:
@@ -53,7 +54,7 @@ class Result(C.Structure):
         return np.array(self.T[:], dtype=np.float64).reshape(4, 4).T.copy()
 
     def as_dict(self) -> dict:
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("T", "reserved")}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "T"}
         d["T"] = self.matrix()
         return d
 
@@ -69,7 +70,7 @@ class CorrSet(C.Structure):
 RESULT_DTYPE = np.dtype([
     ("valid", "<i4"), ("status", "<i4"), ("n_src_vox", "<i4"), ("n_tgt_vox", "<i4"), ("n_mutual", "<i4"),
     ("n_corr", "<i4"), ("max_core", "<i4"), ("clique_size", "<i4"), ("gnc_iters", "<i4"), ("n_rot_inliers", "<i4"),
-    ("n_final_inliers", "<i4"), ("reserved", "<i4"), ("n_edges", "<i8"), ("cost", "<f8"), ("T", "<f8", (16,)),
+    ("n_final_inliers", "<i4"), ("flags", "<i4"), ("n_edges", "<i8"), ("cost", "<f8"), ("T", "<f8", (16,)),
 ])
 assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 
@@ -117,6 +118,7 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_match": (i32, [vp, vp, i32, vp, vp, i32, vp, P(Params), vp, i32, P(i32), P(i32)]),
         "qb200_build_graph": (i32, [vp, vp, vp, i32, f64, f64, vp, i32, vp, P(i64)]),
         "qb200_max_clique": (i32, [vp, vp, i32, i32, i32, f64, vp, P(i32), vp, vp, P(i32)]),
+        "qb200_max_clique_ex": (i32, [vp, vp, i32, i32, i32, f64, i64, vp, P(i32), vp, vp, P(i32), P(i32)]),
         "qb200_solve_pose": (i32, [vp, vp, vp, i32, vp, i32, P(Params), P(Result), vp, vp]),
         "qb200_solve_correspondences": (i32, [vp, vp, vp, i32, P(Params), P(Result)]),
         "qb200_match_and_pack": (i32, [vp, vp, i32, vp, i32, P(Params), vp, vp, vp, i32, P(i32)]),
@@ -159,7 +161,7 @@ def load_library(build: bool = True) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "qb200_default_params", "qb200_default_config", "qb200_version", "qb200_create", "qb200_destroy",
     "qb200_set_stream", "qb200_last_error", "qb200_launch_count", "qb200_voxelize", "qb200_compute_fpfh",
-    "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_solve_pose", "qb200_solve_correspondences",
+    "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_max_clique_ex", "qb200_solve_pose", "qb200_solve_correspondences",
     "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
@@ -319,6 +321,16 @@ class Handle:
         self._check(self.lib.qb200_max_clique(self.h, _ptr(adj), L, wpr, mode, kcore_thr, _ptr(clique), C.byref(n), _ptr(kcore),
                                               _ptr(order), C.byref(mc)), "qb200_max_clique")
         return clique[: n.value].copy(), kcore[:L].copy(), order[:L].copy(), mc.value
+
+    def max_clique_ex(self, adj, mode: int = PMC_EXACT, kcore_thr: float = 0.5, node_limit: int = 0):
+        """qb200_max_clique_ex: clique, kcore, order, max_core, flags (FLAG_CLIQUE_TRUNCATED when the node limit stopped the search)."""
+        adj = np.ascontiguousarray(adj, np.uint32)
+        L, wpr = adj.shape
+        clique, kcore, order = (np.zeros(max(L, 1), np.int32) for _ in range(3))
+        n, mc, fl = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.qb200_max_clique_ex(self.h, _ptr(adj), L, wpr, mode, kcore_thr, node_limit, _ptr(clique), C.byref(n),
+                                                 _ptr(kcore), _ptr(order), C.byref(mc), C.byref(fl)), "qb200_max_clique_ex")
+        return clique[: n.value].copy(), kcore[:L].copy(), order[:L].copy(), mc.value, fl.value
 
     def solve_pose(self, a4, b4, clique, params: Params):
         a4, b4 = _f32(a4, 4), _f32(b4, 4)

@@ -152,7 +152,7 @@ int alloc_all(qb200_handle* h) {
   QB_CUDA_TRY(h, cudaMemset(h->d_results, 0, S * sizeof(qb200_result)));
   QB_CUDA_TRY(h, cudaMallocHost((void**)&h->h_results, S * sizeof(qb200_result)));
   // counters: one int block so a wave reset is a single launch.  n_edges (long long) lives at an 8-byte offset.
-  const size_t n_ints = C * 5 + C * 6 + S * 6 + 2 * S + 2;
+  const size_t n_ints = C * 5 + C * 6 + S * 7 + 2 * S + 2;
   QB_ALLOC(h, h->ctr_block, n_ints);
   h->ctr_ints = n_ints;
   int* p = h->ctr_block;
@@ -169,6 +169,7 @@ int alloc_all(qb200_handle* h) {
   h->ctr.n_clique = p; p += S;
   h->ctr.max_core = p; p += S;
   h->ctr.n_final = p; p += S;
+  h->ctr.flags = p; p += S;
   for (int i = 0; i < 9; ++i) QB_CUDA_TRY(h, cudaEventCreate(&h->ev[i]));
   for (int i = 0; i < 4; ++i) QB_CUDA_TRY(h, cudaEventCreate(&h->kev[i]));
   return QB200_OK;
@@ -200,7 +201,7 @@ bool params_ok(const qb200_params* p) {
   if (p->normal_radius > p->fpfh_radius) return false;  // FPFHManager::setFeaturePair throws here, fpfh_manager.hpp:99-102
   if (!(p->noise_bound > 0) || !(p->cbar2 > 0) || !(p->cote_noise_bound > 0)) return false;
   if (p->cote_mode != QB200_COTE_MEDIAN && p->cote_mode != QB200_COTE_WEIGHTED_MEAN) return false;  // quatro.hpp:911
-  if (p->inlier_selection_mode < 0 || p->inlier_selection_mode > 3) return false;
+  if (p->inlier_selection_mode < 0 || p->inlier_selection_mode > 3 || p->max_clique_node_limit < 0) return false;
   if (p->rotation_max_iterations < 0 || p->tuple_trials_per_corr < 0) return false;
   return true;
 }
@@ -218,7 +219,7 @@ int run_solver(qb200_handle* h, int n_pairs, const qb200_params& p, int have_fro
   } else {
     if ((rc = launch_graph(h, n_pairs, p.noise_bound, p.cbar2))) return rc;
     if (h->ev[5]) cudaEventRecord(h->ev[5], h->stream);
-    if ((rc = launch_clique(h, n_pairs, p.inlier_selection_mode, p.kcore_heuristic_threshold))) return rc;
+    if ((rc = launch_clique(h, n_pairs, p.inlier_selection_mode, p.kcore_heuristic_threshold, p.max_clique_node_limit))) return rc;
   }
   if (h->ev[6]) cudaEventRecord(h->ev[6], h->stream);
   if ((rc = launch_fill_counters(h, n_pairs, have_frontend))) return rc;
@@ -346,7 +347,7 @@ void qb200_destroy(qb200_handle* h) {
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t, h->rowbest, h->colpart, h->colbest,
                       h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats, h->aos_scratch,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
-                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
+                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->ex_stack, h->ex_pool, h->ex_lvl, h->ex_cur, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
                       h->ctr_block};
   for (void* p : dev_ptrs)
     if (p) cudaFree(p);
@@ -537,12 +538,14 @@ int qb200_build_graph(qb200_handle* h, const float* a4, const float* b4, int32_t
 }
 
 // ---- stage: max clique ------------------------------------------------------------------------------
-int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row, int32_t mode, double kcore_thr,
-                     int32_t* clique, int32_t* n_clique, int32_t* kcore, int32_t* kcore_order, int32_t* max_core) {
+int qb200_max_clique_ex(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row, int32_t mode, double kcore_thr,
+                        int64_t node_limit, int32_t* clique, int32_t* n_clique, int32_t* kcore, int32_t* kcore_order, int32_t* max_core,
+                        int32_t* flags) {
   QB_IDLE(h);
   if (!h || !n_clique || L < 0 || (L > 0 && (!adj || !clique)) || words_per_row < (L + 31) / 32) return QB200_ERR_BAD_ARG;
-  if (mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
-  if (mode != QB200_PMC_HEU && mode != QB200_KCORE_HEU) return QB200_ERR_BAD_ARG;
+  if (mode != QB200_PMC_EXACT && mode != QB200_PMC_HEU && mode != QB200_KCORE_HEU) return QB200_ERR_BAD_ARG;
+  if (node_limit < 0) return QB200_ERR_BAD_ARG;
+  if (flags) *flags = 0;
   *n_clique = 0;
   if (max_core) *max_core = 0;
   if (L > h->Lc) { h->fail(__FILE__, __LINE__, "L exceeds max_corr"); return QB200_ERR_BAD_ARG; }
@@ -555,10 +558,12 @@ int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t wo
   QB_CUDA_TRY(h, cudaMemcpy2DAsync(h->adj, (size_t)h->W * 4, adj, (size_t)words_per_row * 4, (size_t)nb * 4, L, cudaMemcpyHostToDevice, h->stream));
   if ((rc = set_counter(h, h->ctr.n_corr, L))) return rc;
   if ((rc = launch_degree(h, 1))) return rc;
-  if ((rc = launch_clique(h, 1, mode, kcore_thr))) return rc;
-  int nc = 0, mc = 0;
+  if ((rc = launch_clique(h, 1, mode, kcore_thr, node_limit))) return rc;
+  int nc = 0, mc = 0, fl = 0;
   if ((rc = get_counter(h, h->ctr.n_clique, &nc))) return rc;
   if ((rc = get_counter(h, h->ctr.max_core, &mc))) return rc;
+  if ((rc = get_counter(h, h->ctr.flags, &fl))) return rc;
+  if (flags) *flags = fl;
   *n_clique = nc;
   if (max_core) *max_core = mc;
   if (nc > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(clique, h->clique, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -567,6 +572,11 @@ int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t wo
   QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->last_n_clique = nc;
   return QB200_OK;
+}
+
+int qb200_max_clique(qb200_handle* h, const uint32_t* adj, int32_t L, int32_t words_per_row, int32_t mode, double kcore_thr,
+                     int32_t* clique, int32_t* n_clique, int32_t* kcore, int32_t* kcore_order, int32_t* max_core) {
+  return qb200_max_clique_ex(h, adj, L, words_per_row, mode, kcore_thr, 0, clique, n_clique, kcore, kcore_order, max_core, nullptr);
 }
 
 // ---- stage: pose given the clique -------------------------------------------------------------------
@@ -596,7 +606,6 @@ int qb200_solve_pose(qb200_handle* h, const float* a4, const float* b4, int32_t 
 // ---- Quatro::computeTransformation ------------------------------------------------------------------
 int qb200_solve_correspondences(qb200_handle* h, const float* a4, const float* b4, int32_t L, const qb200_params* p, qb200_result* res) {
   if (!h || !res || !params_ok(p) || L < 0 || (L > 0 && (!a4 || !b4))) return QB200_ERR_BAD_ARG;
-  if (p->inlier_selection_mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
   cudaSetDevice(h->device);
   int rc = upload_matched(h, a4, b4, L);
   if (rc) return rc;
@@ -609,7 +618,6 @@ int qb200_solve_batch(qb200_handle* h, const qb200_corr_set* sets, int32_t n_set
                       qb200_result* results) {
   QB_IDLE(h);
   if (!h || n_sets < 0 || (n_sets > 0 && (!sets || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
-  if (p->inlier_selection_mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
   for (int i = 0; i < n_sets; ++i)
     if (sets[i].L < 0 || sets[i].L > h->Lc || (sets[i].L > 0 && (!sets[i].a || !sets[i].b))) {
       h->fail(__FILE__, __LINE__, "correspondence set is null or exceeds max_corr");
@@ -822,7 +830,7 @@ int qb200_register_batch(qb200_handle* h, const qb200_pair* pairs, int32_t n_pai
 int qb200_register_batch_enqueue(qb200_handle* h, const qb200_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_mem_kind kind,
                                  qb200_result* results) {
   if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
-  if (p->inlier_selection_mode == QB200_PMC_EXACT || !p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
+  if (!p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
   for (int i = 0; i < n_pairs; ++i) {
     if (pairs[i].n_src < 0 || pairs[i].n_tgt < 0 || pairs[i].n_src > h->R || pairs[i].n_tgt > h->R ||
         (pairs[i].n_src > 0 && !pairs[i].src) || (pairs[i].n_tgt > 0 && !pairs[i].tgt)) {
@@ -1168,7 +1176,7 @@ int qb200_cache_scans(qb200_handle* h, const float* const* scans4, const int32_t
 int qb200_register_cached(qb200_handle* h, const qb200_slot_pair* pairs, int32_t n_pairs, const qb200_params* p, qb200_result* results) {
   QB_IDLE(h);
   if (!h || n_pairs < 0 || (n_pairs > 0 && (!pairs || !results)) || !params_ok(p)) return QB200_ERR_BAD_ARG;
-  if (p->inlier_selection_mode == QB200_PMC_EXACT || !p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
+  if (!p->use_crosscheck) return QB200_ERR_UNSUPPORTED;
   const float cell = lattice_cell(*p);
   for (int i = 0; i < n_pairs; ++i) {
     const int sl[2] = {pairs[i].src_slot, pairs[i].tgt_slot};

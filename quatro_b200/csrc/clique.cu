@@ -536,6 +536,189 @@ __global__ void __launch_bounds__(kCliqueWarps * 32) clique_cta_kernel(const uin
   if (tid == 0) n_clique[pair] = csize;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// PMC_EXACT: bit-parallel branch and bound with greedy-colouring bounds, ONE WARP per pair, in rank space.
+// Replaces the exact finder call of src/graph.cc:106-127 ([EXT] pmc::pmcx_maxclique::search_dense); the canonical search order
+// (which of several maximum cliques is returned) is the one oracle/quatro_oracle.cpp: pmc_exact() states -- the incumbent is the
+// heuristic clique, root candidates = vertices of core number >= |incumbent|, colour classes take the lowest rank first, the
+// branch runs from the end of the (colour, rank) list, a level dies when |C| + colour <= |incumbent|, the search ends after
+// node_limit expanded nodes (QB200_FLAG_CLIQUE_TRUNCATED).  The warp keeps a candidate set as WPL words per lane (word index
+// lane + 32 k, like clique_descent); the level stack -- one candidate bitset and one (rank | colour << 16) list segment per
+// depth -- lives in global scratch (L1/L2-resident: the live part is a few KB), rows come from the shared-memory adjacency cache
+// when the graph fits.  Stack or list-pool exhaustion ends the search like the node limit does.
+// ------------------------------------------------------------------------------------------------
+constexpr int kExactDepth = 1024;      // levels of the stack (a clique larger than this ends the search with the truncation flag)
+constexpr int kExactPool = 1 << 17;    // list entries per pair
+
+template <int WPL>
+__device__ __forceinline__ int exact_colour_sort(const uint32_t* __restrict__ rows, int stride, int nbw, const uint32_t (&P)[WPL], int kmin,
+                                                 uint32_t* __restrict__ list, int cap) {
+  const int lane = lane_id();
+  uint32_t Q[WPL], Qk[WPL];
+#pragma unroll
+  for (int k = 0; k < WPL; ++k) Q[k] = P[k];
+  int col = 0, cnt = 0;
+  for (;;) {
+    uint32_t any = 0u;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) any |= Q[k];
+    if (!__any_sync(0xffffffffu, any != 0u)) break;
+    ++col;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) Qk[k] = Q[k];
+    for (;;) {
+      int cand = 0x7fffffff;  // lowest rank left in the class candidates (a lane's words ascend with k)
+#pragma unroll
+      for (int k = WPL - 1; k >= 0; --k)
+        if (Qk[k]) cand = (lane + 32 * k) * 32 + __ffs(Qk[k]) - 1;
+      const int v = __reduce_min_sync(0xffffffffu, cand);
+      if (v == 0x7fffffff) break;
+      const int vw = v >> 5;
+      const uint32_t vbit = 1u << (v & 31);
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        const int wi = lane + 32 * k;
+        if (wi < nbw) {
+          uint32_t drop = rows[(size_t)v * stride + wi];
+          if (wi == vw) { drop |= vbit; Q[k] &= ~vbit; }
+          Qk[k] &= ~drop;
+        }
+      }
+      if (col > kmin) {
+        if (cnt >= cap) return -1;  // list pool exhausted (warp-uniform)
+        if (lane == 0) list[cnt] = (uint32_t)v | ((uint32_t)col << 16);
+        ++cnt;
+      }
+    }
+  }
+  return cnt;
+}
+
+template <int WPL>
+__global__ void __launch_bounds__(32) clique_exact_kernel(const uint32_t* __restrict__ adjp, const int* __restrict__ n_corr, int Lc, int W,
+                                                         const int* __restrict__ by_rank, const int* __restrict__ rank_of,
+                                                         const int* __restrict__ kbin, const int* __restrict__ max_core_in, long long node_limit,
+                                                         int cache_words, uint32_t* __restrict__ stackP, uint32_t* __restrict__ pool,
+                                                         int* __restrict__ lvl_begin, int* __restrict__ lvl_n, unsigned short* __restrict__ cur_c,
+                                                         int* __restrict__ clique, int* __restrict__ n_clique, int* __restrict__ flags) {
+  extern __shared__ uint32_t ex_cache[];  // [cache_words] rank-space adjacency when it fits
+  const int pair = blockIdx.x, lane = lane_id();
+  const int L = n_corr[pair];
+  if (L <= 0) return;
+  int best = n_clique[pair];
+  const int max_core = max_core_in[pair];
+  const int ub = max_core + 1;
+  if (best <= 0 || best >= ub) return;  // graph.cc:96-104: the heuristic clique already meets the k-core bound
+  const int nbw = (L + 31) >> 5;
+  const uint32_t* __restrict__ G = adjp + (size_t)pair * Lc * W;
+  const bool cached = (long long)L * nbw <= (long long)cache_words;
+  if (cached)
+    for (int idx = lane; idx < L * nbw; idx += 32) ex_cache[idx] = G[(size_t)(idx / nbw) * W + (idx % nbw)];
+  __syncwarp();
+  const uint32_t* rows = cached ? ex_cache : G;
+  const int stride = cached ? nbw : W;
+  const int* __restrict__ br = by_rank + (size_t)pair * (Lc + 2);
+  const int* __restrict__ kb = kbin + (size_t)pair * (Lc + 2);
+  uint32_t* __restrict__ SP = stackP + (size_t)pair * kExactDepth * W;
+  uint32_t* __restrict__ LP = pool + (size_t)pair * kExactPool;
+  int* __restrict__ lb = lvl_begin + (size_t)pair * kExactDepth;
+  int* __restrict__ ln = lvl_n + (size_t)pair * kExactDepth;
+  unsigned short* __restrict__ C = cur_c + (size_t)pair * kExactDepth;
+  int* __restrict__ out = clique + (size_t)pair * Lc;
+
+  uint32_t P[WPL];
+  {  // root: ranks >= kb[best] (core number >= |incumbent|)
+    const int thr = kb[min(best, max_core + 1)];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int wi = lane + 32 * k, lo = wi * 32;
+      uint32_t x = 0u;
+      const int a = max(thr, lo), b = min(L, lo + 32);  // ranks [a, b) of this word are candidates
+      if (wi < nbw && a < b) x = (b - lo >= 32 ? ~0u : ((1u << (b - lo)) - 1u)) & (~0u << (a - lo));
+      P[k] = x;
+      if (wi < nbw) SP[wi] = x;
+    }
+  }
+  int used = exact_colour_sort<WPL>(rows, stride, nbw, P, best, LP, kExactPool);
+  bool truncated = used < 0;
+  int depth = truncated ? -1 : 0;
+  if (lane == 0 && !truncated) { lb[0] = 0; ln[0] = used; }
+  __syncwarp();
+  long long nodes = 0;
+  bool improved = false;
+  while (depth >= 0) {
+    const int n_here = ln[depth];
+    if (n_here == 0) { --depth; continue; }
+    const int begin = lb[depth];
+    const uint32_t e = LP[begin + n_here - 1];
+    __syncwarp();
+    if (lane == 0) ln[depth] = n_here - 1;
+    const int v = (int)(e & 0xFFFFu), col = (int)(e >> 16);
+    if (depth + col <= best) {  // nothing left on this level can beat the incumbent
+      if (lane == 0) ln[depth] = 0;
+      __syncwarp();
+      continue;
+    }
+    if (lane == 0) C[depth] = (unsigned short)v;
+    uint32_t* __restrict__ Pl = SP + (size_t)depth * W;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int wi = lane + 32 * k;
+      uint32_t x = 0u;
+      if (wi < nbw) {
+        const uint32_t pw = Pl[wi];
+        x = pw & rows[(size_t)v * stride + wi];
+        if (wi == (v >> 5)) Pl[wi] = pw & ~(1u << (v & 31));  // v leaves this level's candidates
+      }
+      P[k] = x;
+      cnt += __popc(x);
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    __syncwarp();
+    if (cnt == 0) {
+      if (depth + 1 > best) {  // a maximal clique larger than the incumbent: record it (ranks -> ids, sorted at the end)
+        best = depth + 1;
+        improved = true;
+        for (int t = lane; t <= depth; t += 32) out[t] = br[C[t]];
+        __syncwarp();
+        if (best >= ub) break;
+      }
+      continue;
+    }
+    if (depth + 1 + cnt <= best) continue;
+    if (++nodes > node_limit || depth + 1 >= kExactDepth) { truncated = true; break; }
+    const int nbegin = begin + n_here - 1;  // the consumed entry's slot and everything behind it is free again
+    uint32_t* __restrict__ Pn = SP + (size_t)(depth + 1) * W;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+      const int wi = lane + 32 * k;
+      if (wi < nbw) Pn[wi] = P[k];
+    }
+    const int nl = exact_colour_sort<WPL>(rows, stride, nbw, P, best - (depth + 1), LP + nbegin, kExactPool - nbegin);
+    if (nl < 0) { truncated = true; break; }
+    if (lane == 0) { lb[depth + 1] = nbegin; ln[depth + 1] = nl; }
+    __syncwarp();
+    ++depth;
+  }
+  __syncwarp();
+  if (improved) {
+    // ascending ids (std::sort(max_clique_), quatro.hpp:806): rank = number of smaller ids (ids are distinct, cliques are small);
+    // lvl_begin is free now and serves as the second buffer (best <= kExactDepth)
+    for (int t = lane; t < best; t += 32) {
+      const int x = out[t];
+      int r = 0;
+      for (int u = 0; u < best; ++u) r += out[u] < x ? 1 : 0;
+      lb[r] = x;
+    }
+    __syncwarp();
+    for (int t = lane; t < best; t += 32) out[t] = lb[t];
+    if (lane == 0) n_clique[pair] = best;
+  }
+  if (lane == 0 && truncated) flags[pair] |= QB200_FLAG_CLIQUE_TRUNCATED;
+}
+
 template <int WPL>
 static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
   const int Lc = h->Lc, W = h->W;
@@ -555,9 +738,29 @@ static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
   return QB200_OK;
 }
 
-int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
+// PMC_EXACT scratch (level stack, list pool), allocated on the first exact call of a handle
+static int ensure_exact_scratch(qb200_handle* h) {
+  if (h->ex_stack) return QB200_OK;
+  const size_t S = h->S;
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_stack, S * kExactDepth * (size_t)h->W * sizeof(uint32_t)));
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_pool, S * (size_t)kExactPool * sizeof(uint32_t)));
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_lvl, S * 2 * (size_t)kExactDepth * sizeof(int)));
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_cur, S * (size_t)kExactDepth * sizeof(unsigned short)));
+  return QB200_OK;
+}
+
+template <int WPL>
+static int launch_exact(qb200_handle* h, int n_pairs, long long node_limit, int cache_words) {
+  if (int rc = ensure_dyn_smem(h, (const void*)clique_exact_kernel<WPL>, (size_t)cache_words * 4)) return rc;
+  clique_exact_kernel<WPL><<<n_pairs, 32, (size_t)cache_words * 4, h->stream>>>(
+      h->adjp, h->ctr.n_corr, h->Lc, h->W, h->by_rank, h->rank_of, h->kbin, h->ctr.max_core, node_limit, cache_words, h->ex_stack, h->ex_pool,
+      h->ex_lvl, h->ex_lvl + (size_t)h->S * kExactDepth, h->ex_cur, h->clique, h->ctr.n_clique, h->ctr.flags);
+  h->launches++;
+  return QB200_OK;
+}
+
+int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr, long long node_limit) {
   if (n_pairs <= 0) return QB200_OK;
-  if (mode == QB200_PMC_EXACT) return QB200_ERR_UNSUPPORTED;
   const int Lc = h->Lc, W = h->W;
   // shared-memory adjacency cache of the descent: 14336 words (56 KB) hold graphs up to L ~ 660
   const int cache_words = 14336;
@@ -565,6 +768,7 @@ int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
   const bool set_attr = true;
   int rc;
   if ((rc = ensure_dyn_smem(h, (const void*)clique_cta_kernel, sm_clique))) return rc;
+  if (mode == QB200_PMC_EXACT && (rc = ensure_exact_scratch(h))) return rc;
   if (W <= 32) rc = launch_kcore<1>(h, n_pairs, set_attr);
   else if (W <= 64) rc = launch_kcore<2>(h, n_pairs, set_attr);
   else if (W <= 128) rc = launch_kcore<4>(h, n_pairs, set_attr);
@@ -572,10 +776,19 @@ int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr) {
   if (rc) return rc;
   const dim3 gp((Lc + 7) / 8, n_pairs);
   permute_adj_kernel<<<gp, 256, 8 * W * sizeof(uint32_t), h->stream>>>(h->adj, h->ctr.n_corr, Lc, W, h->rank_of, h->adjp);
+  // PMC_EXACT starts from the heuristic clique (graph.cc:88-104: in.lb = pmc_heu.search, returned as is when lb == ub)
   clique_cta_kernel<<<n_pairs, kCliqueWarps * 32, sm_clique, h->stream>>>(h->adjp, h->ctr.n_corr, Lc, W, h->kcore, h->korder, h->rank_of, h->by_rank,
-                                                                          h->kbin, h->ctr.max_core, mode, kcore_thr, cache_words, h->clique,
-                                                                          h->ctr.n_clique);
+                                                                          h->kbin, h->ctr.max_core, mode == QB200_PMC_EXACT ? QB200_PMC_HEU : mode,
+                                                                          kcore_thr, cache_words, h->clique, h->ctr.n_clique);
   h->launches += 3;
+  if (mode == QB200_PMC_EXACT) {
+    const long long lim = node_limit > 0 ? node_limit : (long long)QB200_DEFAULT_CLIQUE_NODE_LIMIT;
+    if (W <= 32) rc = launch_exact<1>(h, n_pairs, lim, cache_words);
+    else if (W <= 64) rc = launch_exact<2>(h, n_pairs, lim, cache_words);
+    else if (W <= 128) rc = launch_exact<4>(h, n_pairs, lim, cache_words);
+    else rc = launch_exact<8>(h, n_pairs, lim, cache_words);
+    if (rc) return rc;
+  }
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
 }

@@ -51,6 +51,7 @@ struct WaveCounters {
   int* n_clique;     // [slots]
   int* max_core;     // [slots]
   int* n_final;      // [slots]
+  int* flags;        // [slots] QB200_FLAG_* bits of the pair
   long long* n_edges;// [slots]
 };
 

@@ -70,6 +70,9 @@ struct qb200_handle {
   int* deg;                   // [S*Lc]
   int *kcore, *korder, *rank_of, *by_rank, *kbin;  // [S*(Lc+2)]
   int* clique;                // [S*Lc] ascending ids
+  uint32_t *ex_stack, *ex_pool;  // PMC_EXACT scratch, allocated on first use: [S*1024*W] candidate sets per level, [S*2^17] list entries
+  int* ex_lvl;                // [2*S*1024] list segment (begin | remaining) per level
+  unsigned short* ex_cur;     // [S*1024] clique under construction (ranks)
   int* final_inl;             // [S*Lc]
   unsigned char *rot_mask, *trans_mask;  // [S*Lc]
   // ---- results ----
@@ -120,7 +123,7 @@ int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int s
 int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_radius, float cell);
 int launch_match(qb200_handle* h, int n_pairs, const qb200_params& p);
 int launch_graph(qb200_handle* h, int n_pairs, double noise_bound, double cbar2);
-int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr);
+int launch_clique(qb200_handle* h, int n_pairs, int mode, double kcore_thr, long long node_limit);
 int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p);
 int launch_fill_counters(qb200_handle* h, int n_pairs, int have_frontend);
 int launch_finalize_status(qb200_handle* h, int n_pairs);

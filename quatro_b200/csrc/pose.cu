@@ -327,7 +327,7 @@ __global__ void fill_counters_kernel(qb200_result* __restrict__ results, int n_p
   r->n_corr = c.n_corr[pair];
   r->max_core = c.max_core[pair];
   r->n_edges = c.n_edges[pair] / 2;
-  r->reserved = 0;
+  r->flags = c.flags[pair];
 }
 
 // status fix-up after the solve: front-end failures (capacity / voxel overflow) invalidate the pair

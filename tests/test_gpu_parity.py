@@ -357,6 +357,51 @@ def test_kcore_and_clique_structured_graphs(handle, oracle):
         assert np.array_equal(c_got, c_ref), f"{name}: clique membership differs"
 
 
+def test_exact_clique_matches_oracle(handle, oracle):
+    """PMC_EXACT (src/graph.cc:106-127): same clique as the oracle's canonical branch and bound -- size AND membership -- on graphs
+    where the heuristic is already maximum, where the search improves it, and where the node limit cuts it short."""
+    from quatro_b200.capi import PMC_EXACT, FLAG_CLIQUE_TRUNCATED
+    cases = [(n, p, pl, 0) for n, p, pl in ((2, 1.0, 0), (40, 0.3, 0), (150, 0.03, 25), (500, 0.1, 60), (1000, 0.02, 0), (600, 0.2, 0),
+                                             (1200, 0.08, 0), (3000, 0.02, 300), (4096, 0.01, 100))]
+    cases += [(300, 0.7, 0, 3000), (700, 0.5, 0, 5000), (90, 0.6, 0, 0)]
+    improved = truncated = 0
+    for n, p, planted, limit in cases:
+        adj = dense_to_adj(_random_graph(np.random.default_rng(n + planted), n, p, planted))
+        ref = oracle.max_clique_ex(adj, PMC_EXACT, 0.5, limit)
+        got = handle.max_clique_ex(adj, PMC_EXACT, 0.5, limit)
+        assert got[3] == ref[3] and got[4] == ref[4], (n, p, got[3:], ref[3:])
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        assert np.array_equal(got[0], ref[0]), (n, p, planted, limit, got[0], ref[0])
+        improved += len(ref[0]) > len(oracle.max_clique(adj, PMC_HEU)[0])
+        truncated += bool(ref[4] & FLAG_CLIQUE_TRUNCATED)
+    assert improved >= 3 and truncated >= 2
+    for name, R in _structured_graphs():
+        adj = dense_to_adj(R)
+        ref = oracle.max_clique_ex(adj, PMC_EXACT, 0.5, 20000)
+        got = handle.max_clique_ex(adj, PMC_EXACT, 0.5, 20000)
+        assert np.array_equal(got[0], ref[0]) and got[4] == ref[4], name
+
+
+def test_exact_mode_pipeline(handle, oracle):
+    from quatro_b200.capi import PMC_EXACT
+    p = default_params()
+    p.inlier_selection_mode = PMC_EXACT
+    for seed, L, ratio in ((5, 300, 0.3), (6, 1500, 0.1), (7, 3000, 0.05)):
+        a4, b4, T, inl = synth.matched_pairs(seed, L, inlier_ratio=ratio, noise=0.05)
+        r_g, st_g = handle.solve_correspondences(a4, b4, p)
+        r_o, st_o = oracle.solve_correspondences(a4, b4, p)
+        assert st_g == st_o and r_g.clique_size == r_o.clique_size and r_g.flags == r_o.flags
+        assert np.array_equal(handle.last_clique(), np.sort(handle.last_clique()))
+        assert np.allclose(r_g.matrix(), r_o.matrix(), atol=1e-9)
+    # whole pairs through the batch path (several pairs per wave, exact search per pair)
+    pairs = [synth.outdoor_pair(40 + i, rings=32, azimuths=900)[:2] for i in range(3)]
+    res = handle.register_batch(pairs, p)
+    for (src, tgt), r in zip(pairs, res):
+        ref, st_ref = oracle.register_pair(src, tgt, p)
+        assert r["clique_size"] == ref.clique_size and r["n_corr"] == ref.n_corr and r["flags"] == ref.flags
+        assert np.allclose(np.asarray(r["T"]).reshape(4, 4).T, ref.matrix(), atol=1e-9)
+
+
 def test_graph_and_clique_wide_handle(oracle):
     """max_corr = 8192: 256-word rows (8-warp peel, 64-bit packed group sizes, 8 adjacency words per lane in the descent)."""
     with Handle(max_batch_slots=2, max_corr=8192) as h:

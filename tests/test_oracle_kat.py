@@ -289,6 +289,59 @@ def test_kat9_planted_clique(oracle):
     assert len(c3) == 0
 
 
+# ---- KAT-9b exact clique (PMC_EXACT) against networkx's maximal-clique enumeration -----------------------------------
+def test_kat9b_exact_clique_is_maximum(oracle):
+    """src/graph.cc:106-127: the exact finder returns a MAXIMUM clique; its size is pinned by an independent enumeration
+    (networkx, Bron-Kerbosch), membership is only required to be a clique (pmc's own choice depends on thread timing)."""
+    import networkx as nx
+    from quatro_b200.capi import PMC_EXACT, FLAG_CLIQUE_TRUNCATED
+    rng = np.random.default_rng(91)
+    improved = 0
+    for n, p_, planted in ((40, 0.3, 0), (60, 0.5, 0), (150, 0.05, 12), (300, 0.1, 0), (600, 0.03, 9), (1200, 0.02, 0), (90, 0.6, 0)):
+        R = rng.uniform(size=(n, n)) < p_
+        R = np.triu(R, 1); R = R | R.T
+        if planted:
+            m = rng.choice(n, planted, replace=False)
+            R[np.ix_(m, m)] = True
+        np.fill_diagonal(R, False)
+        adj = dense_to_adj(R)
+        heu = oracle.max_clique(adj, PMC_HEU)[0]
+        c, k, order, mc, flags = oracle.max_clique_ex(adj, PMC_EXACT)
+        best = max(len(x) for x in nx.find_cliques(nx.from_numpy_array(R)))
+        assert flags == 0 and len(c) == best, (n, p_, len(c), best)
+        assert np.all(np.diff(c) > 0) and R[np.ix_(c, c)].sum() == len(c) * (len(c) - 1)
+        assert len(heu) <= best <= mc + 1
+        if len(heu) == best:
+            assert c.tolist() == heu.tolist()          # only a strictly larger clique replaces the heuristic one (graph.cc:96-104)
+        else:
+            improved += 1
+    assert improved >= 2                               # the branch and bound really ran
+    # node limit: the search stops, says so, and still returns a clique at least as large as the heuristic one
+    R = rng.uniform(size=(400, 400)) < 0.6
+    R = np.triu(R, 1); R = R | R.T
+    adj = dense_to_adj(R)
+    heu = oracle.max_clique(adj, PMC_HEU)[0]
+    c, *_, flags = oracle.max_clique_ex(adj, PMC_EXACT, 0.5, 2000)
+    assert flags & FLAG_CLIQUE_TRUNCATED and len(c) >= len(heu) and R[np.ix_(c, c)].sum() == len(c) * (len(c) - 1)
+    c2, *_, flags2 = oracle.max_clique_ex(adj, PMC_EXACT, 0.5, 20000)
+    assert len(c2) >= len(c)
+    # PMC_HEU / KCORE_HEU through the _ex entry are unchanged
+    assert oracle.max_clique_ex(adj, PMC_HEU)[0].tolist() == heu.tolist()
+
+
+def test_exact_mode_through_the_solver(oracle):
+    from quatro_b200 import synth
+    from quatro_b200.capi import PMC_EXACT, default_params
+    a4, b4, T, inl = synth.matched_pairs(77, 400, inlier_ratio=0.3, noise=0.05)
+    p = default_params()
+    r_heu, st_heu = oracle.solve_correspondences(a4, b4, p)
+    p.inlier_selection_mode = PMC_EXACT
+    r_ex, st_ex = oracle.solve_correspondences(a4, b4, p)
+    assert st_ex == 0 and r_ex.valid == 1 and r_ex.clique_size >= r_heu.clique_size and r_ex.flags == 0
+    rot, tr = synth.pose_error(r_ex.matrix(), T)
+    assert rot < 2.0 and tr < 0.3
+
+
 def test_kcore_heuristic_mode(oracle):
     K = np.ones((8, 8), bool); np.fill_diagonal(K, False)
     G = np.zeros((10, 10), bool); G[:8, :8] = K
