@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kCliqueWarps * 32) clique_cta_kernel(const uin
 // ------------------------------------------------------------------------------------------------
 // PMC_EXACT: bit-parallel branch and bound with greedy-colouring bounds, ONE WARP per pair, in rank space.
 // Replaces the exact finder call of src/graph.cc:106-127 ([EXT] pmc::pmcx_maxclique::search_dense); the canonical search order
-// (which of several maximum cliques is returned) is the one oracle/quatro_oracle.cpp: pmc_exact() states -- the incumbent is the
+// (which of several maximum cliques is returned) is the canonical sequential one of DESIGN.md 5.3 -- the incumbent is the
 // heuristic clique, root candidates = vertices of core number >= |incumbent|, colour classes take the lowest rank first, the
 // branch runs from the end of the (colour, rank) list, a level dies when |C| + colour <= |incumbent|, the search ends after
 // node_limit expanded nodes (QB200_FLAG_CLIQUE_TRUNCATED).  The warp keeps a candidate set as WPL words per lane (word index
