@@ -4,6 +4,7 @@
  * This is the drop-in boundary.  Every entry point replaces one stage
  * boundary of the reference (url-kaist/Quatro, paths relative to the reference root):
  *
+ *   qb200_patchwork             <- PatchWork<PointT>::estimate_ground   include/patchwork.hpp:329-455 (pre-processing, 8f-1)
  *   qb200_voxelize              <- voxelize<T>()                    include/quatro.hpp:49-57
  *   qb200_compute_fpfh          <- FPFHEstimation::computeFPFHFeatures  src/teaser_utils/fpfh.cc:44-75
  *   qb200_match                 <- Matcher::calculateCorrespondences    include/teaser_utils/feature_matcher.h:42-74
@@ -154,6 +155,44 @@ int64_t qb200_launch_count(const qb200_handle* h);
  * (k,j,i) cell; non-finite points (and w<0 points when skip_flagged) are dropped. */
 int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, int32_t skip_flagged,
                    float* out4, int32_t cap, int32_t* n_out);
+
+/* --- pre-processing before the path: ground removal ------------------------------
+ * qb200_patchwork <- PatchWork<PointT>::estimate_ground, include/patchwork.hpp:329-455 (concentric zone model
+ * :512-543, region-wise ground plane fit :278-324,548-590, ground likelihood estimation :386-440), de-ROS-ed: the
+ * parameters the reference reads from the ROS parameter server (patchwork.hpp:50-95, config/patchwork_params.yaml)
+ * travel in this POD. */
+#define QB200_PW_MAX_ZONES 4
+#define QB200_PW_MAX_THRESHOLDS 8
+typedef struct qb200_patchwork_params {
+  double sensor_height;                   /* 1.723   patchwork_params.yaml:1 */
+  double th_seeds;                        /* 0.25 */
+  double th_dist;                         /* 0.125 */
+  double max_range;                       /* 80.0 */
+  double min_range;                       /* 2.7 (= min_ranges_each_zone[0]) */
+  double uprightness_thr;                 /* 0.707 */
+  double adaptive_seed_selection_margin;  /* -1.1 */
+  double global_elevation_threshold;      /* -0.5 */
+  double min_ranges_each_zone[QB200_PW_MAX_ZONES];       /* 2.7, 12.3625, 22.025, 41.35 */
+  double elevation_thresholds[QB200_PW_MAX_THRESHOLDS];  /* -1.2, -0.9984, -0.851, -0.605 */
+  double flatness_thresholds[QB200_PW_MAX_THRESHOLDS];   /* 0.0001, 0.000125, 0.000185, 0.000185 */
+  int32_t num_iter;                       /* 3 */
+  int32_t num_lpr;                        /* 20 */
+  int32_t num_min_pts;                    /* 80 */
+  int32_t using_global_elevation;         /* 0 */
+  int32_t num_zones;                      /* 4 (the reference's binning is written for exactly four zones, patchwork.hpp:520-539) */
+  int32_t num_thresholds;                 /* 4 = rings of interest (elevation_thresholds.size()) */
+  int32_t num_sectors_each_zone[QB200_PW_MAX_ZONES];     /* 16, 32, 54, 32 */
+  int32_t num_rings_each_zone[QB200_PW_MAX_ZONES];       /* 2, 4, 4, 4 */
+} qb200_patchwork_params;
+void qb200_default_patchwork_params(qb200_patchwork_params* p);
+
+/* ground4 / nonground4: room for n points each (either may be NULL: only the counts are returned).  Point order of both
+ * outputs = the reference's: patches in (zone, ring, sector) order, inside a patch ascending (z, input index); a patch whose
+ * plane is rejected hands its ground part, then its non-ground part, to the non-ground output (patchwork.hpp:399-436).
+ * Points outside (min_range, max_range], below -1.8 sensor_height, non-finite, or in patches of <= num_min_pts points appear in
+ * neither output (as in the reference).  QB200_CAPACITY_EXCEEDED: a patch holds more than 16384 points. */
+int qb200_patchwork(qb200_handle* h, const float* pts4, int32_t n, const qb200_patchwork_params* p,
+                    float* ground4, int32_t* n_ground, float* nonground4, int32_t* n_nonground);
 
 /* normals4: n x {nx,ny,nz,curvature}; desc33: n x 33 floats (pcl::FPFHSignature33). Either may be NULL. */
 int qb200_compute_fpfh(qb200_handle* h, const float* pts4, int32_t n, float normal_radius,

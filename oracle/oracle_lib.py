@@ -16,7 +16,7 @@ LIB = HERE / "build" / "libquatro_oracle.so"
 
 class Oracle:
     def __init__(self, build: bool = True):
-        srcs = [HERE / "quatro_oracle.cpp", HERE / "qo_math.h", HERE.parent / "include" / "quatro_b200.h"]
+        srcs = [HERE / "quatro_oracle.cpp", HERE / "preprocess_oracle.inc", HERE / "qo_math.h", HERE.parent / "include" / "quatro_b200.h"]
         stale = (not LIB.exists()) or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs)
         if stale and build:
             r = subprocess.run(["make", "-C", str(HERE)], capture_output=True, text=True)
@@ -163,6 +163,16 @@ class Oracle:
         st = self.lib.qo_build_graph(_ptr(a4), _ptr(b4), L, noise_bound, cbar2, _ptr(adj), wpr, _ptr(deg), C.byref(ne))
         assert st == 0
         return adj, deg, ne.value
+
+    def patchwork(self, pts, pp):
+        pts = _f32(pts, 4)
+        n = len(pts)
+        g, ng = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 4), np.float32)
+        a, b = C.c_int(0), C.c_int(0)
+        self.lib.qo_patchwork.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+        st = self.lib.qo_patchwork(_ptr(pts), n, C.byref(pp), _ptr(g), C.byref(a), _ptr(ng), C.byref(b))
+        assert st >= 0, st
+        return g[: a.value].copy(), ng[: b.value].copy(), st
 
     def max_clique(self, adj, mode: int = 1, kcore_thr: float = 0.5):
         adj = np.ascontiguousarray(adj, np.uint32)

@@ -1125,6 +1125,8 @@ int solve_correspondences(const P4* a, const P4* b, int L, const qb200_params& p
   return solve_pose(a, b, L, so.clique.data(), (int)so.clique.size(), prm, res, so.rot_mask, so.trans_mask, so.final_inliers);
 }
 
+#include "preprocess_oracle.inc"
+
 double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -1212,6 +1214,18 @@ int qo_build_graph(const float* a4, const float* b4, int L, double noise_bound, 
   if (wpr < (L + 31) / 32) return QB200_ERR_BAD_ARG;
   build_graph(reinterpret_cast<const P4*>(a4), reinterpret_cast<const P4*>(b4), L, noise_bound, cbar2, adj, wpr, degree, n_edges);
   return QB200_OK;
+}
+
+int qo_patchwork(const float* pts4, int n, const qb200_patchwork_params* pp, float* ground4, int* n_ground, float* nonground4,
+                 int* n_nonground) {
+  std::vector<P4> g, ng;
+  const int st = patchwork(reinterpret_cast<const P4*>(pts4), n, *pp, g, ng);
+  if (st < 0) return st;
+  *n_ground = (int)g.size();
+  *n_nonground = (int)ng.size();
+  if (ground4 && !g.empty()) memcpy(ground4, g.data(), g.size() * sizeof(P4));
+  if (nonground4 && !ng.empty()) memcpy(nonground4, ng.data(), ng.size() * sizeof(P4));
+  return st;
 }
 
 int qo_max_clique_ex(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, int64_t node_limit, int* clique, int* n_clique,

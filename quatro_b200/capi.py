@@ -59,6 +59,19 @@ class Result(C.Structure):
         return d
 
 
+class PatchworkParams(C.Structure):
+    """qb200_patchwork_params (config/patchwork_params.yaml of the reference)."""
+    _fields_ = [
+        ("sensor_height", C.c_double), ("th_seeds", C.c_double), ("th_dist", C.c_double), ("max_range", C.c_double),
+        ("min_range", C.c_double), ("uprightness_thr", C.c_double), ("adaptive_seed_selection_margin", C.c_double),
+        ("global_elevation_threshold", C.c_double), ("min_ranges_each_zone", C.c_double * 4),
+        ("elevation_thresholds", C.c_double * 8), ("flatness_thresholds", C.c_double * 8),
+        ("num_iter", C.c_int32), ("num_lpr", C.c_int32), ("num_min_pts", C.c_int32), ("using_global_elevation", C.c_int32),
+        ("num_zones", C.c_int32), ("num_thresholds", C.c_int32), ("num_sectors_each_zone", C.c_int32 * 4),
+        ("num_rings_each_zone", C.c_int32 * 4),
+    ]
+
+
 class Pair(C.Structure):
     _fields_ = [("src", C.c_void_p), ("tgt", C.c_void_p), ("n_src", C.c_int32), ("n_tgt", C.c_int32)]
 
@@ -114,6 +127,8 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_last_error": (C.c_char_p, [vp]),
         "qb200_launch_count": (i64, [vp]),
         "qb200_voxelize": (i32, [vp, vp, i32, f32, i32, vp, i32, P(i32)]),
+        "qb200_default_patchwork_params": (None, [P(PatchworkParams)]),
+        "qb200_patchwork": (i32, [vp, vp, i32, P(PatchworkParams), vp, P(i32), vp, P(i32)]),
         "qb200_compute_fpfh": (i32, [vp, vp, i32, f32, f32, f32, vp, vp]),
         "qb200_match": (i32, [vp, vp, i32, vp, vp, i32, vp, P(Params), vp, i32, P(i32), P(i32)]),
         "qb200_build_graph": (i32, [vp, vp, vp, i32, f64, f64, vp, i32, vp, P(i64)]),
@@ -161,7 +176,7 @@ def load_library(build: bool = True) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "qb200_default_params", "qb200_default_config", "qb200_version", "qb200_create", "qb200_destroy",
     "qb200_set_stream", "qb200_last_error", "qb200_launch_count", "qb200_voxelize", "qb200_compute_fpfh",
-    "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_max_clique_ex", "qb200_solve_pose", "qb200_solve_correspondences",
+    "qb200_default_patchwork_params", "qb200_patchwork", "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_max_clique_ex", "qb200_solve_pose", "qb200_solve_correspondences",
     "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
@@ -219,6 +234,12 @@ def register_batch_sharded(handles: Sequence["Handle"], pairs: Sequence, params:
     if st != 0:
         raise QuatroB200Error(st, "qb200_register_batch_sharded " + handles[0].last_error())
     return out
+
+
+def default_patchwork_params() -> PatchworkParams:
+    p = PatchworkParams()
+    load_library().qb200_default_patchwork_params(C.byref(p))
+    return p
 
 
 def default_config() -> Config:
@@ -310,6 +331,15 @@ class Handle:
         self._check(self.lib.qb200_build_graph(self.h, _ptr(a4), _ptr(b4), L, noise_bound, cbar2, _ptr(adj), wpr, _ptr(deg), C.byref(ne)),
                     "qb200_build_graph")
         return adj, deg, ne.value
+
+    def patchwork(self, pts, pp: "PatchworkParams"):
+        """qb200_patchwork: (ground (g,4), nonground (m,4), status)."""
+        pts = _f32(pts, 4)
+        n = len(pts)
+        g, ng = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 4), np.float32)
+        a, b = C.c_int32(0), C.c_int32(0)
+        st = self._check(self.lib.qb200_patchwork(self.h, _ptr(pts), n, C.byref(pp), _ptr(g), C.byref(a), _ptr(ng), C.byref(b)), "qb200_patchwork")
+        return g[: a.value].copy(), ng[: b.value].copy(), st
 
     def max_clique(self, adj, mode: int = PMC_HEU, kcore_thr: float = 0.5):
         adj = np.ascontiguousarray(adj, np.uint32)

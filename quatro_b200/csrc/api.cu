@@ -347,7 +347,7 @@ void qb200_destroy(qb200_handle* h) {
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t, h->rowbest, h->colpart, h->colbest,
                       h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats, h->aos_scratch,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
-                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->ex_stack, h->ex_pool, h->ex_lvl, h->ex_cur, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
+                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->ex_stack, h->ex_pool, h->ex_lvl, h->ex_cur, h->pw_ints, h->pw_out, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
                       h->ctr_block};
   for (void* p : dev_ptrs)
     if (p) cudaFree(p);
@@ -423,6 +423,27 @@ int qb200_voxelize(qb200_handle* h, const float* pts4, int32_t n, float leaf, in
   }
   if (st == QB200_CAPACITY_EXCEEDED || nv > cap) return QB200_CAPACITY_EXCEEDED;
   return QB200_OK;
+}
+
+// ---- pre-processing: ground removal (patchwork.hpp:329-455) ---------------------------------------------
+int qb200_patchwork(qb200_handle* h, const float* pts4, int32_t n, const qb200_patchwork_params* p, float* ground4, int32_t* n_ground,
+                    float* nonground4, int32_t* n_nonground) {
+  QB_IDLE(h);
+  if (!h || !p || !n_ground || !n_nonground || n < 0 || (n > 0 && !pts4)) return QB200_ERR_BAD_ARG;
+  *n_ground = *n_nonground = 0;
+  if (n > h->R) { h->fail(__FILE__, __LINE__, "n exceeds max_raw_points"); return QB200_ERR_BAD_ARG; }
+  cudaSetDevice(h->device);
+  if (n > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(h->raw_stage, pts4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  int ng = 0, nn = 0, st = 0;
+  const int rc = launch_patchwork(h, h->raw_stage, n, *p, &ng, &nn, &st);
+  if (rc) return rc;
+  *n_ground = ng;
+  *n_nonground = nn;
+  if (ground4 && ng > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(ground4, h->pw_out, (size_t)ng * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  if (nonground4 && nn > 0)
+    QB_CUDA_TRY(h, cudaMemcpyAsync(nonground4, h->pw_out + h->R, (size_t)nn * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return st;
 }
 
 // ---- stage: normals + FPFH ------------------------------------------------------------------------

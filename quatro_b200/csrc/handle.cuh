@@ -75,6 +75,9 @@ struct qb200_handle {
   unsigned short* ex_cur;     // [S*1024] clique under construction (ranks)
   int* final_inl;             // [S*Lc]
   unsigned char *rot_mask, *trans_mask;  // [S*Lc]
+  // ---- pre-processing (preprocess.cu), allocated on first use ----
+  int* pw_ints;               // patch id / rank per point, per-patch counters and offsets
+  float4* pw_out;             // [2*R] ground | non-ground
   // ---- results ----
   qb200_result* d_results;    // [S]
   qb200_result* h_results;    // pinned [S]
@@ -128,6 +131,7 @@ int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p);
 int launch_fill_counters(qb200_handle* h, int n_pairs, int have_frontend);
 int launch_finalize_status(qb200_handle* h, int n_pairs);
 int launch_iota_clique(qb200_handle* h, int n_pairs);
+int launch_patchwork(qb200_handle* h, const float4* pts, int n, const qb200_patchwork_params& pp, int* n_ground, int* n_nonground, int* status);
 int launch_match_nn(qb200_handle* h, int n_pairs);
 int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);
 int launch_tc_debug_tile(qb200_handle* h, float* d_out);

@@ -1,0 +1,116 @@
+"""Pre-processing before the path: ground removal, include/patchwork.hpp:329-455.
+
+CPU part: the oracle restatement against properties that do not depend on it (the generator's own ground labels, a numpy plane
+model) and the reference's documented edge behaviour.  GPU part (-m gpu): qb200_patchwork through the C-ABI is bit-identical to the
+oracle -- same points, same order, in both outputs."""
+import numpy as np
+import pytest
+
+from quatro_b200 import synth
+from quatro_b200.capi import default_patchwork_params
+
+
+def _scene(seed, n_obj=40):
+    """Flat ground at z = -1.723 seen from the origin + boxes standing on it: labels known by construction."""
+    rng = np.random.default_rng(seed)
+    az = rng.uniform(0, 2 * np.pi, 60000)
+    r = rng.uniform(3.0, 70.0, 60000)
+    g = np.stack([r * np.cos(az), r * np.sin(az), -1.723 + rng.normal(0, 0.02, len(r))], 1)
+    objs = []
+    for _ in range(n_obj):
+        c = rng.uniform(-50, 50, 2)
+        if np.hypot(*c) < 5:
+            continue
+        k = 600
+        # walls of a 2 x 2 x 2.5 m box
+        side = rng.integers(0, 4, k)
+        u, v = rng.uniform(-1, 1, k), rng.uniform(-1.4, 1.1, k)
+        x = np.where(side < 2, np.where(side == 0, -1.0, 1.0), u) + c[0]
+        y = np.where(side < 2, u, np.where(side == 2, -1.0, 1.0)) + c[1]
+        objs.append(np.stack([x, y, v], 1))
+    o = np.concatenate(objs)
+    pts = np.concatenate([g, o]).astype(np.float32)
+    lab = np.concatenate([np.ones(len(g), bool), np.zeros(len(o), bool)])
+    perm = rng.permutation(len(pts))
+    out = np.ones((len(pts), 4), np.float32)
+    out[:, :3] = pts[perm]
+    out[:, 3] = np.where(lab[perm], -1.0, 1.0)      # w < 0 marks true ground (travels with the point)
+    return out
+
+
+def test_patchwork_separates_ground_from_objects(oracle):
+    pp = default_patchwork_params()
+    pts = _scene(1)
+    g, ng, st = oracle.patchwork(pts, pp)
+    assert st == 0
+    r = np.hypot(pts[:, 0], pts[:, 1])
+    assert len(g) + len(ng) <= int(((r > pp.min_range) & (r <= pp.max_range)).sum())   # nothing is duplicated
+    # ground output is ground; objects end in the non-ground output (walls standing on the plane leave a thin skirt: th_dist)
+    assert (g[:, 3] < 0).mean() > 0.97
+    wall = ng[ng[:, 3] > 0]
+    assert len(wall) > 0.85 * (pts[:, 3] > 0).sum()
+    assert (ng[:, 3] < 0).sum() < 0.1 * (pts[:, 3] < 0).sum()
+    # generator scans: the ground flag of the synthetic LiDAR agrees with the estimate
+    src, _, _ = synth.outdoor_pair(5, rings=32, azimuths=900)
+    g, ng, st = oracle.patchwork(src, pp)
+    assert (g[:, 3] < 0).mean() > 0.95 and (ng[:, 3] < 0).mean() < 0.02
+
+
+def test_patchwork_order_and_edge_cases(oracle):
+    pp = default_patchwork_params()
+    pts = _scene(2, n_obj=10)
+    g, ng, _ = oracle.patchwork(pts, pp)
+    # every output point is an input point, bit for bit, used once
+    key = lambda a: {tuple(x) for x in a.view(np.uint32).reshape(len(a), 4).tolist()}
+    assert key(g) | key(ng) <= key(pts) and not (key(g) & key(ng))
+    # permutation of the input changes nothing but tie order: ground / non-ground SETS are equal
+    perm = np.random.default_rng(0).permutation(len(pts))
+    g2, ng2, _ = oracle.patchwork(pts[perm], pp)
+    assert key(g2) == key(g) and key(ng2) == key(ng)
+    # empty, all-NaN, below the mirror-reflection cut (-1.8 h), fewer than num_min_pts per patch -> nothing comes out
+    for bad in (np.zeros((0, 4), np.float32), np.full((100, 4), np.nan, np.float32),
+                np.array([[10, 0, -5.0, 1]] * 200, np.float32), pts[:50]):
+        g0, n0, st = oracle.patchwork(bad, pp)
+        assert st == 0 and len(g0) == 0 and len(n0) == 0
+    # a tilted / vertical patch is rejected as a whole: its "ground" part joins the non-ground output first (patchwork.hpp:399-402)
+    rng = np.random.default_rng(3)
+    wall = np.stack([np.full(400, 6.0), rng.uniform(-1.0, 1.0, 400), rng.uniform(-1.7, 1.0, 400), np.ones(400)], 1).astype(np.float32)
+    g3, n3, _ = oracle.patchwork(wall, pp)
+    assert len(g3) == 0 and len(n3) == 400
+
+
+@pytest.mark.gpu
+def test_patchwork_gpu_matches_oracle(handle, oracle):
+    pp = default_patchwork_params()
+    scans = [synth.outdoor_pair(11)[0], synth.outdoor_pair(12, rings=32, azimuths=900)[1], _scene(4)]
+    scans[2][::97, 2] = np.nan                       # non-finite points are dropped
+    scans[2][5::113, 2] = -0.0
+    for pts in scans:
+        g_o, n_o, st_o = oracle.patchwork(pts, pp)
+        g_g, n_g, st_g = handle.patchwork(pts, pp)
+        assert st_g == st_o == 0
+        assert g_g.shape == g_o.shape and n_g.shape == n_o.shape
+        assert np.array_equal(g_g.view(np.uint32), g_o.view(np.uint32)), "ground output differs (points or order)"
+        assert np.array_equal(n_g.view(np.uint32), n_o.view(np.uint32)), "non-ground output differs (points or order)"
+    # other parameters: more iterations, global elevation test, looser uprightness
+    pp2 = default_patchwork_params()
+    pp2.num_iter, pp2.using_global_elevation, pp2.uprightness_thr, pp2.num_min_pts = 5, 1, 0.5, 10
+    g_o, n_o, _ = oracle.patchwork(scans[0], pp2)
+    g_g, n_g, _ = handle.patchwork(scans[0], pp2)
+    assert np.array_equal(g_g.view(np.uint32), g_o.view(np.uint32)) and np.array_equal(n_g.view(np.uint32), n_o.view(np.uint32))
+    # edge cases
+    for bad in (np.zeros((0, 4), np.float32), np.full((100, 4), np.nan, np.float32), scans[0][:50]):
+        g_g, n_g, st = handle.patchwork(bad, pp)
+        assert st == 0 and len(g_g) == 0 and len(n_g) == 0
+    # the ground-free scan goes through the registration path like a flagged one
+    from quatro_b200.capi import default_params
+    src, tgt, T = synth.outdoor_pair(13)
+    p = default_params()
+    p.skip_flagged = 0
+    ns, nt = handle.patchwork(src, pp)[1], handle.patchwork(tgt, pp)[1]
+    res, st = handle.register_pair(ns, nt, p)
+    ref, st_ref = oracle.register_pair(oracle.patchwork(src, pp)[1], oracle.patchwork(tgt, pp)[1], p)
+    assert st == st_ref == 0 and res.n_corr == ref.n_corr and res.clique_size == ref.clique_size
+    assert np.allclose(res.matrix(), ref.matrix(), atol=1e-9)
+    rot, tr = synth.pose_error(res.matrix(), T)
+    assert rot < 2.0 and tr < 1.0      # the same pair with the generator's ground flags: 0.99 deg / 0.55 m
