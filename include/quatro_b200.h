@@ -5,6 +5,7 @@
  * boundary of the reference (url-kaist/Quatro, paths relative to the reference root):
  *
  *   qb200_patchwork             <- PatchWork<PointT>::estimate_ground   include/patchwork.hpp:329-455 (pre-processing, 8f-1)
+ *   qb200_segment_cloud         <- ImageProjection::segmentCloud        include/imageProjection.hpp:273-294 (pre-processing, 8f-1)
  *   qb200_voxelize              <- voxelize<T>()                    include/quatro.hpp:49-57
  *   qb200_compute_fpfh          <- FPFHEstimation::computeFPFHFeatures  src/teaser_utils/fpfh.cc:44-75
  *   qb200_match                 <- Matcher::calculateCorrespondences    include/teaser_utils/feature_matcher.h:42-74
@@ -193,6 +194,31 @@ void qb200_default_patchwork_params(qb200_patchwork_params* p);
  * neither output (as in the reference).  QB200_CAPACITY_EXCEEDED: a patch holds more than 16384 points. */
 int qb200_patchwork(qb200_handle* h, const float* pts4, int32_t n, const qb200_patchwork_params* p,
                     float* ground4, int32_t* n_ground, float* nonground4, int32_t* n_nonground);
+
+/* qb200_segment_cloud <- ImageProjection::segmentCloud in "Patchwork" mode, include/imageProjection.hpp:273-294: range-image
+ * projection (:308-352), connected components of the range image under the LeGO-LOAM angle criterion (labelComponents, :483-579)
+ * and the extraction of the valid segments / outliers (:424-481, getValidSegments :214-216, getOutliers :230-232).
+ * The constructor's per-sensor constants (:86-131) travel in this POD; qb200_default_segment_params = "Velodyne-64-HDE",
+ * "4CrossNeighbor" (examples/run_global_registration.cpp:53-55). */
+enum { QB200_NEIGHBORS_4 = 0, QB200_NEIGHBORS_8 = 1, QB200_NEIGHBORS_4_CROSS = 2 };
+typedef struct qb200_segment_params {
+  int32_t n_scan;                     /* 64   (<= 64) */
+  int32_t horizon_scan;               /* 1800 */
+  float ang_res_x;                    /* 360 / 1800 */
+  float ang_res_y;                    /* 26.9 / 63 */
+  float ang_bottom;                   /* 25.0 */
+  float segment_theta;                /* 60 deg in radians */
+  int32_t neighbor_mode;              /* QB200_NEIGHBORS_4_CROSS */
+  int32_t min_pts_for_subclustering;  /* 30 */
+  int32_t segment_valid_point_num;    /* 5 */
+  int32_t segment_valid_line_num;     /* 3 */
+} qb200_segment_params;
+void qb200_default_segment_params(qb200_segment_params* p);
+
+/* valid4 / outlier4: room for n_scan * horizon_scan points each (either may be NULL).  Both outputs are in row-major pixel
+ * order; a pixel holds the LAST input point projected into it (:340-346); w = 1. */
+int qb200_segment_cloud(qb200_handle* h, const float* pts4, int32_t n, const qb200_segment_params* p,
+                        float* valid4, int32_t* n_valid, float* outlier4, int32_t* n_outlier);
 
 /* normals4: n x {nx,ny,nz,curvature}; desc33: n x 33 floats (pcl::FPFHSignature33). Either may be NULL. */
 int qb200_compute_fpfh(qb200_handle* h, const float* pts4, int32_t n, float normal_radius,

@@ -174,6 +174,16 @@ class Oracle:
         assert st >= 0, st
         return g[: a.value].copy(), ng[: b.value].copy(), st
 
+    def segment_cloud(self, pts, sp):
+        pts = _f32(pts, 4)
+        npix = sp.n_scan * sp.horizon_scan
+        v, o = np.zeros((npix, 4), np.float32), np.zeros((npix, 4), np.float32)
+        a, b = C.c_int(0), C.c_int(0)
+        self.lib.qo_segment_cloud.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+        st = self.lib.qo_segment_cloud(_ptr(pts), len(pts), C.byref(sp), _ptr(v), C.byref(a), _ptr(o), C.byref(b))
+        assert st >= 0, st
+        return v[: a.value].copy(), o[: b.value].copy()
+
     def max_clique(self, adj, mode: int = 1, kcore_thr: float = 0.5):
         adj = np.ascontiguousarray(adj, np.uint32)
         L, wpr = adj.shape

@@ -1228,6 +1228,17 @@ int qo_patchwork(const float* pts4, int n, const qb200_patchwork_params* pp, flo
   return st;
 }
 
+int qo_segment_cloud(const float* pts4, int n, const qb200_segment_params* sp, float* valid4, int* n_valid, float* outlier4, int* n_outlier) {
+  std::vector<P4> v, o;
+  const int st = segment_cloud(reinterpret_cast<const P4*>(pts4), n, *sp, v, o);
+  if (st < 0) return st;
+  *n_valid = (int)v.size();
+  *n_outlier = (int)o.size();
+  if (valid4 && !v.empty()) memcpy(valid4, v.data(), v.size() * sizeof(P4));
+  if (outlier4 && !o.empty()) memcpy(outlier4, o.data(), o.size() * sizeof(P4));
+  return st;
+}
+
 int qo_max_clique_ex(const uint32_t* adj, int L, int wpr, int mode, double kcore_thr, int64_t node_limit, int* clique, int* n_clique,
                      int* kcore, int* kcore_order, int* max_core, int* flags) {
   std::vector<int> c, k, o;

@@ -72,6 +72,13 @@ class PatchworkParams(C.Structure):
     ]
 
 
+class SegmentParams(C.Structure):
+    """qb200_segment_params (per-sensor constants of the ImageProjection constructor)."""
+    _fields_ = [("n_scan", C.c_int32), ("horizon_scan", C.c_int32), ("ang_res_x", C.c_float), ("ang_res_y", C.c_float),
+                ("ang_bottom", C.c_float), ("segment_theta", C.c_float), ("neighbor_mode", C.c_int32),
+                ("min_pts_for_subclustering", C.c_int32), ("segment_valid_point_num", C.c_int32), ("segment_valid_line_num", C.c_int32)]
+
+
 class Pair(C.Structure):
     _fields_ = [("src", C.c_void_p), ("tgt", C.c_void_p), ("n_src", C.c_int32), ("n_tgt", C.c_int32)]
 
@@ -128,6 +135,8 @@ def load_library(build: bool = True) -> C.CDLL:
         "qb200_launch_count": (i64, [vp]),
         "qb200_voxelize": (i32, [vp, vp, i32, f32, i32, vp, i32, P(i32)]),
         "qb200_default_patchwork_params": (None, [P(PatchworkParams)]),
+        "qb200_default_segment_params": (None, [P(SegmentParams)]),
+        "qb200_segment_cloud": (i32, [vp, vp, i32, P(SegmentParams), vp, P(i32), vp, P(i32)]),
         "qb200_patchwork": (i32, [vp, vp, i32, P(PatchworkParams), vp, P(i32), vp, P(i32)]),
         "qb200_compute_fpfh": (i32, [vp, vp, i32, f32, f32, f32, vp, vp]),
         "qb200_match": (i32, [vp, vp, i32, vp, vp, i32, vp, P(Params), vp, i32, P(i32), P(i32)]),
@@ -176,7 +185,7 @@ def load_library(build: bool = True) -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "qb200_default_params", "qb200_default_config", "qb200_version", "qb200_create", "qb200_destroy",
     "qb200_set_stream", "qb200_last_error", "qb200_launch_count", "qb200_voxelize", "qb200_compute_fpfh",
-    "qb200_default_patchwork_params", "qb200_patchwork", "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_max_clique_ex", "qb200_solve_pose", "qb200_solve_correspondences",
+    "qb200_default_patchwork_params", "qb200_patchwork", "qb200_default_segment_params", "qb200_segment_cloud", "qb200_match", "qb200_build_graph", "qb200_max_clique", "qb200_max_clique_ex", "qb200_solve_pose", "qb200_solve_correspondences",
     "qb200_match_and_pack", "qb200_register_pair", "qb200_register_batch", "qb200_get_last_clique",
     "qb200_get_last_final_inliers", "qb200_get_last_correspondences", "qb200_get_stage_ms", "qb200_get_kernel_ms",
     "qb200_debug_tc_distances",
@@ -239,6 +248,12 @@ def register_batch_sharded(handles: Sequence["Handle"], pairs: Sequence, params:
 def default_patchwork_params() -> PatchworkParams:
     p = PatchworkParams()
     load_library().qb200_default_patchwork_params(C.byref(p))
+    return p
+
+
+def default_segment_params() -> SegmentParams:
+    p = SegmentParams()
+    load_library().qb200_default_segment_params(C.byref(p))
     return p
 
 
@@ -340,6 +355,16 @@ class Handle:
         a, b = C.c_int32(0), C.c_int32(0)
         st = self._check(self.lib.qb200_patchwork(self.h, _ptr(pts), n, C.byref(pp), _ptr(g), C.byref(a), _ptr(ng), C.byref(b)), "qb200_patchwork")
         return g[: a.value].copy(), ng[: b.value].copy(), st
+
+    def segment_cloud(self, pts, sp: "SegmentParams"):
+        """qb200_segment_cloud: (valid segments (v,4), outliers (o,4))."""
+        pts = _f32(pts, 4)
+        npix = sp.n_scan * sp.horizon_scan
+        v, o = np.zeros((npix, 4), np.float32), np.zeros((npix, 4), np.float32)
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.qb200_segment_cloud(self.h, _ptr(pts), len(pts), C.byref(sp), _ptr(v), C.byref(a), _ptr(o), C.byref(b)),
+                    "qb200_segment_cloud")
+        return v[: a.value].copy(), o[: b.value].copy()
 
     def max_clique(self, adj, mode: int = PMC_HEU, kcore_thr: float = 0.5):
         adj = np.ascontiguousarray(adj, np.uint32)

@@ -347,7 +347,7 @@ void qb200_destroy(qb200_handle* h) {
                       h->vox_start, h->vox_pts, h->cell_key, h->cell_start, h->normals, h->spfh, h->nbr_list, h->nbr_cnt, h->desc_t, h->rowbest, h->colpart, h->colbest,
                       h->desc_tiles, h->desc_norm, h->tc_fallback, h->tc_stats, h->aos_scratch,
                       h->mut_i, h->mut_j, h->mark, h->partner, h->mean, h->corr_src, h->corr_tgt, h->ma, h->mb, h->adj, h->adjp, h->deg,
-                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->ex_stack, h->ex_pool, h->ex_lvl, h->ex_cur, h->pw_ints, h->pw_out, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
+                      h->kcore, h->korder, h->rank_of, h->by_rank, h->kbin, h->clique, h->ex_stack, h->ex_pool, h->ex_lvl, h->ex_cur, h->pw_ints, h->pw_out, h->ip_buf, h->final_inl, h->rot_mask, h->trans_mask, h->d_results,
                       h->ctr_block};
   for (void* p : dev_ptrs)
     if (p) cudaFree(p);
@@ -444,6 +444,27 @@ int qb200_patchwork(qb200_handle* h, const float* pts4, int32_t n, const qb200_p
     QB_CUDA_TRY(h, cudaMemcpyAsync(nonground4, h->pw_out + h->R, (size_t)nn * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
   QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return st;
+}
+
+// ---- pre-processing: range-image sub-cluster removal (imageProjection.hpp:273-294) ------------------------
+int qb200_segment_cloud(qb200_handle* h, const float* pts4, int32_t n, const qb200_segment_params* p, float* valid4, int32_t* n_valid,
+                        float* outlier4, int32_t* n_outlier) {
+  QB_IDLE(h);
+  if (!h || !p || !n_valid || !n_outlier || n < 0 || (n > 0 && !pts4)) return QB200_ERR_BAD_ARG;
+  *n_valid = *n_outlier = 0;
+  if (n > h->R) { h->fail(__FILE__, __LINE__, "n exceeds max_raw_points"); return QB200_ERR_BAD_ARG; }
+  cudaSetDevice(h->device);
+  if (n > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(h->raw_stage, pts4, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  int nv = 0, no = 0;
+  const float4 *dv = nullptr, *dout = nullptr;
+  const int rc = launch_segment_cloud(h, h->raw_stage, n, *p, &nv, &no, &dv, &dout);
+  if (rc) return rc;
+  *n_valid = nv;
+  *n_outlier = no;
+  if (valid4 && nv > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(valid4, dv, (size_t)nv * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  if (outlier4 && no > 0) QB_CUDA_TRY(h, cudaMemcpyAsync(outlier4, dout, (size_t)no * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return QB200_OK;
 }
 
 // ---- stage: normals + FPFH ------------------------------------------------------------------------

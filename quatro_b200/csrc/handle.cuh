@@ -78,6 +78,7 @@ struct qb200_handle {
   // ---- pre-processing (preprocess.cu), allocated on first use ----
   int* pw_ints;               // patch id / rank per point, per-patch counters and offsets
   float4* pw_out;             // [2*R] ground | non-ground
+  void* ip_buf; int ip_npix;  // range-image scratch (per pixel: winner, parent, size, range, row set, two outputs)
   // ---- results ----
   qb200_result* d_results;    // [S]
   qb200_result* h_results;    // pinned [S]
@@ -131,6 +132,8 @@ int launch_pose(qb200_handle* h, int n_pairs, const qb200_params& p);
 int launch_fill_counters(qb200_handle* h, int n_pairs, int have_frontend);
 int launch_finalize_status(qb200_handle* h, int n_pairs);
 int launch_iota_clique(qb200_handle* h, int n_pairs);
+int launch_segment_cloud(qb200_handle* h, const float4* pts, int n, const qb200_segment_params& sp, int* n_valid, int* n_outlier,
+                         const float4** valid_dev, const float4** outlier_dev);
 int launch_patchwork(qb200_handle* h, const float4* pts, int n, const qb200_patchwork_params& pp, int* n_ground, int* n_nonground, int* status);
 int launch_match_nn(qb200_handle* h, int n_pairs);
 int launch_match_exact(qb200_handle* h, int n_pairs, const int* only);

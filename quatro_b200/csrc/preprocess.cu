@@ -389,6 +389,216 @@ int launch_patchwork(qb200_handle* h, const float4* pts, int n, const qb200_patc
   return QB200_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Range-image sub-cluster removal: ImageProjection::segmentCloud in "Patchwork" mode (include/imageProjection.hpp:273-294).
+// The reference grows one segment at a time with a breadth-first queue (labelComponents, :483-579); the pair criterion
+// (angle between neighbouring range pixels, :530-541) is symmetric, so its segments are the connected components of the pixel
+// graph -- built here with a lock-free union-find (roots = lowest pixel index = the reference's seed pixel in its row-major
+// sweep, :427-430), followed by per-component statistics and an ordered extraction.
+//   ip_project_kernel  point -> pixel (:308-352); the LAST input point of a pixel wins (atomicMax on the input index)
+//   ip_range_kernel    winner -> range image, parent = own pixel (or -1: nothing projected, maskGround :354-363)
+//   ip_union_kernel    one thread per pixel and forward neighbour: union when the angle criterion holds
+//   ip_stats_kernel    flatten; component size and the set of rows touched by its pixels other than the seed (lineCountFlag, :545)
+//   ip_extract_kernel  feasibility (:559-571) and the two outputs in row-major order (:424-481)
+// ------------------------------------------------------------------------------------------------
+struct IpDev {
+  qb200_segment_params p;
+  float sin_x, cos_x, sin_y, cos_y;
+  int nnb;
+  int nb[8][2];
+};
+
+__device__ __forceinline__ bool ip_project(const float4 pt, const qb200_segment_params& sp, int* row, int* col, float* range) {
+  const float vert = (float)((double)(qb_atan2f(pt.z, sqrtf(pt.x * pt.x + pt.y * pt.y)) * 180.0f) / 3.14159265358979323846);
+  const float rf = (vert + sp.ang_bottom) / sp.ang_res_y;
+  if (!(rf > -1.0f) || !(rf < (float)sp.n_scan)) return false;
+  const int r = (int)rf;
+  if (r < 0 || r >= sp.n_scan) return false;
+  const float hor = (float)((double)(qb_atan2f(pt.x, pt.y) * 180.0f) / 3.14159265358979323846);
+  const double cd = -round(((double)hor - 90.0) / (double)sp.ang_res_x) + (double)(sp.horizon_scan / 2);
+  if (!(cd >= 0.0) || !(cd < 4.0e9)) return false;
+  long long c = (long long)cd;
+  if (c >= sp.horizon_scan) c -= sp.horizon_scan;
+  if (c < 0 || c >= sp.horizon_scan) return false;
+  const float rg = sqrtf(pt.x * pt.x + pt.y * pt.y + pt.z * pt.z);
+  if (rg < 0.1f) return false;
+  *row = r; *col = (int)c; *range = rg;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) ip_project_kernel(const float4* __restrict__ pts, int n, IpDev c, int* __restrict__ winner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) return;   // copyPointCloud, :260-266
+  int r, col; float rg;
+  if (!ip_project(p, c.p, &r, &col, &rg)) return;
+  atomicMax(&winner[r * c.p.horizon_scan + col], i);
+}
+
+__global__ void __launch_bounds__(256) ip_range_kernel(const float4* __restrict__ pts, int npix, const int* __restrict__ winner,
+                                                       float* __restrict__ range, int* __restrict__ parent, int* __restrict__ size,
+                                                       unsigned long long* __restrict__ rows) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npix) return;
+  const int w = winner[q];
+  float rg = FLT_MAX;
+  if (w >= 0) {
+    const float4 p = pts[w];
+    rg = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+  }
+  range[q] = rg;
+  parent[q] = w >= 0 ? q : -1;
+  size[q] = 0;
+  rows[q] = 0ull;
+}
+
+__device__ __forceinline__ int ip_find(const int* parent, int a) {
+  for (;;) {
+    const int pa = ((volatile const int*)parent)[a];
+    if (pa == a) return a;
+    a = pa;
+  }
+}
+
+__global__ void __launch_bounds__(256) ip_union_kernel(int npix, IpDev c, const float* __restrict__ range, int* parent) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npix) return;
+  const float ra = range[q];
+  if (ra == FLT_MAX) return;
+  const int H = c.p.n_scan, Wd = c.p.horizon_scan;
+  const int fx = q / Wd, fy = q - fx * Wd;
+  for (int t = 0; t < c.nnb; ++t) {
+    const int tx = fx + c.nb[t][0];
+    int ty = fy + c.nb[t][1];
+    if (tx < 0 || tx >= H) continue;
+    if (ty < 0) ty = Wd - 1;
+    if (ty >= Wd) ty = 0;
+    const int o = tx * Wd + ty;
+    if (o <= q) continue;             // every pixel pair once (the criterion is symmetric); o == q: Wd wrap of a 1-column image
+    const float rb = range[o];
+    if (rb == FLT_MAX) continue;
+    const float d1 = fmaxf(ra, rb), d2 = fminf(ra, rb);
+    const bool same_row = c.nb[t][0] == 0;
+    const float angle = qb_atan2f(d2 * (same_row ? c.sin_x : c.sin_y), d1 - d2 * (same_row ? c.cos_x : c.cos_y));
+    if (!(angle > c.p.segment_theta)) continue;
+    int a = q, b = o;
+    for (;;) {   // link the larger root under the smaller one
+      a = ip_find(parent, a);
+      b = ip_find(parent, b);
+      if (a == b) break;
+      if (a < b) { const int tmp = a; a = b; b = tmp; }
+      const int old = atomicMin(&parent[a], b);
+      if (old == a) break;
+      a = old;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ip_stats_kernel(int npix, int Wd, int* parent, int* __restrict__ size, unsigned long long* __restrict__ rows) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= npix) return;
+  if (((volatile int*)parent)[q] < 0) return;
+  const int root = ip_find(parent, q);
+  atomicAdd(&size[root], 1);
+  if (q != root) atomicOr(&rows[root], 1ull << (q / Wd));
+}
+
+// one CTA: ordered extraction (row-major) of the valid-segment points and of the outliers
+__global__ void __launch_bounds__(1024) ip_extract_kernel(const float4* __restrict__ pts, int npix, IpDev c, const int* __restrict__ winner,
+                                                          const int* parent, const int* __restrict__ size,
+                                                          const unsigned long long* __restrict__ rows, float4* __restrict__ valid,
+                                                          float4* __restrict__ outlier, int* __restrict__ out_n) {
+  __shared__ int sm[33];
+  int cv = 0, co = 0;
+  for (int base = 0; base < npix; base += 1024) {
+    const int q = base + threadIdx.x;
+    int kind = 0;  // 1 valid segment, 2 outlier
+    if (q < npix && winner[q] >= 0) {
+      const int root = ip_find(parent, q);
+      const int sz = size[root];
+      bool feasible = sz >= c.p.min_pts_for_subclustering;
+      if (!feasible && sz >= c.p.segment_valid_point_num) feasible = __popcll(rows[root]) >= c.p.segment_valid_line_num;
+      kind = feasible ? 1 : 2;
+    }
+    int both;
+    const int ex = block_excl_scan((kind == 1 ? 1 : 0) | ((kind == 2 ? 1 : 0) << 16), sm, &both);
+    if (kind) {
+      float4 p = pts[winner[q]];
+      p.w = 1.0f;
+      if (kind == 1) valid[cv + (ex & 0xFFFF)] = p;
+      else outlier[co + (ex >> 16)] = p;
+    }
+    cv += both & 0xFFFF;
+    co += both >> 16;
+  }
+  if (threadIdx.x == 0) { out_n[0] = cv; out_n[1] = co; }
+}
+
+static int ensure_ip_scratch(qb200_handle* h, int npix) {
+  if (h->ip_buf && h->ip_npix >= npix) return QB200_OK;
+  if (h->ip_buf) { cudaFree(h->ip_buf); h->ip_buf = nullptr; }
+  // per pixel: rows u64 | valid float4 | outlier float4 | winner, parent, size int | range float ; + out_n [2]
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ip_buf, (size_t)npix * (8 + 16 + 16 + 4 * 4) + 16));
+  h->ip_npix = npix;
+  return QB200_OK;
+}
+
+static bool ip_params_valid(const qb200_segment_params& sp) {
+  return sp.n_scan >= 1 && sp.n_scan <= 64 && sp.horizon_scan >= 8 && sp.horizon_scan <= 8192 && sp.ang_res_x > 0 && sp.ang_res_y > 0 &&
+         sp.neighbor_mode >= 0 && sp.neighbor_mode <= 2 && sp.min_pts_for_subclustering >= 0 && sp.segment_valid_point_num >= 0 &&
+         sp.segment_valid_line_num >= 0;
+}
+
+// pts: n device points.  Leaves the outputs in the handle's scratch; *valid_dev / *outlier_dev point at them.
+int launch_segment_cloud(qb200_handle* h, const float4* pts, int n, const qb200_segment_params& sp, int* n_valid, int* n_outlier,
+                         const float4** valid_dev, const float4** outlier_dev) {
+  *n_valid = *n_outlier = 0;
+  if (!ip_params_valid(sp)) return QB200_ERR_BAD_ARG;
+  const int npix = sp.n_scan * sp.horizon_scan;
+  if (int rc = ensure_ip_scratch(h, npix)) return rc;
+  unsigned char* b = reinterpret_cast<unsigned char*>(h->ip_buf);
+  unsigned long long* rows = reinterpret_cast<unsigned long long*>(b); b += (size_t)npix * 8;
+  float4* valid = reinterpret_cast<float4*>(b); b += (size_t)npix * 16;
+  float4* outlier = reinterpret_cast<float4*>(b); b += (size_t)npix * 16;
+  int* winner = reinterpret_cast<int*>(b); b += (size_t)npix * 4;
+  int* parent = reinterpret_cast<int*>(b); b += (size_t)npix * 4;
+  int* size = reinterpret_cast<int*>(b); b += (size_t)npix * 4;
+  float* range = reinterpret_cast<float*>(b); b += (size_t)npix * 4;
+  int* out_n = reinterpret_cast<int*>(b);
+  *valid_dev = valid; *outlier_dev = outlier;
+  IpDev c;
+  c.p = sp;
+  // segmentAlphaX / segmentAlphaY and their sine / cosine (:132-133, :535-541): constants of the call, evaluated on the host
+  const float alpha_x = (float)((double)sp.ang_res_x / 180.0 * 3.14159265358979323846), alpha_y = (float)((double)sp.ang_res_y / 180.0 * 3.14159265358979323846);
+  c.sin_x = sinf(alpha_x); c.cos_x = cosf(alpha_x); c.sin_y = sinf(alpha_y); c.cos_y = cosf(alpha_y);
+  static const int n4[4][2] = {{-1, 0}, {0, 1}, {0, -1}, {1, 0}};
+  static const int n8[8][2] = {{-1, 0}, {0, 1}, {0, -1}, {1, 0}, {-1, -1}, {-1, 1}, {1, 1}, {1, -1}};
+  static const int nx[4][2] = {{-1, -1}, {-1, 1}, {1, 1}, {1, -1}};
+  c.nnb = sp.neighbor_mode == QB200_NEIGHBORS_8 ? 8 : 4;
+  for (int i = 0; i < 8; ++i) { c.nb[i][0] = 0; c.nb[i][1] = 0; }
+  for (int i = 0; i < c.nnb; ++i) {
+    const int(*src)[2] = sp.neighbor_mode == QB200_NEIGHBORS_4 ? n4 : (sp.neighbor_mode == QB200_NEIGHBORS_8 ? n8 : nx);
+    c.nb[i][0] = src[i][0]; c.nb[i][1] = src[i][1];
+  }
+  QB_CUDA_TRY(h, cudaMemsetAsync(winner, 0xFF, (size_t)npix * sizeof(int), h->stream));   // -1
+  const int gp = (npix + 255) / 256;
+  if (n > 0) ip_project_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(pts, n, c, winner);
+  ip_range_kernel<<<gp, 256, 0, h->stream>>>(pts, npix, winner, range, parent, size, rows);
+  ip_union_kernel<<<gp, 256, 0, h->stream>>>(npix, c, range, parent);
+  ip_stats_kernel<<<gp, 256, 0, h->stream>>>(npix, sp.horizon_scan, parent, size, rows);
+  ip_extract_kernel<<<1, 1024, 0, h->stream>>>(pts, npix, c, winner, parent, size, rows, valid, outlier, out_n);
+  h->launches += 5;
+  QB_CUDA_TRY(h, cudaGetLastError());
+  int host_n[2];
+  QB_CUDA_TRY(h, cudaMemcpyAsync(host_n, out_n, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  *n_valid = host_n[0];
+  *n_outlier = host_n[1];
+  return QB200_OK;
+}
+
 }  // namespace qb
 
 extern "C" void qb200_default_patchwork_params(qb200_patchwork_params* p) {  // config/patchwork_params.yaml:1-48
@@ -416,4 +626,19 @@ extern "C" void qb200_default_patchwork_params(qb200_patchwork_params* p) {  // 
   p->using_global_elevation = 0;
   p->num_zones = 4;
   p->num_thresholds = 4;
+}
+
+extern "C" void qb200_default_segment_params(qb200_segment_params* p) {  // "Velodyne-64-HDE", imageProjection.hpp:87-94; "4CrossNeighbor"
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->n_scan = 64;
+  p->horizon_scan = 1800;
+  p->ang_res_x = (float)(360.0 / (double)(float)1800);
+  p->ang_res_y = (float)(26.9 / (double)(float)63);
+  p->ang_bottom = 25.0f;
+  p->segment_theta = (float)(60.0 / 180.0 * 3.14159265358979323846);
+  p->neighbor_mode = QB200_NEIGHBORS_4_CROSS;
+  p->min_pts_for_subclustering = 30;
+  p->segment_valid_point_num = 5;
+  p->segment_valid_line_num = 3;
 }

@@ -114,3 +114,124 @@ def test_patchwork_gpu_matches_oracle(handle, oracle):
     assert np.allclose(res.matrix(), ref.matrix(), atol=1e-9)
     rot, tr = synth.pose_error(res.matrix(), T)
     assert rot < 2.0 and tr < 1.0      # the same pair with the generator's ground flags: 0.99 deg / 0.55 m
+
+
+# ---- range-image sub-cluster removal (include/imageProjection.hpp:273-294) ------------------------------------------------
+def _numpy_segments(pts, sp):
+    """Independent restatement: numpy float32 projection, scipy connected components, segment statistics."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    H, W = sp.n_scan, sp.horizon_scan
+    p = pts[np.isfinite(pts[:, :3]).all(1)]
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    vert = (np.arctan2(z, np.sqrt(x * x + y * y)).astype(np.float32) * np.float32(180.0)).astype(np.float64) / np.pi
+    rf = (vert.astype(np.float32) + np.float32(sp.ang_bottom)) / np.float32(sp.ang_res_y)
+    hor = ((np.arctan2(x, y).astype(np.float32) * np.float32(180.0)).astype(np.float64) / np.pi).astype(np.float32)
+    qd = (hor.astype(np.float64) - 90.0) / np.float64(np.float32(sp.ang_res_x))
+    col = (-(np.sign(qd) * np.floor(np.abs(qd) + 0.5)) + W // 2).astype(np.int64)      # C round(): halves away from zero
+    col = np.where(col >= W, col - W, col)
+    rng = np.sqrt(x * x + y * y + z * z)
+    ok = (rf > -1) & (rf < H) & (col >= 0) & (col < W) & (rng >= 0.1)
+    row = np.trunc(rf).astype(np.int64)
+    pix = (row * W + col)[ok]
+    win = np.full(H * W, -1, np.int64)
+    np.maximum.at(win, pix, np.nonzero(ok)[0])
+    img = np.full(H * W, np.inf, np.float32)
+    img[win >= 0] = rng[win[win >= 0]]
+    img = img.reshape(H, W)
+    offs = {0: [(-1, 0), (0, 1), (0, -1), (1, 0)], 2: [(-1, -1), (-1, 1), (1, 1), (1, -1)]}[sp.neighbor_mode] if sp.neighbor_mode != 1 else \
+        [(-1, 0), (0, 1), (0, -1), (1, 0), (-1, -1), (-1, 1), (1, 1), (1, -1)]
+    ax, ay = np.float32(np.float64(sp.ang_res_x) / 180 * np.pi), np.float32(np.float64(sp.ang_res_y) / 180 * np.pi)
+    ii, jj = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    src, dst = [], []
+    for di, dj in offs:
+        ti, tj = ii + di, (jj + dj) % W
+        inb = (ti >= 0) & (ti < H)
+        a, b = img[ii[inb], jj[inb]], img[ti[inb], tj[inb]]
+        both = np.isfinite(a) & np.isfinite(b)
+        d1, d2 = np.maximum(a, b), np.minimum(a, b)
+        al = ax if di == 0 else ay
+        with np.errstate(invalid="ignore"):
+            ang = np.arctan2(d2 * np.sin(al), d1 - d2 * np.cos(al))
+        e = both & (ang > sp.segment_theta)
+        src.append((ii[inb] * W + jj[inb])[e]); dst.append((ti[inb] * W + tj[inb])[e])
+    src, dst = np.concatenate(src), np.concatenate(dst)
+    n_comp, lab = connected_components(coo_matrix((np.ones(len(src)), (src, dst)), shape=(H * W, H * W)), directed=False)
+    occupied = np.nonzero(win >= 0)[0]
+    n_valid = n_out = 0
+    order = np.argsort(lab[occupied], kind="stable")
+    groups = np.split(occupied[order], np.nonzero(np.diff(lab[occupied][order]))[0] + 1)
+    for gpx in groups:
+        rows_wo_seed = np.unique(gpx[1:] // W)            # gpx is ascending: gpx[0] is the seed of the row-major sweep
+        ok_seg = len(gpx) >= sp.min_pts_for_subclustering or (len(gpx) >= sp.segment_valid_point_num and len(rows_wo_seed) >= sp.segment_valid_line_num)
+        if ok_seg: n_valid += len(gpx)
+        else: n_out += len(gpx)
+    return n_valid, n_out
+
+
+def test_segment_cloud_against_numpy_scipy(oracle):
+    from quatro_b200.capi import default_segment_params
+    pp = default_patchwork_params()
+    src, _, _ = synth.outdoor_pair(21)
+    ng = oracle.patchwork(src, pp)[1]
+    # The synthetic LiDAR's rings sit EXACTLY on the row boundaries of the range image (elevation = -25 + k * 26.9 / 63 degrees), where
+    # the last ulp of atan2f decides the row: a slightly tilted and shifted sensor frame moves them off the boundaries, so that the
+    # comparison with numpy's atan2 (a different last ulp) is about the algorithm, not about rounding.
+    a, b = np.radians(0.37), np.radians(-0.23)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    ng = ng.copy()
+    ng[:, :3] = (ng[:, :3].astype(np.float64) @ (Rx @ Ry).T + np.array([0.11, -0.05, 0.07])).astype(np.float32)
+    for mode in (2, 0, 1):
+        sp = default_segment_params()
+        sp.neighbor_mode = mode
+        v, o = oracle.segment_cloud(ng, sp)
+        nv, no = _numpy_segments(ng, sp)
+        assert abs(len(v) + len(o) - (nv + no)) <= 3               # same occupied pixels (a point on a pixel boundary may move)
+        assert abs(len(v) - nv) <= 0.005 * (nv + no) + 5, (mode, len(v), nv)   # float32 atan2 differs in the last ulp at a few edges
+        assert len(v) > 0.5 * (nv + no)
+        # outputs are input points (w = 1), each at most once
+        allp = {tuple(r) for r in ng[:, :3].view(np.uint32).tolist()}
+        got = [tuple(r) for r in np.concatenate([v, o])[:, :3].view(np.uint32).tolist()]
+        assert set(got) <= allp and len(set(got)) == len(got)
+    # nothing in, nothing out; isolated points are outliers
+    sp = default_segment_params()
+    v, o = oracle.segment_cloud(np.zeros((0, 4), np.float32), sp)
+    assert len(v) == 0 and len(o) == 0
+    lone = np.array([[10, 0, 0, 1], [0, 20, -2, 1], [-30, 5, 0.5, 1]], np.float32)
+    v, o = oracle.segment_cloud(lone, sp)
+    assert len(v) == 0 and len(o) == 3
+
+
+@pytest.mark.gpu
+def test_segment_cloud_gpu_matches_oracle(handle, oracle):
+    from quatro_b200.capi import default_segment_params, default_params
+    pp = default_patchwork_params()
+    clouds = [oracle.patchwork(synth.outdoor_pair(31)[0], pp)[1], synth.outdoor_pair(32, rings=32, azimuths=900)[1], _scene(6)]
+    clouds[2][::53, 0] = np.nan
+    for pts in clouds:
+        for mode in (2, 0, 1):
+            sp = default_segment_params()
+            sp.neighbor_mode = mode
+            v_o, o_o = oracle.segment_cloud(pts, sp)
+            v_g, o_g = handle.segment_cloud(pts, sp)
+            assert np.array_equal(v_g.view(np.uint32), v_o.view(np.uint32)), f"valid segments differ (mode {mode})"
+            assert np.array_equal(o_g.view(np.uint32), o_o.view(np.uint32)), f"outliers differ (mode {mode})"
+    sp = default_segment_params()
+    sp.n_scan, sp.horizon_scan, sp.ang_res_x, sp.ang_res_y, sp.ang_bottom = 16, 1800, 0.2, 2.0, 15.1     # "VLP-16", imageProjection.hpp:95-102
+    v_o, o_o = oracle.segment_cloud(clouds[1], sp)
+    v_g, o_g = handle.segment_cloud(clouds[1], sp)
+    assert np.array_equal(v_g.view(np.uint32), v_o.view(np.uint32)) and np.array_equal(o_g.view(np.uint32), o_o.view(np.uint32))
+    v_g, o_g = handle.segment_cloud(np.zeros((0, 4), np.float32), default_segment_params())
+    assert len(v_g) == 0 and len(o_g) == 0
+    # the example's pre-processing chain (run_global_registration.cpp:136-162) in front of the registration path
+    sp = default_segment_params()
+    src, tgt, T = synth.outdoor_pair(33)
+    chain_g = lambda c: handle.segment_cloud(handle.patchwork(c, pp)[1], sp)[0]
+    chain_o = lambda c: oracle.segment_cloud(oracle.patchwork(c, pp)[1], sp)[0]
+    p = default_params()
+    p.skip_flagged = 0
+    res, st = handle.register_pair(chain_g(src), chain_g(tgt), p)
+    ref, st_ref = oracle.register_pair(chain_o(src), chain_o(tgt), p)
+    assert st == st_ref and res.n_src_vox == ref.n_src_vox and res.n_corr == ref.n_corr and res.clique_size == ref.clique_size
+    assert np.allclose(res.matrix(), ref.matrix(), atol=1e-9)
