@@ -29,6 +29,17 @@ __host__ __device__ __forceinline__ uint64_t cell_key(int i, int j, int k) {
   return ((uint64_t)(k + kOffK) << 36) | ((uint64_t)(j + kOffIJ) << 18) | (uint64_t)(i + kOffIJ);
 }
 
+// ---- voxel keys (frontend.cu, voxsort.cu) ----
+constexpr int kVoxShift = 31;
+constexpr uint64_t kVoxMask = (1ull << kVoxShift) - 1;
+constexpr uint64_t kVoxInvalid = kVoxMask;  // dx dy dz <= INT_MAX: a valid index is at most 2^31 - 2
+constexpr int kVsChunks = 64;               // contiguous chunks of a raw scan whose kept points the bbox pass counts
+
+__device__ __forceinline__ bool raw_point_kept(const float4 p, int skip_flagged) {
+  return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(skip_flagged && p.w < 0.0f);
+}
+__host__ __device__ __forceinline__ int vox_chunk_size(int n) { return n > 0 ? (n + kVsChunks - 1) / kVsChunks : 1; }
+
 constexpr int kDescDim = 33;   // pcl::FPFHSignature33
 constexpr int kDescPad = 36;   // floats per SPFH row (16-byte multiple: float4 gathers)
 constexpr int kDescK = 40;     // rows (K extent) of the dimension-major FPFH matrices: 33 bins + zero padding to a multiple of
@@ -78,6 +89,23 @@ __host__ __device__ __forceinline__ float ordered_float(int i) {
   return f;
 #endif
 }
+
+// number of 8-bit digits the voxel keys of a cloud occupy: the keys are below dx dy dz of pcl::VoxelGrid's own linear index
+// (voxel_keys / voxel_pack use the same min_b / div_b expressions)
+__device__ __forceinline__ int vox_digits(const int* __restrict__ bbox, int n_valid, float inv_leaf) {
+  if (n_valid <= 0) return 0;
+  const long long m0 = (long long)floorf(ordered_float(bbox[0]) * inv_leaf), m1 = (long long)floorf(ordered_float(bbox[1]) * inv_leaf),
+                  m2 = (long long)floorf(ordered_float(bbox[2]) * inv_leaf);
+  const long long d0 = (long long)floorf(ordered_float(bbox[3]) * inv_leaf) - m0 + 1, d1 = (long long)floorf(ordered_float(bbox[4]) * inv_leaf) - m1 + 1,
+                  d2 = (long long)floorf(ordered_float(bbox[5]) * inv_leaf) - m2 + 1;
+  unsigned long long span = (unsigned long long)d0 * (unsigned long long)d1;   // each factor < 2^18 (cell_ok)
+  if (span > (1ull << 31) || span * (unsigned long long)d2 > (1ull << 31)) return 4;  // refused by run_heads (overflow); any order will do
+  span *= (unsigned long long)d2;
+  int bits = 0;
+  while (bits < 31 && (1ull << bits) < span) ++bits;
+  return (bits + 7) >> 3;
+}
+
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 

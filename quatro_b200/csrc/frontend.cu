@@ -12,6 +12,9 @@
 // uses, so the single-pass float covariance matches bit for bit.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "fpfh_math.cuh"
 #include "handle.cuh"
 
@@ -57,44 +60,53 @@ static int clog2(int n) {
 // called from include/quatro.hpp:49-57), which the library requires to fit an int: 31 key bits + the cloud id, so the
 // radix sort of the whole wave needs 5 passes instead of the 8 an absolute (k, j, i) lattice key would take.
 // ------------------------------------------------------------------------------------------------
-constexpr int kVoxShift = 31;
-constexpr uint64_t kVoxMask = (1ull << kVoxShift) - 1;
-constexpr uint64_t kVoxInvalid = kVoxMask;  // dx dy dz <= INT_MAX: a valid index is at most 2^31 - 2
-
-__device__ __forceinline__ bool raw_point_kept(const float4 p, int skip_flagged) {
-  return isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(skip_flagged && p.w < 0.0f);
-}
 
 __global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
                                                          float inv_leaf, int skip_flagged, int* __restrict__ bbox,
-                                                         int* __restrict__ n_valid, int* __restrict__ cloud_status) {
+                                                         int* __restrict__ n_valid, int* __restrict__ cloud_status, int* __restrict__ chunk_cnt) {
   const int cloud = blockIdx.y;
   const int n = cloud_n[cloud];
   const float4* __restrict__ pts = cloud_ptr[cloud];
   int mn0 = INT_MAX, mn1 = INT_MAX, mn2 = INT_MAX, mx0 = INT_MIN, mx1 = INT_MIN, mx2 = INT_MIN, cnt = 0, bad = 0;
   // eight independent 16-byte loads in flight per thread and ~30 points per thread: this pass streams the raw scans (230 MB per
-  // 64-pair wave) from HBM, and the reduction tail (shuffles, atomics) is paid once per 30 points instead of once per 7
+  // 64-pair wave) from HBM, and the reduction tail (shuffles, atomics) is paid once per 30 points instead of once per 7.
+  // A CTA walks kVsChunks / gridDim.x CONTIGUOUS chunks of the scan and also reports how many points of each chunk are kept:
+  // the pack pass (voxsort.cu) writes the kept points compacted, in scan order, from these counts.
   constexpr int kInFlight = 8;
-  const int stride = gridDim.x * blockDim.x;
-  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kInFlight * stride) {
-    float4 pp[kInFlight];
+  __shared__ int s_cc[kVsChunks];
+  if (threadIdx.x < kVsChunks) s_cc[threadIdx.x] = 0;
+  __syncthreads();
+  const int cs = vox_chunk_size(n);
+  const int per_cta = kVsChunks / gridDim.x;
+  for (int cl = 0; cl < per_cta; ++cl) {
+    const int ch = blockIdx.x * per_cta + cl;
+    const int c0 = ch * cs, c1 = min(n, c0 + cs);
+    int ccnt = 0;
+    for (int i0 = c0 + threadIdx.x; i0 < c1; i0 += kInFlight * 256) {
+      float4 pp[kInFlight];
 #pragma unroll
-    for (int j = 0; j < kInFlight; ++j) pp[j] = i0 + j * stride < n ? __ldg(pts + i0 + j * stride) : make_float4(NAN, NAN, NAN, 0.f);  // NaN = not kept
+      for (int j = 0; j < kInFlight; ++j) pp[j] = i0 + j * 256 < c1 ? __ldg(pts + i0 + j * 256) : make_float4(NAN, NAN, NAN, 0.f);  // NaN = not kept
 #pragma unroll
-    for (int j = 0; j < kInFlight; ++j) {
-      const float4 p = pp[j];
-      if (i0 + j * stride >= n || !raw_point_kept(p, skip_flagged)) continue;
-      const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
-      if (cell_ok(ci, cj, ck)) {
-        const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
-        mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
-        mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
-        ++cnt;
-      } else {
-        bad = 1;  // outside the representable lattice: PCL's index would overflow as well
+      for (int j = 0; j < kInFlight; ++j) {
+        const float4 p = pp[j];
+        if (i0 + j * 256 >= c1 || !raw_point_kept(p, skip_flagged)) continue;
+        const int ci = (int)floorf(p.x * inv_leaf), cj = (int)floorf(p.y * inv_leaf), ck = (int)floorf(p.z * inv_leaf);
+        if (cell_ok(ci, cj, ck)) {
+          const int ox = float_ordered(p.x), oy = float_ordered(p.y), oz = float_ordered(p.z);
+          mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+          mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+          ++ccnt;
+        } else {
+          bad = 1;  // outside the representable lattice: PCL's index would overflow as well
+        }
       }
     }
+    cnt += ccnt;
+    ccnt = __reduce_add_sync(0xffffffffu, ccnt);
+    if (lane_id() == 0 && ccnt) atomicAdd(&s_cc[ch], ccnt);
   }
+  __syncthreads();
+  if ((int)threadIdx.x < per_cta) chunk_cnt[cloud * kVsChunks + blockIdx.x * per_cta + threadIdx.x] = s_cc[blockIdx.x * per_cta + threadIdx.x];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, o)); mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(256) voxel_keys_kernel(const float4* const* __
 //   mode 0 (voxels): segment = [raw_off, raw_off + n_raw), writes starts[], n_out = #voxels
 //   mode 1 (cells):  segment = [cloud*V, cloud*V + V),     writes starts[] and cell keys
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_t* __restrict__ keys, const int* __restrict__ seg_off,
+__global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_t* keys, const uint64_t* keys_alt, const int* __restrict__ seg_off,
                                                          const int* __restrict__ seg_n, int V, int key_shift, float inv_leaf, const int* __restrict__ bbox,
                                                          const int* __restrict__ n_valid_in, int* __restrict__ starts,
                                                          uint64_t* __restrict__ cell_keys, int* __restrict__ n_out, int* __restrict__ n_valid_out,
@@ -172,7 +184,11 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
   __shared__ int s_overflow;
   const int cloud = blockIdx.x;
   const int off = mode == 0 ? seg_off[cloud] : cloud * V;
-  const int n = mode == 0 ? seg_n[cloud] : V;
+  int n = mode == 0 ? seg_n[cloud] : V;
+  if (mode == 0 && keys_alt) {  // own voxel sort: the kept points only, in A or B by the parity of the cloud's digit count
+    n = n_valid_in[cloud];
+    if (vox_digits(bbox + cloud * 6, n, inv_leaf) & 1) keys = keys_alt;
+  }
   if (threadIdx.x == 0) {
     int ov = 0;
     if (mode == 0 && n_valid_in[cloud] > 0) {
@@ -250,12 +266,14 @@ __global__ void __launch_bounds__(1024) run_heads_kernel(int mode, const uint64_
 // K1c: centroid of each voxel, summed in original point order (stable sort) -> identical to the
 // sequential CPU sum.  One thread per voxel; points are gathered through the sorted index.
 __global__ void __launch_bounds__(128) voxel_centroid_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ raw_off,
-                                                             const uint64_t* __restrict__ sorted_keys, uint64_t idx_mask,
+                                                             const uint64_t* sorted_keys, const uint64_t* keys_alt, const int* __restrict__ bbox,
+                                                             const int* __restrict__ n_valid, float inv_leaf, uint64_t idx_mask,
                                                              const int* __restrict__ starts, const int* __restrict__ n_vox, int V,
                                                              float4* __restrict__ vox_pts) {
   const int cloud = blockIdx.y;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_vox[cloud]) return;
+  if (keys_alt && (vox_digits(bbox + cloud * 6, n_valid[cloud], inv_leaf) & 1)) sorted_keys = keys_alt;
   const float4* __restrict__ pts = cloud_ptr[cloud];
   const int off = raw_off[cloud];
   const int a = starts[(size_t)cloud * (V + 1) + r], b = starts[(size_t)cloud * (V + 1) + r + 1];
@@ -661,18 +679,31 @@ int launch_voxel(qb200_handle* h, int n_clouds, int total_raw, float leaf, int s
   const float inv = 1.0f / leaf;
   const dim3 gk(64, n_clouds);
   const dim3 gb(n_clouds >= 16 ? 16 : 64, n_clouds);  // ~30 points per thread when the batch fills the device on its own
-  voxel_bbox_kernel<<<gb, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid, h->ctr.cloud_status);
+  int* chunk_cnt = reinterpret_cast<int*>(h->val_b);   // [clouds][kVsChunks]
+  voxel_bbox_kernel<<<gb, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid, h->ctr.cloud_status,
+                                               chunk_cnt);
   const int idx_bits = clog2(h->R > 2 ? h->R : 2);  // point index inside its scan
-  voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid,
-                                               idx_bits, h->key_a);
-  h->launches += 2;
-  const int rc = sort_keys(h, total_raw, idx_bits, idx_bits + kVoxShift + clog2(n_clouds > 1 ? n_clouds : 2));
-  if (rc) return rc;
-  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(0, h->key_b, h->d_raw_off, h->d_cloud_n, h->V, idx_bits, inv, h->ctr.bbox, h->ctr.n_valid,
+  // QB200_VOXEL_SORT=cub: round 1's device-wide library sort of every raw point (kept for A/B runs; results are identical)
+  static const bool use_cub = getenv("QB200_VOXEL_SORT") && !strcmp(getenv("QB200_VOXEL_SORT"), "cub");
+  const bool own = !use_cub && h->R >= 16384;   // the histogram scratch (val_a) holds 256 x R / 2048 words per cloud
+  const uint64_t* keys_alt = nullptr;
+  if (own) {
+    h->launches += 1;
+    if (int rc = launch_voxel_sort(h, n_clouds, inv, skip_flagged, idx_bits)) return rc;
+    keys_alt = h->key_b;
+  } else {
+    voxel_keys_kernel<<<gk, 256, 0, h->stream>>>(h->d_cloud_ptr, h->d_cloud_n, h->d_raw_off, inv, skip_flagged, h->ctr.bbox, h->ctr.n_valid,
+                                                 idx_bits, h->key_a);
+    h->launches += 2;
+    const int rc = sort_keys(h, total_raw, idx_bits, idx_bits + kVoxShift + clog2(n_clouds > 1 ? n_clouds : 2));
+    if (rc) return rc;
+  }
+  const uint64_t* sorted = own ? h->key_a : h->key_b;
+  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(0, sorted, keys_alt, h->d_raw_off, h->d_cloud_n, h->V, idx_bits, inv, h->ctr.bbox, h->ctr.n_valid,
                                                      h->vox_start, nullptr, h->ctr.n_vox, nullptr, h->ctr.cloud_status);
   const dim3 gc((h->V + 127) / 128, n_clouds);
-  voxel_centroid_kernel<<<gc, 128, 0, h->stream>>>(h->d_cloud_ptr, h->d_raw_off, h->key_b, (1ull << idx_bits) - 1, h->vox_start, h->ctr.n_vox, h->V,
-                                                   h->vox_pts);
+  voxel_centroid_kernel<<<gc, 128, 0, h->stream>>>(h->d_cloud_ptr, h->d_raw_off, sorted, keys_alt, h->ctr.bbox, h->ctr.n_valid, inv,
+                                                   (1ull << idx_bits) - 1, h->vox_start, h->ctr.n_vox, h->V, h->vox_pts);
   h->launches += 2;
   QB_CUDA_TRY(h, cudaGetLastError());
   return QB200_OK;
@@ -691,7 +722,7 @@ int launch_fpfh(qb200_handle* h, int n_clouds, float normal_radius, float fpfh_r
   int rc = launch_cloud_sort(h, n_clouds, h->ctr.n_vox, 18, 36);  // fields of cell_key(): i | j | k
   if (rc == QB200_ERR_UNSUPPORTED) rc = sort_pairs(h, n_clouds * V, kCloudShift + clog2(n_clouds > 1 ? n_clouds : 2));
   if (rc) return rc;
-  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, V, 0, inv, nullptr, nullptr, h->cell_start, h->cell_key,
+  run_heads_kernel<<<n_clouds, 1024, 0, h->stream>>>(1, h->key_b, nullptr, nullptr, nullptr, V, 0, inv, nullptr, nullptr, h->cell_start, h->cell_key,
                                                      h->ctr.n_cells, h->ctr.n_lat, h->ctr.cloud_status);
   const dim3 gp((V + 127) / 128, n_clouds);
   nbr_list_kernel<<<gp, kNbrThreads, 0, h->stream>>>(h->vox_pts, h->ctr.n_vox, V, h->cell_key, h->cell_start, h->val_b, h->ctr.n_cells, inv, mf,

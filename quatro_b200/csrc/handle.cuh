@@ -149,6 +149,7 @@ int collect_batch(qb200_handle* h, const qb200_result* dst);  // api.cu: wait fo
 int ensure_dyn_smem(qb200_handle* h, const void* kernel, size_t bytes);
 int sort_pairs(qb200_handle* h, int n_items, int end_bit);
 int sort_keys(qb200_handle* h, int n_items, int begin_bit, int end_bit);
+int launch_voxel_sort(qb200_handle* h, int n_clouds, float inv_leaf, int skip_flagged, int idx_bits);
 int launch_cloud_sort(qb200_handle* h, int n_clouds, const int* n_items, int f1, int f2);
 
 }  // namespace qb
