@@ -4,7 +4,8 @@
 //
 //   g++ -std=c++17 -Iinclude examples/run_global_registration.cpp -Lquatro_b200/lib -lquatro_b200
 //       -Wl,-rpath,$PWD/quatro_b200/lib -o run_example
-//   ./run_example src.bin tgt.bin        (KITTI .bin: float32 x,y,z,intensity records)
+//   ./run_example src.bin tgt.bin              (KITTI .bin: float32 x,y,z,intensity records; the scans are used as they are)
+//   ./run_example src.bin tgt.bin --preprocess (ground removal + sub-cluster rejection first, the reference's STEP 2 / STEP 3)
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -13,6 +14,8 @@
 #include <memory>
 
 #include "quatro_b200/fpfh_manager.hpp"
+#include "quatro_b200/imageProjection.hpp"
+#include "quatro_b200/patchwork.hpp"
 #include "quatro_b200/quatro.hpp"
 
 using namespace std;
@@ -55,7 +58,7 @@ static pcl::PointCloud<PointType>::ConstPtr read_kitti_bin(const std::string& pa
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::cerr << "usage: " << argv[0] << " <src.bin> <tgt.bin>" << std::endl;
+    std::cerr << "usage: " << argv[0] << " <src.bin> <tgt.bin> [--preprocess]" << std::endl;
     return 2;
   }
   // config/params.yaml
@@ -67,6 +70,33 @@ int main(int argc, char** argv) {
   pcl::PointCloud<PointType>::ConstPtr srcRaw = read_kitti_bin(argv[1]);
   pcl::PointCloud<PointType>::ConstPtr tgtRaw = read_kitti_bin(argv[2]);
   if (!srcRaw || !tgtRaw) return 1;
+
+  if (argc > 3 && std::string(argv[3]) == "--preprocess") {
+    // ===== reference examples/run_global_registration.cpp:124-162 ("Patchwork" ground mode) =====
+    std::string lidarType = "Velodyne-64-HDE", neighborSelectionMode = "4CrossNeighbor", groundSegMode = "Patchwork";
+    pcl::PointCloud<PointType> srcGround, tgtGround, srcInvalidSegments, tgtInvalidSegments;
+    pcl::PointCloud<PointType>::Ptr ptrSrcNonground(new pcl::PointCloud<PointType>), ptrTgtNonground(new pcl::PointCloud<PointType>);
+    pcl::PointCloud<PointType>::Ptr srcValidSegments(new pcl::PointCloud<PointType>), tgtValidSegments(new pcl::PointCloud<PointType>);
+    ImageProjection IPSrc(lidarType, neighborSelectionMode, groundSegMode);
+    ImageProjection IPTgt(lidarType, neighborSelectionMode, groundSegMode);
+    std::unique_ptr<PatchWork<PointType>> patchwork;
+    double tSrc = 0, tTgt = 0;
+    patchwork.reset(new PatchWork<PointType>());
+    patchwork->estimate_ground(*(srcRaw), srcGround, *ptrSrcNonground, tSrc);
+    patchwork->estimate_ground(*(tgtRaw), tgtGround, *ptrTgtNonground, tTgt);
+    IPSrc.segmentCloud(ptrSrcNonground);
+    IPTgt.segmentCloud(ptrTgtNonground);
+    IPSrc.getValidSegments(*srcValidSegments);
+    IPTgt.getValidSegments(*tgtValidSegments);
+    IPSrc.getOutliers(srcInvalidSegments);
+    IPTgt.getOutliers(tgtInvalidSegments);
+    cout << "# of raw cloud       | " << srcRaw->size() << " | " << tgtRaw->size() << endl;
+    cout << "# of ground          | " << srcGround.size() << " | " << tgtGround.size() << endl;
+    cout << "# of valid segments  | " << srcValidSegments->size() << " | " << tgtValidSegments->size() << endl;
+    cout << "# of outliers        | " << srcInvalidSegments.size() << " | " << tgtInvalidSegments.size() << endl;
+    srcRaw = srcValidSegments;
+    tgtRaw = tgtValidSegments;
+  }
 
   // ===================================================================================================
   Quatro<PointType, PointType> quatro;

@@ -42,6 +42,45 @@ def test_shim_keeps_the_reference_surface():
         assert name in f, name
 
 
+def test_preprocessing_shims_keep_the_reference_surface():
+    """examples/run_global_registration.cpp:124-162 of the reference: PatchWork<PointT>::estimate_ground, ImageProjection."""
+    pw = (ROOT / "include" / "quatro_b200" / "patchwork.hpp").read_text()
+    ip = (ROOT / "include" / "quatro_b200" / "imageProjection.hpp").read_text()
+    for name in ["class PatchWork", "void estimate_ground(const pcl::PointCloud<PointT>& cloud_in, pcl::PointCloud<PointT>& cloud_out",
+                 "check_input_parameters_are_correct"]:
+        assert name in pw, name
+    for name in ["class ImageProjection", "void segmentCloud(", "getValidSegments", "getOutliers", "Velodyne-64-HDE", "VLP-16", "HDL-32E",
+                 "Ouster-OS1-16", "Ouster-OS1-64", "4CrossNeighbor", "N_SCAN", "Horizon_SCAN"]:
+        assert name in ip, name
+
+
+@pytest.mark.gpu
+def test_example_with_preprocessing_reproduces_the_oracle(tmp_path, oracle):
+    """--preprocess: PatchWork + ImageProjection through the C++ shim in front of the path, against the oracle's chain."""
+    from quatro_b200 import synth
+    from quatro_b200.capi import default_params, default_patchwork_params, default_segment_params
+    exe = build_example(tmp_path)
+    src, tgt, T = synth.outdoor_pair(2)
+    src[:, 3] = 1.0; tgt[:, 3] = 1.0                  # the .bin loader drops the 4th channel anyway
+    (tmp_path / "src.bin").write_bytes(src.astype(np.float32).tobytes())
+    (tmp_path / "tgt.bin").write_bytes(tgt.astype(np.float32).tobytes())
+    r = subprocess.run([str(exe), str(tmp_path / "src.bin"), str(tmp_path / "tgt.bin"), "--preprocess"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    T_cpp = np.array([list(map(float, ln.split()[1:])) for ln in r.stdout.splitlines() if re.match(r"^T ", ln)])
+    pp, sp = default_patchwork_params(), default_segment_params()
+    chain = lambda c: oracle.segment_cloud(oracle.patchwork(c, pp)[1], sp)[0]
+    cs, ct = chain(src), chain(tgt)
+    m = re.search(r"# of valid segments\s+\| (\d+) \| (\d+)", r.stdout)
+    assert m and (int(m.group(1)), int(m.group(2))) == (len(cs), len(ct))
+    p = default_params()
+    sv, _ = oracle.voxelize(cs, 0.3, 0)
+    tv, _ = oracle.voxelize(ct, 0.3, 0)
+    corr, sm, tm, _ = oracle.match_and_pack(sv, tv, p)
+    ref, st = oracle.solve_correspondences(sm, tm, p)
+    assert st == 0 and f"# after voxelization | {len(sv)} | {len(tv)}" in r.stdout
+    assert np.allclose(T_cpp, ref.matrix(), atol=1e-6)
+
+
 @pytest.mark.gpu
 def test_example_reproduces_the_oracle(tmp_path, oracle):
     from quatro_b200 import synth
