@@ -495,6 +495,41 @@ def main():
                  "stages_ms_one_wave_one_lane": {"pairs": n1, **{k: float(v) for k, v in zip(names, serial)}},
                  "single_pair_latency_ms": d_single, "cpu_baseline": d_cpu}
 
+    # ---- pre-processing before the path: ground removal + range-image sub-cluster rejection, per scan, host buffers ----
+    preprocess = None
+    if args.scene == "street" and world == 1 and rank == 0 and not args.no_dense:
+        from quatro_b200.capi import default_patchwork_params, default_segment_params
+        pp_, sp_ = default_patchwork_params(), default_segment_params()
+        scans = [pairs[i][0] for i in range(min(8, P))]
+        hp = Handle(device=local_rank, max_batch_slots=2)
+        for sc in scans[:2]:
+            hp.segment_cloud(hp.patchwork(sc, pp_)[1], sp_)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        outs = []
+        for sc in scans:
+            g_, ng_, _ = hp.patchwork(sc, pp_)
+            outs.append((g_, ng_) + hp.segment_cloud(ng_, sp_))
+        gpu_ms = (time.perf_counter() - t0) * 1e3 / len(scans)
+        hp.close()
+        cpu_ms, same = None, None
+        if not args.no_cpu_baseline:
+            from oracle import Oracle
+            o_ = Oracle()
+            t0 = time.perf_counter()
+            same = True
+            for sc, (g_, ng_, v_, ol_) in zip(scans, outs):
+                og, ong, _ = o_.patchwork(sc, pp_)
+                ov, ool = o_.segment_cloud(ong, sp_)
+                same = same and np.array_equal(og, g_) and np.array_equal(ong, ng_) and np.array_equal(ov, v_) and np.array_equal(ool, ol_)
+            cpu_ms = (time.perf_counter() - t0) * 1e3 / len(scans)
+            assert same, "pre-processing outputs differ from the CPU oracle"
+        preprocess = {"what": "qb200_patchwork + qb200_segment_cloud per scan through the C-ABI, host buffers in and out (the reference's STEP 2 / STEP 3, "
+                              "examples/run_global_registration.cpp:136-162); wall clock per scan, blocking calls",
+                      "scans": len(scans), "ms_per_scan": gpu_ms, "cpu_oracle_ms_per_scan": cpu_ms, "identical_to_oracle": same,
+                      "mean_points": float(np.mean([len(x) for x in scans])), "mean_ground": float(np.mean([len(x[0]) for x in outs])),
+                      "mean_valid_segment_points": float(np.mean([len(x[2]) for x in outs]))}
+
     if rank == 0:
         peaks = load_peaks()
         facts = load_ncu_facts()
@@ -585,7 +620,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_graph": roofline_graph,
-            "roofline_graph_3k": roofline_graph_3k, "cpu_baseline": cpu, "cpu_best_case": best, "dense": dense, "cross_rank_check": cross,
+            "roofline_graph_3k": roofline_graph_3k, "cpu_baseline": cpu, "cpu_best_case": best, "dense": dense, "preprocess": preprocess, "cross_rank_check": cross,
             "stages_ms_per_step": {k: float(v / args.steps) for k, v in zip(["h2d", "voxel", "fpfh", "match", "graph", "clique", "pose", "d2h"], sms)},
             "valid_pairs": int(res_dev["valid"].sum()), "mean_n_vox": float((nA.mean() + nB.mean()) / 2), "mean_L": float(L.mean()),
             "mean_clique": float(res_dev["clique_size"].mean()),

@@ -2,7 +2,7 @@
 """Extract the per-launch facts bench.py quotes (DRAM traffic, duration, pipe utilisation) from an `ncu --set full` report and the
 JSON line the profiled bench run printed, and write them to profiles/r02_ncu_facts.json (+ a markdown summary).
 
-    python tools/ncu_facts.py gpurun_out/prof_r2c.ncu-rep gpurun_out/r2_prof_c.json [--md profiles/r02_ncu_summary.md]
+    python tools/ncu_facts.py gpurun_out/prof_r2c.ncu-rep gpurun_out/r2_prof_c.json [--md profiles/r02_ncu_summary.md] [--key k1_wave]
 
 Kernels: tc_nn_kernel (K6), tim_graph_kernel (K8), kcore_warp_kernel / clique_cta_kernel (K9).  For every kernel the LARGEST launch of
 the capture is reported (the captures hold a 64-pair wave plus single-pair passes)."""
@@ -74,7 +74,13 @@ def main():
             f["algorithmic_flops_per_launch"] = line["roofline"]["flops_per_launch"]
             f["algorithmic_bytes_per_launch"] = line["roofline"].get("algorithmic_bytes_per_launch")
         facts[key] = f
-    (ROOT / "profiles" / "r02_ncu_facts.json").write_text(json.dumps(facts, indent=1))
+    out = ROOT / "profiles" / "r02_ncu_facts.json"
+    if "--key" in sys.argv:   # merge this capture under its own key, leave the rest of the file alone
+        allf = json.loads(out.read_text()) if out.exists() else {}
+        allf[sys.argv[sys.argv.index("--key") + 1]] = facts
+        out.write_text(json.dumps(allf, indent=1))
+    else:
+        out.write_text(json.dumps(facts, indent=1))
     print(json.dumps(facts, indent=1))
     if md:
         with open(md, "w") as fh:
