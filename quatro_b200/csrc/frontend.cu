@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kSpfhThreads) spfh_kernel(const float4* __rest
 // (own 11 accumulators, own fp64 normaliser), so a point is served by three threads in three different warps -- 11 accumulators
 // and three 16-byte gathers per neighbour each instead of 33 and nine: 3x the warps at well under half the registers.
 // Per-bin accumulation order (lattice order of the neighbours) is unchanged.
-__global__ void __launch_bounds__(3 * kNbrThreads) fpfh_list_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
+__global__ void __launch_bounds__(3 * kNbrThreads, 3) fpfh_list_kernel(const float4* __restrict__ pts, const int* __restrict__ n_pts, int V,
                                                                     const float* __restrict__ spfh, const unsigned short* __restrict__ nbr_list,
                                                                     const int* __restrict__ nbr_cnt, float* __restrict__ desc_t) {
   const int cloud = blockIdx.y;
@@ -586,15 +586,25 @@ __global__ void __launch_bounds__(3 * kNbrThreads) fpfh_list_kernel(const float4
   for (int b = 0; b < 11; ++b) o[b] = 0.0f;
   double sum = 0.0;
   const unsigned short* __restrict__ gl = nbr_list + (size_t)cloud * kNbrGlobalCap * V + q;
+  // Two-deep software pipeline: the index of neighbour t + 2 and the point / SPFH third of neighbour t + 1 are in flight while
+  // neighbour t is accumulated (the chain index -> rows -> 11 dependent adds was one full L1/L2 latency per step: 66 % of the
+  // scheduler cycles had no eligible warp).  The accumulation order is unchanged.
+  int p_n = kq > 0 ? (int)gl[0] : 0;
+  int p_nn = kq > 1 ? (int)gl[(size_t)V] : 0;
+  float4 pp_n = P[p_n];
+  float4 a0 = __ldg(sp + (size_t)p_n * (kDescPad / 4)), a1 = __ldg(sp + (size_t)p_n * (kDescPad / 4) + 1), a2 = __ldg(sp + (size_t)p_n * (kDescPad / 4) + 2);
   for (int t = 0; t < kq; ++t) {
-    const int p = (int)gl[(size_t)t * V];
-    const float4 pp = P[p];
+    const float4 pp = pp_n, t0 = a0, t1 = a1, t2 = a2;
+    if (t + 1 < kq) {
+      const int pn = p_nn;
+      if (t + 2 < kq) p_nn = (int)gl[(size_t)(t + 2) * V];
+      pp_n = P[pn];
+      a0 = __ldg(sp + (size_t)pn * (kDescPad / 4)); a1 = __ldg(sp + (size_t)pn * (kDescPad / 4) + 1); a2 = __ldg(sp + (size_t)pn * (kDescPad / 4) + 2);
+    }
     const float dx = pq.x - pp.x, dy = pq.y - pp.y, dz = pq.z - pp.z;
     const float d2 = (dx * dx + dy * dy) + dz * dz;  // the same expression as the neighbour test: bit-identical
     if (d2 == 0.0f) continue;
     const float weight = 1.0f / d2;
-    const float4 t0 = __ldg(sp + (size_t)p * (kDescPad / 4)), t1 = __ldg(sp + (size_t)p * (kDescPad / 4) + 1),
-                 t2 = __ldg(sp + (size_t)p * (kDescPad / 4) + 2);
     const float sv[11] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z};
 #pragma unroll
     for (int b = 0; b < 11; ++b) { const float v = sv[b] * weight; sum += v; o[b] += v; }
