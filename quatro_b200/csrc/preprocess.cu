@@ -400,7 +400,8 @@ int launch_patchwork(qb200_handle* h, const float4* pts, int n, const qb200_patc
 //   ip_range_kernel    winner -> range image, parent = own pixel (or -1: nothing projected, maskGround :354-363)
 //   ip_union_kernel    one thread per pixel and forward neighbour: union when the angle criterion holds
 //   ip_stats_kernel    flatten; component size and the set of rows touched by its pixels other than the seed (lineCountFlag, :545)
-//   ip_extract_kernel  feasibility (:559-571) and the two outputs in row-major order (:424-481)
+//   ip_kind_kernel     feasibility of every pixel's segment (:559-571), counts per block of 1024 pixels
+//   ip_extract_kernel  the two outputs in row-major order (:424-481): block base from the counts, one block scan inside
 // ------------------------------------------------------------------------------------------------
 struct IpDev {
   qb200_segment_params p;
@@ -505,42 +506,65 @@ __global__ void __launch_bounds__(256) ip_stats_kernel(int npix, int Wd, int* pa
   if (q != root) atomicOr(&rows[root], 1ull << (q / Wd));
 }
 
-// one CTA: ordered extraction (row-major) of the valid-segment points and of the outliers
-__global__ void __launch_bounds__(1024) ip_extract_kernel(const float4* __restrict__ pts, int npix, IpDev c, const int* __restrict__ winner,
-                                                          const int* parent, const int* __restrict__ size,
-                                                          const unsigned long long* __restrict__ rows, float4* __restrict__ valid,
-                                                          float4* __restrict__ outlier, int* __restrict__ out_n) {
-  __shared__ int sm[33];
-  int cv = 0, co = 0;
-  for (int base = 0; base < npix; base += 1024) {
-    const int q = base + threadIdx.x;
-    int kind = 0;  // 1 valid segment, 2 outlier
-    if (q < npix && winner[q] >= 0) {
-      const int root = ip_find(parent, q);
-      const int sz = size[root];
-      bool feasible = sz >= c.p.min_pts_for_subclustering;
-      if (!feasible && sz >= c.p.segment_valid_point_num) feasible = __popcll(rows[root]) >= c.p.segment_valid_line_num;
-      kind = feasible ? 1 : 2;
-    }
-    int both;
-    const int ex = block_excl_scan((kind == 1 ? 1 : 0) | ((kind == 2 ? 1 : 0) << 16), sm, &both);
-    if (kind) {
-      float4 p = pts[winner[q]];
-      p.w = 1.0f;
-      if (kind == 1) valid[cv + (ex & 0xFFFF)] = p;
-      else outlier[co + (ex >> 16)] = p;
-    }
-    cv += both & 0xFFFF;
-    co += both >> 16;
+// feasibility of every occupied pixel's segment (:559-571) -> kind[] (0 empty, 1 valid segment, 2 outlier) and the two counts of
+// every block of 1024 pixels
+__global__ void __launch_bounds__(1024) ip_kind_kernel(int npix, IpDev c, const int* __restrict__ winner, const int* parent, const int* __restrict__ size,
+                                                       const unsigned long long* __restrict__ rows, unsigned char* __restrict__ kind_out,
+                                                       int* __restrict__ blk_cnt) {
+  __shared__ int s_v, s_o;
+  if (threadIdx.x == 0) { s_v = 0; s_o = 0; }
+  __syncthreads();
+  const int q = blockIdx.x * 1024 + threadIdx.x;
+  int kind = 0;
+  if (q < npix && winner[q] >= 0) {
+    const int root = ip_find(parent, q);
+    const int sz = size[root];
+    bool feasible = sz >= c.p.min_pts_for_subclustering;
+    if (!feasible && sz >= c.p.segment_valid_point_num) feasible = __popcll(rows[root]) >= c.p.segment_valid_line_num;
+    kind = feasible ? 1 : 2;
   }
-  if (threadIdx.x == 0) { out_n[0] = cv; out_n[1] = co; }
+  if (q < npix) kind_out[q] = (unsigned char)kind;
+  const unsigned bv = __ballot_sync(0xffffffffu, kind == 1), bo = __ballot_sync(0xffffffffu, kind == 2);
+  if ((threadIdx.x & 31) == 0) {
+    if (bv) atomicAdd(&s_v, __popc(bv));
+    if (bo) atomicAdd(&s_o, __popc(bo));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { blk_cnt[2 * blockIdx.x] = s_v; blk_cnt[2 * blockIdx.x + 1] = s_o; }
+}
+
+// ordered extraction (row-major, :424-481): block base = counts of the preceding blocks, one block scan inside
+__global__ void __launch_bounds__(1024) ip_extract_kernel(const float4* __restrict__ pts, int npix, const int* __restrict__ winner,
+                                                          const unsigned char* __restrict__ kind_in, const int* __restrict__ blk_cnt,
+                                                          float4* __restrict__ valid, float4* __restrict__ outlier, int* __restrict__ out_n) {
+  __shared__ int sm[33];
+  __shared__ int s_base[2];
+  int bv = 0, bo = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) { bv += blk_cnt[2 * b]; bo += blk_cnt[2 * b + 1]; }
+  int tot;
+  block_excl_scan(bv, sm, &tot);
+  if (threadIdx.x == 0) s_base[0] = tot;
+  block_excl_scan(bo, sm, &tot);
+  if (threadIdx.x == 0) s_base[1] = tot;
+  __syncthreads();
+  const int q = blockIdx.x * 1024 + threadIdx.x;
+  const int kind = q < npix ? (int)kind_in[q] : 0;
+  int both;
+  const int ex = block_excl_scan((kind == 1 ? 1 : 0) | ((kind == 2 ? 1 : 0) << 16), sm, &both);
+  if (kind) {
+    float4 p = pts[winner[q]];
+    p.w = 1.0f;
+    if (kind == 1) valid[s_base[0] + (ex & 0xFFFF)] = p;
+    else outlier[s_base[1] + (ex >> 16)] = p;
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { out_n[0] = s_base[0] + (both & 0xFFFF); out_n[1] = s_base[1] + (both >> 16); }
 }
 
 static int ensure_ip_scratch(qb200_handle* h, int npix) {
   if (h->ip_buf && h->ip_npix >= npix) return QB200_OK;
   if (h->ip_buf) { cudaFree(h->ip_buf); h->ip_buf = nullptr; }
-  // per pixel: rows u64 | valid float4 | outlier float4 | winner, parent, size int | range float ; + out_n [2]
-  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ip_buf, (size_t)npix * (8 + 16 + 16 + 4 * 4) + 16));
+  // per pixel: rows u64 | valid float4 | outlier float4 | winner, parent, size int | range float | kind u8 ; + out_n [2] + block counts
+  QB_CUDA_TRY(h, cudaMalloc((void**)&h->ip_buf, (size_t)npix * (8 + 16 + 16 + 4 * 4 + 1) + 16 + 8 * (size_t)((npix + 1023) / 1024) + 64));
   h->ip_npix = npix;
   return QB200_OK;
 }
@@ -559,14 +583,16 @@ int launch_segment_cloud(qb200_handle* h, const float4* pts, int n, const qb200_
   const int npix = sp.n_scan * sp.horizon_scan;
   if (int rc = ensure_ip_scratch(h, npix)) return rc;
   unsigned char* b = reinterpret_cast<unsigned char*>(h->ip_buf);
-  unsigned long long* rows = reinterpret_cast<unsigned long long*>(b); b += (size_t)npix * 8;
-  float4* valid = reinterpret_cast<float4*>(b); b += (size_t)npix * 16;
+  float4* valid = reinterpret_cast<float4*>(b); b += (size_t)npix * 16;      // 16-byte records first: aligned for any image size
   float4* outlier = reinterpret_cast<float4*>(b); b += (size_t)npix * 16;
+  unsigned long long* rows = reinterpret_cast<unsigned long long*>(b); b += (size_t)npix * 8;
   int* winner = reinterpret_cast<int*>(b); b += (size_t)npix * 4;
   int* parent = reinterpret_cast<int*>(b); b += (size_t)npix * 4;
   int* size = reinterpret_cast<int*>(b); b += (size_t)npix * 4;
   float* range = reinterpret_cast<float*>(b); b += (size_t)npix * 4;
-  int* out_n = reinterpret_cast<int*>(b);
+  int* out_n = reinterpret_cast<int*>(b); b += 16;
+  int* blk_cnt = reinterpret_cast<int*>(b); b += 8 * (size_t)((npix + 1023) / 1024);
+  unsigned char* kind = b;
   *valid_dev = valid; *outlier_dev = outlier;
   IpDev c;
   c.p = sp;
@@ -588,8 +614,10 @@ int launch_segment_cloud(qb200_handle* h, const float4* pts, int n, const qb200_
   ip_range_kernel<<<gp, 256, 0, h->stream>>>(pts, npix, winner, range, parent, size, rows);
   ip_union_kernel<<<gp, 256, 0, h->stream>>>(npix, c, range, parent);
   ip_stats_kernel<<<gp, 256, 0, h->stream>>>(npix, sp.horizon_scan, parent, size, rows);
-  ip_extract_kernel<<<1, 1024, 0, h->stream>>>(pts, npix, c, winner, parent, size, rows, valid, outlier, out_n);
-  h->launches += 5;
+  const int nblk = (npix + 1023) / 1024;
+  ip_kind_kernel<<<nblk, 1024, 0, h->stream>>>(npix, c, winner, parent, size, rows, kind, blk_cnt);
+  ip_extract_kernel<<<nblk, 1024, 0, h->stream>>>(pts, npix, winner, kind, blk_cnt, valid, outlier, out_n);
+  h->launches += 6;
   QB_CUDA_TRY(h, cudaGetLastError());
   int host_n[2];
   QB_CUDA_TRY(h, cudaMemcpyAsync(host_n, out_n, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
