@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(kCliqueWarps * 32) clique_cta_kernel(const uin
 // ------------------------------------------------------------------------------------------------
 constexpr int kExactDepth = 1024;      // levels of the stack (a clique larger than this ends the search with the truncation flag)
 constexpr int kExactPool = 1 << 17;    // list entries per pair
+constexpr int kExactChunk = 64;        // pairs searched by one launch (the scratch is sized for these, not for max_batch_slots)
 
 template <int WPL>
 __device__ __forceinline__ int exact_colour_sort(const uint32_t* __restrict__ rows, int stride, int nbw, const uint32_t (&P)[WPL], int kmin,
@@ -599,11 +600,11 @@ template <int WPL>
 __global__ void __launch_bounds__(32) clique_exact_kernel(const uint32_t* __restrict__ adjp, const int* __restrict__ n_corr, int Lc, int W,
                                                          const int* __restrict__ by_rank, const int* __restrict__ rank_of,
                                                          const int* __restrict__ kbin, const int* __restrict__ max_core_in, long long node_limit,
-                                                         int cache_words, uint32_t* __restrict__ stackP, uint32_t* __restrict__ pool,
+                                                         int cache_words, int pair_base, uint32_t* __restrict__ stackP, uint32_t* __restrict__ pool,
                                                          int* __restrict__ lvl_begin, int* __restrict__ lvl_n, unsigned short* __restrict__ cur_c,
                                                          int* __restrict__ clique, int* __restrict__ n_clique, int* __restrict__ flags) {
   extern __shared__ uint32_t ex_cache[];  // [cache_words] rank-space adjacency when it fits
-  const int pair = blockIdx.x, lane = lane_id();
+  const int pair = pair_base + blockIdx.x, slot = blockIdx.x, lane = lane_id();   // scratch is per launch slot, data per pair
   const int L = n_corr[pair];
   if (L <= 0) return;
   int best = n_clique[pair];
@@ -620,11 +621,11 @@ __global__ void __launch_bounds__(32) clique_exact_kernel(const uint32_t* __rest
   const int stride = cached ? nbw : W;
   const int* __restrict__ br = by_rank + (size_t)pair * (Lc + 2);
   const int* __restrict__ kb = kbin + (size_t)pair * (Lc + 2);
-  uint32_t* __restrict__ SP = stackP + (size_t)pair * kExactDepth * W;
-  uint32_t* __restrict__ LP = pool + (size_t)pair * kExactPool;
-  int* __restrict__ lb = lvl_begin + (size_t)pair * kExactDepth;
-  int* __restrict__ ln = lvl_n + (size_t)pair * kExactDepth;
-  unsigned short* __restrict__ C = cur_c + (size_t)pair * kExactDepth;
+  uint32_t* __restrict__ SP = stackP + (size_t)slot * kExactDepth * W;
+  uint32_t* __restrict__ LP = pool + (size_t)slot * kExactPool;
+  int* __restrict__ lb = lvl_begin + (size_t)slot * kExactDepth;
+  int* __restrict__ ln = lvl_n + (size_t)slot * kExactDepth;
+  unsigned short* __restrict__ C = cur_c + (size_t)slot * kExactDepth;
   int* __restrict__ out = clique + (size_t)pair * Lc;
 
   uint32_t P[WPL];
@@ -741,7 +742,7 @@ static int launch_kcore(qb200_handle* h, int n_pairs, bool set_attr) {
 // PMC_EXACT scratch (level stack, list pool), allocated on the first exact call of a handle
 static int ensure_exact_scratch(qb200_handle* h) {
   if (h->ex_stack) return QB200_OK;
-  const size_t S = h->S;
+  const size_t S = h->S < kExactChunk ? h->S : kExactChunk;
   QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_stack, S * kExactDepth * (size_t)h->W * sizeof(uint32_t)));
   QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_pool, S * (size_t)kExactPool * sizeof(uint32_t)));
   QB_CUDA_TRY(h, cudaMalloc((void**)&h->ex_lvl, S * 2 * (size_t)kExactDepth * sizeof(int)));
@@ -752,10 +753,14 @@ static int ensure_exact_scratch(qb200_handle* h) {
 template <int WPL>
 static int launch_exact(qb200_handle* h, int n_pairs, long long node_limit, int cache_words) {
   if (int rc = ensure_dyn_smem(h, (const void*)clique_exact_kernel<WPL>, (size_t)cache_words * 4)) return rc;
-  clique_exact_kernel<WPL><<<n_pairs, 32, (size_t)cache_words * 4, h->stream>>>(
-      h->adjp, h->ctr.n_corr, h->Lc, h->W, h->by_rank, h->rank_of, h->kbin, h->ctr.max_core, node_limit, cache_words, h->ex_stack, h->ex_pool,
-      h->ex_lvl, h->ex_lvl + (size_t)h->S * kExactDepth, h->ex_cur, h->clique, h->ctr.n_clique, h->ctr.flags);
-  h->launches++;
+  const int chunk = h->S < kExactChunk ? h->S : kExactChunk;
+  for (int base = 0; base < n_pairs; base += chunk) {   // chunks run one after the other on the stream and share the scratch
+    const int np = n_pairs - base < chunk ? n_pairs - base : chunk;
+    clique_exact_kernel<WPL><<<np, 32, (size_t)cache_words * 4, h->stream>>>(
+        h->adjp, h->ctr.n_corr, h->Lc, h->W, h->by_rank, h->rank_of, h->kbin, h->ctr.max_core, node_limit, cache_words, base, h->ex_stack,
+        h->ex_pool, h->ex_lvl, h->ex_lvl + (size_t)chunk * kExactDepth, h->ex_cur, h->clique, h->ctr.n_clique, h->ctr.flags);
+    h->launches++;
+  }
   return QB200_OK;
 }
 

@@ -70,9 +70,9 @@ struct qb200_handle {
   int* deg;                   // [S*Lc]
   int *kcore, *korder, *rank_of, *by_rank, *kbin;  // [S*(Lc+2)]
   int* clique;                // [S*Lc] ascending ids
-  uint32_t *ex_stack, *ex_pool;  // PMC_EXACT scratch, allocated on first use: [S*1024*W] candidate sets per level, [S*2^17] list entries
-  int* ex_lvl;                // [2*S*1024] list segment (begin | remaining) per level
-  unsigned short* ex_cur;     // [S*1024] clique under construction (ranks)
+  uint32_t *ex_stack, *ex_pool;  // PMC_EXACT scratch, allocated on first use: [min(S,64)*1024*W] candidate sets per level, [min(S,64)*2^17] list entries
+  int* ex_lvl;                // [2*min(S,64)*1024] list segment (begin | remaining) per level
+  unsigned short* ex_cur;     // [min(S,64)*1024] clique under construction (ranks)
   int* final_inl;             // [S*Lc]
   unsigned char *rot_mask, *trans_mask;  // [S*Lc]
   // ---- pre-processing (preprocess.cu), allocated on first use ----

@@ -393,6 +393,14 @@ def test_exact_mode_pipeline(handle, oracle):
         assert st_g == st_o and r_g.clique_size == r_o.clique_size and r_g.flags == r_o.flags
         assert np.array_equal(handle.last_clique(), np.sort(handle.last_clique()))
         assert np.allclose(r_g.matrix(), r_o.matrix(), atol=1e-9)
+    # a wave of more than 64 sets: the exact search runs 64 pairs per launch on shared scratch
+    with Handle(max_batch_slots=72, max_raw_points=16384, max_voxel_points=2048, max_corr=512) as hb:
+        sets = [synth.matched_pairs(100 + i, 150 + 3 * i, inlier_ratio=0.15, noise=0.05)[:2] for i in range(72)]
+        out = hb.solve_batch(sets, p)
+        for i in (0, 1, 31, 63, 64, 65, 71):
+            r_o, st_o = oracle.solve_correspondences(sets[i][0], sets[i][1], p)
+            assert out[i]["clique_size"] == r_o.clique_size and out[i]["flags"] == r_o.flags and out[i]["status"] == st_o
+            assert np.allclose(np.asarray(out[i]["T"]).reshape(4, 4).T, r_o.matrix(), atol=1e-9)
     # whole pairs through the batch path (several pairs per wave, exact search per pair)
     pairs = [synth.outdoor_pair(40 + i, rings=32, azimuths=900)[:2] for i in range(3)]
     res = handle.register_batch(pairs, p)
