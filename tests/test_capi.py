@@ -62,3 +62,37 @@ def test_product_does_not_reference_the_oracle():
     for f in list((ROOT / "quatro_b200").rglob("*.py")) + list((ROOT / "quatro_b200" / "csrc").glob("*")) + list((ROOT / "include").rglob("*.h*")):
         txt = f.read_text(errors="ignore")
         assert "quatro_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt and "qo_" not in txt.replace("qo_math", ""), f
+
+
+def test_pod_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of every POD of include/quatro_b200.h have the size and field offsets a C compiler gives them."""
+    import subprocess
+    from quatro_b200 import capi
+    src = tmp_path / "pod.c"
+    src.write_text('''
+#include <stddef.h>
+#include <stdio.h>
+#include "quatro_b200.h"
+#define S(t) printf("%s %zu\\n", #t, sizeof(t))
+#define O(t, f) printf("%s.%s %zu\\n", #t, #f, offsetof(t, f))
+int main(void) {
+  S(qb200_params); S(qb200_config); S(qb200_result); S(qb200_pair); S(qb200_patchwork_params); S(qb200_segment_params);
+  O(qb200_params, seed); O(qb200_params, noise_bound); O(qb200_params, max_clique_node_limit); O(qb200_params, RyRx);
+  O(qb200_result, flags); O(qb200_result, n_edges); O(qb200_result, T);
+  O(qb200_patchwork_params, min_ranges_each_zone); O(qb200_patchwork_params, num_iter); O(qb200_patchwork_params, num_rings_each_zone);
+  O(qb200_segment_params, segment_theta); O(qb200_segment_params, segment_valid_line_num);
+  return 0;
+}
+''')
+    exe = tmp_path / "pod"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    mirror = {"qb200_params": capi.Params, "qb200_config": capi.Config, "qb200_result": capi.Result, "qb200_pair": capi.Pair,
+              "qb200_patchwork_params": capi.PatchworkParams, "qb200_segment_params": capi.SegmentParams}
+    for name, val in got.items():
+        if "." in name:
+            t, f = name.split(".")
+            assert getattr(mirror[t], f).offset == int(val), name
+        else:
+            assert C.sizeof(mirror[name]) == int(val), name
