@@ -5,8 +5,9 @@
 // pcl::FPFHEstimationOMP, pcl::search::KdTree).
 //
 // Design: every cloud of a batch wave is processed by the same launches (grid.y = cloud); sizes
-// stay on the device.  Voxelisation is one 64-bit radix sort of (cloud | cell) keys followed by a
-// segmented, in-order centroid sum (bit-identical to the sequential CPU sum).  The kd-tree is
+// stay on the device.  Voxelisation is a stable per-cloud radix sort of the (voxel | point index) items of the KEPT
+// points (voxsort.cu; the device-wide library sort below is the fallback for handles too small for its scratch and the
+// QB200_VOXEL_SORT=cub A/B switch) followed by a segmented, in-order centroid sum (bit-identical to the sequential CPU sum).  The kd-tree is
 // replaced by a sorted-cell lattice: a point's neighbours are found by (2m+1)^2 binary searches for
 // x-runs of cells, visited in ascending (cell, index) order -- the accumulation order the CPU oracle
 // uses, so the single-pass float covariance matches bit for bit.
@@ -57,8 +58,8 @@ static int clog2(int n) {
 // ------------------------------------------------------------------------------------------------
 // K1a: bounding box of the kept raw points (one pass, 128-bit loads), then raw point -> (cloud | voxel) key.
 // The voxel key is PCL's own linear index  (i - min_i) + (j - min_j) dx + (k - min_k) dx dy  ([EXT] pcl::VoxelGrid,
-// called from include/quatro.hpp:49-57), which the library requires to fit an int: 31 key bits + the cloud id, so the
-// radix sort of the whole wave needs 5 passes instead of the 8 an absolute (k, j, i) lattice key would take.
+// called from include/quatro.hpp:49-57), which the library requires to fit an int: at most 31 key bits, and for a given cloud
+// only the bits of dx dy dz (vox_digits()); the library-sort fallback adds the cloud id above them (5 passes over 38 bits).
 // ------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) voxel_bbox_kernel(const float4* const* __restrict__ cloud_ptr, const int* __restrict__ cloud_n,
