@@ -235,3 +235,69 @@ def test_segment_cloud_gpu_matches_oracle(handle, oracle):
     ref, st_ref = oracle.register_pair(chain_o(src), chain_o(tgt), p)
     assert st == st_ref and res.n_src_vox == ref.n_src_vox and res.n_corr == ref.n_corr and res.clique_size == ref.clique_size
     assert np.allclose(res.matrix(), ref.matrix(), atol=1e-9)
+
+
+# ---- independent float64 restatement of Patchwork (numpy: two-pass covariance, LAPACK SVD) ---------------------------------
+def _numpy_patchwork(pts, pp):
+    """patchwork.hpp:329-455 in float64 numpy, written from the reference text: returns boolean masks (ground, nonground) over pts."""
+    P = pts[:, :3].astype(np.float64)
+    n = len(P)
+    ok = np.isfinite(P).all(1) & ~(P[:, 2] < -1.8 * pp.sensor_height)
+    r = np.hypot(P[:, 0], P[:, 1])
+    th = np.arctan2(P[:, 1], P[:, 0]); th = np.where(th > 0, th, th + 2 * np.pi)
+    ok &= (r <= pp.max_range) & (r > pp.min_range)
+    mr = list(pp.min_ranges_each_zone) + [pp.max_range]
+    zone = np.clip(np.searchsorted(np.array(mr[1:4]), r, side="right"), 0, 3)
+    ground, nonground = np.zeros(n, bool), np.zeros(n, bool)
+    concentric = 0
+    for k in range(4):
+        nr, ns = pp.num_rings_each_zone[k], pp.num_sectors_each_zone[k]
+        ring = np.minimum(((r - mr[k]) / ((mr[k + 1] - mr[k]) / nr)).astype(int), nr - 1)
+        sec = np.minimum((th / (2 * np.pi / ns)).astype(int), ns - 1)
+        for ri in range(nr):
+            for si in range(ns):
+                idx = np.nonzero(ok & (zone == k) & (ring == ri) & (sec == si))[0]
+                if len(idx) <= pp.num_min_pts:
+                    continue
+                idx = idx[np.argsort(P[idx, 2], kind="stable")]
+                z = P[idx, 2]
+                init = int((z < pp.adaptive_seed_selection_margin * pp.sensor_height).sum()) if k == 0 else 0
+                lpr = z[init:init + pp.num_lpr].mean() if len(z[init:init + pp.num_lpr]) else 0.0
+                g = z < lpr + pp.th_seeds
+                for _ in range(pp.num_iter):
+                    Q = P[idx][g]
+                    mean = Q.mean(0)
+                    cov = (Q - mean).T @ (Q - mean) / len(Q)
+                    U, S, _ = np.linalg.svd(cov)
+                    nrm = U[:, 2] if U[2, 2] >= 0 else -U[:, 2]
+                    g = P[idx] @ nrm < pp.th_dist + nrm @ mean
+                keep = abs(nrm[2]) >= pp.uprightness_thr
+                if keep and concentric + ri < pp.num_thresholds:
+                    if mean[2] > pp.elevation_thresholds[ri + 2 * k]:
+                        keep = pp.flatness_thresholds[ri + 2 * k] > S[2] / S.sum()
+                elif keep and pp.using_global_elevation and mean[2] > pp.global_elevation_threshold:
+                    keep = False
+                if keep:
+                    ground[idx[g]] = True; nonground[idx[~g]] = True
+                else:
+                    nonground[idx] = True
+        concentric += nr
+    return ground, nonground
+
+
+def test_patchwork_against_float64_numpy(oracle):
+    """The oracle's canonical choices (float single-pass sums in a fixed tree, closed-form eigen solve, n_z >= 0) against a float64
+    two-pass covariance + LAPACK SVD restatement: the same points are kept, and the labels agree for >= 99.5 % of them (a point within
+    float rounding of the th_dist plane may flip, and with it the next iteration's fit of its patch)."""
+    pp = default_patchwork_params()
+    for pts in (synth.outdoor_pair(41)[0], _scene(7)):
+        pts = pts.copy()
+        pts[:, 3] = np.arange(len(pts), dtype=np.float32)          # the 4th channel carries the point id through the outputs
+        assert len(pts) < 2 ** 24
+        g, ng, _ = oracle.patchwork(pts, pp)
+        G, N = _numpy_patchwork(pts, pp)
+        got_g, got_n = np.zeros(len(pts), bool), np.zeros(len(pts), bool)
+        got_g[g[:, 3].astype(int)] = True; got_n[ng[:, 3].astype(int)] = True
+        assert np.array_equal(got_g | got_n, G | N)                 # the same points survive the range / height / patch-size rules
+        agree = ((got_g == G) & (got_n == N))[G | N].mean()
+        assert agree >= 0.995, agree
